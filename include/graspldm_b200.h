@@ -1,0 +1,184 @@
+/*
+ * graspldm_b200 - C ABI of the B200-native (sm_100a) GraspLDM generation path.
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*), launches
+ * asynchronously on that stream and returns 0 on success or a negative GLDM_E* code; the text of
+ * the last error of the calling thread is available from gldm_last_error().  No torch types.
+ *
+ * Section A replaces, one for one, the pybind11 surface of the reference's operator extension
+ * `_pvcnn_backend` (R = /root/reference/grasp_ldm/models/modules/ext/pvcnn/modules/functional/src):
+ * the reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ * Section B are the fused entry points behind the model-class API (boundary A of SURVEY.md 8b).
+ */
+#ifndef GRASPLDM_B200_H_
+#define GRASPLDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLDM_OK 0
+#define GLDM_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define GLDM_ECUDA (-2)    /* CUDA runtime error at launch */
+#define GLDM_ENOSUP (-3)   /* configuration not supported by this build */
+
+const char* gldm_last_error(void);
+int gldm_version(void);
+/* number of kernels this library has launched since load (bench.py reports the delta) */
+unsigned long long gldm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Section A - operator FFI (replaces R/bindings.cpp:10-37)
+ * ------------------------------------------------------------------------------------------ */
+
+/* avg_voxelize_forward            R/voxelization/vox.cpp:17-43, vox.cu:18-72
+ * features f32[b,c,n], coords i32[b,3,n] (voxel coords in [0,r)) ->
+ * out f32[b,c,r^3], ind i32[b,n], cnt i32[b,r^3].  All outputs are fully written (no pre-zeroing
+ * needed).  Sums run in ascending point order, so the result is run-to-run deterministic
+ * (the reference uses float atomics). */
+int gldm_avg_voxelize_forward(const float* features, const int* coords, int b, int c, int n, int r,
+                              float* out, int* ind, int* cnt, void* stream);
+/* avg_voxelize_backward           R/voxelization/vox.cpp:54-77, vox.cu:86-110
+ * grad_y f32[b,c,r^3], ind i32[b,n], cnt i32[b,r^3] -> grad_x f32[b,c,n] */
+int gldm_avg_voxelize_backward(const float* grad_y, const int* ind, const int* cnt, int b, int c, int n,
+                               int r3, float* grad_x, void* stream);
+
+/* trilinear_devoxelize_forward    R/interpolate/trilinear_devox.cpp:18-55, trilinear_devox.cu:21-105
+ * coords f32[b,3,n] (voxel units), features f32[b,c,r^3] -> outs f32[b,c,n];
+ * inds i32[b,8,n] / wgts f32[b,8,n] are written only when is_training != 0 (may be NULL otherwise). */
+int gldm_trilinear_devoxelize_forward(const float* coords, const float* features, int b, int c, int n, int r,
+                                      int is_training, float* outs, int* inds, float* wgts, void* stream);
+/* trilinear_devoxelize_backward   R/interpolate/trilinear_devox.cpp:67-92
+ * grad_y f32[b,c,n], inds i32[b,8,n], wgts f32[b,8,n] -> grad_x f32[b,c,r3] (zeroed by the call) */
+int gldm_trilinear_devoxelize_backward(const float* grad_y, const int* inds, const float* wgts, int b, int c,
+                                       int n, int r3, float* grad_x, void* stream);
+
+/* furthest_point_sampling         R/sampling/sampling.cpp:43-58, sampling.cu:86-167
+ * coords f32[b,3,n] -> indices i32[b,m]; bit-exact index contract (start 0, FMA chain
+ * fma(dz,dz,fma(dx,dx,dy*dy)), ties -> smallest (k mod 512) then smallest k). */
+int gldm_furthest_point_sampling(const float* coords, int b, int n, int m, int* indices, void* stream);
+
+/* gather_features_forward/backward R/sampling/sampling.cpp:6-41, sampling.cu:17-73
+ * features f32[b,c,n], indices i32[b,m] -> out f32[b,c,m];  backward: grad_y f32[b,c,m] -> grad_x f32[b,c,n] */
+int gldm_gather_features_forward(const float* features, const int* indices, int b, int c, int n, int m,
+                                 float* out, void* stream);
+int gldm_gather_features_backward(const float* grad_y, const int* indices, int b, int c, int n, int m,
+                                  float* grad_x, void* stream);
+
+/* ball_query                      R/ball_query/ball_query.cpp:6-30, ball_query.cu:19-50
+ * centers f32[b,3,m], points f32[b,3,n], radius, u -> neighbors i32[b,m,u] (bit-exact) */
+int gldm_ball_query(const float* centers, const float* points, int b, int n, int m, float radius, int u,
+                    int* neighbors, void* stream);
+
+/* grouping_forward/backward       R/grouping/grouping.cpp:6-45, grouping.cu:18-72
+ * features f32[b,c,n], indices i32[b,m,u] -> out f32[b,c,m,u];  backward -> grad_x f32[b,c,n] */
+int gldm_grouping_forward(const float* features, const int* indices, int b, int c, int n, int m, int u,
+                          float* out, void* stream);
+int gldm_grouping_backward(const float* grad_y, const int* indices, int b, int c, int n, int m, int u,
+                           float* grad_x, void* stream);
+
+/* three_nearest_neighbors_interpolate_forward/backward
+ *                                 R/interpolate/neighbor_interpolate.cpp:6-64, neighbor_interpolate.cu:20-160
+ * points f32[b,3,n], centers f32[b,3,m], feats f32[b,c,m] -> out f32[b,c,n], idx i32[b,3,n], w f32[b,3,n] */
+int gldm_three_nn_interpolate_forward(const float* points, const float* centers, const float* feats, int b,
+                                      int c, int m, int n, float* out, int* idx, float* w, void* stream);
+int gldm_three_nn_interpolate_backward(const float* grad_y, const int* idx, const float* w, int b, int c,
+                                       int n, int m, float* grad_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Section B - fused generation path (boundary A: model classes call these)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Voxelization.forward + avg_voxelize in one launch
+ *   (R/../pvcnn/modules/voxelization.py:16-35, normalize=False branch, + vox.cu:18-72)
+ * features f32[b,c,n], coords f32[b,3,n] -> grid f32[b,c,r^3], norm_coords f32[b,3,n]
+ * (the clamped float coordinates devoxelize consumes), vox i32[b,3,n] (optional, may be NULL). */
+int gldm_voxelize_fused(const float* features, const float* coords, int b, int c, int n, int r, float* grid,
+                        float* norm_coords, int* vox, void* stream);
+
+/* ---- dense fp32 building blocks of the encoder (SIMT, strict-fp32 parity mode) ---- */
+/* y[b,co,n] = act(scale[co] * (sum_ci W[co,ci] x[b,ci,n]) + shift[co]) (+ add[b,co,n] when add != NULL)
+ * act: 0 none, 1 relu.  Conv1d k=1 + folded bias/BatchNorm(eval) + ReLU == SharedMLP
+ * (R/../pvcnn/modules/shared_mlp.py:18-28), conv_downscale, out_layer.0 (R/models/modules/pc_encoders.py:60-75) */
+int gldm_pointwise_conv_f32(const float* x, const float* w, const float* scale, const float* shift,
+                            const float* add, int b, int ci, int co, int n, int act, float* y, void* stream);
+/* Conv3d k=3 pad=1 + bias on [b,ci,r,r,r] -> [b,co,r,r,r]   (R/../pvcnn/modules/pvconv.py:48-67) */
+int gldm_conv3d_k3_f32(const float* x, const float* w, const float* bias, int b, int ci, int co, int r,
+                       float* y, void* stream);
+/* GroupNorm(groups, eps) + Swish in place on [b,c,s]; when se_mean != NULL also writes the per-(b,c) mean of
+ * the activated output (SE3d squeeze, R/../pvcnn/modules/se.py:22-25). */
+int gldm_groupnorm_swish_f32(float* x, const float* gamma, const float* beta, int b, int c, int s, int groups,
+                             float eps, float* se_mean, void* stream);
+/* SE3d excite: gate[b,c] = sigmoid(W2 swish(W1 mean[b,:])) ; x[b,c,:] *= gate[b,c]  (se.py:12-25) */
+int gldm_se_gate_f32(const float* mean, const float* w1, const float* w2, int b, int c, int cr, float* gate,
+                     void* stream);
+/* trilinear devoxelize of (grid * gate) fused with the residual add of the point branch:
+ * out[b,c,n] = devox(grid[b,c,:] * gate[b,c], coords)[n] + point[b,c,n]    (pvconv.py:79-83) */
+int gldm_devox_gate_add_f32(const float* coords, const float* grid, const float* gate, const float* point,
+                            int b, int c, int n, int r, float* out, void* stream);
+/* Linear over the point axis: y[b,c,f] = sum_n x[b,c,n] W[f,n] + bias[f]   (pc_encoders.py:76-79) */
+int gldm_linear_lastdim_f32(const float* x, const float* w, const float* bias, int rows, int n, int f, float* y,
+                            void* stream);
+
+/* ---- ResNet1D family (denoiser / decoder), SURVEY.md 8a rows a17-a19 ---- */
+typedef struct GldmResNetCfg {
+  int L;             /* sequence length: latent dim D (denoiser) / feature_resolution (decoder) */
+  int n_stages;      /* 4 */
+  int ch[6];         /* ch[0] = dim, ch[1..n_stages] = block_channels */
+  int emb_dim;       /* 4 * dim */
+  int cond_ch;       /* conditioning channels (3) */
+  int cond_dim;      /* conditioning features (64 fpc / 256 ppc) */
+  int groups;        /* GroupNorm groups (4) */
+  int time_cond;     /* 1: TimeConditionedResNet1D, 0: ResNet1D */
+  int fourier_half;  /* 8 (learned_sinusoidal_dim / 2) */
+  int heads;         /* 4 */
+  int dim_head;      /* 32 */
+} GldmResNetCfg;
+
+/* Number of floats in the canonical raw parameter blob (state_dict tensors, fixed key order documented in
+ * graspldm_b200/engine.py:resnet_param_keys) and in the prepared blob the kernels read. */
+long long gldm_resnet_raw_floats(const GldmResNetCfg* cfg);
+long long gldm_resnet_prepared_floats(const GldmResNetCfg* cfg);
+/* One-time weight preparation on the device: weight standardisation (R/models/modules/resnets.py:85-91),
+ * [k][co] transposition.  raw and prepared are device pointers. */
+int gldm_resnet_prepare(const GldmResNetCfg* cfg, const float* raw, float* prepared, void* stream);
+
+/* Sampler descriptor: per executed step i (loop order, t descending) the integer timestep and the
+ * scheduler coefficients, computed on the host in diffusers' operator order (oracle/schedulers.py
+ * restates them): coef[i] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt_or_eps, sigma, 0,0,0}. */
+#define GLDM_SCHED_DDPM 0
+#define GLDM_SCHED_DDIM 1
+/* Whole T-step reverse diffusion in ONE launch  (GaussianDiffusion1D.sample,
+ * R/models/diffusion/gaussian_diffusion.py:232-277 + TimeConditionedResNet1D.forward resnets.py:558-616):
+ *   x_T f32[n,D] initial latents, z_obj f32[n_obj,cond_ch,cond_dim] per-object conditioning,
+ *   sample s uses object s / grasps_per_obj.
+ *   noise f32[n_steps,n,D] pre-drawn per-step noise (parity mode) or NULL -> in-kernel Philox4x32-10
+ *   + Box-Muller keyed by (seed, sample, step).
+ *   x_out f32[n,D]; x_all f32[n_steps+1,n,D] optional trajectory (may be NULL). */
+int gldm_sampler_run_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x_T, const float* z_obj,
+                         int n, int grasps_per_obj, int n_steps, const int* timesteps_host,
+                         const float* coef_host, int sched_kind, int clip_sample, const float* noise,
+                         unsigned long long seed, float* x_out, float* x_all, void* stream);
+/* One denoiser evaluation (eps prediction) with per-sample timesteps: TimeConditionedResNet1D.forward.
+ * x f32[n,D], t i32[n], z_cond f32[n,cond_ch,cond_dim] (per sample) -> eps f32[n,D] */
+int gldm_denoiser_forward_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x, const int* t,
+                              const float* z_cond, int n, float* eps, void* stream);
+/* ConditionalGraspPoseDecoder.forward (R/models/grasp_vae.py:401-436): in_layer -> ResNet1D -> heads.
+ * head weights: in_w f32[L,D] in_b[L]  tmrp_w[6,L] tmrp_b[6]  cls_w[1,L] cls_b[1] packed in `head` in
+ * that order.  z_h f32[n,D], z_obj f32[n_obj,cond_ch,cond_dim] -> tmrp f32[n,6], logit f32[n,1] */
+int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, const float* head, int D,
+                             const float* z_h, const float* z_obj, int n, int grasps_per_obj, float* tmrp,
+                             float* logit, void* stream);
+
+/* Pose post-processing (R/../tools/inference.py:627-656, R/utils/rotations.py:298-302):
+ * tmrp f32[n,6], logit f32[n], grasp_mean/std f32[6] -> grasp_tmrp f32[n,6], H f32[n,4,4], conf f32[n] */
+int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,
+                          int n, float* grasp_tmrp, float* H, float* conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRASPLDM_B200_H_ */

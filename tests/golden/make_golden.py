@@ -1,0 +1,186 @@
+"""Golden-vector generator (runs ONLY in the build container, where /root/reference exists).
+
+Imports the UNMODIFIED reference python modules from /root/reference, builds the models of the
+named configs from seeded random init, runs the reference forward passes on CPU and stores small
+input/output fixtures next to this file.  Three things stand in for packages/hardware that are
+not available here (all under tests/golden/_shims or patched below, never shipped in the product):
+
+  * addict.Dict, yapf.FormatCode           - tiny stand-ins (config plumbing only)
+  * diffusers.DDPMScheduler/DDIMScheduler  - oracle/schedulers.py restatement (parity unpinned)
+  * the CUDA-only `_pvcnn_backend` ops      - oracle/ops_np.py (the reference has no CPU path;
+                                              oracle/ops_np.py itself is pinned on the GPU box
+                                              against oracle/_ref, see make_golden_gpu.py)
+
+Usage:  python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from oracle import ops_np  # noqa: E402
+
+
+def _install_cpu_backend():
+    """Replace the reference's JIT-built CUDA module by a CPU object backed by oracle/ops_np.py."""
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    class _Backend:
+        @staticmethod
+        def avg_voxelize_forward(f, c, r):
+            return tuple(t(a) for a in ops_np.avg_voxelize_forward(f.numpy(), c.numpy(), r))
+
+        @staticmethod
+        def trilinear_devoxelize_forward(r, training, c, f):
+            return tuple(t(a) for a in ops_np.trilinear_devoxelize_forward(r, training, c.numpy(), f.numpy()))
+
+        @staticmethod
+        def furthest_point_sampling(c, m):
+            return t(ops_np.furthest_point_sampling(c.numpy(), m))
+
+        @staticmethod
+        def gather_features_forward(f, i):
+            return t(ops_np.gather_features_forward(f.numpy(), i.numpy()))
+
+        @staticmethod
+        def ball_query(c, p, r, u):
+            return t(ops_np.ball_query(c.numpy(), p.numpy(), r, u))
+
+        @staticmethod
+        def grouping_forward(f, i):
+            return t(ops_np.grouping_forward(f.numpy(), i.numpy()))
+
+        @staticmethod
+        def three_nearest_neighbors_interpolate_forward(p, c, f):
+            return tuple(t(a) for a in ops_np.three_nearest_neighbors_interpolate_forward(p.numpy(), c.numpy(), f.numpy()))
+
+    name = "grasp_ldm.models.modules.ext.pvcnn.modules.functional.backend"
+    mod = types.ModuleType(name)
+    mod._backend = _Backend()
+    mod.__all__ = ["_backend"]
+    sys.modules[name] = mod
+
+
+_install_cpu_backend()
+
+from grasp_ldm.models import GraspCVAE, GraspLatentDDM  # noqa: E402
+from grasp_ldm.models.modules.resnets import TimeConditionedResNet1D  # noqa: E402
+from grasp_ldm.utils.config import Config  # noqa: E402
+from grasp_ldm.utils.rotations import tmrp_to_H  # noqa: E402
+
+CONFIGS = {
+    "fpc": f"{REF}/configs/generation/fpc/fpc_1a_latentc3_z4_pc64_180k.py",
+    "ppc": f"{REF}/configs/generation/partial_pc/ppc_1a_partial_63cat8k_filtered_latentc3_z16_pc256_180k.py",
+}
+
+
+def build_reference_ldm(name, seed=0, scheduler="ddpm"):
+    """Construction order of tools/inference.py:514-516: DDM first, then the VAE."""
+    cfg = Config.fromfile(CONFIGS[name])
+    cfg.model.ddm.model.args.noise_scheduler_type = scheduler
+    # models/builder.py:59-91 builds nested `model=` dicts depth-first (denoiser, then the DDM);
+    # builder.py itself cannot be imported here (it pulls in trimesh via grasp_classifier.py).
+    torch.manual_seed(seed)
+    ddm_args = dict(cfg.model.ddm.model.args)
+    assert ddm_args["model"]["type"] == "TimeConditionedResNet1D"
+    ddm_args["model"] = TimeConditionedResNet1D(**ddm_args["model"]["args"])
+    model = GraspLatentDDM(**ddm_args)
+    model.set_vae_model(GraspCVAE(**cfg.model.vae.model.args))
+    return model.eval()
+
+
+def synthetic_clouds(B, N=1024, seed=1234, dist="S"):
+    """(S) sphere surface with per-axis scale, (G) randn*0.7."""
+    g = torch.Generator().manual_seed(seed)
+    if dist == "S":
+        p = torch.randn(B, N, 3, generator=g)
+        p = p / p.norm(dim=-1, keepdim=True)
+        p = p * (0.5 + torch.rand(B, 1, 3, generator=g))
+        return p - p.mean(1, keepdim=True)
+    return torch.randn(B, N, 3, generator=g) * 0.7
+
+
+def manifest(sd):
+    out = {}
+    for k, v in sd.items():
+        a = v.detach().cpu().contiguous().numpy()
+        out[k] = dict(shape=list(a.shape), dtype=str(a.dtype), sha=hashlib.sha256(a.tobytes()).hexdigest()[:16])
+    return out
+
+
+def main():
+    torch.set_num_threads(8)
+    np_ = lambda x: x.detach().cpu().numpy()
+    man = {}
+    for name in ("fpc", "ppc"):
+        model = build_reference_ldm(name)
+        man[name] = manifest(model.state_dict())
+        D = model.diffusion_model.n_dims
+        Dc = 64 if name == "fpc" else 256
+        den = model.diffusion_model.model
+        vae = model.vae_model
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            # ---- denoiser forward (resnets.py:558-616)
+            B = 6
+            x = torch.randn(B, 1, D, generator=g)
+            t = torch.tensor([0, 1, 10, 500, 990, 999])
+            zc = torch.randn(B, 3, Dc, generator=g)
+            eps = den(x, time=t, z_cond=zc)
+            # ---- decoder (grasp_vae.py:401-436)
+            zh = torch.randn(B, D, generator=g)
+            tmrp, logit = vae.decoder(zh, zc)
+            np.savez_compressed(f"{HERE}/dense_{name}.npz", x=np_(x), t=np_(t), z_cond=np_(zc), eps=np_(eps),
+                                z_h=np_(zh), tmrp=np_(tmrp), logit=np_(logit))
+            # ---- encoder (pc_encoders.py:87-115), sphere + gaussian clouds
+            xyz = torch.cat([synthetic_clouds(2, seed=1234, dist="S"), synthetic_clouds(1, seed=99, dist="G")])
+            z_pc = vae.encode_pc(xyz)
+            np.savez_compressed(f"{HERE}/encoder_{name}.npz", z_pc=np_(z_pc))
+            if name != "fpc":
+                continue
+            # ---- LDM sampling: reference loop + scheduler restatement, injected noise
+            nobj, G = 2, 3
+            for sched, nsteps in (("ddpm", 10), ("ddpm", 100), ("ddim", 5), ("ddpm", None)):
+                m = build_reference_ldm(name, scheduler=sched)
+                if nsteps:
+                    m.set_inference_timesteps(nsteps)
+                n_exec = nsteps if nsteps else 1000
+                gg = torch.Generator().manual_seed(42)
+                noise = torch.randn(n_exec, nobj * G, 1, D, generator=gg)
+                m.diffusion_model.noise_scheduler.injected_noise = list(noise)
+                torch.manual_seed(42)   # x_T comes from the global CPU generator (gaussian_diffusion.py:253)
+                x_T = torch.randn((nobj * G, 1, D))
+                torch.manual_seed(42)
+                (tm, lg), _ = m.generate_grasps(xyz[:nobj], num_grasps=G, device="cpu")
+                tag = f"{sched}{nsteps if nsteps else 'full'}"
+                np.savez_compressed(f"{HERE}/ldm_{name}_{tag}.npz", x_T=np_(x_T), noise=np_(noise),
+                                    tmrp=np_(tm), logit=np_(lg))
+            # ---- VAE mode (grasp_vae.py:226-255)
+            torch.manual_seed(5)
+            z_h = torch.randn(nobj * G, D)
+            torch.manual_seed(5)
+            tm, lg = vae.generate_grasps(xyz[:nobj], num_grasps=G)
+            # ---- pose post-processing (tools/inference.py:627-656, rotations.py:298-302)
+            metas = dict(grasp_std=torch.tensor([[.05, .05, .05, .5, .5, .5]]), grasp_mean=torch.zeros(1, 6))
+            g_un = tm.view(nobj, G, 6) * metas["grasp_std"].unsqueeze(-2) + metas["grasp_mean"].unsqueeze(-2)
+            H = tmrp_to_H(g_un)
+            np.savez_compressed(f"{HERE}/vae_{name}.npz", z_h=np_(z_h), tmrp=np_(tm), logit=np_(lg),
+                                grasp_tmrp=np_(g_un), H=np_(H))
+    with open(f"{HERE}/state_dict_manifest.json", "w") as f:
+        json.dump(man, f, indent=0, sort_keys=True)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
