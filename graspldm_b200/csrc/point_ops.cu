@@ -234,34 +234,47 @@ __global__ void __launch_bounds__(256) three_nn_grad_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------
 // voxelisation                                   R/voxelization/vox.cu:18-72 (+ voxelization.py:16-35 when FUSED)
-// One block per cloud.  s_cnt[r^3] lives in shared memory.  Points are ranked inside their voxel in
-// ascending point index by processing 32-point chunks in order (one warp per chunk, match.any gives
-// the in-chunk rank, s_cnt carries the running base), then accumulated rank by rank - the same order
-// the oracle uses, so averages are bit-reproducible.
+// One block per cloud; per-voxel state (count, list tail) lives in shared memory as 16-bit values.
+// Phase B threads the points of each voxel into a linked list in ascending point index: 32-point chunks
+// are processed in order (one warp per chunk), match.any finds the in-chunk predecessor and s_tail
+// carries the link across chunks.  Phase C gives every (list head, channel) pair to one thread, which
+// walks the list and sums in index order - the order the oracle uses - so the averages are
+// bit-reproducible (the reference's float atomics are not) and no global atomics are issued.
 // ------------------------------------------------------------------------------------------------
-constexpr int kVoxMaxPPT = 16;  // 512 threads x 16 -> n <= 8192 points per cloud
+constexpr int kVoxMaxPPT = 16;      // 512 threads x 16 -> n <= 8192 points per cloud
+constexpr int kVoxMaxPoints = 8192;
 template <bool FUSED>
 __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__ feat,
                                                         const void* __restrict__ coords_in, int c, int n, int r,
                                                         float* __restrict__ out, int* __restrict__ ind_out,
                                                         int* __restrict__ cnt_out, float* __restrict__ norm_out,
                                                         int* __restrict__ vox_out) {
-  extern __shared__ int s_cnt[];
+  extern __shared__ unsigned char s_raw[];
   __shared__ double s_red[3][16];
   __shared__ float s_mean[3];
-  __shared__ int s_max;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int r2 = r * r, r3 = r2 * r;
+  // carve: cnt u16[r3] | tail i16[r3] | next i16[n] | vox i32[n]
+  unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_raw);
+  short* s_tail = reinterpret_cast<short*>(s_cnt + ((r3 + 1) & ~1));
+  short* s_next = s_tail + ((r3 + 1) & ~1);
+  int* s_vox = reinterpret_cast<int*>(s_next + ((n + 1) & ~1));
   const float* fb = feat + (size_t)b * c * n;
   float* ob = out + (size_t)b * c * r3;
 
-  for (int i = tid; i < r3; i += nthreads) s_cnt[i] = 0;
-  if (tid == 0) s_max = 0;
-  // zero the output grid (the reference relies on torch::zeros)
-  for (size_t i = tid; i < (size_t)c * r3; i += nthreads) ob[i] = 0.f;
-
-  int vox[kVoxMaxPPT], rank[kVoxMaxPPT];
+  for (int i = tid; i < r3; i += nthreads) { s_cnt[i] = 0; s_tail[i] = -1; }
+  for (int i = tid; i < n; i += nthreads) s_next[i] = -1;
+  // zero the output grid (the reference relies on torch::zeros); 128-bit stores when aligned
+  {
+    size_t tot = (size_t)c * r3;
+    if ((tot & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (size_t i = tid; i < tot / 4; i += nthreads) reinterpret_cast<float4*>(ob)[i] = z;
+    } else {
+      for (size_t i = tid; i < tot; i += nthreads) ob[i] = 0.f;
+    }
+  }
   const int ppt = (n + nthreads - 1) / nthreads;
   if (FUSED) {
     const float* cf = reinterpret_cast<const float*>(coords_in) + (size_t)b * 3 * n;
@@ -289,81 +302,71 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
     }
     __syncthreads();
     const float rf = (float)r, hi = (float)(r - 1);
+    for (int i = tid; i < n; i += nthreads) {
+      int v3[3];
 #pragma unroll
-    for (int j = 0; j < kVoxMaxPPT; ++j) {
-      int i = tid + j * nthreads;
-      vox[j] = -1;
-      if (j < ppt && i < n) {
-        int v3[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          float x = __fsub_rn(cf[i + a * n], s_mean[a]);
-          x = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);               // (x + 1) / 2.0
-          x = fminf(fmaxf(__fmul_rn(x, rf), 0.f), hi);             // clamp(x * r, 0, r-1)
-          norm_out[((size_t)b * 3 + a) * n + i] = x;
-          v3[a] = (int)rintf(x);                                   // torch.round: half to even
-          if (vox_out) vox_out[((size_t)b * 3 + a) * n + i] = v3[a];
-        }
-        vox[j] = v3[0] * r2 + v3[1] * r + v3[2];
+      for (int a = 0; a < 3; ++a) {
+        float x = __fsub_rn(cf[i + a * n], s_mean[a]);
+        x = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);               // (x + 1) / 2.0
+        x = fminf(fmaxf(__fmul_rn(x, rf), 0.f), hi);             // clamp(x * r, 0, r-1)
+        norm_out[((size_t)b * 3 + a) * n + i] = x;
+        v3[a] = (int)rintf(x);                                   // torch.round: half to even
+        if (vox_out) vox_out[((size_t)b * 3 + a) * n + i] = v3[a];
       }
+      s_vox[i] = v3[0] * r2 + v3[1] * r + v3[2];
     }
   } else {
     const int* ci = reinterpret_cast<const int*>(coords_in) + (size_t)b * 3 * n;
-#pragma unroll
-    for (int j = 0; j < kVoxMaxPPT; ++j) {
-      int i = tid + j * nthreads;
-      vox[j] = (j < ppt && i < n) ? ci[i] * r2 + ci[i + n] * r + ci[i + 2 * n] : -1;
-    }
+    for (int i = tid; i < n; i += nthreads) s_vox[i] = ci[i] * r2 + ci[i + n] * r + ci[i + 2 * n];
   }
   __syncthreads();
-  // ordered ranking: chunk (j, w) = points [j*nthreads + 32w, +32)
-  int mymax = 0;
-#pragma unroll
-  for (int j = 0; j < kVoxMaxPPT; ++j) {
-    if (j < ppt) {
-      for (int w = 0; w < nwarps; ++w) {
-        if (wid == w) {
-          int v = vox[j];
-          unsigned act = __ballot_sync(0xffffffffu, v >= 0);
-          if (v >= 0) {
-            unsigned same = __match_any_sync(act, v);
-            int base = s_cnt[v];
-            __syncwarp(act);
-            if ((same & ((1u << lane) - 1u)) == 0) s_cnt[v] = base + __popc(same);
-            rank[j] = base + __popc(same & ((1u << lane) - 1u));
-            mymax = max(mymax, rank[j] + 1);
-          }
+  // Phase B: ordered chunks.  Chunk q covers points [32q, 32q+32); warp (q mod nwarps) owns it and the
+  // block barrier between consecutive groups of nwarps chunks keeps the order.
+  const int nchunks = (n + 31) >> 5;
+  for (int q0 = 0; q0 < nchunks; q0 += nwarps) {
+    for (int w = 0; w < nwarps; ++w) {
+      if (wid == w && q0 + w < nchunks) {
+        const int i = ((q0 + w) << 5) + lane;
+        const bool valid = i < n;
+        const int v = valid ? s_vox[i] : -1;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          const unsigned same = __match_any_sync(act, v);
+          const unsigned below = same & ((1u << lane) - 1u);
+          const int base = s_cnt[v];
+          const int tail = s_tail[v];
+          __syncwarp(act);
+          const int pred = below ? i - (lane - (31 - __clz(below))) : tail;
+          if (pred >= 0) s_next[pred] = (short)i;
+          if (below == 0) s_cnt[v] = (unsigned short)(base + __popc(same));
+          if ((same >> lane) == 1u) s_tail[v] = (short)i;       // highest lane of the group
         }
-        __syncthreads();
       }
+      __syncthreads();
     }
   }
-  mymax = __reduce_max_sync(0xffffffffu, mymax);
-  if (lane == 0) atomicMax(&s_max, mymax);
-  __syncthreads();
-  const int maxcnt = s_max;
-#pragma unroll
-  for (int j = 0; j < kVoxMaxPPT; ++j) {
-    int i = tid + j * nthreads;
-    if (j < ppt && i < n && ind_out) ind_out[(size_t)b * n + i] = vox[j];
-  }
+  if (ind_out)
+    for (int i = tid; i < n; i += nthreads) ind_out[(size_t)b * n + i] = s_vox[i];
   if (cnt_out)
     for (int i = tid; i < r3; i += nthreads) cnt_out[(size_t)b * r3 + i] = s_cnt[i];
-  // rank-ordered accumulation: in round k exactly one point per voxel updates it
-  for (int k = 0; k < maxcnt; ++k) {
-#pragma unroll
-    for (int j = 0; j < kVoxMaxPPT; ++j) {
-      int i = tid + j * nthreads;
-      if (j < ppt && i < n && rank[j] == k) {
-        int v = vox[j];
-        float div = (float)(1.0 / (double)(float)s_cnt[v]);        // vox.cu:65
-        for (int ch = 0; ch < c; ++ch) {
-          float* o = ob + (size_t)ch * r3 + v;
-          *o = __fadd_rn(*o, __fmul_rn(fb[(size_t)ch * n + i], div));
-        }
-      }
-    }
-    __syncthreads();
+  __syncthreads();
+  // Phase C: item (ch, i) with i a list head (the first point of its voxel, i.e. no point links to it).
+  // Successors are marked by setting bit 30 of their s_vox entry.
+  for (int i = tid; i < n; i += nthreads) {
+    int nx = s_next[i];
+    if (nx >= 0) atomicOr(&s_vox[nx], 0x40000000);               // successor is not a head
+  }
+  __syncthreads();
+  const int items = c * n;
+  for (int it = tid; it < items; it += nthreads) {
+    const int ch = it / n, i = it - ch * n;
+    const int vv = s_vox[i];
+    if (vv & 0x40000000) continue;
+    const float div = (float)(1.0 / (double)(float)s_cnt[vv]);    // vox.cu:65
+    const float* f = fb + (size_t)ch * n;
+    float acc = 0.f;
+    for (int p = i; p >= 0; p = s_next[p]) acc = __fadd_rn(acc, __fmul_rn(__ldg(f + p), div));
+    ob[(size_t)ch * r3 + vv] = acc;
   }
 }
 
@@ -588,11 +591,11 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
                            float* out, int* ind, int* cnt, float* norm, int* vox, cudaStream_t s) {
   GLDM_REQUIRE(feat && coords && out, "voxelize: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "voxelize: bad sizes b=%d c=%d n=%d r=%d", b, c, n, r);
-  GLDM_REQUIRE(n <= 512 * kVoxMaxPPT, "voxelize: n=%d > %d points per cloud not supported", n,
-               512 * kVoxMaxPPT);
-  GLDM_REQUIRE(r <= 36, "voxelize: resolution %d > 36 not supported (shared-memory histogram)", r);
+  GLDM_REQUIRE(n <= kVoxMaxPoints, "voxelize: n=%d > %d points per cloud not supported", n, kVoxMaxPoints);
+  GLDM_REQUIRE(r <= 36, "voxelize: resolution %d > 36 not supported (shared-memory voxel table)", r);
   if (b == 0) return GLDM_OK;
-  size_t smem = sizeof(int) * (size_t)r * r * r;
+  const size_t r3 = (size_t)r * r * r;
+  size_t smem = 2 * ((r3 + 1) & ~(size_t)1) * 2 + (((size_t)n + 1) & ~(size_t)1) * 2 + (size_t)n * 4;
   int threads = min(512, ceil_div(n, 32) * 32);
   if (fused) {
     static bool attr = false;

@@ -1,0 +1,330 @@
+"""Host-side orchestration of the CUDA generation path: weight packing (one-time) and kernel launches.
+
+Everything numerical happens in libgraspldm_b200.so (include/graspldm_b200.h).  PyTorch is used for
+device memory, streams and one-time layout work on weights (permutes, BatchNorm folding constants).
+There is no CPU path: tensors must live on a CUDA device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GldmResNetCfg
+
+PRECISIONS = ("fp32",)   # "bf16" (tcgen05 tensor-core path) is registered by engine_tc when built
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (graspldm_b200 has no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------------
+# ResNet1D family
+# --------------------------------------------------------------------------------------------------
+def make_resnet_cfg(L, dims, emb_dim, cond_ch, cond_dim, groups, time_cond, fourier_half):
+    cfg = GldmResNetCfg()
+    cfg.L = int(L)
+    cfg.n_stages = len(dims) - 1
+    for i, d in enumerate(dims):
+        cfg.ch[i] = int(d)
+    cfg.emb_dim, cfg.cond_ch, cfg.cond_dim = int(emb_dim), int(cond_ch), int(cond_dim)
+    cfg.groups, cfg.time_cond, cfg.fourier_half = int(groups), int(bool(time_cond)), int(fourier_half)
+    cfg.heads, cfg.dim_head = 4, 32
+    return cfg
+
+
+def resnet_param_keys(n_stages, time_cond):
+    """Canonical order of the raw parameter blob (must match make_layout in csrc/resnet1d_f32.cu)."""
+    def rb(p):
+        return [p + "mlp.1.weight", p + "mlp.1.bias", p + "block1.proj.weight", p + "block1.proj.bias",
+                p + "block1.norm.weight", p + "block1.norm.bias", p + "block2.proj.weight", p + "block2.proj.bias",
+                p + "block2.norm.weight", p + "block2.norm.bias"]
+    keys = ["init_conv.weight", "init_conv.bias"]
+    if time_cond:
+        keys += ["time_mlp.0.weights", "time_mlp.1.weight", "time_mlp.1.bias", "time_mlp.3.weight", "time_mlp.3.bias"]
+    keys += ["input_emb_layers.0.weight", "input_emb_layers.0.bias"]
+    for i in range(n_stages):
+        b = f"blocks.{i}."
+        keys += rb(b + "0.") + rb(b + "1.")
+        keys += [b + "2.fn.norm.g", b + "2.fn.fn.to_qkv.weight", b + "2.fn.fn.to_out.0.weight",
+                 b + "2.fn.fn.to_out.0.bias", b + "2.fn.fn.to_out.1.g", b + "3.weight", b + "3.bias"]
+    keys += rb("final_res_block.") + ["final_conv.weight", "final_conv.bias"]
+    return keys
+
+
+def _flatten_padded(tensors, device):
+    parts = []
+    for t in tensors:
+        f = t.detach().to(device=device, dtype=torch.float32).reshape(-1)
+        pad = (-f.numel()) % 4
+        parts.append(f)
+        if pad:
+            parts.append(torch.zeros(pad, device=device, dtype=torch.float32))
+    return torch.cat(parts).contiguous()
+
+
+def _signature(module):
+    ps = list(module.parameters())
+    return (ps[0].device, ps[0].data_ptr(), sum(p._version for p in ps))
+
+
+class PackedResNet:
+    def __init__(self, module, L, cond_ch):
+        ps = list(module.parameters())
+        dev = ps[0].device
+        _require_cuda(ps[0], "model parameters")
+        self.cfg = module.kernel_cfg(L, cond_ch)
+        sd = module.state_dict()
+        keys = resnet_param_keys(self.cfg.n_stages, self.cfg.time_cond)
+        with torch.cuda.device(dev):
+            raw = _flatten_padded([sd[k] for k in keys], dev)
+            want = _lib.lib().gldm_resnet_raw_floats(ctypes.byref(self.cfg))
+            if want != raw.numel():
+                raise RuntimeError(f"resnet blob size mismatch: packed {raw.numel()} floats, library expects {want} "
+                                   f"({_lib.lib().gldm_last_error().decode()})")
+            self.prepared = torch.empty(_lib.lib().gldm_resnet_prepared_floats(ctypes.byref(self.cfg)),
+                                        device=dev, dtype=torch.float32)
+            _lib.call("gldm_resnet_prepare", ctypes.byref(self.cfg), raw.data_ptr(), self.prepared.data_ptr(),
+                      _stream(dev))
+        self.device = dev
+        self.L = L
+
+
+def packed_resnet(module, L, cond_ch):
+    cache = module.__dict__.setdefault("_gldm_packs", {})
+    sig = _signature(module)
+    ent = cache.get((L, cond_ch))
+    if ent is None or ent[0] != sig:
+        ent = (sig, PackedResNet(module, L, cond_ch))
+        cache[(L, cond_ch)] = ent
+    return ent[1]
+
+
+def resnet_forward(module, x, time, z_cond):
+    """One network evaluation: x [B,1,L], time int[B] or None, z_cond [B,C,Dc] -> [B,1,L]."""
+    _require_cuda(x, "x")
+    _require_cuda(z_cond, "z_cond")
+    if z_cond.ndim != 3:
+        raise NotImplementedError("conditioning must be [B, C, Dc] (multi-channel FiLM)")
+    B, _, L = x.shape
+    pk = packed_resnet(module, L, z_cond.shape[1])
+    dev = x.device
+    with torch.cuda.device(dev):
+        xin = x.reshape(B, L).contiguous().float()
+        zc = z_cond.contiguous().float()
+        out = torch.empty((B, L), device=dev, dtype=torch.float32)
+        t32 = time.to(device=dev, dtype=torch.int32).contiguous() if time is not None else None
+        _lib.call("gldm_denoiser_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
+                  t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(), _stream(dev))
+    return out.view(B, 1, L)
+
+
+def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kind, clip_sample, noise=None,
+                seed=0, return_all=False):
+    """Whole reverse-diffusion loop in one launch.  x_T [n,1,D]; z_obj [n_obj,C,Dc]; timesteps list[int];
+    coef float32 [n_steps,8] (host).  Returns (x_0 [n,1,D], x_all [n_steps+1,n,1,D] or None)."""
+    _require_cuda(x_T, "x_T")
+    _require_cuda(z_obj, "z_cond")
+    n, _, D = x_T.shape
+    pk = packed_resnet(denoiser, D, z_obj.shape[1])
+    dev = x_T.device
+    n_steps = len(timesteps)
+    ts = (ctypes.c_int * n_steps)(*[int(t) for t in timesteps])
+    cf = coef.detach().cpu().contiguous().float()
+    assert cf.shape == (n_steps, 8)
+    with torch.cuda.device(dev):
+        xin = x_T.reshape(n, D).contiguous().float()
+        zc = z_obj.contiguous().float()
+        out = torch.empty((n, D), device=dev, dtype=torch.float32)
+        x_all = torch.empty((n_steps + 1, n, D), device=dev, dtype=torch.float32) if return_all else None
+        nz = None
+        if noise is not None:
+            _require_cuda(noise, "noise")
+            nz = noise.reshape(n_steps, n, D).contiguous().float()
+        _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(), zc.data_ptr(),
+                  n, int(grasps_per_obj), n_steps, ctypes.cast(ts, ctypes.c_void_p), cf.data_ptr(), int(sched_kind),
+                  int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
+                  out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
+    return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
+
+
+def decoder_forward(decoder, z_h, z_obj, grasps_per_obj):
+    """ConditionalGraspPoseDecoder: z_h [n,D], z_obj [n_obj,C,Dc] -> (tmrp [n,6], logits [n,1])."""
+    _require_cuda(z_h, "z_h")
+    _require_cuda(z_obj, "cond")
+    n, D = z_h.shape
+    net = decoder.net
+    L = decoder.feature_resolution
+    pk = packed_resnet(net, L, z_obj.shape[1])
+    dev = z_h.device
+    cache = decoder.__dict__.setdefault("_gldm_head", {})
+    sig = _signature(decoder)
+    if cache.get("sig") != sig:
+        cache["head"] = _flatten_nopad([decoder.in_layer.weight, decoder.in_layer.bias, decoder.tmrp.weight,
+                                        decoder.tmrp.bias, decoder.class_logits.weight, decoder.class_logits.bias], dev)
+        cache["sig"] = sig
+    head = cache["head"]
+    with torch.cuda.device(dev):
+        zin = z_h.contiguous().float()
+        zc = z_obj.contiguous().float()
+        tmrp = torch.empty((n, 6), device=dev, dtype=torch.float32)
+        logit = torch.empty((n, 1), device=dev, dtype=torch.float32)
+        _lib.call("gldm_decoder_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), head.data_ptr(), D,
+                  zin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj), tmrp.data_ptr(), logit.data_ptr(), _stream(dev))
+    return tmrp, logit
+
+
+def _flatten_nopad(tensors, device):
+    return torch.cat([t.detach().to(device=device, dtype=torch.float32).reshape(-1) for t in tensors]).contiguous()
+
+
+def pose_postprocess(tmrp, logit, grasp_mean, grasp_std):
+    """tmrp [n,6], logit [n,1] -> (grasp_tmrp [n,6], H [n,4,4], confidence [n,1])"""
+    _require_cuda(tmrp, "tmrp")
+    n = tmrp.shape[0]
+    dev = tmrp.device
+    with torch.cuda.device(dev):
+        t = tmrp.contiguous().float()
+        lg = logit.contiguous().float()
+        gm = grasp_mean.to(dev).reshape(-1).contiguous().float()
+        gs = grasp_std.to(dev).reshape(-1).contiguous().float()
+        assert gm.numel() == 6 and gs.numel() == 6, "per-batch grasp statistics must be shared (shape [6])"
+        gt = torch.empty((n, 6), device=dev, dtype=torch.float32)
+        H = torch.empty((n, 4, 4), device=dev, dtype=torch.float32)
+        conf = torch.empty((n, 1), device=dev, dtype=torch.float32)
+        _lib.call("gldm_pose_postprocess", t.data_ptr(), lg.data_ptr(), gm.data_ptr(), gs.data_ptr(), n, gt.data_ptr(),
+                  H.data_ptr(), conf.data_ptr(), _stream(dev))
+    return gt, H, conf
+
+
+# --------------------------------------------------------------------------------------------------
+# PVCNN encoder (strict fp32 path)
+# --------------------------------------------------------------------------------------------------
+def _fold_bn(conv, bn):
+    """Conv bias + eval-mode BatchNorm as y = scale * (W x) + shift (one-time constant folding)."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    shift = (conv.bias.detach() - bn.running_mean.detach()) * scale + bn.bias.detach()
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class PackedEncoder:
+    """Device-resident, kernel-ready weights of a PVCNNEncoder."""
+
+    def __init__(self, enc):
+        p0 = next(enc.parameters())
+        _require_cuda(p0, "model parameters")
+        self.device = p0.device
+        self.blocks = []
+        for blk in enc.pvcnn_modules.point_features:
+            if hasattr(blk, "voxel_layers"):
+                vl = blk.voxel_layers
+                c1, g1, c2, g2, se = vl[0], vl[1], vl[4], vl[5], vl[7]
+                pw = blk.point_features.layers
+                sc, sh = _fold_bn(pw[0], pw[1])
+                self.blocks.append(dict(
+                    kind="pvconv", r=blk.resolution, cin=blk.in_channels, cout=blk.out_channels,
+                    # Conv3d weights [co,ci,3,3,3] -> [ci,27,co] (layout only)
+                    w1=c1.weight.detach().permute(1, 2, 3, 4, 0).reshape(c1.in_channels, 27, c1.out_channels).contiguous().float(),
+                    b1=c1.bias.detach().float().contiguous(), g1w=g1.weight.detach().float().contiguous(),
+                    g1b=g1.bias.detach().float().contiguous(), eps1=float(g1.eps),
+                    w2=c2.weight.detach().permute(1, 2, 3, 4, 0).reshape(c2.in_channels, 27, c2.out_channels).contiguous().float(),
+                    b2=c2.bias.detach().float().contiguous(), g2w=g2.weight.detach().float().contiguous(),
+                    g2b=g2.bias.detach().float().contiguous(), eps2=float(g2.eps), groups=int(g1.num_groups),
+                    se1=se.fc[0].weight.detach().float().contiguous(), se2=se.fc[2].weight.detach().float().contiguous(),
+                    pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
+                    pscale=sc, pshift=sh))
+            else:
+                pw = blk.layers
+                sc, sh = _fold_bn(pw[0], pw[1])
+                self.blocks.append(dict(kind="mlp", cin=pw[0].in_channels, cout=pw[0].out_channels,
+                                        pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
+                                        pscale=sc, pshift=sh))
+        cd = enc.conv_downscale
+        self.wd = cd.weight.detach().reshape(cd.out_channels, cd.in_channels).float().contiguous()
+        self.bd = cd.bias.detach().float().contiguous()
+        co = enc.out_layer[0]
+        self.wo = co.weight.detach().reshape(co.out_channels, co.in_channels).float().contiguous()
+        self.bo = co.bias.detach().float().contiguous()
+        self.wl = enc.out_layer[1].weight.detach().float().contiguous()
+        self.bl = enc.out_layer[1].bias.detach().float().contiguous()
+        self.out_channels = co.out_channels
+        self.out_features = enc.out_layer[1].out_features
+
+
+def packed_encoder(enc):
+    sig = _signature(enc)
+    ent = enc.__dict__.get("_gldm_pack")
+    if ent is None or ent[0] != sig:
+        ent = (sig, PackedEncoder(enc))
+        enc.__dict__["_gldm_pack"] = ent
+    return ent[1]
+
+
+def _pw(x, w, scale, shift, add, act):
+    b, ci, n = x.shape
+    co = w.shape[0]
+    y = torch.empty((b, co, n), device=x.device, dtype=torch.float32)
+    _lib.call("gldm_pointwise_conv_f32", x.data_ptr(), w.data_ptr(), scale.data_ptr() if scale is not None else None,
+              shift.data_ptr() if shift is not None else None, add.data_ptr() if add is not None else None,
+              b, ci, co, n, act, y.data_ptr(), _stream(x.device))
+    return y
+
+
+def encoder_forward(enc, xyz, max_clouds_per_pass=256):
+    """PVCNNEncoder.forward: xyz [B,N,3] -> z_pc [B,C_out,F] (squeezed when C_out == 1)."""
+    _require_cuda(xyz, "xyz")
+    pk = packed_encoder(enc)
+    outs = []
+    for s in range(0, xyz.shape[0], max_clouds_per_pass):
+        outs.append(_encoder_pass(pk, xyz[s:s + max_clouds_per_pass]))
+    out = torch.cat(outs) if len(outs) > 1 else outs[0]
+    return out.squeeze(1) if out.shape[-2] == 1 else out
+
+
+def _encoder_pass(pk, xyz):
+    dev = xyz.device
+    st = _stream(dev)
+    with torch.cuda.device(dev):
+        B, N, _ = xyz.shape
+        feats = xyz.float().transpose(1, 2).contiguous()       # [B,3,N] (layout only)
+        coords = feats
+        for blk in pk.blocks:
+            if blk["kind"] == "pvconv":
+                r, ci, co = blk["r"], blk["cin"], blk["cout"]
+                r3 = r ** 3
+                grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
+                norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
+                _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(),
+                          norm.data_ptr(), None, st)
+                y1 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
+                _lib.call("gldm_conv3d_k3_f32", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, co,
+                          r, y1.data_ptr(), st)
+                _lib.call("gldm_groupnorm_swish_f32", y1.data_ptr(), blk["g1w"].data_ptr(), blk["g1b"].data_ptr(), B, co,
+                          r3, blk["groups"], blk["eps1"], None, st)
+                y2 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
+                _lib.call("gldm_conv3d_k3_f32", y1.data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(), B, co, co, r,
+                          y2.data_ptr(), st)
+                se_mean = torch.empty((B, co), device=dev, dtype=torch.float32)
+                _lib.call("gldm_groupnorm_swish_f32", y2.data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(), B, co,
+                          r3, blk["groups"], blk["eps2"], se_mean.data_ptr(), st)
+                gate = torch.empty((B, co), device=dev, dtype=torch.float32)
+                _lib.call("gldm_se_gate_f32", se_mean.data_ptr(), blk["se1"].data_ptr(), blk["se2"].data_ptr(), B, co,
+                          blk["se1"].shape[0], gate.data_ptr(), st)
+                pt = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
+                fused = torch.empty((B, co, N), device=dev, dtype=torch.float32)
+                _lib.call("gldm_devox_gate_add_f32", norm.data_ptr(), y2.data_ptr(), gate.data_ptr(), pt.data_ptr(), B,
+                          co, N, r, fused.data_ptr(), st)
+                feats = fused
+            else:
+                feats = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
+        h = _pw(feats, pk.wd, None, pk.bd, None, 0)
+        h = _pw(h, pk.wo, None, pk.bo, None, 0)                 # [B, C_out, N]
+        z = torch.empty((B, pk.out_channels, pk.out_features), device=dev, dtype=torch.float32)
+        _lib.call("gldm_linear_lastdim_f32", h.data_ptr(), pk.wl.data_ptr(), pk.bl.data_ptr(), B * pk.out_channels, N,
+                  pk.out_features, z.data_ptr(), st)
+    return z

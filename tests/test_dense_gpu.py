@@ -1,0 +1,178 @@
+"""GPU parity of the fused generation path (boundary A) in strict-fp32 mode, through the model classes and the
+C ABI, against the CPU oracle on the same seeded inputs and against the committed reference fixtures.
+Tolerances (fp32 SIMT vs fp32 CPU, different summation orders) are written next to each check."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _data
+import _models
+from oracle import model_torch as M
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def maxerr(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+@pytest.fixture(scope="module")
+def fpc(cuda):
+    m = _models.build("fpc")
+    vae, ddm = _models.split_state_dicts(m)
+    return m.to(cuda), vae, ddm
+
+
+@pytest.mark.parametrize("name", ["fpc", "ppc"])
+def test_denoiser_and_decoder_forward(cuda, name):
+    m = _models.build(name)
+    vae, ddm = _models.split_state_dicts(m)
+    m = m.to(cuda)
+    g = np.load(os.path.join(G, f"dense_{name}.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    eps = m.diffusion_model.model(t("x").to(cuda), time=t("t").to(cuda), z_cond=t("z_cond").to(cuda))
+    tm, lg = m.vae_model.decoder(t("z_h").to(cuda), t("z_cond").to(cuda))
+    print(f"[{name}] denoiser max|err| {maxerr(eps.cpu(), g['eps']):.2e}  decoder tmrp {maxerr(tm.cpu(), g['tmrp']):.2e} "
+          f"logit {maxerr(lg.cpu(), g['logit']):.2e}")
+    np.testing.assert_allclose(eps.cpu().numpy(), g["eps"], rtol=1e-4, atol=2e-5)      # vs reference module (golden)
+    np.testing.assert_allclose(tm.cpu().numpy(), g["tmrp"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(lg.cpu().numpy(), g["logit"], rtol=1e-4, atol=2e-5)
+    # a batch that does not fill the last tile, every timestep class, vs the oracle live
+    gen = torch.Generator().manual_seed(11)
+    D, Dc = g["x"].shape[-1], g["z_cond"].shape[-1]
+    B = 37
+    x, zc = torch.randn(B, 1, D, generator=gen), torch.randn(B, 3, Dc, generator=gen)
+    tt = torch.randint(0, 1000, (B,), generator=gen)
+    with torch.no_grad():
+        want = M.denoiser_forward(ddm, "diffusion_model.model.", x, tt, zc)
+        wt, wl = M.decoder_forward(vae, "decoder.", x[:, 0], zc)
+    got = m.diffusion_model.model(x.to(cuda), time=tt.to(cuda), z_cond=zc.to(cuda))
+    gt, gl = m.vae_model.decoder(x[:, 0].to(cuda), zc.to(cuda))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gt.cpu().numpy(), wt.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(gl.cpu().numpy(), wl.numpy(), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["fpc", "ppc"])
+def test_encoder_forward(cuda, name):
+    m = _models.build(name)
+    vae, _ = _models.split_state_dicts(m)
+    m = m.to(cuda)
+    xyz = torch.cat([_data.synthetic_clouds(2, seed=1234, dist="S"), _data.synthetic_clouds(1, seed=99, dist="G")])
+    z = m.vae_model.encode_pc(xyz.to(cuda))
+    want = np.load(os.path.join(G, f"encoder_{name}.npz"))["z_pc"]
+    print(f"[{name}] encoder max|err| {maxerr(z.cpu(), want):.2e} (|z| max {np.abs(want).max():.3f})")
+    # 8 GFLOP of fp32 accumulation per cloud in a different order than the CPU path
+    np.testing.assert_allclose(z.cpu().numpy(), want, rtol=2e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag,kind,steps", [("ddpm10", "ddpm", 10), ("ddim5", "ddim", 5), ("ddpm100", "ddpm", 100),
+                                            ("ddpmfull", "ddpm", None)])
+def test_ldm_generation_matches_reference_fixture(cuda, tag, kind, steps):
+    g = np.load(os.path.join(G, f"ldm_fpc_{tag}.npz"))
+    m = _models.build("fpc", scheduler=kind).to(cuda)
+    if steps:
+        m.set_inference_timesteps(steps)
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S").to(cuda)
+    (tm, lg), steps_out = m.generate_grasps(xyz, num_grasps=3, x_T=torch.from_numpy(g["x_T"]).to(cuda),
+                                            noise=torch.from_numpy(g["noise"]).to(cuda))
+    assert steps_out == []
+    print(f"[{tag}] tmrp max|err| {maxerr(tm.cpu(), g['tmrp']):.2e} logit {maxerr(lg.cpu(), g['logit']):.2e}")
+    # fp32 end to end; the recurrence damps eps errors (x0 coefficient ~2e-2 per step), clamp flips aside
+    np.testing.assert_allclose(tm.cpu().numpy(), g["tmrp"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(lg.cpu().numpy(), g["logit"], rtol=1e-3, atol=1e-3)
+
+
+def test_sampler_trajectory_and_return_all(fpc, cuda):
+    m, vae, ddm = fpc
+    m.set_inference_timesteps(20)
+    gen = torch.Generator().manual_seed(3)
+    n_obj, G_ = 3, 5
+    z = torch.randn(n_obj, 3, 64, generator=gen)
+    x_T = torch.randn(n_obj * G_, 1, 4, generator=gen)
+    noise = torch.randn(20, n_obj * G_, 1, 4, generator=gen)
+    x0, allx = m.diffusion_model.sample(z_cond=z.to(cuda), batch_size=n_obj * G_, return_all=True, x_T=x_T.to(cuda),
+                                        noise=noise.to(cuda), grasps_per_object=G_)
+    assert len(allx) == 21 and torch.equal(allx[0].cpu(), x_T) and torch.equal(allx[-1], x0)
+    with torch.no_grad():
+        want, wall = M.ldm_sample(ddm, z.repeat_interleave(G_, 0), x_T, noise=noise, num_inference_steps=20, return_all=True)
+    for i in (1, 5, 20):
+        np.testing.assert_allclose(allx[i].cpu().numpy(), wall[i].numpy(), rtol=1e-3, atol=5e-4)
+    # reference call convention: z_cond already repeated per grasp, grasps_per_object defaulted
+    x0b, _ = m.diffusion_model.sample(z_cond=z.repeat_interleave(G_, 0).to(cuda), batch_size=n_obj * G_,
+                                      x_T=x_T.to(cuda), noise=noise.to(cuda))
+    assert torch.equal(x0, x0b)
+    m.diffusion_model.noise_scheduler.num_inference_steps = None
+
+
+def test_vae_mode_and_pose_postprocessing(fpc, cuda):
+    m, _, _ = fpc
+    g = np.load(os.path.join(G, "vae_fpc.npz"))
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S")
+    from graspldm_b200.inference import InferenceVAE, default_metas
+    inf = InferenceVAE(m.vae_model, device=cuda)
+    res = inf.generate_grasps(xyz, default_metas(2), num_grasps=3, z_h=torch.from_numpy(g["z_h"]).to(cuda))
+    np.testing.assert_allclose(res["grasp_tmrp"].cpu().numpy(), g["grasp_tmrp"], rtol=1e-3, atol=1e-4)
+    assert res["grasps"].shape == (2, 3, 4, 4) and res["confidence"].shape == (2, 3, 1) and res["pc"].shape == (2, 1024, 3)
+    # pose kernel against the reference's tmrp_to_H on the reference's own poses (pure fp32, same op order)
+    from graspldm_b200.rotations import tmrp_to_H
+    H = tmrp_to_H(torch.from_numpy(g["grasp_tmrp"]).to(cuda))
+    np.testing.assert_allclose(H.cpu().numpy(), g["H"], rtol=1e-6, atol=1e-7)
+    R = H[..., :3, :3]
+    eye = torch.eye(3, device=cuda).expand_as(R)
+    torch.testing.assert_close(R @ R.transpose(-1, -2), eye, rtol=0, atol=1e-5)     # proper rotations
+    # same seed -> same grasps through the reference-style RNG (z_h drawn on the CPU generator)
+    torch.manual_seed(5)
+    a = m.vae_model.generate_grasps(xyz.to(cuda), 3)[0]
+    np.testing.assert_allclose(a.cpu().numpy(), g["tmrp"], rtol=1e-3, atol=1e-4)
+
+
+def test_full_size_properties_config2(fpc, cuda):
+    """BASELINE config 2 (64 objects x 20 grasps, 100 DDPM steps): size-independent properties."""
+    from graspldm_b200.inference import InferenceLDM, default_metas
+    m, _, _ = fpc
+    m.set_inference_timesteps(100)
+    m.diffusion_model.rng_mode = "fused"
+    inf = InferenceLDM(m, device=cuda)
+    pcs = _data.synthetic_clouds(64, seed=1234, dist="S")
+    a = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7)
+    b = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7)
+    assert all(torch.equal(a[k], b[k]) for k in ("grasps", "grasp_tmrp", "confidence"))     # deterministic
+    assert torch.isfinite(a["grasps"]).all() and a["grasps"].shape == (64, 20, 4, 4)
+    assert (a["confidence"] > 0).all() and (a["confidence"] < 1).all()
+    # objects are independent: generating a slice alone gives the same grasps for those objects
+    x_T = torch.randn(64 * 20, 1, 4, generator=torch.Generator().manual_seed(1)).to(cuda)
+    full = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7, x_T=x_T)
+    part = inf.generate_grasps(pcs[16:24], default_metas(8), num_grasps=20, seed=7, x_T=x_T[16 * 20:24 * 20])
+    # (the fused RNG is keyed by the sample index within the call, so compare a DDIM-free quantity: the encoder)
+    z_full = m.vae_model.encode_pc(pcs.to(cuda))
+    z_part = m.vae_model.encode_pc(pcs[16:24].to(cuda))
+    assert torch.equal(z_full[16:24], z_part)
+    assert full["grasps"].shape[0] == 64 and part["grasps"].shape[0] == 8
+    c = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=8)
+    assert not torch.equal(a["grasp_tmrp"], c["grasp_tmrp"])                                # the seed matters
+    m.diffusion_model.rng_mode = "reference"
+    m.diffusion_model.noise_scheduler.num_inference_steps = None
+
+
+def test_fused_rng_is_standard_normal(fpc, cuda):
+    """DDPM with eps weights zeroed is not available; instead sample the in-kernel Philox stream through a
+    1-step run: x_prev - mu = sigma * z  ->  z recovered from two runs that differ only in the noise source."""
+    m, _, _ = fpc
+    m.set_inference_timesteps(2)          # t = 500, 0
+    n = 20000
+    z = torch.zeros(1, 3, 64, device=cuda)
+    x_T = torch.zeros(n, 1, 4, device=cuda)
+    zero = torch.zeros(2, n, 1, 4, device=cuda)
+    x_a, all_a = m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, noise=zero, grasps_per_object=n, return_all=True)
+    m.diffusion_model.rng_mode = "fused"
+    x_b, all_b = m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, grasps_per_object=n, seed=123, return_all=True)
+    _, coef = m.diffusion_model.noise_scheduler.table()
+    zz = ((all_b[1] - all_a[1]) / coef[0, 4].item()).flatten().double().cpu()
+    assert abs(zz.mean().item()) < 0.02 and abs(zz.std().item() - 1.0) < 0.02
+    assert abs((zz ** 3).mean().item()) < 0.05 and abs((zz ** 4).mean().item() - 3.0) < 0.15
+    m.diffusion_model.rng_mode = "reference"
+    m.diffusion_model.noise_scheduler.num_inference_steps = None
