@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Headline benchmark: grasps/sec of full LDM grasp generation (PVCNN encoder + 100 DDPM latent-denoising
+steps + grasp decoder + pose post-processing) on synthetic point clouds - BASELINE.json's metric on its
+config 2 (fpc_1a_latentc3_z4_pc64, 64 objects x 20 grasps per GPU, random-init weights).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one generation pass over one batch.  `value` is timed with the point clouds resident in HBM;
+`e2e` goes through graspldm_b200.inference.InferenceLDM.generate_grasps with pinned HOST buffers (H2D of
+the clouds and D2H of poses + confidences inside the timed region).  N > 1: one rank per GPU (torchrun),
+objects sharded by rank, no collective on the compute path, one final all_gather of the results
+(weak scaling: 64 objects per GPU).  `--impl reference` times the CPU oracle port (the reference's own
+python cannot travel to the GPU box and its encoder has no CPU path at all, SURVEY.md finding 6) on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+import torch  # noqa: E402
+
+N_OBJ, N_GRASPS, N_STEPS_DDPM, N_POINTS = 64, 20, 100, 1024
+METRIC, UNIT = "grasps/sec (LDM 100 steps)", "grasps/s"
+# algorithmic work (SURVEY.md 8d / BASELINE.md section 2), FLOPs
+F_ENCODER_PER_CLOUD = 8.115e9
+F_DENOISER_PER_SAMPLE_STEP = 7.589e6
+F_DECODER_PER_GRASP = 30.70e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
+                    samples=len(self.rows))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on the host cores, all threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import _data
+    import _models
+    from oracle import model_torch as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_obj = 2
+    model = _models.build("fpc")
+    vae_sd, ddm_sd = _models.split_state_dicts(model)
+    pcs = _data.synthetic_clouds(n_obj, seed=1234, dist="S")
+    metas = dict(pc_mean=torch.zeros(n_obj, 3), pc_std=torch.full((n_obj, 3), 0.05), grasp_mean=torch.zeros(1, 6),
+                 grasp_std=torch.tensor([[.05, .05, .05, .5, .5, .5]]))
+
+    def one():
+        g = torch.Generator().manual_seed(42)
+        x_T = torch.randn(n_obj * N_GRASPS, 1, 4, generator=g)
+        with torch.no_grad():
+            tm, lg = M.generate_grasps_ldm(vae_sd, ddm_sd, pcs, N_GRASPS, x_T, num_inference_steps=N_STEPS_DDPM)
+            return M.postprocess(tm, lg, pcs, metas, n_obj, N_GRASPS)
+
+    for _ in range(min(args.warmup, 1)):
+        one()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    v = n_obj * N_GRASPS / dt
+    sample = f"{n_obj} objects x {N_GRASPS} grasps, {N_STEPS_DDPM} DDPM steps per step ({steps} steps timed)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fpc_1a_latentc3_z4_pc64 LDM 100 DDPM steps, CPU oracle port (plain PyTorch fp32 + numpy ops)",
+                   "objects_per_step": n_obj, "grasps_per_object": N_GRASPS},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample of the same workload on the host cores (reported beside the GPU number)."""
+    import _data
+    import _models
+    from oracle import model_torch as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_obj = 2
+    model = _models.build("fpc")
+    vae_sd, ddm_sd = _models.split_state_dicts(model)
+    pcs = _data.synthetic_clouds(n_obj, seed=1234, dist="S")
+    g = torch.Generator().manual_seed(42)
+    x_T = torch.randn(n_obj * N_GRASPS, 1, 4, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        M.generate_grasps_ldm(vae_sd, ddm_sd, pcs, N_GRASPS, x_T, num_inference_steps=N_STEPS_DDPM)
+    dt = time.perf_counter() - t0
+    return {"value": n_obj * N_GRASPS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_obj} objects x {N_GRASPS} grasps, {N_STEPS_DDPM} DDPM steps, 1 pass, {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import _data
+    import _models
+    from graspldm_b200 import _lib, engine, sharding
+    from graspldm_b200.inference import InferenceLDM, default_metas
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = _models.build("fpc").to(dev)
+    model.set_inference_timesteps(N_STEPS_DDPM)
+    model.diffusion_model.rng_mode = "fused"          # noise drawn inside the sampler kernel (Philox4x32-10)
+    inf = InferenceLDM(model, device=dev)
+    n_total = N_OBJ * world                            # weak scaling: 64 objects per GPU
+    lo, hi = sharding.shard_bounds(n_total, world, rank)
+    pcs_host = _data.synthetic_clouds(hi - lo, N_POINTS, seed=1234 + rank, dist="S").pin_memory()
+    metas = default_metas(hi - lo)
+    metas_dev = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in metas.items()}
+    pcs_dev = pcs_host.to(dev)
+    counts = sharding.shard_counts(n_total, world)
+    out_host = {"grasps": torch.empty((hi - lo, N_GRASPS, 4, 4)).pin_memory(),
+                "confidence": torch.empty((hi - lo, N_GRASPS, 1)).pin_memory()}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def gen_resident(seed):
+        out = inf.generate_grasps(pcs_dev, metas_dev, num_grasps=N_GRASPS, seed=seed)
+        if world > 1:
+            out = sharding.gather_results({"grasps": out["grasps"], "confidence": out["confidence"]}, counts)
+        return out
+
+    def gen_e2e(seed):
+        out = inf.generate_grasps(pcs_host, metas, num_grasps=N_GRASPS, seed=seed)   # H2D inside
+        out_host["grasps"].copy_(out["grasps"], non_blocking=True)                     # D2H of the result
+        out_host["confidence"].copy_(out["confidence"], non_blocking=True)
+        if world > 1:
+            sharding.gather_results({"grasps": out["grasps"], "confidence": out["confidence"]}, counts)
+        return out
+
+    def timed(fn, steps, warmup, sections=False):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        evs = []
+        engine.SECTIONS.enabled = sections
+        engine.SECTIONS.events = []
+        for i in range(steps):
+            flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(1000 + i)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        engine.SECTIONS.enabled = False
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, engine.SECTIONS.collect()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = _lib.launch_count()
+    total_ms, sections = timed(gen_resident, args.steps, args.warmup, sections=True)
+    launches = (_lib.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    clk = clocks.finish()
+    e2e_ms, _ = timed(gen_e2e, args.steps, args.warmup)
+
+    ms_per_step = total_ms / args.steps
+    grasps_per_step = n_total * N_GRASPS
+    value = grasps_per_step / (ms_per_step * 1e-3)
+    e2e_value = grasps_per_step / (e2e_ms / args.steps * 1e-3)
+
+    pk = peaks()
+    n_local = (hi - lo) * N_GRASPS
+    samp_ms = sum(sections.get("sampler", [0.0])) / max(1, len(sections.get("sampler", [])))
+    enc_ms = sum(sections.get("encoder", [0.0])) / max(1, len(sections.get("encoder", [])))
+    dec_ms = sum(sections.get("decoder", [0.0])) / max(1, len(sections.get("decoder", [])))
+    samp_flops = n_local * N_STEPS_DDPM * F_DENOISER_PER_SAMPLE_STEP
+    achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "resnet_kernel<4> (persistent 100-step sampler, one launch per step)",
+                "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
+                "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
+                "note": "strict-fp32 SIMT (FFMA) parity path; fp32 FFMA peak is ~74 TFLOP/s (derived), the tensor-core path is the next milestone"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "fpc_1a_latentc3_z4_pc64 LDM-mode generation, 100 DDPM steps, 64 objects x 20 grasps per GPU "
+                               "(BASELINE.json configs[1]), random-init weights, 1024-point synthetic clouds",
+                   "objects": n_total, "grasps_per_object": N_GRASPS, "denoising_steps": N_STEPS_DDPM,
+                   "parallelism": f"objects sharded over {world} rank(s), one final all_gather",
+                   "l2": "256 MiB buffer written between timed iterations", "precision": args.precision,
+                   "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcs_host.numel() * 4 + n_local * 4 * 4),
+                "d2h_bytes_per_step": int(out_host["grasps"].numel() * 4 + out_host["confidence"].numel() * 4),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

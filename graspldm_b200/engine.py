@@ -18,6 +18,38 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class _Sections:
+    """Optional CUDA-event timing of the path's sections on the launching stream (bench.py turns it on to get
+    the per-kernel durations the roofline is computed from; off by default, zero overhead)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = []
+
+    def start(self, name, dev):
+        if not self.enabled:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream(dev))
+        return (name, a, b, dev)
+
+    def stop(self, tok):
+        if tok is not None:
+            tok[2].record(torch.cuda.current_stream(tok[3]))
+            self.events.append(tok[:3])
+
+    def collect(self):
+        """-> {name: [ms, ...]} (call after a synchronize)"""
+        out = {}
+        for name, a, b in self.events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        self.events = []
+        return out
+
+
+SECTIONS = _Sections()
+
+
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (graspldm_b200 has no CPU fallback)")
@@ -146,10 +178,12 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
         if noise is not None:
             _require_cuda(noise, "noise")
             nz = noise.reshape(n_steps, n, D).contiguous().float()
+        tok = SECTIONS.start("sampler", dev)
         _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(), zc.data_ptr(),
                   n, int(grasps_per_obj), n_steps, ctypes.cast(ts, ctypes.c_void_p), cf.data_ptr(), int(sched_kind),
                   int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
                   out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
+        SECTIONS.stop(tok)
     return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
 
 
@@ -174,8 +208,10 @@ def decoder_forward(decoder, z_h, z_obj, grasps_per_obj):
         zc = z_obj.contiguous().float()
         tmrp = torch.empty((n, 6), device=dev, dtype=torch.float32)
         logit = torch.empty((n, 1), device=dev, dtype=torch.float32)
+        tok = SECTIONS.start("decoder", dev)
         _lib.call("gldm_decoder_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), head.data_ptr(), D,
                   zin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj), tmrp.data_ptr(), logit.data_ptr(), _stream(dev))
+        SECTIONS.stop(tok)
     return tmrp, logit
 
 
@@ -280,8 +316,10 @@ def encoder_forward(enc, xyz, max_clouds_per_pass=256):
     _require_cuda(xyz, "xyz")
     pk = packed_encoder(enc)
     outs = []
+    tok = SECTIONS.start("encoder", xyz.device)
     for s in range(0, xyz.shape[0], max_clouds_per_pass):
         outs.append(_encoder_pass(pk, xyz[s:s + max_clouds_per_pass]))
+    SECTIONS.stop(tok)
     out = torch.cat(outs) if len(outs) > 1 else outs[0]
     return out.squeeze(1) if out.shape[-2] == 1 else out
 
