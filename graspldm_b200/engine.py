@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import GldmResNetCfg
 
-PRECISIONS = ("fp32",)   # "bf16" (tcgen05 tensor-core path) is registered by engine_tc when built
+PRECISIONS = ("fp32", "bf16")   # "bf16": tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation)
 
 
 def _stream(dev):
@@ -123,8 +123,25 @@ class PackedResNet:
                                         device=dev, dtype=torch.float32)
             _lib.call("gldm_resnet_prepare", ctypes.byref(self.cfg), raw.data_ptr(), self.prepared.data_ptr(),
                       _stream(dev))
+        self.raw = raw
         self.device = dev
         self.L = L
+        self._tc_pack = None
+
+    def tc_pack(self):
+        """bf16 UMMA weight images for the tensor-core kernels (built on first use)."""
+        if self._tc_pack is None:
+            nbytes = _lib.lib().gldm_sampler_tc_pack_bytes(ctypes.byref(self.cfg))
+            if nbytes < 0:
+                raise NotImplementedError(f"precision='bf16': {_lib.lib().gldm_last_error().decode()}")
+            with torch.cuda.device(self.device):
+                pack = torch.empty(nbytes + 1024, device=self.device, dtype=torch.uint8)
+                off = (-pack.data_ptr()) % 1024
+                pack = pack[off:off + nbytes]
+                _lib.call("gldm_sampler_tc_prepare", ctypes.byref(self.cfg), self.raw.data_ptr(), pack.data_ptr(),
+                          _stream(self.device))
+            self._tc_pack = pack
+        return self._tc_pack
 
 
 def packed_resnet(module, L, cond_ch):
@@ -137,8 +154,14 @@ def packed_resnet(module, L, cond_ch):
     return ent[1]
 
 
-def resnet_forward(module, x, time, z_cond):
+def _check_precision(precision):
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+
+
+def resnet_forward(module, x, time, z_cond, precision="fp32"):
     """One network evaluation: x [B,1,L], time int[B] or None, z_cond [B,C,Dc] -> [B,1,L]."""
+    _check_precision(precision)
     _require_cuda(x, "x")
     _require_cuda(z_cond, "z_cond")
     if z_cond.ndim != 3:
@@ -151,15 +174,21 @@ def resnet_forward(module, x, time, z_cond):
         zc = z_cond.contiguous().float()
         out = torch.empty((B, L), device=dev, dtype=torch.float32)
         t32 = time.to(device=dev, dtype=torch.int32).contiguous() if time is not None else None
-        _lib.call("gldm_denoiser_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
-                  t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(), _stream(dev))
+        if precision == "bf16":
+            _lib.call("gldm_denoiser_forward_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pk.tc_pack().data_ptr(),
+                      xin.data_ptr(), t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(),
+                      _stream(dev))
+        else:
+            _lib.call("gldm_denoiser_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
+                      t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(), _stream(dev))
     return out.view(B, 1, L)
 
 
 def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kind, clip_sample, noise=None,
-                seed=0, return_all=False):
+                seed=0, return_all=False, precision="fp32"):
     """Whole reverse-diffusion loop in one launch.  x_T [n,1,D]; z_obj [n_obj,C,Dc]; timesteps list[int];
     coef float32 [n_steps,8] (host).  Returns (x_0 [n,1,D], x_all [n_steps+1,n,1,D] or None)."""
+    _check_precision(precision)
     _require_cuda(x_T, "x_T")
     _require_cuda(z_obj, "z_cond")
     n, _, D = x_T.shape
@@ -178,11 +207,17 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
         if noise is not None:
             _require_cuda(noise, "noise")
             nz = noise.reshape(n_steps, n, D).contiguous().float()
+        tail = (n, int(grasps_per_obj), n_steps, ctypes.cast(ts, ctypes.c_void_p), cf.data_ptr(), int(sched_kind),
+                int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
+                out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
+        pack = pk.tc_pack() if precision == "bf16" else None      # built before the timed section
         tok = SECTIONS.start("sampler", dev)
-        _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(), zc.data_ptr(),
-                  n, int(grasps_per_obj), n_steps, ctypes.cast(ts, ctypes.c_void_p), cf.data_ptr(), int(sched_kind),
-                  int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
-                  out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
+        if precision == "bf16":
+            _lib.call("gldm_sampler_run_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pack.data_ptr(), xin.data_ptr(),
+                      zc.data_ptr(), *tail)
+        else:
+            _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
+                      zc.data_ptr(), *tail)
         SECTIONS.stop(tok)
     return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
 

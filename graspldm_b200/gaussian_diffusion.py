@@ -34,6 +34,7 @@ class GaussianDiffusion1D(nn.Module):
         self.noise_scheduler = NoiseSchedule(noise_scheduler_type, num_steps, beta_start, beta_end, self.beta_schedule,
                                              variance_type, pred_type, clip_sample)
         assert self.model.out_channels == 1, "fixed-variance samplers need a single eps channel"
+        self.precision = "fp32"       # "bf16": tcgen05 tensor-core sampler (bf16 operands, fp32 accumulation)
         self.rng_mode = "reference"   # "reference": per-step torch.randn on the device generator, as diffusers;
                                       # "fused": Philox4x32-10 + Box-Muller inside the sampler kernel
 
@@ -72,5 +73,6 @@ class GaussianDiffusion1D(nn.Module):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if noise is None else 0
         x0, x_all = engine.sampler_run(self.model, x_T, z_cond, grasps_per_object, ts, coef, kind, self.clip_sample,
-                                       noise=noise, seed=seed, return_all=return_all)
+                                       noise=noise, seed=seed, return_all=return_all,
+                                       precision=kwargs.get("precision", self.precision))
         return x0, (list(x_all) if return_all else [])

@@ -175,4 +175,4 @@ class TimeConditionedResNet1D(_ResNetBase):
     @torch.no_grad()
     def forward(self, x, *, time=None, z_cond=None, x_self_cond=None, **kwargs):
         assert time is not None
-        return engine.resnet_forward(self, x, time, z_cond)
+        return engine.resnet_forward(self, x, time, z_cond, precision=kwargs.get("precision", "fp32"))

@@ -173,6 +173,21 @@ int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, co
                              const float* z_h, const float* z_obj, int n, int grasps_per_obj, float* tmrp,
                              float* logit, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM) sampler: bf16 operands, fp32 accumulation ----
+ * Same contract as gldm_sampler_run_f32 / gldm_denoiser_forward_f32, but the GEMMs run on the 5th-generation
+ * tensor cores.  `raw` is the canonical fp32 parameter blob (per-channel parameters are read from it), `pack`
+ * the bf16 UMMA weight images produced once by gldm_sampler_tc_prepare (gldm_sampler_tc_pack_bytes bytes,
+ * 1024-byte aligned).  Supported: the fpc latent denoiser family (L = 4, emb 16, 4 stages of width <= 128,
+ * final width <= 256); anything else returns GLDM_ENOSUP. */
+long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg);
+int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* raw, void* pack, void* stream);
+int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x_T,
+                        const float* z_obj, int n, int grasps_per_obj, int n_steps, const int* timesteps_host,
+                        const float* coef_host, int sched_kind, int clip_sample, const float* noise,
+                        unsigned long long seed, float* x_out, float* x_all, void* stream);
+int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
+                             const int* t, const float* z_cond, int n, float* eps, void* stream);
+
 /* Pose post-processing (R/../tools/inference.py:627-656, R/utils/rotations.py:298-302):
  * tmrp f32[n,6], logit f32[n], grasp_mean/std f32[6] -> grasp_tmrp f32[n,6], H f32[n,4,4], conf f32[n] */
 int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,
