@@ -44,24 +44,50 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  Uses NVML in-process
+    (a light query) and falls back to polling nvidia-smi, which the recipe names."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        self.rows.append([str(sm), str(mx), f"{pw:.1f}"] + [("Active" if r & b else "Not Active") for _, b in bits])
 
     def run(self):
         while not self._halt.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05 if self.nvml is not None else 0.2)
 
     def finish(self):
         self._halt.set()
@@ -71,7 +97,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
-                    samples=len(self.rows))
+                    samples=len(self.rows), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def run_reference(args, rank, world):
@@ -143,7 +169,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation); fp32: strict-fp32 SIMT parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -169,6 +196,7 @@ def main():
     model = _models.build("fpc").to(dev)
     model.set_inference_timesteps(N_STEPS_DDPM)
     model.diffusion_model.rng_mode = "fused"          # noise drawn inside the sampler kernel (Philox4x32-10)
+    model.diffusion_model.precision = args.precision
     inf = InferenceLDM(model, device=dev)
     n_total = N_OBJ * world                            # weak scaling: 64 objects per GPU
     lo, hi = sharding.shard_bounds(n_total, world, rank)
@@ -244,12 +272,15 @@ def main():
     dec_ms = sum(sections.get("decoder", [0.0])) / max(1, len(sections.get("decoder", [])))
     samp_flops = n_local * N_STEPS_DDPM * F_DENOISER_PER_SAMPLE_STEP
     achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "resnet_kernel<4> (persistent 100-step sampler, one launch per step)",
+    kname = ("sampler_tc_kernel (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
+             else "resnet_kernel<4> (fp32 SIMT persistent 100-step sampler, one launch per batch)")
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
                 "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": "strict-fp32 SIMT (FFMA) parity path; fp32 FFMA peak is ~74 TFLOP/s (derived), the tensor-core path is the next milestone"}
+                "note": ("sampler on tcgen05 (bf16 operands, fp32 accumulate); encoder and decoder still on the fp32 SIMT kernels"
+                         if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,8 +288,8 @@ def main():
     cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "fpc_1a_latentc3_z4_pc64 LDM-mode generation, 100 DDPM steps, 64 objects x 20 grasps per GPU "
                                "(BASELINE.json configs[1]), random-init weights, 1024-point synthetic clouds",
                    "objects": n_total, "grasps_per_object": N_GRASPS, "denoising_steps": N_STEPS_DDPM,

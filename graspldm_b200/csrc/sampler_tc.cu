@@ -28,9 +28,9 @@ constexpr int SLAB = BROWS * 128;          // bytes per 64-channel K-block of th
 constexpr int BSLABS = 4;                  // up to 256 channels
 constexpr int CHUNK = 16384, STAGES = 8;   // weight ring
 constexpr int EMB = 16;
-constexpr int MAXJOBS = 40;
+constexpr int MAXJOBS = 32;
 constexpr uint32_t T_ACC = 0, T_RES = 192, T_FILM = 320;   // TMEM column map (512 allocated)
-constexpr int NCOMPUTE = 256, NTHREADS = 320;
+constexpr int NCOMPUTE = 256, NTHREADS = 256;   // thread 0 additionally drives the weight ring and issues the UMMAs
 
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int SM_B = 0;                                  // B operand             49152
@@ -41,12 +41,32 @@ constexpr int SM_XCH = SM_SCR + 8 * 256 * 4;             // cross-warp exchange 
 constexpr int SM_INEMB = SM_XCH + 2 * 4 * 64 * 4;        // in_emb [16][3][16] floats = 3072
 constexpr int SM_X = SM_INEMB + NS * 3 * EMB * 4;        // sampler state [16][4] floats = 256
 constexpr int SM_BAR = SM_X + NS * L * 4;                // mbarriers
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int MAXCHUNKS = 192;
+constexpr int SM_CHUNKS = SM_BAR + 256;                  // weight chunk table {pack offset, bytes} x MAXCHUNKS
+constexpr int SM_JOBS = SM_CHUNKS + MAXCHUNKS * 8;       // job table copy
+constexpr int MAXOPS = 256;
+constexpr int SM_OPS = SM_JOBS + MAXJOBS * 48;           // UMMA op table, 16 bytes per block of up to 4 UMMAs
+constexpr int SM_OPBEG = SM_OPS + MAXOPS * 16;           // first op of every job
+constexpr int SM_TOTAL = SM_OPBEG + (MAXJOBS + 2) * 4 + 16;
 }  // namespace stc
 
+// epilogue recipe of a job (what the epilogue warps do with its accumulator)
+enum : uint16_t {
+  E_GN = 1,         // + bias, GroupNorm * gamma + beta
+  E_FILM = 2,       // * (scale + 1) + shift   (FiLM tiles of the same job)
+  E_SILU = 4,
+  E_LN = 8,         // + bias, channel LayerNorm * g           (to_out)
+  E_ADDRES = 16,    // + residual stream
+  E_STORERES = 32,  // result becomes the residual stream
+  E_LNNEXT = 64,    // operand of the next job = LayerNorm(result) * g2   (PreNorm of the attention)
+  E_FINAL = 128,    // no operand: final_conv dot product (weights at o_g2) + scheduler update
+  E_ATTN = 256,     // linear-attention core on the q, k, v tiles
+};
 struct TcJob {
   uint32_t a_off, bytes;                      // image location in the pack
-  uint16_t mtiles, taps, kpt, a_swb, film_tiles, pad;
+  uint16_t mtiles, taps, kpt, a_swb, film_tiles, flags;
+  int ch;                                     // valid output channels
+  int o_bias, o_gamma, o_beta, o_mlpb, o_g, o_g2;   // float offsets into the raw blob (-1: unused)
 };
 
 struct TcParams {
@@ -68,6 +88,7 @@ struct TcParams {
   unsigned long long seed;
   float* x_out;
   float* x_all;
+  long long* prof;         // development aid: per-job clock stamps of CTA 0 (NULL in production)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -82,33 +103,41 @@ static uint32_t job_bytes(const TcJob& j) {
 }
 
 static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes) {
+  ResNetLayout l;
+  make_layout(c, l);
   int n = 0;
   uint32_t off = 0;
-  auto add = [&](int cout, int cin, int taps, int film_c) {
+  auto add = [&](int cout, int cin, int taps, int film_c, uint16_t flags, int o_bias, int o_gamma, int o_beta,
+                 int o_mlpb, int o_g, int o_g2) {
     TcJob j = {};
     j.mtiles = (uint16_t)((cout + 127) / 128);
     j.taps = (uint16_t)taps;
     j.kpt = (uint16_t)pad16(cin);
     j.a_swb = (uint16_t)swb_for(j.kpt);
     j.film_tiles = (uint16_t)(film_c ? 2 * ((film_c + 127) / 128) : 0);
+    j.flags = flags;
+    j.ch = cout;
+    j.o_bias = o_bias; j.o_gamma = o_gamma; j.o_beta = o_beta; j.o_mlpb = o_mlpb; j.o_g = o_g; j.o_g2 = o_g2;
     j.a_off = off;
     j.bytes = job_bytes(j);
     off += (j.bytes + 1023) & ~1023u;
     jobs[n++] = j;
   };
+  auto add_rb = [&](const RbOff& o, int ch, uint16_t extra2, int o_g2) {
+    add(ch, ch, 3, ch, E_GN | E_FILM | E_SILU, o.p1_b, o.n1_w, o.n1_b, o.mlp_b, -1, -1);
+    add(ch, ch, 3, 0, (uint16_t)(E_GN | E_SILU | E_ADDRES | extra2), o.p2_b, o.n2_w, o.n2_b, -1, -1, o_g2);
+  };
   for (int s = 0; s < c.n_stages; ++s) {
     const int ch = c.ch[s], cn = c.ch[s + 1];
-    for (int rb = 0; rb < 2; ++rb) {
-      add(ch, ch, 3, ch);   // block1 (+ FiLM tiles)
-      add(ch, ch, 3, 0);    // block2
-    }
-    add(384, ch, 1, 0);     // to_qkv
-    add(ch, 128, 1, 0);     // to_out
-    add(cn, ch, 3, 0);      // stage conv
+    const StageOff& so = l.st[s];
+    add_rb(so.rb[0], ch, E_STORERES, -1);
+    add_rb(so.rb[1], ch, E_STORERES | E_LNNEXT, so.ln_g);
+    add(384, ch, 1, 0, E_ATTN, -1, -1, -1, -1, -1, -1);                              // to_qkv
+    add(ch, 128, 1, 0, E_LN | E_ADDRES, so.out_b, -1, -1, -1, so.out_g, -1);          // to_out
+    add(cn, ch, 3, 0, E_STORERES, so.down_b, -1, -1, -1, -1, -1);                     // stage conv
   }
   const int cl = c.ch[c.n_stages];
-  add(cl, cl, 3, cl);
-  add(cl, cl, 3, 0);
+  add_rb(l.fin, cl, E_FINAL, l.fc_w);
   *total_bytes = off;
   return n;
 }
@@ -232,16 +261,31 @@ struct Ctx {
   uint32_t xoff[8];     // swizzled 16-byte-chunk offset (+ element offset) of this thread's channel for row&7 = j
 };
 
-// 32 values of this thread's channel of accumulator/residual tile at column base `col`: v[l*8 + j], j = sample - 8g
+// 32 values of this thread's channel of accumulator/residual tile at column base `col`: v[l*8 + j], j = sample - 8g.
+// tm_issue* start the asynchronous loads; tm_wait() + tm_use*() make the registers safe to read.
+__device__ __forceinline__ void tm_issue32(const Ctx& c, uint32_t col, uint32_t (&r)[32]) {
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    uint32_t(&q)[8] = *reinterpret_cast<uint32_t(*)[8]>(&r[l * 8]);
+    tmem_ld8(c.tmem + col + l * 16 + c.g * 8, q);
+  }
+}
+__device__ __forceinline__ void tm_issue8(const Ctx& c, uint32_t col, uint32_t (&r)[8]) { tmem_ld8(c.tmem + col, r); }
+__device__ __forceinline__ void tm_wait() { tmem_ld_wait(); }
+template <int N>
+__device__ __forceinline__ void tm_use(const uint32_t (&r)[N], float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    uint32_t x = r[i];
+    asm volatile("" : "+r"(x));     // ordered after the tcgen05.wait::ld above (volatile asm keeps program order)
+    v[i] = __uint_as_float(x);
+  }
+}
 __device__ __forceinline__ void tm_load32(const Ctx& c, uint32_t col, float (&v)[32]) {
-  uint32_t r[4][8];
-#pragma unroll
-  for (int l = 0; l < 4; ++l) tmem_ld8(c.tmem + col + l * 16 + c.g * 8, r[l]);
-  tmem_ld_wait();
-#pragma unroll
-  for (int l = 0; l < 4; ++l)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[l * 8 + j] = __uint_as_float(r[l][j]);
+  uint32_t r[32];
+  tm_issue32(c, col, r);
+  tm_wait();
+  tm_use(r, v);
 }
 __device__ __forceinline__ void tm_store32(const Ctx& c, uint32_t col, const float (&v)[32]) {
 #pragma unroll
@@ -255,10 +299,9 @@ __device__ __forceinline__ void tm_store32(const Ctx& c, uint32_t col, const flo
 }
 __device__ __forceinline__ void tm_load8(const Ctx& c, uint32_t col, float (&v)[8]) {
   uint32_t r[8];
-  tmem_ld8(c.tmem + col, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+  tm_issue8(c, col, r);
+  tm_wait();
+  tm_use(r, v);
 }
 
 // write this thread's channel (tile t) of the next B operand: rows HALO + l*16 + 8g + j
@@ -400,6 +443,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
   float* s_inemb = reinterpret_cast<float*>(smem + SM_INEMB);
   float* s_x = reinterpret_cast<float*>(smem + SM_X);
+  TcJob* s_jobs = reinterpret_cast<TcJob*>(smem + SM_JOBS);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * NS;
@@ -408,16 +452,19 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   const float* W = p.W;
   const int R = cfg.cond_ch;
   const int n_steps = (p.mode == 0) ? p.n_steps : 1;
+  const int n_jobs = p.n_jobs;
 
   // ---- one-time setup
   for (int i = tid; i < (SM_RING) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < n_jobs * (int)(sizeof(TcJob) / 4); i += NTHREADS)
+    reinterpret_cast<uint32_t*>(s_jobs)[i] = reinterpret_cast<const uint32_t*>(p.jobs)[i];
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(b_ready, NCOMPUTE);
+    mbar_init(b_ready, NCOMPUTE / 32);
     mbar_init(acc_ready, 1);
     fence_barrier_init();
   }
-  if (wid == 9) tmem_alloc<512>(tmem_slot);
+  if (wid == 0) tmem_alloc<512>(tmem_slot);
   // conditioning embedding SiLU(Linear(z_cond))  (resnets.py:531-533,596), once per launch
   for (int idx = tid; idx < NS * R * EMB; idx += NTHREADS) {
     const int e = idx % EMB, r = (idx / EMB) % R, s = idx / (EMB * R);
@@ -444,370 +491,409 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (wid == 8) {
-    // =========================== weight producer ===========================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int step = 0; step < n_steps; ++step)
-        for (int j = 0; j < p.n_jobs; ++j) {
-          const TcJob& job = p.jobs[j];
-          for (uint32_t off = 0; off < job.bytes; off += CHUNK, ++it) {
-            const uint32_t s = it % STAGES, round = it / STAGES;
-            if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-            const uint32_t sz = min((uint32_t)CHUNK, job.bytes - off);
-            mbar_arrive_expect_tx(&full[s], sz);
-            bulk_g2s(smem + SM_RING + s * CHUNK, p.pack + job.a_off + off, sz, &full[s]);
-          }
-        }
-    }
-  } else if (wid == 9) {
-    // =========================== UMMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc64 = idesc_bf16(128, NCOL), idesc16 = idesc_bf16(128, 16);
-      const uint32_t b_base = smem_u32(smem + SM_B), u_base = smem_u32(smem + SM_U), ring = smem_u32(smem + SM_RING);
-      uint32_t it = 0, jobn = 0;
-      for (int step = 0; step < n_steps; ++step)
-        for (int j = 0; j < p.n_jobs; ++j, ++jobn) {
-          const TcJob& job = p.jobs[j];
-          mbar_wait(b_ready, jobn & 1);
-          tc_fence_after();
-          const uint32_t a_swb = job.a_swb, blk = 128 * a_swb, epr = a_swb / 2;
-          const uint32_t nkb = (job.kpt + epr - 1) / epr, ksteps = min(epr, (uint32_t)job.kpt) / 16;
-          const uint32_t a_layout = a_swb == 128 ? SW_128 : a_swb == 64 ? SW_64 : SW_32;
-          uint32_t off = 0, sbase = 0;
-          auto next_chunk = [&]() {
-            if (off != 0) { umma_commit(&empty[(it - 1) % STAGES]); }
-            const uint32_t s = it % STAGES;
-            mbar_wait(&full[s], (it / STAGES) & 1);
-            tc_fence_after();
-            sbase = ring + s * CHUNK;
-            ++it;
-          };
-          for (uint32_t t = 0; t < job.mtiles; ++t)
-            for (uint32_t tap = 0; tap < job.taps; ++tap)
-              for (uint32_t kb = 0; kb < nkb; ++kb) {
-                if ((off & (CHUNK - 1)) == 0) next_chunk();
-                const uint32_t a_addr = sbase + (off & (CHUNK - 1));
-                const uint32_t row_off = (job.taps == 3 ? tap : 1u) * HALO * 128;
-                for (uint32_t ks = 0; ks < ksteps; ++ks) {
-                  const uint32_t k = kb * epr + ks * 16;
-                  const uint64_t ad = smem_desc(a_addr + ks * 32, 8 * a_swb, a_layout);
-                  const uint64_t bd = smem_desc(b_base + (k >> 6) * SLAB + row_off + (k & 63) * 2, 1024, SW_128);
-                  umma_bf16(tmem_base + T_ACC + t * NCOL, ad, bd, idesc64, (tap | kb | ks) != 0);
-                }
-                off += blk;
-              }
-          for (uint32_t f = 0; f < job.film_tiles; ++f) {
-            if ((off & (CHUNK - 1)) == 0) next_chunk();
-            const uint64_t ad = smem_desc(sbase + (off & (CHUNK - 1)), 256, SW_32);
-            const uint64_t bd = smem_desc(u_base, 1024, SW_128);
-            umma_bf16(tmem_base + T_FILM + f * 16, ad, bd, idesc16, 0);
-            off += 4096;
-          }
-          umma_commit(&empty[(it - 1) % STAGES]);
-          umma_commit(acc_ready);
-        }
-    }
-  } else {
-    // =========================== epilogue warps ===========================
-    Ctx c;
-    c.lane = lane; c.q = wid & 3; c.g = wid >> 2; c.ch = c.q * 32 + lane;
-    c.tmem = tmem_base + ((uint32_t)(c.q * 32) << 16);
-    c.smem = smem;
-    c.scr = reinterpret_cast<float*>(smem + SM_SCR) + wid * 256;
-    c.xch = reinterpret_cast<float*>(smem + SM_XCH) + c.g * 256;
+  Ctx c;
+  c.lane = lane; c.q = wid & 3; c.g = wid >> 2; c.ch = c.q * 32 + lane;
+  c.tmem = tmem_base + ((uint32_t)(c.q * 32) << 16);
+  c.smem = smem;
+  c.scr = reinterpret_cast<float*>(smem + SM_SCR) + wid * 256;
+  c.xch = reinterpret_cast<float*>(smem + SM_XCH) + c.g * 256;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c.xoff[j] = ((uint32_t)((((c.ch & 63) >> 3) ^ j) << 4)) + (c.ch & 7) * 2;
-    uint32_t jobn = 0;
-    auto arrive_b = [&]() {
+  for (int j = 0; j < 8; ++j) c.xoff[j] = ((uint32_t)((((c.ch & 63) >> 3) ^ j) << 4)) + (c.ch & 7) * 2;
+  const int sgl = c.g * 8;   // first sample of this warp-group inside the CTA
+
+  // ---- driver (warp 7, warp-uniform control flow; single instructions are issued by one elected lane):
+  //      weight ring producer + UMMA issuer, run at every job hand-off.  Everything address-like is precomputed
+  //      once into a per-step op table in shared memory (the ring stage of a weight chunk is a static function of
+  //      its position in the step), so the issue loop is a table walk: one 16-byte load and ~20 instructions per
+  //      block of up to four UMMAs.  The kernel is laid out for a small per-step instruction stream (one generic
+  //      epilogue, one driver); it is otherwise instruction-fetch bound.
+  const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
+  const bool is_driver = wid_u == 7;       // UMMA issuer
+  const bool is_producer = wid_u == 6;     // weight ring producer (a different scheduler partition than the issuer)
+  uint2* chunk_tab = reinterpret_cast<uint2*>(smem + SM_CHUNKS);
+  uint4* ops = reinterpret_cast<uint4*>(smem + SM_OPS);
+  uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + SM_OPBEG);
+  uint16_t* chunk_end = op_begin + MAXJOBS + 2;      // one past the last weight chunk of every job (index in the step)
+  // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
+  //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA)
+  if (tid == 0) {
+    const uint32_t ring_a = smem_u32(smem + SM_RING), b_base = smem_u32(smem + SM_B);
+    uint32_t nops = 0, chunk_base = 0, ncp = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+      const TcJob& job = p.jobs[j];
+      for (uint32_t off = 0; off < job.bytes; off += CHUNK)
+        chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, job.bytes - off));
+      op_begin[j] = (uint16_t)nops;
+      const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+      const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
+                            ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
+      const uint32_t f_hi = (256u >> 4) | (1u << 14) | ((uint32_t)SW_32 << 29);
+      uint32_t off = 0;
+      auto emit = [&](uint32_t hi, uint32_t b_addr, uint32_t col, uint32_t ks, uint32_t acc, uint32_t film, uint32_t bytes) {
+        const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
+        const uint32_t a_addr = ring_a + stage * CHUNK + (off % CHUNK);
+        const uint32_t w = col | (ks << 9) | (acc << 12) | ((off % CHUNK == 0 ? 1u : 0u) << 13) | (film << 14) |
+                           ((off == 0 ? 1u : 0u) << 15) | (stage << 16);
+        ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
+        off += bytes;
+      };
+      for (uint32_t t = 0; t < job.mtiles; ++t)
+        for (uint32_t tap = 0; tap < job.taps; ++tap)
+          for (uint32_t kb = 0; kb < nkb; ++kb)
+            emit(a_hi, b_base + (job.taps == 3 ? tap : 1u) * (HALO * 128) + kb * SLAB, T_ACC + t * NCOL, a_swb >> 5,
+                 (tap | kb) != 0 ? 1u : 0u, 0u, blk);
+      for (uint32_t f = 0; f < job.film_tiles; ++f) emit(f_hi, smem_u32(smem + SM_U), T_FILM + f * 16, 1u, 0u, 1u, 4096u);
+      chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
+      chunk_end[j] = (uint16_t)ncp;
+    }
+    // the ring stage of a chunk is (index within the step) % STAGES, so a step must span a whole number of ring
+    // revolutions: pad with 16-byte dummy chunks consumed by no-op entries of the last job
+    while (ncp % STAGES) {
+      ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
+      chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
+    }
+    chunk_end[n_jobs - 1] = (uint16_t)ncp;
+    op_begin[n_jobs] = (uint16_t)nops;
+    chunk_end[n_jobs] = (uint16_t)ncp;      // chunks per step
+  }
+  __syncthreads();
+  const uint32_t cps = chunk_end[n_jobs];
+  // producer state (warp 6): position in the chunk stream and per-stage bit masks
+  uint32_t ld_idx = 0, ld_step = 0, ld_used = 0, ld_par = 0;
+  // called by the producer warp at the hand-off of job j of step `step`: loads every chunk this job still needs
+  // (waiting for ring stages to be released by the issuer) and prefetches later chunks into stages that are free
+  auto produce = [&](int step, int j) {
+    const uint32_t must_end = chunk_end[j];
+#pragma unroll 1
+    while (ld_step < (uint32_t)n_steps) {
+      const bool must = ld_step < (uint32_t)step || (ld_step == (uint32_t)step && ld_idx < must_end);
+      const uint32_t s = ld_idx % STAGES;
+      if ((ld_used >> s) & 1u) {
+        const uint32_t par = ((ld_par >> s) & 1u) ^ 1u;
+        if (must) mbar_wait(&empty[s], par);
+        else if (!mbar_test(&empty[s], par)) break;
+      }
+      ld_used |= 1u << s;
+      ld_par ^= 1u << s;
+      const uint2 e = chunk_tab[ld_idx];
+      bulk_g2s_elect(smem + SM_RING + s * CHUNK, p.pack + e.x, e.y, &full[s]);
+      if (++ld_idx == cps) { ld_idx = 0; ++ld_step; }
+    }
+  };
+  uint32_t full_par = 0;   // issuer state (warp 7): per-stage phase parity of the full barriers
+  uint32_t jobn = 0;     // jobs handed off so far (parity of b_ready / acc_ready)
+  int prof_step = -1;
+
+  auto drive_job = [&](int j) {
+    const uint32_t idesc64 = idesc_bf16(128, NCOL), idesc16 = idesc_bf16(128, 16);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const bool rec = p.prof && blockIdx.x == 0 && prof_step == 1 && lane == 0;
+    long long* pr = p.prof + 8 * j;
+    if (rec) pr[2] = clock64();
+    const uint32_t o0 = op_begin[j], o1 = op_begin[j + 1];
+    mbar_wait(b_ready, jobn & 1);
+    tc_fence_after();
+    if (rec) pr[3] = clock64();
+    uint32_t prev_stage = 0;
+    long long ta = 0, tb = 0, tc_ = 0;
+#pragma unroll 1
+    for (uint32_t i = o0; i < o1; ++i) {
+      const long long c0 = p.prof ? clock64() : 0;
+      const uint4 op = ops[i];
+      const uint32_t stage = (op.w >> 16) & 7u;
+      if (op.w & (1u << 13)) {                       // first block of a weight chunk
+        if (!(op.w & (1u << 15))) {
+          umma_commit_elect(&empty[prev_stage]);      // the previous chunk of this job is free once its UMMAs retire
+        }
+        const long long c1 = p.prof ? clock64() : 0;
+        mbar_wait(&full[stage], (full_par >> stage) & 1u);
+        full_par ^= 1u << stage;
+        tc_fence_after();
+        prev_stage = stage;
+        if (p.prof) { ta += c1 - c0; tb += clock64() - c1; }
+      }
+      const long long c2 = p.prof ? clock64() : 0;
+      if (op.w & (1u << 19)) continue;               // ring padding entry
+      const uint64_t ad = ((uint64_t)op.z << 32) | op.x;
+      const uint64_t bd = ((uint64_t)b_hi << 32) | op.y;
+      const uint32_t d = tmem_base + (op.w & 0x1FFu), acc = (op.w >> 12) & 1u, ks = (op.w >> 9) & 7u;
+      if (op.w & (1u << 14)) umma_bf16_block_elect<1>(d, ad, bd, idesc16, 0u);
+      else if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc64, acc);
+      else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc64, acc);
+      else umma_bf16_block_elect<1>(d, ad, bd, idesc64, acc);
+      if (p.prof) tc_ += clock64() - c2;
+    }
+    if (rec) { pr[4] = clock64(); pr[6] = ta; pr[7] = tb; p.prof[336 + j] = tc_; }
+    umma_commit_elect(&empty[prev_stage]);
+    umma_commit_elect(acc_ready);
+    if (rec) pr[5] = clock64();
+  };
+
+#pragma unroll 1
+  for (int step = 0; step < n_steps; ++step) {
+    prof_step = step;
+    if (p.prof && blockIdx.x == 0 && tid == 0 && (step == 1 || step == 2)) p.prof[320 + step - 1] = clock64();
+    // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16)
+    {
+      const int s = tid >> 4, e = tid & 15;
+      const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
+      const float te = __ldg(p.te + (size_t)ti * EMB + e);
+      float a = 0.f;
+      for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
+      *reinterpret_cast<__nv_bfloat16*>(smem + SM_U + swz_off<128>(s, e >> 3) + (e & 7) * 2) = __float2bfloat16(a);
+    }
+    // ---- init_conv: Conv1d(1 -> ch0, k7, p3) on the state -> residual stream tile 0 and B operand
+    {
+      const int c0 = cfg.ch[0];
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      if (c.ch < c0) {
+        float w7[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) w7[t] = __ldg(W + lay.init_w + c.ch * 7 + t);
+        const float b = __ldg(W + lay.init_b + c.ch);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xs[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            float a = b;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+              const int ll = l + t - 3;
+              if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
+            }
+            v[l * 8 + j] = a;
+          }
+        }
+      }
+      tm_store32(c, T_RES, v);
+      write_b(c, 0, v, c.ch < c0);
+    }
+
+#pragma unroll 1
+    for (int j = 0; j < n_jobs; ++j) {
+      const TcJob job = s_jobs[j];
+      // ---- hand the operand of job j to the tensor core (one arrival per warp), driver issues its UMMAs
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(b_ready);
-    };
-    auto wait_acc = [&]() {
-      mbar_wait(acc_ready, jobn & 1);
-      ++jobn;
-      tc_fence_after();
-    };
-    const int sgl = c.g * 8;   // first sample of this warp-group inside the CTA
-
-    for (int step = 0; step < n_steps; ++step) {
-      // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16)
-      {
-        const int s = tid >> 4, e = tid & 15;
-        const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
-        const float te = __ldg(p.te + (size_t)ti * EMB + e);
-        float a = 0.f;
-        for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
-        *reinterpret_cast<__nv_bfloat16*>(smem + SM_U + swz_off<128>(s, e >> 3) + (e & 7) * 2) = __float2bfloat16(a);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready);
+      if (is_driver) drive_job(j);
+      if (is_producer) produce(step, j);
+      // ---- per-channel parameters of this job, fetched while the UMMAs run
+      const int flags = job.flags, ch = job.ch, nt = job.mtiles;
+      float pbias[2], pgam[2], pbet[2], pcs[2], pch[2], pg[2], pg2[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int chan = t * 128 + c.ch;
+        const bool valid = t < nt && chan < ch && !(flags & E_ATTN);
+        pbias[t] = (valid && job.o_bias >= 0) ? __ldg(W + job.o_bias + chan) : 0.f;
+        pgam[t] = (valid && job.o_gamma >= 0) ? __ldg(W + job.o_gamma + chan) : 0.f;
+        pbet[t] = (valid && job.o_beta >= 0) ? __ldg(W + job.o_beta + chan) : 0.f;
+        pcs[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + chan) + (float)R : 0.f;
+        pch[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + ch + chan) : 0.f;
+        pg[t] = (valid && job.o_g >= 0) ? __ldg(W + job.o_g + chan) : 0.f;
+        pg2[t] = (valid && job.o_g2 >= 0) ? __ldg(W + job.o_g2 + chan) : 0.f;
       }
-      // ---- init_conv: Conv1d(1 -> ch0, k7, p3) on the state -> residual stream tile 0 and B operand
+      // ---- wait for the accumulator
       {
-        const int c0 = cfg.ch[0];
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        if (c.ch < c0) {
-          float w7[7];
-#pragma unroll
-          for (int t = 0; t < 7; ++t) w7[t] = __ldg(W + lay.init_w + c.ch * 7 + t);
-          const float b = __ldg(W + lay.init_b + c.ch);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float xs[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-              float a = b;
-#pragma unroll
-              for (int t = 0; t < 7; ++t) {
-                const int ll = l + t - 3;
-                if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
-              }
-              v[l * 8 + j] = a;
-            }
-          }
-        }
-        tm_store32(c, T_RES, v);
-        write_b(c, 0, v, c.ch < c0);
+        const bool rec = p.prof && blockIdx.x == 0 && tid == 0 && prof_step == 1;
+        const long long t0 = rec ? clock64() : 0;
+        mbar_wait(acc_ready, jobn & 1);
+        if (rec) { p.prof[8 * j] = t0; p.prof[8 * j + 1] = clock64(); }
+        ++jobn;
+        tc_fence_after();
       }
-      arrive_b();
-
-      // ---- stages
-      for (int st = 0; st <= cfg.n_stages; ++st) {
-        const bool fin = (st == cfg.n_stages);
-        const int ch = cfg.ch[st];
-        const int nt = (ch + 127) >> 7;
-        const StageOff& so = lay.st[fin ? 0 : st];
-        for (int rb = 0; rb < (fin ? 1 : 2); ++rb) {
-          const RbOff& o = fin ? lay.fin : so.rb[rb];
-          // ======== block1: conv -> GN -> FiLM -> SiLU
-          wait_acc();
-          for (int t = 0; t < nt; ++t) {
-            const int chan = t * 128 + c.ch;
-            const bool valid = chan < ch;
-            float v[32], mean[8], rstd[8];
-            tm_load32(c, T_ACC + t * NCOL, v);
-            const float bias = valid ? __ldg(W + o.p1_b + chan) : 0.f;
+      if (flags & E_ATTN) {
+        // ======== linear attention (resnets.py:211-235): qkv -> core -> operand of to_out
+        float kk[32], e[32];
+        tm_load32(c, T_ACC + 1 * NCOL, kk);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias;
-            gn_stats_dispatch(c, ch, v, mean, rstd);
-            float fs[8], fh[8];
-            tm_load8(c, T_FILM + t * 16 + c.g * 8, fs);
-            tm_load8(c, T_FILM + (nt + t) * 16 + c.g * 8, fh);
-            const float ga = valid ? __ldg(W + o.n1_w + chan) : 0.f, be = valid ? __ldg(W + o.n1_b + chan) : 0.f;
-            const float cs = valid ? (float)R * __ldg(W + o.mlp_b + chan) + (float)R : 0.f;
-            const float chh = valid ? (float)R * __ldg(W + o.mlp_b + ch + chan) : 0.f;
+        for (int jj = 0; jj < 8; ++jj) {   // softmax over the 4 positions (dim=-1)
+          const float m = fmaxf(fmaxf(kk[jj], kk[8 + jj]), fmaxf(kk[16 + jj], kk[24 + jj]));
+          float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a = rstd[j] * ga, b = be - mean[j] * a;
-              const float sc = fs[j] + cs, sh = fh[j] + chh;
+          for (int l = 0; l < 4; ++l) { kk[l * 8 + jj] = __expf(kk[l * 8 + jj] - m); sum += kk[l * 8 + jj]; }
+          const float inv = __fdividef(1.0f, sum);
 #pragma unroll
-              for (int l = 0; l < 4; ++l) {
-                float y = fmaf(v[l * 8 + j], a, b);
-                y = fmaf(y, sc, sh);
-                v[l * 8 + j] = silu_fast(y);
-              }
-            }
-            write_b(c, t, v, valid);
+          for (int l = 0; l < 4; ++l) kk[l * 8 + jj] *= inv;
+        }
+        tm_load32(c, T_ACC + 0 * NCOL, e);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = __expf(fminf(e[i], 80.f));   // softmax over d: normalised by Z below
+        // lane sums over d (this warp = one head): A[j][n'][n] = sum_d k[n'][j] e[n][j], Z[n][j] = sum_d e[n][j]
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          float pr[32];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int n1 = 0; n1 < 4; ++n1)
+#pragma unroll
+              for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
+          c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
+        }
+        {
+          float z[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) z[i] = e[i];
+          c.scr[128 + lane] = reduce_scatter32(z, lane);
+        }
+        __syncwarp();
+        float vv[32], o[32];
+        tm_load32(c, T_ACC + 2 * NCOL, vv);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float A[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (jj >> 1) * 32 + (jj & 1) * 16 + i);
+            A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
           }
-          arrive_b();
-          // ======== block2: conv -> GN -> SiLU, + residual
-          wait_acc();
-          const bool to_attn = !fin && rb == 1;
-          float fc_part[32];
-          if (fin) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) fc_part[i] = 0.f;
-          }
-          for (int t = 0; t < nt; ++t) {
-            const int chan = t * 128 + c.ch;
-            const bool valid = chan < ch;
-            float v[32], mean[8], rstd[8], res[32];
-            tm_load32(c, T_ACC + t * NCOL, v);
-            const float bias = valid ? __ldg(W + o.p2_b + chan) : 0.f;
+          for (int n = 0; n < 4; ++n) {
+            float acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias;
-            gn_stats_dispatch(c, ch, v, mean, rstd);
-            tm_load32(c, T_RES + t * NCOL, res);
-            const float ga = valid ? __ldg(W + o.n2_w + chan) : 0.f, be = valid ? __ldg(W + o.n2_b + chan) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a = rstd[j] * ga, b = be - mean[j] * a;
-#pragma unroll
-              for (int l = 0; l < 4; ++l) {
-                const float y = fmaf(v[l * 8 + j], a, b);
-                v[l * 8 + j] = valid ? silu_fast(y) + res[l * 8 + j] : 0.f;
-              }
-            }
-            if (fin) {
-              const float wfc = valid ? __ldg(W + lay.fc_w + chan) : 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(wfc, v[i], fc_part[i]);
-            } else {
-              tm_store32(c, T_RES + t * NCOL, v);
-              if (!to_attn) {
-                write_b(c, t, v, valid);
-              } else {
-                // PreNorm LayerNorm (resnets.py:104-124) -> qkv operand
-                float mr[32], rs[32];
-                ln_stats(c, ch, v, mr, rs);
-                const float gg = valid ? __ldg(W + so.ln_g + chan) : 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * gg;
-                write_b(c, t, v, valid);
-              }
-            }
-          }
-          if (fin) {
-            // ======== final_conv (1x1 -> 1 channel) + scheduler update
-            const float part = reduce_scatter32(fc_part, lane);     // lane r: row r = l*8 + j of this warp's 32 channels
-            c.xch[c.q * 64 + lane] = part;
-            wg_sync(c.g);
-            if (c.q == 0) {
-              float eps = __ldg(W + lay.fc_b);
-#pragma unroll
-              for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
-              const int l = lane >> 3, j = lane & 7, s = sgl + j;
-              const bool ok = s0 + s < p.n;
-              if (p.mode == 0) {
-                const float* cf = p.coef + (size_t)step * 8;
-                const float x = s_x[s * 4 + l];
-                float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
-                if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-                float prev;
-                if (p.sched_kind == GLDM_SCHED_DDPM) {
-                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
-                  const float sg = __ldg(cf + 4);
-                  if (sg > 0.f && ok) {
-                    const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
-                                            : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
-                    prev = __fadd_rn(prev, __fmul_rn(sg, z));
-                  }
-                } else {
-                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
-                }
-                s_x[s * 4 + l] = prev;
-                if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
-              } else {
-                s_x[s * 4 + l] = eps;
-              }
-            }
-            wg_sync(c.g);
-          } else {
-            arrive_b();
+            for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + jj], A[n1 * 4 + n], acc);
+            const float zinv = __fdividef(0.17677669529663687f, c.scr[128 + n * 8 + jj]);   // scale 32^-0.5 / Z
+            o[n * 8 + jj] = acc * zinv;
           }
         }
-        if (fin) break;
-        // ======== linear attention (resnets.py:211-235): qkv -> core -> out operand
-        wait_acc();
-        {
-          float kk[32], e[32];
-          tm_load32(c, T_ACC + 1 * NCOL, kk);
+        __syncwarp();
+        write_b(c, 0, o, true);
+      } else {
+        // ======== generic epilogue: bias, GroupNorm / LayerNorm, FiLM, SiLU, residual, PreNorm, operand write
+        float fc_part[32];
+        if (flags & E_FINAL) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {   // softmax over the 4 positions (dim=-1)
-            const float m = fmaxf(fmaxf(kk[j], kk[8 + j]), fmaxf(kk[16 + j], kk[24 + j]));
-            float s = 0.f;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) { kk[l * 8 + j] = __expf(kk[l * 8 + j] - m); s += kk[l * 8 + j]; }
-            const float inv = __fdividef(1.0f, s);
-#pragma unroll
-            for (int l = 0; l < 4; ++l) kk[l * 8 + j] *= inv;
-          }
-          tm_load32(c, T_ACC + 0 * NCOL, e);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) e[i] = __expf(fminf(e[i], 80.f));   // softmax over d: normalised by Z below
-          // lane sums over d (this warp = one head): A[j][n'][n] = sum_d k[n'][j] e[n][j], Z[n][j] = sum_d e[n][j]
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            float pr[32];
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1)
-#pragma unroll
-                for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
-            c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
-          }
-          {
-            float z[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = e[i];
-            c.scr[128 + lane] = reduce_scatter32(z, lane);
-          }
-          __syncwarp();
-          float vv[32], o[32];
-          tm_load32(c, T_ACC + 2 * NCOL, vv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float A[16];
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (j >> 1) * 32 + (j & 1) * 16 + i);
-              A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
-            }
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-              float acc = 0.f;
-#pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + j], A[n1 * 4 + n], acc);
-              const float zinv = __fdividef(0.17677669529663687f, c.scr[128 + n * 8 + j]);   // scale 32^-0.5 / Z
-              o[n * 8 + j] = acc * zinv;
-            }
-          }
-          __syncwarp();
-          write_b(c, 0, o, true);
+          for (int i = 0; i < 32; ++i) fc_part[i] = 0.f;
         }
-        arrive_b();
-        // ======== to_out: conv(128 -> ch) + bias -> LayerNorm -> + residual
-        wait_acc();
-        {
-          const bool valid = c.ch < ch;
-          float v[32], mr[32], rs[32], res[32];
-          tm_load32(c, T_ACC, v);
-          const float bias = valid ? __ldg(W + so.out_b + c.ch) : 0.f;
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+          const bool valid = t * 128 + c.ch < ch;
+          const float bias = t ? pbias[1] : pbias[0], gam = t ? pgam[1] : pgam[0], bet = t ? pbet[1] : pbet[0];
+          const float cs = t ? pcs[1] : pcs[0], chh = t ? pch[1] : pch[0], g1 = t ? pg[1] : pg[0], g2 = t ? pg2[1] : pg2[0];
+          uint32_t rv[32], rr[32], rs8[8], rh8[8];
+          tm_issue32(c, T_ACC + t * NCOL, rv);
+          if (flags & E_ADDRES) tm_issue32(c, T_RES + t * NCOL, rr);
+          if (flags & E_FILM) {
+            tm_issue8(c, T_FILM + t * 16 + c.g * 8, rs8);
+            tm_issue8(c, T_FILM + (nt + t) * 16 + c.g * 8, rh8);
+          }
+          tm_wait();
+          float v[32];
+          tm_use(rv, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += bias;
-          ln_stats(c, ch, v, mr, rs);
-          tm_load32(c, T_RES, res);
-          const float gg = valid ? __ldg(W + so.out_g + c.ch) : 0.f;
+          if (flags & E_GN) {
+            float mean[8], rstd[8];
+            gn_stats_dispatch(c, ch, v, mean, rstd);
+            if (flags & E_FILM) {
+              float fs[8], fh[8];
+              tm_use(rs8, fs);
+              tm_use(rh8, fh);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = valid ? (v[i] - mr[i]) * rs[i] * gg + res[i] : 0.f;
-          // the residual stream is replaced by the stage conv below; only the operand is needed
-          write_b(c, 0, v, valid);
-        }
-        arrive_b();
-        // ======== stage conv: Conv1d(ch -> cn, k3) + bias -> new residual stream
-        wait_acc();
-        {
-          const int cn = cfg.ch[st + 1];
-          const int ntn = (cn + 127) >> 7;
-          for (int t = 0; t < ntn; ++t) {
-            const int chan = t * 128 + c.ch;
-            const bool valid = chan < cn;
-            float v[32];
-            tm_load32(c, T_ACC + t * NCOL, v);
-            const float bias = valid ? __ldg(W + so.down_b + chan) : 0.f;
+              for (int jj = 0; jj < 8; ++jj) {
+                const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+                const float sc = fs[jj] + cs, sh = fh[jj] + chh;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + bias : 0.f;
-            tm_store32(c, T_RES + t * NCOL, v);
+                for (int l = 0; l < 4; ++l) v[l * 8 + jj] = fmaf(fmaf(v[l * 8 + jj], a, b), sc, sh);
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) v[l * 8 + jj] = fmaf(v[l * 8 + jj], a, b);
+              }
+            }
+          }
+          if (flags & E_SILU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+          }
+          if (flags & E_LN) {
+            float mr[32], rs[32];
+            ln_stats(c, ch, v, mr, rs);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g1;
+          }
+          if (flags & E_ADDRES) {
+            float res[32];
+            tm_use(rr, res);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += res[i];
+          }
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (flags & E_STORERES) tm_store32(c, T_RES + t * NCOL, v);
+          if (flags & E_LNNEXT) {
+            float mr[32], rs[32];
+            ln_stats(c, ch, v, mr, rs);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g2;
+          }
+          if (flags & E_FINAL) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(g2, v[i], fc_part[i]);
+          } else {
             write_b(c, t, v, valid);
           }
         }
-        arrive_b();
+        if (flags & E_FINAL) {
+          // ======== final_conv (1x1 -> 1 channel) + scheduler update
+          const float part = reduce_scatter32(fc_part, lane);     // lane r: row r = l*8 + j of this warp's 32 channels
+          c.xch[c.q * 64 + lane] = part;
+          wg_sync(c.g);
+          if (c.q == 0) {
+            float eps = __ldg(W + lay.fc_b);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
+            const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+            const bool ok = s0 + s < p.n;
+            if (p.mode == 0) {
+              const float* cf = p.coef + (size_t)step * 8;
+              const float x = s_x[s * 4 + l];
+              float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
+              if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+              float prev;
+              if (p.sched_kind == GLDM_SCHED_DDPM) {
+                prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
+                const float sg = __ldg(cf + 4);
+                if (sg > 0.f && ok) {
+                  const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
+                                          : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
+                  prev = __fadd_rn(prev, __fmul_rn(sg, z));
+                }
+              } else {
+                prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
+              }
+              s_x[s * 4 + l] = prev;
+              if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
+            } else {
+              s_x[s * 4 + l] = eps;
+            }
+          }
+          wg_sync(c.g);
+        }
       }
     }
-    // ---- outputs
-    wg_sync(c.g);
-    if (c.q == 0) {
-      const int l = lane >> 3, j = lane & 7, s = sgl + j;
-      if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
-    }
+  }
+  // ---- outputs
+  wg_sync(c.g);
+  if (c.q == 0) {
+    const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+    if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
   }
   tc_fence_before();
   __syncthreads();
-  if (wid == 9) tmem_dealloc<512>(tmem_base);
+  if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 
 static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, const void* pack) {
@@ -823,7 +909,10 @@ static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, cons
   return GLDM_OK;
 }
 
-static int launch_tc(const TcParams& p, cudaStream_t s) {
+static long long* g_tc_prof = nullptr;
+
+static int launch_tc(TcParams& p, cudaStream_t s) {
+  p.prof = g_tc_prof;
   static bool attr = false;
   const int smem = stc::SM_TOTAL + 1024;
   if (!attr) {
@@ -837,6 +926,11 @@ static int launch_tc(const TcParams& p, cudaStream_t s) {
 }  // namespace gldm
 
 using namespace gldm;
+
+extern "C" int gldm_sampler_tc_set_profile(long long* dev_buf) {
+  g_tc_prof = dev_buf;
+  return GLDM_OK;
+}
 
 extern "C" long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg) {
   if (check_tc_cfg(cfg) != GLDM_OK) return -1;

@@ -180,6 +180,9 @@ int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, co
  * 1024-byte aligned).  Supported: the fpc latent denoiser family (L = 4, emb 16, 4 stages of width <= 128,
  * final width <= 256); anything else returns GLDM_ENOSUP. */
 long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg);
+/* development aid: when dev_buf != NULL (>= 512 int64 on the device) CTA 0 stamps clock64() around every
+ * accumulator wait of its second denoising step; NULL (default) disables it */
+int gldm_sampler_tc_set_profile(long long* dev_buf);
 int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* raw, void* pack, void* stream);
 int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x_T,
                         const float* z_obj, int n, int grasps_per_obj, int n_steps, const int* timesteps_host,
