@@ -1,0 +1,274 @@
+// Tensor-core (tcgen05 / TMEM) GEMM for the point-wise layers of the PVCNN encoder:
+//   SharedMLP 96->768, 768->1536 (Conv1d k1 + folded BatchNorm + ReLU, R/../pvcnn/modules/shared_mlp.py:18-28) and
+//   conv_downscale 1536->768 (R/models/modules/pc_encoders.py:60-67) - 61 % of the encoder's FLOPs.
+//
+//   Y[m, n] = act(scale[n] * sum_k X[m, k] * W[n, k] + shift[n]),   m = cloud * N_points + point
+//
+// Operands live in HBM as ready-made UMMA "images": [row tile of 128][K block of 64][128 rows x 128 bytes,
+// SWIZZLE_128B] bf16, so a pipeline stage is two 16 KB 1-D bulk copies (no tensor maps) and the epilogue of one layer
+// writes the next layer's A image directly.  One CTA computes a 128 x 128 output tile: warp 0 streams the operand
+// blocks through a 3-stage mbarrier ring, warp 1 issues the UMMAs (M = 128, N = 128, K = 16, fp32 accumulator in
+// TMEM), warps 2-5 run the epilogue (TMEM -> registers -> scale/shift/ReLU -> bf16 -> image).  Two CTAs fit per SM
+// (96 KB of shared memory, 128 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gldm {
+using namespace tc;
+
+namespace gtc {
+constexpr int BLOCK = 16384;                 // one operand block: 128 rows x 64 bf16
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 192;
+constexpr int SMEM = STAGES * 2 * BLOCK + 1024 + 256;
+}  // namespace gtc
+
+struct GemmTcParams {
+  const uint8_t* a_img;     // [m_tiles][k_blocks][BLOCK]
+  const uint8_t* b_img;     // [n_tiles][k_blocks][BLOCK]
+  uint8_t* out_img;         // [m_tiles][n_tiles * 2][BLOCK]  (A image of the next layer, K = n_tiles * 128)
+  const float* scale;       // [n] or NULL (1)
+  const float* shift;       // [n] or NULL (0)
+  int k_blocks, n_tiles, relu;
+};
+
+__global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+  using namespace gtc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * BLOCK);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nt = blockIdx.x, mt = blockIdx.y;
+  const int kb_n = p.k_blocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (wid == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer
+    const uint8_t* a = p.a_img + (size_t)mt * kb_n * BLOCK;
+    const uint8_t* b = p.b_img + (size_t)nt * kb_n * BLOCK;
+#pragma unroll 1
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const int s = kb % STAGES, round = kb / STAGES;
+      if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full[s], 2 * BLOCK);
+        bulk_g2s(smem + (2 * s) * BLOCK, a + (size_t)kb * BLOCK, BLOCK, &full[s]);
+        bulk_g2s(smem + (2 * s + 1) * BLOCK, b + (size_t)kb * BLOCK, BLOCK, &full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer
+    const uint32_t idesc = idesc_bf16(128, 128);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const uint32_t base = smem_u32(smem);
+#pragma unroll 1
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (kb / STAGES) & 1);
+      tc_fence_after();
+      const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s) * BLOCK) >> 4));
+      const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s + 1) * BLOCK) >> 4));
+      umma_bf16_block_elect<4>(tmem, ad, bd, idesc, kb != 0);
+      umma_commit_elect(&empty[s]);
+    }
+    umma_commit_elect(acc_full);
+  } else {
+    // ---- epilogue: warp w reads TMEM lanes 32 * (w % 4); thread <-> output row
+    const int q = wid & 3, r = q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 2) * BLOCK;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int n = nt * 128 + c0 + j8 * 8 + 2 * h;
+          float y0 = __uint_as_float(v[j8 * 8 + 2 * h]), y1 = __uint_as_float(v[j8 * 8 + 2 * h + 1]);
+          const float s0 = p.scale ? __ldg(p.scale + n) : 1.f, s1 = p.scale ? __ldg(p.scale + n + 1) : 1.f;
+          const float h0 = p.shift ? __ldg(p.shift + n) : 0.f, h1 = p.shift ? __ldg(p.shift + n + 1) : 0.f;
+          y0 = fmaf(y0, s0, h0);
+          y1 = fmaf(y1, s1, h1);
+          if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+          pk[h] = pack_bf16(y0, y1);
+        }
+        const int c = c0 + j8 * 8;                         // column inside the 128-wide tile
+        uint8_t* dst = out_tile + (size_t)(c >> 6) * BLOCK + swz_off<128>(r, (c & 63) >> 3);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<128>(tmem);
+}
+
+// fp32 channel-major activations [b, c, n] -> A image (rows m = b * n + point, K = c padded to a multiple of 64)
+__global__ void __launch_bounds__(256) to_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int c, int n,
+                                                       long long rows, int k_blocks) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;                 // 8 channels
+  if (m >= rows) return;
+  const long long b = m / n;
+  const int pt = (int)(m - b * n);
+  const float* xb = x + ((size_t)b * c) * n + pt;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = chunk * 8 + j;
+    v[j] = ch < c ? __ldg(xb + (size_t)ch * n) : 0.f;
+  }
+  const long long mt = m >> 7;
+  const int r = (int)(m & 127), kb = chunk >> 3;
+  uint8_t* dst = img + ((size_t)mt * k_blocks + kb) * gtc::BLOCK + swz_off<128>(r, chunk & 7);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                              pack_bf16(v[6], v[7]));
+}
+
+// few-output point-wise conv reading an A image: y[b, o, pt] = sum_k W[o, k] * X[m, k] + bias[o]   (out_layer.0)
+template <int CO>
+__global__ void __launch_bounds__(128) image_small_co_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int k, int k_blocks, int n,
+                                                             long long rows, float* __restrict__ y) {
+  extern __shared__ float s_w[];   // [CO][k]
+  for (int i = threadIdx.x; i < CO * k; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const long long mt = m >> 7;
+  const int r = (int)(m & 127);
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+  for (int kb = 0; kb < k_blocks; ++kb) {
+    const uint8_t* row = img + ((size_t)mt * k_blocks + kb) * gtc::BLOCK + (size_t)r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                      // logical chunk j sits at physical chunk j ^ (r & 7)
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + ((j ^ (r & 7)) << 4)));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[h]));
+        const int kk = kb * 64 + j * 8 + 2 * h;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[o] = fmaf(s_w[o * k + kk + 1], f.y, fmaf(s_w[o * k + kk], f.x, acc[o]));
+      }
+    }
+  }
+  const long long b = m / n;
+  const int pt = (int)(m - b * n);
+#pragma unroll
+  for (int o = 0; o < CO; ++o) y[((size_t)b * CO + o) * n + pt] = acc[o] + (bias ? bias[o] : 0.f);
+}
+
+// weight matrix fp32 [n_out][k] -> B image [n_tiles][k_blocks][BLOCK]
+__global__ void __launch_bounds__(256) weight_image_kernel(const float* __restrict__ w, uint8_t* __restrict__ img, int n_out,
+                                                           int k, int k_blocks) {
+  const int nrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // one warp per row
+  const int n_tiles = gridDim.x * (blockDim.x >> 5) / 128;
+  if (nrow >= n_tiles * 128) return;
+  for (int chunk = lane; chunk < k_blocks * 8; chunk += 32) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = chunk * 8 + j;
+      v[j] = (nrow < n_out && kk < k) ? w[(size_t)nrow * k + kk] : 0.f;
+    }
+    uint8_t* dst = img + ((size_t)(nrow >> 7) * k_blocks + (chunk >> 3)) * gtc::BLOCK + swz_off<128>(nrow & 127, chunk & 7);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                                pack_bf16(v[6], v[7]));
+  }
+}
+
+}  // namespace gldm
+
+using namespace gldm;
+
+extern "C" long long gldm_gemm_tc_image_bytes(long long rows, int k) {
+  if (rows <= 0 || k <= 0) return -1;
+  return ((rows + 127) / 128) * (long long)((k + 63) / 64) * gtc::BLOCK;
+}
+
+extern "C" int gldm_gemm_tc_pack_weight(const float* w, int n_out, int k, void* img, void* stream) {
+  GLDM_REQUIRE(w && img, "gemm_tc_pack_weight: null pointer");
+  GLDM_REQUIRE(n_out > 0 && k > 0, "gemm_tc_pack_weight: bad sizes");
+  const int n_tiles = (n_out + 127) / 128, kb = (k + 63) / 64;
+  weight_image_kernel<<<n_tiles * 128 / 8, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<uint8_t*>(img), n_out, k, kb);
+  return check_launch("weight_image_kernel");
+}
+
+extern "C" int gldm_gemm_tc_to_image(const float* x, int b, int c, int n, void* img, void* stream) {
+  GLDM_REQUIRE(x && img, "gemm_tc_to_image: null pointer");
+  GLDM_REQUIRE(b >= 0 && c > 0 && n > 0, "gemm_tc_to_image: bad sizes");
+  const long long rows = (long long)b * n;
+  GLDM_REQUIRE(rows % 128 == 0, "gemm_tc_to_image: b * n = %lld must be a multiple of 128", rows);
+  if (rows == 0) return GLDM_OK;
+  const int kb = (c + 63) / 64;
+  dim3 grid((unsigned)((rows + 255) / 256), kb * 8);
+  to_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint8_t*>(img), c, n, rows, kb);
+  return check_launch("to_image_kernel");
+}
+
+extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, const float* shift,
+                                long long rows, int k, int n_out, int relu, void* out_img, void* stream) {
+  GLDM_REQUIRE(a_img && w_img && out_img, "gemm_tc_run: null pointer");
+  GLDM_REQUIRE(rows >= 0 && rows % 128 == 0, "gemm_tc_run: rows = %lld must be a multiple of 128", rows);
+  GLDM_REQUIRE(k > 0 && n_out > 0 && n_out % 128 == 0, "gemm_tc_run: n_out = %d must be a multiple of 128", n_out);
+  if (rows == 0) return GLDM_OK;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM);
+    attr = true;
+  }
+  GemmTcParams p;
+  p.a_img = reinterpret_cast<const uint8_t*>(a_img);
+  p.b_img = reinterpret_cast<const uint8_t*>(w_img);
+  p.out_img = reinterpret_cast<uint8_t*>(out_img);
+  p.scale = scale; p.shift = shift;
+  p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
+  dim3 grid(p.n_tiles, (unsigned)(rows / 128));
+  gemm_tc_kernel<<<grid, gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
+  return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int gldm_gemm_tc_image_small_co(const void* img, const float* w, const float* bias, long long rows, int k,
+                                           int co, int n, float* y, void* stream) {
+  GLDM_REQUIRE(img && w && y, "gemm_tc_image_small_co: null pointer");
+  GLDM_REQUIRE(rows >= 0 && k > 0 && k % 64 == 0 && co >= 1 && co <= 4 && n > 0 && rows % n == 0,
+               "gemm_tc_image_small_co: bad sizes");
+  if (rows == 0) return GLDM_OK;
+  const int kb = k / 64;
+  const size_t smem = sizeof(float) * co * k;
+  dim3 grid((unsigned)((rows + 127) / 128));
+  const uint8_t* im = reinterpret_cast<const uint8_t*>(img);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (co) {
+    case 1: image_small_co_kernel<1><<<grid, 128, smem, s>>>(im, w, bias, k, kb, n, rows, y); break;
+    case 2: image_small_co_kernel<2><<<grid, 128, smem, s>>>(im, w, bias, k, kb, n, rows, y); break;
+    case 3: image_small_co_kernel<3><<<grid, 128, smem, s>>>(im, w, bias, k, kb, n, rows, y); break;
+    default: image_small_co_kernel<4><<<grid, 128, smem, s>>>(im, w, bias, k, kb, n, rows, y); break;
+  }
+  return check_launch("image_small_co_kernel");
+}

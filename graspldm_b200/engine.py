@@ -273,6 +273,30 @@ def pose_postprocess(tmrp, logit, grasp_mean, grasp_std):
     return gt, H, conf
 
 
+def _pointwise_tail_tc(pk, feats, st):
+    """SharedMLPs after the last PVConv -> conv_downscale -> out_layer.0 on the tensor cores.  Activations stay in
+    HBM as bf16 UMMA images (rows = points of all clouds); only the [B, C_out, N] result is fp32."""
+    dev = feats.device
+    B, C, N = feats.shape
+    rows = B * N
+    if rows % 128:
+        raise NotImplementedError("precision='bf16': clouds * points must be a multiple of 128")
+    L = _lib.lib()
+    img = _aligned_bytes(L.gldm_gemm_tc_image_bytes(rows, C), dev)
+    _lib.call("gldm_gemm_tc_to_image", feats.data_ptr(), B, C, N, img.data_ptr(), st)
+    for layer in pk.tc_weights():
+        out = _aligned_bytes(L.gldm_gemm_tc_image_bytes(rows, layer["n"]), dev)
+        _lib.call("gldm_gemm_tc_run", img.data_ptr(), layer["img"].data_ptr(),
+                  layer["scale"].data_ptr() if layer["scale"] is not None else None,
+                  layer["shift"].data_ptr() if layer["shift"] is not None else None,
+                  rows, layer["k"], layer["n"], layer["relu"], out.data_ptr(), st)
+        img, k = out, layer["n"]
+    h = torch.empty((B, pk.out_channels, N), device=dev, dtype=torch.float32)
+    _lib.call("gldm_gemm_tc_image_small_co", img.data_ptr(), pk.wo.data_ptr(), pk.bo.data_ptr(), rows, k,
+              pk.out_channels, N, h.data_ptr(), st)
+    return h
+
+
 # --------------------------------------------------------------------------------------------------
 # PVCNN encoder (strict fp32 path)
 # --------------------------------------------------------------------------------------------------
@@ -325,6 +349,33 @@ class PackedEncoder:
         self.bl = enc.out_layer[1].bias.detach().float().contiguous()
         self.out_channels = co.out_channels
         self.out_features = enc.out_layer[1].out_features
+        self._tc = None
+
+    def tc_weights(self):
+        """bf16 UMMA images of the point-wise layers that run on the tensor cores (built on first use):
+        every SharedMLP after the last PVConv block, then conv_downscale."""
+        if self._tc is None:
+            dev = self.device
+            layers = []
+            tail = [b for b in self.blocks if b["kind"] == "mlp"]
+            specs = [(b["pw"], b["pscale"], b["pshift"], 1) for b in tail] + [(self.wd, None, self.bd, 0)]
+            with torch.cuda.device(dev):
+                for w, sc, sh, relu in specs:
+                    n_out, k = w.shape
+                    if n_out % 128:
+                        raise NotImplementedError(f"precision='bf16': point-wise layer width {n_out} is not a multiple of 128")
+                    nbytes = _lib.lib().gldm_gemm_tc_image_bytes(n_out, k)
+                    img = _aligned_bytes(nbytes, dev)
+                    _lib.call("gldm_gemm_tc_pack_weight", w.data_ptr(), n_out, k, img.data_ptr(), _stream(dev))
+                    layers.append(dict(img=img, scale=sc, shift=sh, relu=relu, k=k, n=n_out))
+            self._tc = layers
+        return self._tc
+
+
+def _aligned_bytes(nbytes, dev, align=1024):
+    buf = torch.empty(nbytes + align, device=dev, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off:off + nbytes]
 
 
 def packed_encoder(enc):
@@ -346,20 +397,23 @@ def _pw(x, w, scale, shift, add, act):
     return y
 
 
-def encoder_forward(enc, xyz, max_clouds_per_pass=256):
+def encoder_forward(enc, xyz, max_clouds_per_pass=256, precision="fp32"):
     """PVCNNEncoder.forward: xyz [B,N,3] -> z_pc [B,C_out,F] (squeezed when C_out == 1)."""
     _require_cuda(xyz, "xyz")
+    _check_precision(precision)
     pk = packed_encoder(enc)
+    if precision == "bf16":
+        pk.tc_weights()
     outs = []
     tok = SECTIONS.start("encoder", xyz.device)
     for s in range(0, xyz.shape[0], max_clouds_per_pass):
-        outs.append(_encoder_pass(pk, xyz[s:s + max_clouds_per_pass]))
+        outs.append(_encoder_pass(pk, xyz[s:s + max_clouds_per_pass], precision))
     SECTIONS.stop(tok)
     out = torch.cat(outs) if len(outs) > 1 else outs[0]
     return out.squeeze(1) if out.shape[-2] == 1 else out
 
 
-def _encoder_pass(pk, xyz):
+def _encoder_pass(pk, xyz, precision="fp32"):
     dev = xyz.device
     st = _stream(dev)
     with torch.cuda.device(dev):
@@ -393,10 +447,13 @@ def _encoder_pass(pk, xyz):
                 _lib.call("gldm_devox_gate_add_f32", norm.data_ptr(), y2.data_ptr(), gate.data_ptr(), pt.data_ptr(), B,
                           co, N, r, fused.data_ptr(), st)
                 feats = fused
-            else:
+            elif precision == "fp32":
                 feats = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
-        h = _pw(feats, pk.wd, None, pk.bd, None, 0)
-        h = _pw(h, pk.wo, None, pk.bo, None, 0)                 # [B, C_out, N]
+        if precision == "fp32":
+            h = _pw(feats, pk.wd, None, pk.bd, None, 0)
+            h = _pw(h, pk.wo, None, pk.bo, None, 0)             # [B, C_out, N]
+        else:
+            h = _pointwise_tail_tc(pk, feats, st)               # tensor-core chain, [B, C_out, N] fp32
         z = torch.empty((B, pk.out_channels, pk.out_features), device=dev, dtype=torch.float32)
         _lib.call("gldm_linear_lastdim_f32", h.data_ptr(), pk.wl.data_ptr(), pk.bl.data_ptr(), B * pk.out_channels, N,
                   pk.out_features, z.data_ptr(), st)

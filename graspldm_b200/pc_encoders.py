@@ -22,6 +22,7 @@ class PVCNNEncoder(nn.Module):
         self.conv_downscale = nn.Conv1d(self.pvcnn_modules.out_channels, mid, kernel_size=1)
         self.global_attention = None
         self.out_layer = nn.Sequential(nn.Conv1d(mid, out_channels, kernel_size=1), nn.Linear(n_points, out_features))
+        self.precision = "fp32"     # "bf16": point-wise layers on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)
         if load_from_ckpt_path is not None:
             ckpt = torch.load(load_from_ckpt_path)
             self.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
@@ -31,4 +32,4 @@ class PVCNNEncoder(nn.Module):
         """xyz [B,N,3] -> [B,C_out,out_features] ([B,out_features] when C_out == 1)"""
         if self.training:
             raise NotImplementedError("generation path: call .eval() (BatchNorm uses running statistics)")
-        return engine.encoder_forward(self, out)
+        return engine.encoder_forward(self, out, precision=self.precision)

@@ -191,6 +191,21 @@ int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, const void* 
 int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
                              const int* t, const float* z_cond, int n, float* eps, void* stream);
 
+/* ---- tensor-core GEMM for the encoder's point-wise layers (bf16 operands, fp32 accumulation) ----
+ * Operands are "UMMA images": [row tile of 128][K block of 64][128 rows x 128 bytes, SWIZZLE_128B] bf16.
+ * gldm_gemm_tc_image_bytes(rows, k): size of such an image.  gldm_gemm_tc_pack_weight: fp32 W[n_out,k] -> image.
+ * gldm_gemm_tc_to_image: fp32 activations [b,c,n] (channel-major) -> image with rows m = b*n + point.
+ * gldm_gemm_tc_run: out_img[m, n] = act(scale[n] * sum_k A[m,k] W[n,k] + shift[n]) written as the next layer's image
+ *   (SharedMLP / conv_downscale, R/../pvcnn/modules/shared_mlp.py:18-28, R/models/modules/pc_encoders.py:60-67).
+ * gldm_gemm_tc_image_small_co: y f32[b,co,n] = W[co,k] * image + bias, co <= 4 (out_layer.0, pc_encoders.py:68-75). */
+long long gldm_gemm_tc_image_bytes(long long rows, int k);
+int gldm_gemm_tc_pack_weight(const float* w, int n_out, int k, void* img, void* stream);
+int gldm_gemm_tc_to_image(const float* x, int b, int c, int n, void* img, void* stream);
+int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, const float* shift, long long rows,
+                     int k, int n_out, int relu, void* out_img, void* stream);
+int gldm_gemm_tc_image_small_co(const void* img, const float* w, const float* bias, long long rows, int k, int co,
+                                int n, float* y, void* stream);
+
 /* Pose post-processing (R/../tools/inference.py:627-656, R/utils/rotations.py:298-302):
  * tmrp f32[n,6], logit f32[n], grasp_mean/std f32[6] -> grasp_tmrp f32[n,6], H f32[n,4,4], conf f32[n] */
 int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,

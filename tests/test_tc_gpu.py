@@ -56,3 +56,23 @@ def test_sampler_bf16_tracks_fp32(cuda, kind, steps):
     print(f"[{kind}{steps}] bf16 vs fp32 latents after {steps} steps: max|diff| {err:.3e}")
     # the recurrence damps eps errors (x0 coefficient of the posterior mean is O(1e-2) per step)
     np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("name", ["fpc", "ppc"])
+def test_encoder_bf16_pointwise_layers(cuda, name):
+    """Point-wise tail (96->768->1536->768) on the tensor cores vs the committed reference fixture."""
+    m = _models.build(name).to(cuda)
+    enc = m.vae_model.encoder.pc_encoder
+    xyz = torch.cat([_data.synthetic_clouds(2, seed=1234, dist="S"), _data.synthetic_clouds(1, seed=99, dist="G")]).to(cuda)
+    z32 = m.vae_model.encode_pc(xyz)
+    enc.precision = "bf16"
+    try:
+        z16 = m.vae_model.encode_pc(xyz)
+    finally:
+        enc.precision = "fp32"
+    want = np.load(os.path.join(G, f"encoder_{name}.npz"))["z_pc"]
+    err = np.abs(z16.cpu().numpy() - want).max()
+    print(f"[{name}] bf16 encoder tail: max|err| vs reference {err:.3e}, vs fp32 path {(z16 - z32).abs().max().item():.3e}, "
+          f"max|z| {np.abs(want).max():.3f}")
+    # three bf16 GEMM layers (K up to 1536) with fp32 accumulation, then a 1024-term fp32 reduction
+    np.testing.assert_allclose(z16.cpu().numpy(), want, rtol=2e-2, atol=2e-2)
