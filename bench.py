@@ -225,8 +225,11 @@ def main():
         return out
 
     def timed(fn, steps, warmup, sections=False):
+        import gc
         for i in range(warmup):
             fn(i)
+        gc.collect()
+        gc.disable()      # a generational collection inside the timed loop stalls the launching thread for tens of ms
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -246,6 +249,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
         engine.SECTIONS.enabled = False
+        gc.enable()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         if world > 1:
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -280,7 +284,7 @@ def main():
                 "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
                 "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler on tcgen05 (bf16 operands, fp32 accumulate); encoder and decoder still on the fp32 SIMT kernels"
+                "note": ("sampler, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); decoder, voxelize / devoxelize, norms on fp32 SIMT kernels"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:

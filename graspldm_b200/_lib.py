@@ -58,11 +58,16 @@ _SIGS = {
     "gldm_gemm_tc_to_image": [P, c_int, c_int, c_int, P, P],
     "gldm_gemm_tc_run": [P, P, P, P, c_longlong, c_int, c_int, c_int, P, P],
     "gldm_gemm_tc_image_small_co": [P, P, P, c_longlong, c_int, c_int, c_int, P, P],
+    "gldm_conv3d_tc_weight_bytes": [c_int],
+    "gldm_conv3d_tc_grid_bytes": [c_int, c_int, c_int],
+    "gldm_conv3d_tc_pack_weight": [P, c_int, c_int, P, P],
+    "gldm_conv3d_k3_tc": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "gldm_pose_postprocess": [P, P, P, P, c_int, P, P, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})
 _RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong,
-             "gldm_resnet_raw_floats": c_longlong, "gldm_sampler_tc_pack_bytes": c_longlong, "gldm_gemm_tc_image_bytes": c_longlong, "gldm_resnet_prepared_floats": c_longlong}
+             "gldm_resnet_raw_floats": c_longlong, "gldm_sampler_tc_pack_bytes": c_longlong, "gldm_gemm_tc_image_bytes": c_longlong, "gldm_conv3d_tc_weight_bytes": c_longlong,
+             "gldm_conv3d_tc_grid_bytes": c_longlong, "gldm_resnet_prepared_floats": c_longlong}
 
 _lib = None
 

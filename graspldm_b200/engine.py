@@ -273,6 +273,16 @@ def pose_postprocess(tmrp, logit, grasp_mean, grasp_std):
     return gt, H, conf
 
 
+def _conv3d(x, w_f32, w_img, bias, B, ci, co, r, y, st):
+    """Conv3d k3 p1: tensor-core kernel when a packed bf16 weight image is given, strict-fp32 SIMT kernel otherwise."""
+    if w_img is None:
+        _lib.call("gldm_conv3d_k3_f32", x.data_ptr(), w_f32.data_ptr(), bias.data_ptr(), B, ci, co, r, y.data_ptr(), st)
+        return
+    scratch = _aligned_bytes(_lib.lib().gldm_conv3d_tc_grid_bytes(B, ci, r), x.device, 256)
+    _lib.call("gldm_conv3d_k3_tc", x.data_ptr(), w_img.data_ptr(), bias.data_ptr(), B, ci, co, r, scratch.data_ptr(),
+              y.data_ptr(), st)
+
+
 def _pointwise_tail_tc(pk, feats, st):
     """SharedMLPs after the last PVConv -> conv_downscale -> out_layer.0 on the tensor cores.  Activations stay in
     HBM as bf16 UMMA images (rows = points of all clouds); only the [B, C_out, N] result is fp32."""
@@ -323,6 +333,7 @@ class PackedEncoder:
                 sc, sh = _fold_bn(pw[0], pw[1])
                 self.blocks.append(dict(
                     kind="pvconv", r=blk.resolution, cin=blk.in_channels, cout=blk.out_channels,
+                    w1_raw=c1.weight.detach().float().contiguous(), w2_raw=c2.weight.detach().float().contiguous(),
                     # Conv3d weights [co,ci,3,3,3] -> [ci,27,co] (layout only)
                     w1=c1.weight.detach().permute(1, 2, 3, 4, 0).reshape(c1.in_channels, 27, c1.out_channels).contiguous().float(),
                     b1=c1.bias.detach().float().contiguous(), g1w=g1.weight.detach().float().contiguous(),
@@ -350,6 +361,30 @@ class PackedEncoder:
         self.out_channels = co.out_channels
         self.out_features = enc.out_layer[1].out_features
         self._tc = None
+        self._tc_conv = None
+
+    def tc_conv_weights(self):
+        """bf16 UMMA images of the Conv3d weights that qualify for the tensor-core kernel (16 <= ci, co <= 128);
+        one (img1 | None, img2 | None) pair per PVConv block."""
+        if self._tc_conv is None:
+            dev, out = self.device, []
+            with torch.cuda.device(dev):
+                for blk in self.blocks:
+                    if blk["kind"] != "pvconv":
+                        out.append(None)
+                        continue
+                    pair = []
+                    for w in (blk["w1_raw"], blk["w2_raw"]):
+                        co, ci = w.shape[0], w.shape[1]
+                        if 16 <= ci and co <= 128:
+                            img = _aligned_bytes(_lib.lib().gldm_conv3d_tc_weight_bytes(ci), dev)
+                            _lib.call("gldm_conv3d_tc_pack_weight", w.data_ptr(), co, ci, img.data_ptr(), _stream(dev))
+                            pair.append(img)
+                        else:
+                            pair.append(None)
+                    out.append(pair)
+            self._tc_conv = out
+        return self._tc_conv
 
     def tc_weights(self):
         """bf16 UMMA images of the point-wise layers that run on the tensor cores (built on first use):
@@ -404,6 +439,7 @@ def encoder_forward(enc, xyz, max_clouds_per_pass=256, precision="fp32"):
     pk = packed_encoder(enc)
     if precision == "bf16":
         pk.tc_weights()
+        pk.tc_conv_weights()
     outs = []
     tok = SECTIONS.start("encoder", xyz.device)
     for s in range(0, xyz.shape[0], max_clouds_per_pass):
@@ -420,22 +456,21 @@ def _encoder_pass(pk, xyz, precision="fp32"):
         B, N, _ = xyz.shape
         feats = xyz.float().transpose(1, 2).contiguous()       # [B,3,N] (layout only)
         coords = feats
-        for blk in pk.blocks:
+        for bi, blk in enumerate(pk.blocks):
             if blk["kind"] == "pvconv":
                 r, ci, co = blk["r"], blk["cin"], blk["cout"]
+                tcw = pk.tc_conv_weights()[bi] if precision == "bf16" else (None, None)
                 r3 = r ** 3
                 grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
                 norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
                 _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(),
                           norm.data_ptr(), None, st)
                 y1 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
-                _lib.call("gldm_conv3d_k3_f32", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, co,
-                          r, y1.data_ptr(), st)
+                _conv3d(grid, blk["w1"], tcw[0], blk["b1"], B, ci, co, r, y1, st)
                 _lib.call("gldm_groupnorm_swish_f32", y1.data_ptr(), blk["g1w"].data_ptr(), blk["g1b"].data_ptr(), B, co,
                           r3, blk["groups"], blk["eps1"], None, st)
                 y2 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
-                _lib.call("gldm_conv3d_k3_f32", y1.data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(), B, co, co, r,
-                          y2.data_ptr(), st)
+                _conv3d(y1, blk["w2"], tcw[1], blk["b2"], B, co, co, r, y2, st)
                 se_mean = torch.empty((B, co), device=dev, dtype=torch.float32)
                 _lib.call("gldm_groupnorm_swish_f32", y2.data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(), B, co,
                           r3, blk["groups"], blk["eps2"], se_mean.data_ptr(), st)

@@ -206,6 +206,16 @@ int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, c
 int gldm_gemm_tc_image_small_co(const void* img, const float* w, const float* bias, long long rows, int k, int co,
                                 int n, float* y, void* stream);
 
+/* ---- tensor-core Conv3d k3 p1 (bf16 operands, fp32 accumulation), implicit GEMM over a zero-padded channels-last
+ * grid loaded with TMA tensor copies (R/../pvcnn/modules/pvconv.py:48-67).  16 <= ci, co <= 128.
+ * w_img: gldm_conv3d_tc_weight_bytes(ci) bytes from gldm_conv3d_tc_pack_weight(w f32[co,ci,3,3,3]);
+ * scratch: gldm_conv3d_tc_grid_bytes(b, ci, r) bytes, 256-byte aligned.  x f32[b,ci,r^3] -> y f32[b,co,r^3] (+ bias). */
+long long gldm_conv3d_tc_weight_bytes(int ci);
+long long gldm_conv3d_tc_grid_bytes(int b, int ci, int r);
+int gldm_conv3d_tc_pack_weight(const float* w, int co, int ci, void* img, void* stream);
+int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r, void* scratch,
+                      float* y, void* stream);
+
 /* Pose post-processing (R/../tools/inference.py:627-656, R/utils/rotations.py:298-302):
  * tmrp f32[n,6], logit f32[n], grasp_mean/std f32[6] -> grasp_tmrp f32[n,6], H f32[n,4,4], conf f32[n] */
 int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,

@@ -7,6 +7,9 @@ import _data, _models
 from graspldm_b200 import engine
 from graspldm_b200.inference import InferenceLDM, default_metas
 
+import gc
+if os.environ.get("DIAG_NOGC"):
+    gc.disable()
 dev = torch.device("cuda:0")
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 n_obj = int(sys.argv[2]) if len(sys.argv) > 2 else 64
@@ -26,7 +29,7 @@ metas_dev = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in me
 def ev():
     return torch.cuda.Event(enable_timing=True)
 
-def timeit(fn, n=6, label=""):
+def timeit(fn, n=int(os.environ.get("DIAG_N", "6")), label=""):
     ts, hs = [], []
     for i in range(n):
         torch.cuda.synchronize()
