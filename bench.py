@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.05 if self.nvml is not None else 0.2)
+            self._halt.wait(0.1 if self.nvml is not None else 0.2)
 
     def finish(self):
         self._halt.set()
@@ -202,7 +202,7 @@ def main():
     n_total = N_OBJ * world                            # weak scaling: 64 objects per GPU
     lo, hi = sharding.shard_bounds(n_total, world, rank)
     pcs_host = _data.synthetic_clouds(hi - lo, N_POINTS, seed=1234 + rank, dist="S").pin_memory()
-    metas = default_metas(hi - lo)
+    metas = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in default_metas(hi - lo).items()}
     metas_dev = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in metas.items()}
     pcs_dev = pcs_host.to(dev)
     counts = sharding.shard_counts(n_total, world)

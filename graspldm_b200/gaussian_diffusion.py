@@ -60,7 +60,9 @@ class GaussianDiffusion1D(nn.Module):
         device = z_cond.device if z_cond is not None and z_cond.is_cuda else torch.device(device)
         if x_T is None:
             # gaussian_diffusion.py:253 - drawn on the CPU generator, then moved
-            x_T = torch.randn((batch_size, self.channels, self.n_dims)).to(device)
+            # same values as the reference (CPU generator); drawn into pinned memory so the copy does not make the
+            # launching thread wait for the encoder kernels that are still in flight
+            x_T = torch.randn((batch_size, self.channels, self.n_dims), pin_memory=True).to(device, non_blocking=True)
         assert x_T.shape[0] == batch_size == z_cond.shape[0] * grasps_per_object
         ts, coef = self.noise_scheduler.table()
         kind = DDPM if self._noise_scheduler_type == "ddpm" else DDIM

@@ -126,7 +126,7 @@ class GraspCVAE(nn.Module):                        # grasp_vae.py:17-255
         return self.encoder.encode_pc(xyz)
 
     def sample_grasp_latent(self, batch_size: int, device) -> Tensor:
-        return torch.randn(batch_size, self.grasp_latent_size).to(device)
+        return torch.randn(batch_size, self.grasp_latent_size, pin_memory=True).to(device, non_blocking=True)
 
     @torch.no_grad()
     def generate_grasps(self, xyz: Tensor, num_grasps: int = 10, *, z_h: Tensor = None):
@@ -136,5 +136,5 @@ class GraspCVAE(nn.Module):                        # grasp_vae.py:17-255
         num_pcs = xyz.shape[0]
         z_pc = self.encode_pc(xyz)                                   # one row per object; never repeated in HBM
         if z_h is None:
-            z_h = torch.randn(num_pcs * num_grasps, self.grasp_latent_size).to(xyz.device)
+            z_h = torch.randn(num_pcs * num_grasps, self.grasp_latent_size, pin_memory=True).to(xyz.device, non_blocking=True)
         return self.decoder(z_h, z_pc, grasps_per_object=num_grasps)
