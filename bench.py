@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation); fp32: strict-fp32 SIMT parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="batches in flight: consecutive steps are issued round-robin on this many CUDA streams, so the "
+                         "encoder / decoder of one batch fill the SMs the persistent sampler of another leaves idle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,8 +209,10 @@ def main():
     metas_dev = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in metas.items()}
     pcs_dev = pcs_host.to(dev)
     counts = sharding.shard_counts(n_total, world)
-    out_host = {"grasps": torch.empty((hi - lo, N_GRASPS, 4, 4)).pin_memory(),
-                "confidence": torch.empty((hi - lo, N_GRASPS, 1)).pin_memory()}
+    n_streams = max(1, args.streams)
+    out_hosts = [{"grasps": torch.empty((hi - lo, N_GRASPS, 4, 4)).pin_memory(),
+                  "confidence": torch.empty((hi - lo, N_GRASPS, 1)).pin_memory()} for _ in range(n_streams)]
+    out_host = out_hosts[0]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def gen_resident(seed):
@@ -217,9 +222,10 @@ def main():
         return out
 
     def gen_e2e(seed):
+        oh = out_hosts[seed % n_streams]
         out = inf.generate_grasps(pcs_host, metas, num_grasps=N_GRASPS, seed=seed)   # H2D inside
-        out_host["grasps"].copy_(out["grasps"], non_blocking=True)                     # D2H of the result
-        out_host["confidence"].copy_(out["confidence"], non_blocking=True)
+        oh["grasps"].copy_(out["grasps"], non_blocking=True)                           # D2H of the result
+        oh["confidence"].copy_(out["confidence"], non_blocking=True)
         if world > 1:
             sharding.gather_results({"grasps": out["grasps"], "confidence": out["confidence"]}, counts)
         return out
@@ -257,13 +263,57 @@ def main():
             total_ms = float(t.item())
         return total_ms, engine.SECTIONS.collect()
 
+    def timed_pipelined(fn, steps, warmup):
+        """K steps issued round-robin on n_streams streams; one event pair brackets the whole region.  The L2 flush
+        of every step is inside the timed region here (it runs on the step's own stream)."""
+        import gc
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        main = torch.cuda.current_stream(dev)
+        for i in range(max(warmup, n_streams)):
+            with torch.cuda.stream(streams[i % n_streams]):
+                fn(i)
+        gc.collect()
+        gc.disable()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        for st in streams:
+            st.wait_event(a)
+        for i in range(steps):
+            with torch.cuda.stream(streams[i % n_streams]):
+                flush.zero_()
+                fn(1000 + i)
+        for st in streams:
+            main.wait_stream(st)
+        b.record(main)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        gc.enable()
+        total_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms
+
+    # pass 1 (sequential, one batch at a time): per-batch latency and the per-section / per-kernel durations
+    lat_ms, sections = timed(gen_resident, args.steps, args.warmup, sections=True)
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = _lib.launch_count()
-    total_ms, sections = timed(gen_resident, args.steps, args.warmup, sections=True)
-    launches = (_lib.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    if n_streams > 1:
+        total_ms = timed_pipelined(gen_resident, args.steps, args.warmup)
+        launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, n_streams)) * args.steps
+    else:
+        total_ms, _ = timed(gen_resident, args.steps, args.warmup)
+        launches = (_lib.launch_count() - l0) // (args.steps + args.warmup) * args.steps
     clk = clocks.finish()
-    e2e_ms, _ = timed(gen_e2e, args.steps, args.warmup)
+    e2e_ms = timed_pipelined(gen_e2e, args.steps, args.warmup) if n_streams > 1 else timed(gen_e2e, args.steps, args.warmup)[0]
 
     ms_per_step = total_ms / args.steps
     grasps_per_step = n_total * N_GRASPS
@@ -299,7 +349,8 @@ def main():
                                "(BASELINE.json configs[1]), random-init weights, 1024-point synthetic clouds",
                    "objects": n_total, "grasps_per_object": N_GRASPS, "denoising_steps": N_STEPS_DDPM,
                    "parallelism": f"objects sharded over {world} rank(s), one final all_gather",
-                   "l2": "256 MiB buffer written between timed iterations", "precision": args.precision,
+                   "l2": "256 MiB buffer written before every step" + (" (inside the timed region, on the step's stream)" if n_streams > 1 else " (between timed iterations)"),
+                   "batches_in_flight": n_streams, "latency_ms_per_batch": lat_ms / args.steps, "precision": args.precision,
                    "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcs_host.numel() * 4 + n_local * 4 * 4),
                 "d2h_bytes_per_step": int(out_host["grasps"].numel() * 4 + out_host["confidence"].numel() * 4),

@@ -60,7 +60,7 @@ def test_sampler_bf16_tracks_fp32(cuda, kind, steps):
 
 @pytest.mark.parametrize("name", ["fpc", "ppc"])
 def test_encoder_bf16_pointwise_layers(cuda, name):
-    """Point-wise tail (96->768->1536->768) on the tensor cores vs the committed reference fixture."""
+    """Conv3d stacks and the point-wise tail (96->768->1536->768) on the tensor cores vs the committed reference fixture."""
     m = _models.build(name).to(cuda)
     enc = m.vae_model.encoder.pc_encoder
     xyz = torch.cat([_data.synthetic_clouds(2, seed=1234, dist="S"), _data.synthetic_clouds(1, seed=99, dist="G")]).to(cuda)
@@ -75,4 +75,72 @@ def test_encoder_bf16_pointwise_layers(cuda, name):
     print(f"[{name}] bf16 encoder tail: max|err| vs reference {err:.3e}, vs fp32 path {(z16 - z32).abs().max().item():.3e}, "
           f"max|z| {np.abs(want).max():.3f}")
     # three bf16 GEMM layers (K up to 1536) with fp32 accumulation, then a 1024-term fp32 reduction
-    np.testing.assert_allclose(z16.cpu().numpy(), want, rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(z16.cpu().numpy(), want, rtol=1e-2, atol=2e-3)
+
+
+def _rot_angle_deg(Ra, Rb):
+    """geodesic angle between rotation matrices [..., 3, 3]"""
+    R = Ra.transpose(-1, -2) @ Rb
+    c = ((R[..., 0, 0] + R[..., 1, 1] + R[..., 2, 2]) - 1.0) / 2.0
+    return torch.rad2deg(torch.acos(c.clamp(-1.0, 1.0)))
+
+
+def _set_precision(model, prec):
+    model.diffusion_model.precision = prec
+    model.vae_model.encoder.pc_encoder.precision = prec
+
+
+def test_ldm_generation_bf16_vs_reference_fixture(cuda):
+    """End to end (encoder -> 100 DDPM steps -> decoder -> poses) with every tensor-core kernel switched on, against
+    the fixture produced by the unmodified reference modules.  Stated bf16 tolerance of the path:
+    latents / tmrp atol 3e-2, translation < 1 mm, rotation < 2 degrees after un-normalisation."""
+    from graspldm_b200.inference import InferenceLDM, default_metas
+    g = np.load(os.path.join(G, "ldm_fpc_ddpm100.npz"))
+    m = _models.build("fpc").to(cuda)
+    m.set_inference_timesteps(100)
+    _set_precision(m, "bf16")
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S")
+    inf = InferenceLDM(m, device=cuda)
+    out = inf.generate_grasps(xyz, default_metas(2), num_grasps=3, x_T=torch.from_numpy(g["x_T"]).to(cuda),
+                              noise=torch.from_numpy(g["noise"]).to(cuda))
+    want = M.postprocess(torch.from_numpy(g["tmrp"]), torch.from_numpy(g["logit"]), xyz, default_metas(2), 2, 3)
+    got_H, want_H = out["grasps"].cpu(), want["grasps"]
+    dt = (got_H[..., :3, 3] - want_H[..., :3, 3]).norm(dim=-1).max().item()
+    da = _rot_angle_deg(got_H[..., :3, :3], want_H[..., :3, :3]).max().item()
+    dm = (out["grasp_tmrp"].cpu() - want["grasp_tmrp"]).abs().max().item()
+    print(f"[bf16 e2e] max translation error {dt * 1e3:.3f} mm, max rotation error {da:.3f} deg, max|tmrp err| {dm:.3e}")
+    assert dt < 1e-3 and da < 2.0
+    np.testing.assert_allclose(out["confidence"].cpu().numpy(), want["confidence"].numpy(), atol=2e-2)
+
+
+def test_full_size_properties_config2_bf16(cuda):
+    """BASELINE config 2 on the tensor-core path: determinism, finiteness, proper rotations, object independence."""
+    from graspldm_b200.inference import InferenceLDM, default_metas
+    m = _models.build("fpc").to(cuda)
+    m.set_inference_timesteps(100)
+    m.diffusion_model.rng_mode = "fused"
+    _set_precision(m, "bf16")
+    inf = InferenceLDM(m, device=cuda)
+    pcs = _data.synthetic_clouds(64, seed=1234, dist="S")
+    x_T = torch.randn(64 * 20, 1, 4, generator=torch.Generator().manual_seed(1)).to(cuda)
+    a = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7, x_T=x_T)
+    b = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7, x_T=x_T)
+    assert all(torch.equal(a[k], b[k]) for k in ("grasps", "grasp_tmrp", "confidence"))      # run-to-run deterministic
+    assert torch.isfinite(a["grasps"]).all() and a["grasps"].shape == (64, 20, 4, 4)
+    R = a["grasps"][..., :3, :3]
+    torch.testing.assert_close(R @ R.transpose(-1, -2), torch.eye(3, device=cuda).expand_as(R), rtol=0, atol=1e-5)
+    assert (a["confidence"] > 0).all() and (a["confidence"] < 1).all()
+    # objects are independent: a slice generated alone (same per-sample noise keys need the same sample indices, so
+    # compare the deterministic part, the encoder) and a tile-aligned slice of the sampler
+    z_full = m.vae_model.encode_pc(pcs.to(cuda))
+    z_part = m.vae_model.encode_pc(pcs[16:24].to(cuda))
+    torch.testing.assert_close(z_full[16:24], z_part, rtol=0, atol=0)
+    c = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=8, x_T=x_T)
+    assert not torch.equal(a["grasp_tmrp"], c["grasp_tmrp"])                                  # the noise seed matters
+    # bf16 vs strict-fp32 path on the same inputs and the same in-kernel noise stream
+    _set_precision(m, "fp32")
+    f = inf.generate_grasps(pcs, default_metas(64), num_grasps=20, seed=7, x_T=x_T)
+    dt = (a["grasps"][..., :3, 3] - f["grasps"][..., :3, 3]).norm(dim=-1).max().item()
+    da = _rot_angle_deg(a["grasps"][..., :3, :3], f["grasps"][..., :3, :3]).max().item()
+    print(f"[config 2, bf16 vs fp32 path] max translation diff {dt * 1e3:.3f} mm, max rotation diff {da:.3f} deg")
+    assert dt < 1e-3 and da < 2.0
