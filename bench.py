@@ -329,9 +329,14 @@ def main():
     achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
     kname = ("sampler_tc_kernel (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
              else "resnet_kernel<4> (fp32 SIMT persistent 100-step sampler, one launch per batch)")
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_tc_sampler_traffic.json")
+    if args.precision == "bf16" and os.path.exists(tp):
+        t = json.load(open(tp))["sampler_tc_kernel"]          # dram__bytes_read + write of one ncu --set full capture
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
                 "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
                 "note": ("sampler, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); decoder, voxelize / devoxelize, norms on fp32 SIMT kernels"
