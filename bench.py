@@ -201,6 +201,7 @@ def main():
     model.diffusion_model.rng_mode = "fused"          # noise drawn inside the sampler kernel (Philox4x32-10)
     model.diffusion_model.precision = args.precision
     model.vae_model.encoder.pc_encoder.precision = args.precision
+    model.vae_model.decoder.precision = args.precision
     inf = InferenceLDM(model, device=dev)
     n_total = N_OBJ * world                            # weak scaling: 64 objects per GPU
     lo, hi = sharding.shard_bounds(n_total, world, rank)

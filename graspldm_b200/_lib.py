@@ -62,6 +62,7 @@ _SIGS = {
     "gldm_conv3d_tc_grid_bytes": [c_int, c_int, c_int],
     "gldm_conv3d_tc_pack_weight": [P, c_int, c_int, P, P],
     "gldm_conv3d_k3_tc": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
+    "gldm_decoder_forward_tc": [POINTER(GldmResNetCfg), P, P, P, c_int, P, P, c_int, c_int, P, P, P],
     "gldm_pose_postprocess": [P, P, P, P, c_int, P, P, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})

@@ -1,5 +1,6 @@
-// Tensor-core (tcgen05 / TMEM) persistent sampler: the whole T-step reverse-diffusion loop of the fpc latent
-// denoiser in ONE launch, GEMMs on the 5th-generation tensor cores with bf16 operands and fp32 accumulation.
+// Tensor-core (tcgen05 / TMEM) ResNet1D machine.  L = 4: the persistent sampler - the whole T-step reverse-diffusion
+// loop of the fpc latent denoiser in ONE launch; L = 16: the grasp decoder trunk + heads.  GEMMs on the
+// 5th-generation tensor cores with bf16 operands and fp32 accumulation.
 //
 //   TimeConditionedResNet1D.forward   R/models/modules/resnets.py:558-616
 //   GaussianDiffusion1D.sample        R/models/diffusion/gaussian_diffusion.py:232-277
@@ -23,32 +24,45 @@ namespace gldm {
 using namespace tc;
 
 namespace stc {
-constexpr int L = 4, NS = 16, NCOL = L * NS, HALO = 16, BROWS = NCOL + 2 * HALO;
-constexpr int SLAB = BROWS * 128;          // bytes per 64-channel K-block of the B operand
-constexpr int BSLABS = 4;                  // up to 256 channels
-constexpr int CHUNK = 32768, STAGES = 4;   // weight ring (two 16 KB operand blocks per stage)
-constexpr int EMB = 16;
-constexpr int MAXJOBS = 32;
+constexpr int NCOL = 64;                   // GEMM columns per CTA = L * NS
+constexpr int BSLABS = 4;                  // up to 256 channels (64 per K block)
+constexpr int CHUNK = 32768;               // weight ring stage (two 16 KB operand blocks)
+constexpr int MAXJOBS = 32, MAXCHUNKS = 192, MAXOPS = 256;
 constexpr uint32_t T_ACC = 0, T_RES = 192, T_FILM = 320;   // TMEM column map (512 allocated)
-constexpr int NCOMPUTE = 256, NTHREADS = 256;   // thread 0 additionally drives the weight ring and issues the UMMAs
-
-// shared memory map (bytes, from a 1024-aligned base)
-constexpr int SM_B = 0;                                  // B operand             49152
-constexpr int SM_U = SM_B + BSLABS * SLAB;               // FiLM operand (u)       2048
-constexpr int SM_RING = SM_U + 2048;                     // weight ring          131072
-constexpr int SM_SCR = SM_RING + STAGES * CHUNK;         // per-warp scratch 8 x 256 floats = 8192
-constexpr int SM_XCH = SM_SCR + 8 * 256 * 4;             // cross-warp exchange 2 WG x 4 warps x 64 floats = 2048
-constexpr int SM_INEMB = SM_XCH + 2 * 4 * 64 * 4;        // in_emb [16][3][16] floats = 3072
-constexpr int SM_X = SM_INEMB + NS * 3 * EMB * 4;        // sampler state [16][4] floats = 256
-constexpr int SM_BAR = SM_X + NS * L * 4;                // mbarriers
-constexpr int MAXCHUNKS = 192;
-constexpr int SM_CHUNKS = SM_BAR + 256;                  // weight chunk table {pack offset, bytes} x MAXCHUNKS
-constexpr int SM_JOBS = SM_CHUNKS + MAXCHUNKS * 8;       // job table copy
-constexpr int MAXOPS = 256;
-constexpr int SM_OPS = SM_JOBS + MAXJOBS * 48;           // UMMA op table, 16 bytes per block of up to 4 UMMAs
-constexpr int SM_OPBEG = SM_OPS + MAXOPS * 16;           // first op of every job
-constexpr int SM_TOTAL = SM_OPBEG + (MAXJOBS + 2) * 4 + 16;
+constexpr int NCOMPUTE = 256, NTHREADS = 256;   // warp 6 also produces the weight ring, warp 7 also issues the UMMAs
 }  // namespace stc
+
+// Two instantiations of the same machine:
+//   L = 4  : latent denoiser (sampler).  16 samples per CTA, column = position * 16 + sample; the k=3 taps are row
+//            shifts of one operand buffer with 16-row zero halos; FiLM / time embedding width 16.
+//   L = 16 : grasp decoder trunk (ResNet1D, R/models/grasp_vae.py:401-436).  4 samples per CTA, column = sample * 16 +
+//            position; a one-position shift is not a whole 8-row swizzle group, so the epilogue writes three shifted
+//            copies of the operand instead (one per tap); embedding width 64.
+template <int L_>
+struct Tr {
+  static constexpr int L = L_, NS = stc::NCOL / L_;
+  static constexpr int EMB = (L_ == 4) ? 16 : 64;
+  static constexpr int HALO = (L_ == 4) ? 16 : 0;
+  static constexpr int BROWS = stc::NCOL + 2 * HALO;
+  static constexpr int SLAB = BROWS * 128;                       // bytes per 64-channel K block of the B operand
+  static constexpr int COPIES = (L_ == 4) ? 1 : 3;               // operand copies (one per tap for L = 16)
+  static constexpr int STAGES = (L_ == 4) ? 4 : 2;               // weight ring depth (x 32 KB)
+  static constexpr int SCR = (L_ == 4) ? 256 : 576;              // per-warp scratch floats
+  // shared memory map (bytes, from a 1024-aligned base)
+  static constexpr int SM_B = 0;
+  static constexpr int SM_U = SM_B + COPIES * stc::BSLABS * SLAB;   // FiLM operand (u): 16 rows x 128 B
+  static constexpr int SM_RING = SM_U + 2048;
+  static constexpr int SM_SCR = SM_RING + STAGES * stc::CHUNK;
+  static constexpr int SM_XCH = SM_SCR + 8 * SCR * 4;               // cross-warp exchange 2 WG x 4 warps x 64 floats
+  static constexpr int SM_INEMB = SM_XCH + 2 * 4 * 64 * 4;          // in_emb [NS][3][EMB] floats = 3072
+  static constexpr int SM_X = SM_INEMB + NS * 3 * EMB * 4;          // state / trunk input [NS][L] floats = 256
+  static constexpr int SM_BAR = SM_X + NS * L * 4;                  // mbarriers
+  static constexpr int SM_CHUNKS = SM_BAR + 256;                    // weight chunk table {pack offset, bytes}
+  static constexpr int SM_JOBS = SM_CHUNKS + stc::MAXCHUNKS * 8;    // job table copy
+  static constexpr int SM_OPS = SM_JOBS + stc::MAXJOBS * 48;        // UMMA op table, 16 bytes per block of <= 4 UMMAs
+  static constexpr int SM_OPBEG = SM_OPS + stc::MAXOPS * 16;        // first op / last chunk of every job
+  static constexpr int SM_TOTAL = SM_OPBEG + (stc::MAXJOBS + 2) * 4 + 16;
+};
 
 // epilogue recipe of a job (what the epilogue warps do with its accumulator)
 enum : uint16_t {
@@ -76,11 +90,11 @@ struct TcParams {
   const uint8_t* pack;     // bf16 UMMA images
   TcJob jobs[stc::MAXJOBS];
   int n_jobs;
-  int mode;                // 0 sampler, 1 single evaluation (per-sample timestep)
+  int mode;                // 0 sampler, 1 single evaluation (per-sample timestep), 2 decoder (L = 16)
   int n, gpo;
   const float* x_in;       // [n][L]
   const float* z_cond;     // [n_obj][R][cond_dim]
-  const float* te;         // time embedding table [n_steps][EMB] (mode 0) or [n][EMB] (mode 1)
+  const float* te;         // time embedding table [n_steps][EMB] (mode 0) or [n][EMB] (mode 1); unused in mode 2
   int n_steps;
   const float* coef;       // [n_steps][8]
   int sched_kind, clip;
@@ -88,19 +102,29 @@ struct TcParams {
   unsigned long long seed;
   float* x_out;
   float* x_all;
+  const float* head;       // decoder: in_w[L][D] in_b[L] tmrp_w[6][L] tmrp_b[6] cls_w[L] cls_b[1]
+  int D;
+  float* tmrp;             // [n][6]
+  float* logit;            // [n]
   long long* prof;         // development aid: per-job clock stamps of CTA 0 (NULL in production)
 };
 
 // ------------------------------------------------------------------------------------------------
 // job table (host): the order of the GEMMs of one network evaluation and where their weight images live
 // ------------------------------------------------------------------------------------------------
-static int swb_for(int kpt) { return kpt >= 64 ? 128 : kpt >= 32 ? 64 : 32; }
-static int pad16(int k) { return (k + 15) & ~15; }
+__host__ __device__ inline int swb_for(int kpt) { return kpt >= 64 ? 128 : kpt >= 32 ? 64 : 32; }
+__host__ __device__ inline int pad16(int k) { return (k + 15) & ~15; }
 
-static uint32_t job_bytes(const TcJob& j) {
+// FiLM projection tiles: [128 rows x emb] with K = emb (16 -> SWIZZLE_32B 4 KB tiles, 64 -> SWIZZLE_128B 16 KB tiles)
+static uint32_t film_tile_bytes(int emb) { return 128u * swb_for(pad16(emb)); }
+static uint32_t main_bytes(const TcJob& j) {
   const int nkb = (j.kpt * 2 + j.a_swb - 1) / j.a_swb;
-  return (uint32_t)j.mtiles * j.taps * nkb * 128 * j.a_swb + (uint32_t)j.film_tiles * 4096;
+  return (uint32_t)j.mtiles * j.taps * nkb * 128 * j.a_swb;
 }
+// blocks of a job are stored in descending size so that none straddles a ring stage: FiLM tiles first when they
+// are larger than the main blocks
+static bool film_first(const TcJob& j, int emb) { return j.film_tiles && film_tile_bytes(emb) > 128u * j.a_swb; }
+static uint32_t job_bytes(const TcJob& j, int emb) { return main_bytes(j) + (uint32_t)j.film_tiles * film_tile_bytes(emb); }
 
 static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes) {
   ResNetLayout l;
@@ -119,7 +143,7 @@ static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes
     j.ch = cout;
     j.o_bias = o_bias; j.o_gamma = o_gamma; j.o_beta = o_beta; j.o_mlpb = o_mlpb; j.o_g = o_g; j.o_g2 = o_g2;
     j.a_off = off;
-    j.bytes = job_bytes(j);
+    j.bytes = job_bytes(j, c.emb_dim);
     off += (j.bytes + 1023) & ~1023u;
     jobs[n++] = j;
   };
@@ -145,8 +169,11 @@ static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes
 static int check_tc_cfg(const GldmResNetCfg* c) {
   int rc = check_cfg(c);
   if (rc) return rc;
-  if (!(c->L == 4 && c->emb_dim == 16 && c->time_cond && c->n_stages == 4 && c->groups == 4 && c->cond_ch <= 3)) {
-    set_error("sampler_tc: this build covers the fpc latent denoiser (L=4, emb 16, 4 stages, 4 groups)");
+  const bool denoiser = c->L == 4 && c->emb_dim == 16 && c->time_cond;
+  const bool decoder = c->L == 16 && c->emb_dim == 64 && !c->time_cond;
+  if (!((denoiser || decoder) && c->n_stages == 4 && c->groups == 4 && c->cond_ch <= 3 && c->cond_dim <= 1024)) {
+    set_error("resnet_tc: this build covers the fpc latent denoiser (L=4, emb 16, time conditioned) and the grasp "
+              "decoder trunk (L=16, emb 64), 4 stages, 4 groups");
     return GLDM_ENOSUP;
   }
   for (int s = 0; s < c->n_stages; ++s)
@@ -267,16 +294,24 @@ struct Ctx {
   uint32_t xoff[8];     // swizzled 16-byte-chunk offset (+ element offset) of this thread's channel for row&7 = j
 };
 
-// 32 values of this thread's channel of accumulator/residual tile at column base `col`: v[l*8 + j], j = sample - 8g.
+// 32 values of this thread's channel of an accumulator / residual tile at column base `col`.
+//   L = 4 : v[l*8 + j]  <-> column l*16 + 8g + j   (j = sample - 8g)
+//   L = 16: v[jj*16 + l] <-> column 32g + jj*16 + l (jj = sample - 2g)
 // tm_issue* start the asynchronous loads; tm_wait() + tm_use*() make the registers safe to read.
+template <int L>
 __device__ __forceinline__ void tm_issue32(const Ctx& c, uint32_t col, uint32_t (&r)[32]) {
+  if (L == 4) {
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    uint32_t(&q)[8] = *reinterpret_cast<uint32_t(*)[8]>(&r[l * 8]);
-    tmem_ld8(c.tmem + col + l * 16 + c.g * 8, q);
+    for (int l = 0; l < 4; ++l) {
+      uint32_t(&q)[8] = *reinterpret_cast<uint32_t(*)[8]>(&r[l * 8]);
+      tmem_ld8(c.tmem + col + l * 16 + c.g * 8, q);
+    }
+  } else {
+    tmem_ld32(c.tmem + col + c.g * 32, r);
   }
 }
 __device__ __forceinline__ void tm_issue8(const Ctx& c, uint32_t col, uint32_t (&r)[8]) { tmem_ld8(c.tmem + col, r); }
+__device__ __forceinline__ void tm_issue4(const Ctx& c, uint32_t col, uint32_t (&r)[4]) { tmem_ld4(c.tmem + col, r); }
 __device__ __forceinline__ void tm_wait() { tmem_ld_wait(); }
 template <int N>
 __device__ __forceinline__ void tm_use(const uint32_t (&r)[N], float (&v)[N]) {
@@ -287,39 +322,52 @@ __device__ __forceinline__ void tm_use(const uint32_t (&r)[N], float (&v)[N]) {
     v[i] = __uint_as_float(x);
   }
 }
+template <int L>
 __device__ __forceinline__ void tm_load32(const Ctx& c, uint32_t col, float (&v)[32]) {
   uint32_t r[32];
-  tm_issue32(c, col, r);
+  tm_issue32<L>(c, col, r);
   tm_wait();
   tm_use(r, v);
 }
+template <int L>
 __device__ __forceinline__ void tm_store32(const Ctx& c, uint32_t col, const float (&v)[32]) {
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     uint32_t r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[l * 8 + j]);
-    tmem_st8(c.tmem + col + l * 16 + c.g * 8, r);
+    tmem_st8(c.tmem + col + (L == 4 ? l * 16 + c.g * 8 : c.g * 32 + l * 8), r);
   }
   tmem_st_wait();
 }
-__device__ __forceinline__ void tm_load8(const Ctx& c, uint32_t col, float (&v)[8]) {
-  uint32_t r[8];
-  tm_issue8(c, col, r);
-  tm_wait();
-  tm_use(r, v);
-}
 
-// write this thread's channel (tile t) of the next B operand: rows HALO + l*16 + 8g + j
+// write this thread's channel (tile t) of the next B operand.
+//   L = 4 : rows HALO + l*16 + 8g + j of the single (halo-padded) buffer
+//   L = 16: row 32g + i of the centre copy, and the rows one position later / earlier (same sample) of the tap-0 /
+//           tap-2 copies: B_tap[(s, l)] = x[s][l + tap - 1]; the never-written boundary rows stay zero
+template <int L>
 __device__ __forceinline__ void write_b(const Ctx& c, int t, const float (&v)[32], bool valid) {
   if (!valid) return;
+  using T = Tr<L>;
   const int chan = t * 128 + c.ch;
-  uint8_t* base = c.smem + stc::SM_B + (chan >> 6) * stc::SLAB + (stc::HALO + c.g * 8) * 128;
+  if (L == 4) {
+    uint8_t* base = c.smem + T::SM_B + (chan >> 6) * T::SLAB + (T::HALO + c.g * 8) * 128;
 #pragma unroll
-  for (int l = 0; l < 4; ++l)
+    for (int l = 0; l < 4; ++l)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<__nv_bfloat16*>(base + (l * 16 + j) * 128 + c.xoff[j]) = __float2bfloat16(v[l * 8 + j]);
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<__nv_bfloat16*>(base + (l * 16 + j) * 128 + c.xoff[j]) = __float2bfloat16(v[l * 8 + j]);
+  } else {
+    uint8_t* base = c.smem + T::SM_B + (chan >> 6) * T::SLAB + (c.g * 32) * 128;
+    constexpr int COPY = stc::BSLABS * T::SLAB;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const __nv_bfloat16 h = __float2bfloat16(v[i]);
+      *reinterpret_cast<__nv_bfloat16*>(base + COPY + i * 128 + c.xoff[i & 7]) = h;
+      if ((i & 15) != 15) *reinterpret_cast<__nv_bfloat16*>(base + (i + 1) * 128 + c.xoff[(i + 1) & 7]) = h;
+      if ((i & 15) != 0) *reinterpret_cast<__nv_bfloat16*>(base + 2 * COPY + (i - 1) * 128 + c.xoff[(i - 1) & 7]) = h;
+    }
+  }
 }
 
 // GroupNorm statistics of one tile: per sample j the mean / rstd over (channels of the group x 4 positions).
@@ -391,10 +439,44 @@ __device__ __forceinline__ void gn_stats(const Ctx& c, const float (&v)[32], flo
   }
 }
 
-template <bool PAIR_UNUSED = false>
+// L = 16 (two samples per warp-group, 16 positions each): statistics over (channels of the group x 16 positions).
+// Groups are cg = c/4 >= 4 consecutive channels: butterfly over min(cg, 32) lanes, + the partner warp for cg = 64.
+__device__ __forceinline__ void gn_stats16(const Ctx& c, int cg, const float (&v)[32], float (&mean)[8], float (&rstd)[8]) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    a[0] += v[l]; a[2] = fmaf(v[l], v[l], a[2]);
+    a[1] += v[16 + l]; a[3] = fmaf(v[16 + l], v[16 + l], a[3]);
+  }
+  const int gl = cg < 32 ? cg : 32;
+  for (int o = 1; o < gl; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+  }
+  if (cg > 32) {
+    if (c.lane == 0) *reinterpret_cast<float4*>(c.xch + c.q * 64) = make_float4(a[0], a[1], a[2], a[3]);
+    wg_sync(c.g);
+    const float4 o4 = *reinterpret_cast<const float4*>(c.xch + (c.q ^ 1) * 64);
+    a[0] += o4.x; a[1] += o4.y; a[2] += o4.z; a[3] += o4.w;
+    wg_sync(c.g);
+  }
+  const float inv = 1.0f / (float)(cg * 16);
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const float m = a[jj] * inv;
+    mean[jj] = m;
+    rstd[jj] = rsqrtf(fmaxf(a[2 + jj] * inv - m * m, 0.f) + 1e-5f);
+  }
+}
+
+template <int L>
 __device__ __forceinline__ void gn_stats_dispatch(const Ctx& c, int ch_total, const float (&v)[32], float (&mean)[8],
                                                   float (&rstd)[8]) {
   const int cg = ch_total >> 2;                 // channels per group (4 groups)
+  if (L == 16) {
+    gn_stats16(c, cg, v, mean, rstd);
+    return;
+  }
   const float inv = 1.0f / (float)(cg * 4);
   if (cg >= 64) gn_stats<32, true>(c, v, inv, mean, rstd);
   else if (cg == 32) gn_stats<32, false>(c, v, inv, mean, rstd);
@@ -437,19 +519,22 @@ __device__ __forceinline__ void ln_stats(const Ctx& c, int ch_total, const float
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __grid_constant__ TcParams p) {
+template <int L>
+__global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __grid_constant__ TcParams p) {
   using namespace stc;
+  using T = Tr<L>;
+  constexpr int NS = T::NS, EMB = T::EMB, STAGES = T::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::SM_BAR);
   uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* b_ready = bars + 2 * STAGES;
-  uint64_t* acc_ready = bars + 2 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  float* s_inemb = reinterpret_cast<float*>(smem + SM_INEMB);
-  float* s_x = reinterpret_cast<float*>(smem + SM_X);
-  TcJob* s_jobs = reinterpret_cast<TcJob*>(smem + SM_JOBS);
+  uint64_t* empty = bars + 4;            // [STAGES]
+  uint64_t* b_ready = bars + 8;
+  uint64_t* acc_ready = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* s_inemb = reinterpret_cast<float*>(smem + T::SM_INEMB);
+  float* s_x = reinterpret_cast<float*>(smem + T::SM_X);
+  TcJob* s_jobs = reinterpret_cast<TcJob*>(smem + T::SM_JOBS);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * NS;
@@ -461,7 +546,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   const int n_jobs = p.n_jobs;
 
   // ---- one-time setup
-  for (int i = tid; i < (SM_RING) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (T::SM_RING) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < n_jobs * (int)(sizeof(TcJob) / 4); i += NTHREADS)
     reinterpret_cast<uint32_t*>(s_jobs)[i] = reinterpret_cast<const uint32_t*>(p.jobs)[i];
   if (tid == 0) {
@@ -486,10 +571,18 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
     s_inemb[(s * 3 + r) * EMB + e] = a;
   }
   if (tid < NS * L) {
-    const int s = tid >> 2, l = tid & 3;
-    const float v = (s0 + s < p.n) ? __ldg(p.x_in + (size_t)(s0 + s) * L + l) : 0.f;
+    const int s = tid / L, l = tid % L;
+    float v = 0.f;
+    if (s0 + s < p.n) {
+      if (L == 4) {
+        v = __ldg(p.x_in + (size_t)(s0 + s) * L + l);
+      } else {   // decoder in_layer: Linear(D -> L)   (grasp_vae.py:419)
+        v = __ldg(p.head + L * p.D + l);
+        for (int d = 0; d < p.D; ++d) v = fmaf(__ldg(p.head + l * p.D + d), __ldg(p.x_in + (size_t)(s0 + s) * p.D + d), v);
+      }
+    }
     s_x[tid] = v;
-    if (p.mode == 0 && p.x_all && s0 + s < p.n) p.x_all[(size_t)(s0 + s) * L + l] = v;
+    if (L == 4 && p.mode == 0 && p.x_all && s0 + s < p.n) p.x_all[(size_t)(s0 + s) * L + l] = v;
   }
   fence_async_smem();
   tc_fence_before();
@@ -501,29 +594,31 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   c.lane = lane; c.q = wid & 3; c.g = wid >> 2; c.ch = c.q * 32 + lane;
   c.tmem = tmem_base + ((uint32_t)(c.q * 32) << 16);
   c.smem = smem;
-  c.scr = reinterpret_cast<float*>(smem + SM_SCR) + wid * 256;
-  c.xch = reinterpret_cast<float*>(smem + SM_XCH) + c.g * 256;
+  c.scr = reinterpret_cast<float*>(smem + T::SM_SCR) + wid * T::SCR;
+  c.xch = reinterpret_cast<float*>(smem + T::SM_XCH) + c.g * 256;
 #pragma unroll
   for (int j = 0; j < 8; ++j) c.xoff[j] = ((uint32_t)((((c.ch & 63) >> 3) ^ j) << 4)) + (c.ch & 7) * 2;
-  const int sgl = c.g * 8;   // first sample of this warp-group inside the CTA
+  constexpr int NSW = NS / 2;          // samples per warp-group
+  const int sgl = c.g * NSW;           // first sample of this warp-group inside the CTA
 
-  // ---- driver (warp 7, warp-uniform control flow; single instructions are issued by one elected lane):
-  //      weight ring producer + UMMA issuer, run at every job hand-off.  Everything address-like is precomputed
-  //      once into a per-step op table in shared memory (the ring stage of a weight chunk is a static function of
-  //      its position in the step), so the issue loop is a table walk: one 16-byte load and ~20 instructions per
-  //      block of up to four UMMAs.  The kernel is laid out for a small per-step instruction stream (one generic
-  //      epilogue, one driver); it is otherwise instruction-fetch bound.
+  // ---- driver (warp 7) and producer (warp 6): warp-uniform control flow, single instructions issued by one elected
+  //      lane.  Everything address-like is precomputed once into a per-step op table in shared memory (the ring
+  //      stage of a weight chunk is a static function of its position in the step), so the issue loop is a table
+  //      walk.  The kernel is laid out for a small per-step instruction stream (one generic epilogue, one driver);
+  //      it is otherwise instruction-fetch bound.
   const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
   const bool is_driver = wid_u == 7;       // UMMA issuer
   const bool is_producer = wid_u == 6;     // weight ring producer (a different scheduler partition than the issuer)
-  uint2* chunk_tab = reinterpret_cast<uint2*>(smem + SM_CHUNKS);
-  uint4* ops = reinterpret_cast<uint4*>(smem + SM_OPS);
-  uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + SM_OPBEG);
+  uint2* chunk_tab = reinterpret_cast<uint2*>(smem + T::SM_CHUNKS);
+  uint4* ops = reinterpret_cast<uint4*>(smem + T::SM_OPS);
+  uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + T::SM_OPBEG);
   uint16_t* chunk_end = op_begin + MAXJOBS + 2;      // one past the last weight chunk of every job (index in the step)
   // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
   //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA)
   if (tid == 0) {
-    const uint32_t ring_a = smem_u32(smem + SM_RING), b_base = smem_u32(smem + SM_B);
+    const uint32_t ring_a = smem_u32(smem + T::SM_RING), b_base = smem_u32(smem + T::SM_B);
+    const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
+    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
     uint32_t nops = 0, chunk_base = 0, ncp = 0;
     for (int j = 0; j < n_jobs; ++j) {
       const TcJob& job = p.jobs[j];
@@ -533,7 +628,6 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
       const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
       const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
                             ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
-      const uint32_t f_hi = (256u >> 4) | (1u << 14) | ((uint32_t)SW_32 << 29);
       uint32_t off = 0;
       auto emit = [&](uint32_t hi, uint32_t b_addr, uint32_t col, uint32_t ks, uint32_t acc, uint32_t film, uint32_t bytes) {
         const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
@@ -543,12 +637,21 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
         ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
         off += bytes;
       };
+      const bool ffirst = job.film_tiles && f_bytes > blk;      // blocks in descending size (see film_first)
+      auto emit_film = [&]() {
+        for (uint32_t f = 0; f < job.film_tiles; ++f)
+          emit(f_hi, smem_u32(smem + T::SM_U), T_FILM + f * 16, f_swb >> 5, 0u, 1u, f_bytes);
+      };
+      if (ffirst) emit_film();
       for (uint32_t t = 0; t < job.mtiles; ++t)
         for (uint32_t tap = 0; tap < job.taps; ++tap)
-          for (uint32_t kb = 0; kb < nkb; ++kb)
-            emit(a_hi, b_base + (job.taps == 3 ? tap : 1u) * (HALO * 128) + kb * SLAB, T_ACC + t * NCOL, a_swb >> 5,
-                 (tap | kb) != 0 ? 1u : 0u, 0u, blk);
-      for (uint32_t f = 0; f < job.film_tiles; ++f) emit(f_hi, smem_u32(smem + SM_U), T_FILM + f * 16, 1u, 0u, 1u, 4096u);
+          for (uint32_t kb = 0; kb < nkb; ++kb) {
+            const uint32_t tsel = job.taps == 3 ? tap : 1u;
+            const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
+                                             : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
+            emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
+          }
+      if (!ffirst) emit_film();
       chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
       chunk_end[j] = (uint16_t)ncp;
     }
@@ -582,12 +685,12 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
       ld_used |= 1u << s;
       ld_par ^= 1u << s;
       const uint2 e = chunk_tab[ld_idx];
-      bulk_g2s_elect(smem + SM_RING + s * CHUNK, p.pack + e.x, e.y, &full[s]);
+      bulk_g2s_elect(smem + T::SM_RING + s * CHUNK, p.pack + e.x, e.y, &full[s]);
       if (++ld_idx == cps) { ld_idx = 0; ++ld_step; }
     }
   };
   uint32_t full_par = 0;   // issuer state (warp 7): per-stage phase parity of the full barriers
-  uint32_t jobn = 0;     // jobs handed off so far (parity of b_ready / acc_ready)
+  uint32_t jobn = 0;       // jobs handed off so far (parity of b_ready / acc_ready)
   int prof_step = -1;
 
   auto drive_job = [&](int j) {
@@ -618,10 +721,10 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
       const uint64_t ad = ((uint64_t)op.z << 32) | op.x;
       const uint64_t bd = ((uint64_t)b_hi << 32) | op.y;
       const uint32_t d = tmem_base + (op.w & 0x1FFu), acc = (op.w >> 12) & 1u, ks = (op.w >> 9) & 7u;
-      if (op.w & (1u << 14)) umma_bf16_block_elect<1>(d, ad, bd, idesc16, 0u);
-      else if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc64, acc);
-      else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc64, acc);
-      else umma_bf16_block_elect<1>(d, ad, bd, idesc64, acc);
+      const uint32_t idesc = (op.w & (1u << 14)) ? idesc16 : idesc64;
+      if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
+      else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
+      else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
     }
     if (rec) pr[4] = clock64();
     umma_commit_elect(&empty[prev_stage]);
@@ -633,14 +736,17 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   for (int step = 0; step < n_steps; ++step) {
     prof_step = step;
     if (p.prof && blockIdx.x == 0 && tid == 0 && (step == 1 || step == 2)) p.prof[320 + step - 1] = clock64();
-    // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16)
+    // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16), one (s, e) per thread
     {
-      const int s = tid >> 4, e = tid & 15;
-      const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
-      const float te = __ldg(p.te + (size_t)ti * EMB + e);
+      const int s = tid / EMB, e = tid % EMB;
+      float te = 0.f;
+      if (L == 4) {
+        const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
+        te = __ldg(p.te + (size_t)ti * EMB + e);
+      }
       float a = 0.f;
       for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
-      *reinterpret_cast<__nv_bfloat16*>(smem + SM_U + swz_off<128>(s, e >> 3) + (e & 7) * 2) = __float2bfloat16(a);
+      *reinterpret_cast<__nv_bfloat16*>(smem + T::SM_U + swz_off<128>(s, e >> 3) + (e & 7) * 2) = __float2bfloat16(a);
     }
     // ---- init_conv: Conv1d(1 -> ch0, k7, p3) on the state -> residual stream tile 0 and B operand
     {
@@ -653,25 +759,44 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
 #pragma unroll
         for (int t = 0; t < 7; ++t) w7[t] = __ldg(W + lay.init_w + c.ch * 7 + t);
         const float b = __ldg(W + lay.init_b + c.ch);
+        if (L == 4) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float xs[4];
+          for (int j = 0; j < 8; ++j) {
+            float xs[4];
 #pragma unroll
-          for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
+            for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
 #pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            float a = b;
+            for (int l = 0; l < 4; ++l) {
+              float a = b;
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
-              const int ll = l + t - 3;
-              if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
+              for (int t = 0; t < 7; ++t) {
+                const int ll = l + t - 3;
+                if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
+              }
+              v[l * 8 + j] = a;
             }
-            v[l * 8 + j] = a;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            float xs[16];
+#pragma unroll
+            for (int l = 0; l < 16; ++l) xs[l] = s_x[(sgl + jj) * 16 + l];
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+              float a = b;
+#pragma unroll
+              for (int t = 0; t < 7; ++t) {
+                const int ll = l + t - 3;
+                if (ll >= 0 && ll < 16) a = fmaf(w7[t], xs[ll], a);
+              }
+              v[jj * 16 + l] = a;
+            }
           }
         }
       }
-      tm_store32(c, T_RES, v);
-      write_b(c, 0, v, c.ch < c0);
+      tm_store32<L>(c, T_RES, v);
+      write_b<L>(c, 0, v, c.ch < c0);
     }
 
 #pragma unroll 1
@@ -709,62 +834,121 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
         tc_fence_after();
       }
       if (flags & E_ATTN) {
-        // ======== linear attention (resnets.py:211-235): qkv -> core -> operand of to_out
+        // ======== linear attention (resnets.py:211-235): qkv -> core -> operand of to_out.  Warp = head, lane = d.
         float kk[32], e[32];
-        tm_load32(c, T_ACC + 1 * NCOL, kk);
+        tm_load32<L>(c, T_ACC + 1 * NCOL, kk);
+        if (L == 4) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {   // softmax over the 4 positions (dim=-1)
-          const float m = fmaxf(fmaxf(kk[jj], kk[8 + jj]), fmaxf(kk[16 + jj], kk[24 + jj]));
-          float sum = 0.f;
+          for (int jj = 0; jj < 8; ++jj) {   // softmax over the 4 positions (dim=-1)
+            const float m = fmaxf(fmaxf(kk[jj], kk[8 + jj]), fmaxf(kk[16 + jj], kk[24 + jj]));
+            float sum = 0.f;
 #pragma unroll
-          for (int l = 0; l < 4; ++l) { kk[l * 8 + jj] = __expf(kk[l * 8 + jj] - m); sum += kk[l * 8 + jj]; }
-          const float inv = __fdividef(1.0f, sum);
+            for (int l = 0; l < 4; ++l) { kk[l * 8 + jj] = __expf(kk[l * 8 + jj] - m); sum += kk[l * 8 + jj]; }
+            const float inv = __fdividef(1.0f, sum);
 #pragma unroll
-          for (int l = 0; l < 4; ++l) kk[l * 8 + jj] *= inv;
+            for (int l = 0; l < 4; ++l) kk[l * 8 + jj] *= inv;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {   // softmax over the 16 positions
+            float m = kk[jj * 16];
+#pragma unroll
+            for (int l = 1; l < 16; ++l) m = fmaxf(m, kk[jj * 16 + l]);
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) { kk[jj * 16 + l] = __expf(kk[jj * 16 + l] - m); sum += kk[jj * 16 + l]; }
+            const float inv = __fdividef(1.0f, sum);
+#pragma unroll
+            for (int l = 0; l < 16; ++l) kk[jj * 16 + l] *= inv;
+          }
         }
-        tm_load32(c, T_ACC + 0 * NCOL, e);
+        tm_load32<L>(c, T_ACC + 0 * NCOL, e);
 #pragma unroll
         for (int i = 0; i < 32; ++i) e[i] = __expf(fminf(e[i], 80.f));   // softmax over d: normalised by Z below
-        // lane sums over d (this warp = one head): A[j][n'][n] = sum_d k[n'][j] e[n][j], Z[n][j] = sum_d e[n][j]
+        // lane sums over d: A[s][n'][n] = sum_d k[n'][s] e[n][s], Z[n][s] = sum_d e[n][s]
+        constexpr int ZOFF = (L == 4) ? 128 : 512;
+        if (L == 4) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          float pr[32];
+          for (int b = 0; b < 4; ++b) {
+            float pr[32];
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-            for (int n1 = 0; n1 < 4; ++n1)
+              for (int n1 = 0; n1 < 4; ++n1)
 #pragma unroll
-              for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
-          c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
+                for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
+            c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
+          }
+        } else {
+#pragma unroll 1
+          for (int b = 0; b < 16; ++b) {        // sample b >> 3, rows n' = 2 (b & 7) + {0, 1}, all 16 columns n
+            const int jj = b >> 3, n1 = 2 * (b & 7);
+            float k0 = 0.f, k1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {      // select k[jj][n1], k[jj][n1 + 1] without dynamic register indexing
+              k0 = (i == jj * 16 + n1) ? kk[i] : k0;
+              k1 = (i == jj * 16 + n1 + 1) ? kk[i] : k1;
+            }
+            float pr[32];
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+              const float en = jj ? e[16 + n] : e[n];
+              pr[n] = k0 * en;
+              pr[16 + n] = k1 * en;
+            }
+            c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);    // A[jj][n1 + (lane >> 4)][lane & 15]
+          }
         }
         {
           float z[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) z[i] = e[i];
-          c.scr[128 + lane] = reduce_scatter32(z, lane);
+          c.scr[ZOFF + lane] = reduce_scatter32(z, lane);
         }
         __syncwarp();
         float vv[32], o[32];
-        tm_load32(c, T_ACC + 2 * NCOL, vv);
+        tm_load32<L>(c, T_ACC + 2 * NCOL, vv);
+        if (L == 4) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          float A[16];
+          for (int jj = 0; jj < 8; ++jj) {
+            float A[16];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (jj >> 1) * 32 + (jj & 1) * 16 + i);
-            A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
+            for (int i = 0; i < 16; i += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (jj >> 1) * 32 + (jj & 1) * 16 + i);
+              A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
+            }
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              float acc = 0.f;
+#pragma unroll
+              for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + jj], A[n1 * 4 + n], acc);
+              const float zinv = __fdividef(0.17677669529663687f, c.scr[ZOFF + n * 8 + jj]);   // scale 32^-0.5 / Z
+              o[n * 8 + jj] = acc * zinv;
+            }
           }
+        } else {
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            float acc = 0.f;
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;
 #pragma unroll
-            for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + jj], A[n1 * 4 + n], acc);
-            const float zinv = __fdividef(0.17677669529663687f, c.scr[128 + n * 8 + jj]);   // scale 32^-0.5 / Z
-            o[n * 8 + jj] = acc * zinv;
-          }
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+              const float vn = vv[jj * 16 + n1];
+              const float* Ar = c.scr + (jj * 8 + (n1 >> 1)) * 32 + (n1 & 1) * 16;     // A[jj][n1][0..15]
+#pragma unroll
+              for (int n = 0; n < 16; n += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(Ar + n);
+                o[jj * 16 + n] = fmaf(vn, t4.x, o[jj * 16 + n]);
+                o[jj * 16 + n + 1] = fmaf(vn, t4.y, o[jj * 16 + n + 1]);
+                o[jj * 16 + n + 2] = fmaf(vn, t4.z, o[jj * 16 + n + 2]);
+                o[jj * 16 + n + 3] = fmaf(vn, t4.w, o[jj * 16 + n + 3]);
+              }
+            }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= __fdividef(0.17677669529663687f, c.scr[ZOFF + i]);
         }
         __syncwarp();
-        write_b(c, 0, o, true);
+        write_b<L>(c, 0, o, true);
       } else {
         // ======== generic epilogue: bias, GroupNorm / LayerNorm, FiLM, SiLU, residual, PreNorm, operand write
         float fc_part[32];
@@ -778,11 +962,11 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
           const float bias = t ? pbias[1] : pbias[0], gam = t ? pgam[1] : pgam[0], bet = t ? pbet[1] : pbet[0];
           const float cs = t ? pcs[1] : pcs[0], chh = t ? pch[1] : pch[0], g1 = t ? pg[1] : pg[0], g2 = t ? pg2[1] : pg2[0];
           uint32_t rv[32], rr[32], rs8[8], rh8[8];
-          tm_issue32(c, T_ACC + t * NCOL, rv);
-          if (flags & E_ADDRES) tm_issue32(c, T_RES + t * NCOL, rr);
-          if (flags & E_FILM) {
-            tm_issue8(c, T_FILM + t * 16 + c.g * 8, rs8);
-            tm_issue8(c, T_FILM + (nt + t) * 16 + c.g * 8, rh8);
+          tm_issue32<L>(c, T_ACC + t * NCOL, rv);
+          if (flags & E_ADDRES) tm_issue32<L>(c, T_RES + t * NCOL, rr);
+          if (flags & E_FILM) {      // FiLM tile columns = samples: 8 per warp-group (L = 4) or all 4 of the CTA (L = 16)
+            tm_issue8(c, T_FILM + t * 16 + (L == 4 ? c.g * 8 : 0), rs8);
+            tm_issue8(c, T_FILM + (nt + t) * 16 + (L == 4 ? c.g * 8 : 0), rh8);
           }
           tm_wait();
           float v[32];
@@ -791,24 +975,24 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
           for (int i = 0; i < 32; ++i) v[i] += bias;
           if (flags & E_GN) {
             float mean[8], rstd[8];
-            gn_stats_dispatch(c, ch, v, mean, rstd);
+            gn_stats_dispatch<L>(c, ch, v, mean, rstd);
+            float fs[8], fh[8];
             if (flags & E_FILM) {
-              float fs[8], fh[8];
               tm_use(rs8, fs);
               tm_use(rh8, fh);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
-                const float sc = fs[jj] + cs, sh = fh[jj] + chh;
-#pragma unroll
-                for (int l = 0; l < 4; ++l) v[l * 8 + jj] = fmaf(fmaf(v[l * 8 + jj], a, b), sc, sh);
+              if (L == 16) {      // this warp-group's two samples are columns 2g, 2g + 1
+                fs[0] = c.g ? fs[2] : fs[0]; fs[1] = c.g ? fs[3] : fs[1];
+                fh[0] = c.g ? fh[2] : fh[0]; fh[1] = c.g ? fh[3] : fh[1];
               }
-            } else {
+            }
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+            for (int jj = 0; jj < NSW; ++jj) {
+              const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+              const float sc = (flags & E_FILM) ? fs[jj] + cs : 1.f, sh = (flags & E_FILM) ? fh[jj] + chh : 0.f;
 #pragma unroll
-                for (int l = 0; l < 4; ++l) v[l * 8 + jj] = fmaf(v[l * 8 + jj], a, b);
+              for (int l = 0; l < L; ++l) {
+                const int i = (L == 4) ? l * 8 + jj : jj * 16 + l;
+                v[i] = fmaf(fmaf(v[i], a, b), sc, sh);
               }
             }
           }
@@ -832,7 +1016,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          if (flags & E_STORERES) tm_store32(c, T_RES + t * NCOL, v);
+          if (flags & E_STORERES) tm_store32<L>(c, T_RES + t * NCOL, v);
           if (flags & E_LNNEXT) {
             float mr[32], rs[32];
             ln_stats(c, ch, v, mr, rs);
@@ -843,41 +1027,45 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(g2, v[i], fc_part[i]);
           } else {
-            write_b(c, t, v, valid);
+            write_b<L>(c, t, v, valid);
           }
         }
         if (flags & E_FINAL) {
-          // ======== final_conv (1x1 -> 1 channel) + scheduler update
-          const float part = reduce_scatter32(fc_part, lane);     // lane r: row r = l*8 + j of this warp's 32 channels
+          // ======== final_conv (1x1 -> 1 channel) + scheduler update (L = 4) / trunk output (L = 16)
+          const float part = reduce_scatter32(fc_part, lane);     // lane r: value r of this warp's 32 channels
           c.xch[c.q * 64 + lane] = part;
           wg_sync(c.g);
           if (c.q == 0) {
             float eps = __ldg(W + lay.fc_b);
 #pragma unroll
             for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
-            const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
-            const bool ok = s0 + s < p.n;
-            if (p.mode == 0) {
-              const float* cf = p.coef + (size_t)step * 8;
-              const float x = s_x[s * 4 + l];
-              float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
-              if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-              float prev;
-              if (p.sched_kind == GLDM_SCHED_DDPM) {
-                prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
-                const float sg = __ldg(cf + 4);
-                if (sg > 0.f && ok) {
-                  const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
-                                          : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
-                  prev = __fadd_rn(prev, __fmul_rn(sg, z));
-                }
-              } else {
-                prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
-              }
-              s_x[s * 4 + l] = prev;
-              if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
+            if (L == 16) {
+              s_x[sgl * 16 + lane] = eps;                         // value index jj*16 + l
             } else {
-              s_x[s * 4 + l] = eps;
+              const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+              const bool ok = s0 + s < p.n;
+              if (p.mode == 0) {
+                const float* cf = p.coef + (size_t)step * 8;
+                const float x = s_x[s * 4 + l];
+                float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
+                if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+                float prev;
+                if (p.sched_kind == GLDM_SCHED_DDPM) {
+                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
+                  const float sg = __ldg(cf + 4);
+                  if (sg > 0.f && ok) {
+                    const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
+                                            : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
+                    prev = __fadd_rn(prev, __fmul_rn(sg, z));
+                  }
+                } else {
+                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
+                }
+                s_x[s * 4 + l] = prev;
+                if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
+              } else {
+                s_x[s * 4 + l] = eps;
+              }
             }
           }
           wg_sync(c.g);
@@ -887,9 +1075,30 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) sampler_tc_kernel(const __gr
   }
   // ---- outputs
   wg_sync(c.g);
-  if (c.q == 0) {
-    const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
-    if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
+  if (L == 4) {
+    if (c.q == 0) {
+      const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+      if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
+    }
+  } else {
+    // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430)
+    const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
+    const int tl = tid & 127;
+    if (tl < NSW * 7) {
+      const int jj = tl / 7, o = tl - jj * 7, s = sgl + jj;
+      if (s0 + s < p.n) {
+        const float* x = s_x + s * 16;
+        if (o < 6) {
+          float a = __ldg(hw + 6 * L + o);
+          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
+          p.tmrp[(size_t)(s0 + s) * 6 + o] = a;
+        } else {
+          float a = __ldg(hw + 6 * L + 6 + L);
+          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
+          p.logit[s0 + s] = a;
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -911,16 +1120,21 @@ static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, cons
 
 static long long* g_tc_prof = nullptr;
 
-static int launch_tc(TcParams& p, cudaStream_t s) {
-  p.prof = g_tc_prof;
+template <int L>
+static int launch_tc_l(TcParams& p, cudaStream_t s) {
   static bool attr = false;
-  const int smem = stc::SM_TOTAL + 1024;
+  const int smem = Tr<L>::SM_TOTAL + 1024;
   if (!attr) {
-    cudaFuncSetAttribute(sampler_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(resnet_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  sampler_tc_kernel<<<ceil_div(p.n, stc::NS), stc::NTHREADS, smem, s>>>(p);
-  return check_launch("sampler_tc_kernel");
+  resnet_tc_kernel<L><<<ceil_div(p.n, Tr<L>::NS), stc::NTHREADS, smem, s>>>(p);
+  return check_launch(L == 4 ? "resnet_tc_kernel<4>" : "resnet_tc_kernel<16>");
+}
+
+static int launch_tc(TcParams& p, cudaStream_t s) {
+  p.prof = g_tc_prof;
+  return p.cfg.L == 4 ? launch_tc_l<4>(p, s) : launch_tc_l<16>(p, s);
 }
 
 }  // namespace gldm
@@ -953,20 +1167,23 @@ extern "C" int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* ra
   uint8_t* dst = reinterpret_cast<uint8_t*>(pack);
   cudaMemsetAsync(dst, 0, total, s);
   int launches = 0, ji = 0;
+  const int emb = cfg->emb_dim;
+  const uint32_t ftile = film_tile_bytes(emb);
   auto pack_main = [&](const TcJob& j, int src_off, int cout, int cin, int standardize) {
-    pack_image_kernel<<<ceil_div(j.mtiles * 128, 8), 256, 0, s>>>(raw + src_off, dst + j.a_off, cout, 0, cin, j.taps,
-                                                                  j.mtiles, j.kpt, j.a_swb, standardize);
+    uint8_t* m = dst + j.a_off + (film_first(j, emb) ? (size_t)j.film_tiles * ftile : 0);
+    pack_image_kernel<<<ceil_div(j.mtiles * 128, 8), 256, 0, s>>>(raw + src_off, m, cout, 0, cin, j.taps, j.mtiles, j.kpt,
+                                                                  j.a_swb, standardize);
     ++launches;
   };
   auto pack_film = [&](const TcJob& j, int mlp_off, int ch) {
-    const int nkb = (j.kpt * 2 + j.a_swb - 1) / j.a_swb;
-    uint8_t* f = dst + j.a_off + (size_t)j.mtiles * j.taps * nkb * 128 * j.a_swb;
+    uint8_t* f = dst + j.a_off + (film_first(j, emb) ? 0 : main_bytes(j));
     const int ct = (ch + 127) / 128;
     for (int half = 0; half < 2; ++half)
       for (int t = 0; t < ct; ++t) {
         const int row0 = half * ch + t * 128;
-        pack_image_kernel<<<ceil_div(128, 8), 256, 0, s>>>(raw + mlp_off, f + (size_t)(half * ct + t) * 4096,
-                                                           min(128, ch - t * 128), row0, cfg->emb_dim, 1, 1, 16, 32, 0);
+        pack_image_kernel<<<ceil_div(128, 8), 256, 0, s>>>(raw + mlp_off, f + (size_t)(half * ct + t) * ftile,
+                                                           min(128, ch - t * 128), row0, emb, 1, 1, pad16(emb),
+                                                           swb_for(pad16(emb)), 0);
         ++launches;
       }
   };
@@ -1015,6 +1232,7 @@ extern "C" int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, c
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
+  GLDM_REQUIRE(cfg->L == 4, "sampler_run_tc: the sampler needs the denoiser configuration (L = 4)");
   GLDM_REQUIRE(x_T && z_obj && x_out && timesteps_host && coef_host, "sampler_run_tc: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc: bad sizes");
   GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc: bad scheduler");
@@ -1022,7 +1240,7 @@ extern "C" int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, c
   cudaStream_t s = (cudaStream_t)stream;
   void* scratch = nullptr;
   const size_t cb = sizeof(float) * 8 * (size_t)n_steps, tb = sizeof(int) * (size_t)n_steps,
-               eb = sizeof(float) * stc::EMB * (size_t)n_steps;
+               eb = sizeof(float) * p.cfg.emb_dim * (size_t)n_steps;
   if (cudaMallocAsync(&scratch, cb + tb + eb + 256, s) != cudaSuccess) {
     set_error("sampler_run_tc: cudaMallocAsync failed");
     return GLDM_ECUDA;
@@ -1046,12 +1264,13 @@ extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* r
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
+  GLDM_REQUIRE(cfg->L == 4, "denoiser_forward_tc: needs the denoiser configuration (L = 4)");
   GLDM_REQUIRE(x && t && z_cond && eps, "denoiser_forward_tc: null pointer");
   GLDM_REQUIRE(n >= 0, "denoiser_forward_tc: bad n");
   if (n == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   float* d_te = nullptr;
-  if (cudaMallocAsync(reinterpret_cast<void**>(&d_te), sizeof(float) * stc::EMB * (size_t)n, s) != cudaSuccess) {
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_te), sizeof(float) * p.cfg.emb_dim * (size_t)n, s) != cudaSuccess) {
     set_error("denoiser_forward_tc: cudaMallocAsync failed");
     return GLDM_ECUDA;
   }
@@ -1060,4 +1279,19 @@ extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* r
   if (rc == GLDM_OK) rc = launch_tc(p, s);
   cudaFreeAsync(d_te, s);
   return rc;
+}
+
+extern "C" int gldm_decoder_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* head,
+                                       int D, const float* z_h, const float* z_obj, int n, int grasps_per_obj,
+                                       float* tmrp, float* logit, void* stream) {
+  TcParams p = {};
+  int rc = fill_tc(p, cfg, raw, pack);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->L == 16, "decoder_forward_tc: needs the decoder trunk configuration (L = 16)");
+  GLDM_REQUIRE(head && z_h && z_obj && tmrp && logit, "decoder_forward_tc: null pointer");
+  GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && D > 0 && D <= 64, "decoder_forward_tc: bad sizes");
+  if (n == 0) return GLDM_OK;
+  p.mode = 2; p.n = n; p.gpo = grasps_per_obj; p.x_in = z_h; p.z_cond = z_obj; p.n_steps = 1;
+  p.head = head; p.D = D; p.tmrp = tmrp; p.logit = logit;
+  return launch_tc(p, (cudaStream_t)stream);
 }

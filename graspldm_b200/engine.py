@@ -222,8 +222,9 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
     return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
 
 
-def decoder_forward(decoder, z_h, z_obj, grasps_per_obj):
+def decoder_forward(decoder, z_h, z_obj, grasps_per_obj, precision="fp32"):
     """ConditionalGraspPoseDecoder: z_h [n,D], z_obj [n_obj,C,Dc] -> (tmrp [n,6], logits [n,1])."""
+    _check_precision(precision)
     _require_cuda(z_h, "z_h")
     _require_cuda(z_obj, "cond")
     n, D = z_h.shape
@@ -243,9 +244,16 @@ def decoder_forward(decoder, z_h, z_obj, grasps_per_obj):
         zc = z_obj.contiguous().float()
         tmrp = torch.empty((n, 6), device=dev, dtype=torch.float32)
         logit = torch.empty((n, 1), device=dev, dtype=torch.float32)
+        pack = pk.tc_pack() if precision == "bf16" else None      # built before the timed section
         tok = SECTIONS.start("decoder", dev)
-        _lib.call("gldm_decoder_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), head.data_ptr(), D,
-                  zin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj), tmrp.data_ptr(), logit.data_ptr(), _stream(dev))
+        if precision == "bf16":
+            _lib.call("gldm_decoder_forward_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pack.data_ptr(), head.data_ptr(),
+                      D, zin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj), tmrp.data_ptr(), logit.data_ptr(),
+                      _stream(dev))
+        else:
+            _lib.call("gldm_decoder_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), head.data_ptr(), D,
+                      zin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj), tmrp.data_ptr(), logit.data_ptr(),
+                      _stream(dev))
         SECTIONS.stop(tok)
     return tmrp, logit
 

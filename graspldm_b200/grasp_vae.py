@@ -36,12 +36,13 @@ class ConditionalGraspPoseDecoder(nn.Module):      # grasp_vae.py:353-436
         self._use_qualities = False
         self.num_qualities = None
         self.out_features = (6, 1)
+        self.precision = "fp32"     # "bf16": trunk GEMMs on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)
 
     @torch.no_grad()
     def forward(self, z_h: Tensor, cond: Tensor = None, *, grasps_per_object: int = 1) -> Tuple[Tensor, Tensor]:
         """z_h [B,D], cond [B,C,Dc] (or one row per object with grasps_per_object=G) -> (tmrp [B,6], logits [B,1]);
         in_layer, the ResNet1D trunk and both heads run in one kernel launch."""
-        return engine.decoder_forward(self, z_h, cond, grasps_per_object)
+        return engine.decoder_forward(self, z_h, cond, grasps_per_object, precision=self.precision)
 
 
 class ConditionalGraspPoseEncoder(nn.Module):      # grasp_vae.py:439-536 (training only: parameters kept)

@@ -177,8 +177,8 @@ int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, co
  * Same contract as gldm_sampler_run_f32 / gldm_denoiser_forward_f32, but the GEMMs run on the 5th-generation
  * tensor cores.  `raw` is the canonical fp32 parameter blob (per-channel parameters are read from it), `pack`
  * the bf16 UMMA weight images produced once by gldm_sampler_tc_prepare (gldm_sampler_tc_pack_bytes bytes,
- * 1024-byte aligned).  Supported: the fpc latent denoiser family (L = 4, emb 16, 4 stages of width <= 128,
- * final width <= 256); anything else returns GLDM_ENOSUP. */
+ * 1024-byte aligned).  Supported: the fpc latent denoiser family (L = 4, emb 16, time conditioned) and the grasp
+ * decoder trunk (L = 16, emb 64), 4 stages of width <= 128, final width <= 256; anything else returns GLDM_ENOSUP. */
 long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg);
 /* development aid: when dev_buf != NULL (>= 512 int64 on the device) CTA 0 stamps clock64() around every
  * accumulator wait of its second denoising step; NULL (default) disables it */
@@ -190,6 +190,11 @@ int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, const void* 
                         unsigned long long seed, float* x_out, float* x_all, void* stream);
 int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
                              const int* t, const float* z_cond, int n, float* eps, void* stream);
+/* ConditionalGraspPoseDecoder.forward on the tensor cores (same contract as gldm_decoder_forward_f32); cfg is the
+ * decoder trunk (L = 16, emb 64, not time conditioned), pack from gldm_sampler_tc_prepare with that cfg. */
+int gldm_decoder_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* head, int D,
+                            const float* z_h, const float* z_obj, int n, int grasps_per_obj, float* tmrp,
+                            float* logit, void* stream);
 
 /* ---- tensor-core GEMM for the encoder's point-wise layers (bf16 operands, fp32 accumulation) ----
  * Operands are "UMMA images": [row tile of 128][K block of 64][128 rows x 128 bytes, SWIZZLE_128B] bf16.

@@ -88,6 +88,28 @@ def _rot_angle_deg(Ra, Rb):
 def _set_precision(model, prec):
     model.diffusion_model.precision = prec
     model.vae_model.encoder.pc_encoder.precision = prec
+    model.vae_model.decoder.precision = prec
+
+
+@pytest.mark.parametrize("B,gpo", [(1, 1), (4, 1), (37, 1), (40, 20)])
+def test_decoder_forward_bf16(fpc, cuda, B, gpo):
+    """Grasp decoder (in_layer -> ResNet1D trunk L = 16 -> heads) on the tensor cores vs the oracle."""
+    m, vae, _ = fpc
+    gen = torch.Generator().manual_seed(21 + B)
+    n_obj = B // gpo
+    z_h, zc = torch.randn(B, 4, generator=gen), torch.randn(n_obj, 3, 64, generator=gen)
+    with torch.no_grad():
+        wt, wl = M.decoder_forward(vae, "decoder.", z_h, zc.repeat_interleave(gpo, 0))
+    dec = m.vae_model.decoder
+    dec.precision = "bf16"
+    try:
+        gt, gl = dec(z_h.to(cuda), zc.to(cuda), grasps_per_object=gpo)
+    finally:
+        dec.precision = "fp32"
+    et, el = (gt.cpu() - wt).abs().max().item(), (gl.cpu() - wl).abs().max().item()
+    print(f"[B={B}] bf16 tensor-core decoder: max|tmrp err| {et:.3e} (max|tmrp| {wt.abs().max().item():.3f}), max|logit err| {el:.3e}")
+    np.testing.assert_allclose(gt.cpu().numpy(), wt.numpy(), rtol=5e-2, atol=5e-2)
+    np.testing.assert_allclose(gl.cpu().numpy(), wl.numpy(), rtol=5e-2, atol=5e-2)
 
 
 def test_ldm_generation_bf16_vs_reference_fixture(cuda):

@@ -19,6 +19,7 @@ model.set_inference_timesteps(100)
 model.diffusion_model.rng_mode = "fused"
 model.diffusion_model.precision = prec
 model.vae_model.encoder.pc_encoder.precision = prec
+model.vae_model.decoder.precision = prec
 inf = InferenceLDM(model, device=dev)
 pcs = _data.synthetic_clouds(n_obj, 1024, seed=1234, dist="S")
 pcs_dev = pcs.to(dev)
