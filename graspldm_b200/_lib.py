@@ -52,6 +52,9 @@ _SIGS = {
     "gldm_sampler_tc_prepare": [POINTER(GldmResNetCfg), P, P, P],
     "gldm_sampler_run_tc": [POINTER(GldmResNetCfg), P, P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
                             c_ulonglong, P, P, P],
+    "gldm_time_embed_table": [POINTER(GldmResNetCfg), P, P, c_int, P, P],
+    "gldm_sampler_run_tc_dev": [POINTER(GldmResNetCfg), P, P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
+                                c_ulonglong, P, P, P],
     "gldm_denoiser_forward_tc": [POINTER(GldmResNetCfg), P, P, P, P, P, c_int, P, P],
     "gldm_gemm_tc_image_bytes": [c_longlong, c_int],
     "gldm_gemm_tc_pack_weight": [P, c_int, c_int, P, P],

@@ -1259,6 +1259,37 @@ extern "C" int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, c
   return rc;
 }
 
+/* device-table variant: nothing is copied or allocated per call (pageable H2D copies synchronise the stream) */
+extern "C" int gldm_time_embed_table(const GldmResNetCfg* cfg, const float* raw, const int* timesteps_dev, int count,
+                                     float* te_dev, void* stream) {
+  int rc = check_tc_cfg(cfg);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->time_cond && raw && timesteps_dev && te_dev && count > 0, "time_embed_table: bad arguments");
+  TcParams p = {};
+  p.cfg = *cfg;
+  make_layout(*cfg, p.lay);
+  p.W = raw;
+  return run_time_embed(p, timesteps_dev, count, te_dev, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x_T,
+                                       const float* z_obj, int n, int grasps_per_obj, int n_steps, const float* coef_dev,
+                                       const float* te_dev, int sched_kind, int clip_sample, const float* noise,
+                                       unsigned long long seed, float* x_out, float* x_all, void* stream) {
+  TcParams p = {};
+  int rc = fill_tc(p, cfg, raw, pack);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->L == 4, "sampler_run_tc_dev: the sampler needs the denoiser configuration (L = 4)");
+  GLDM_REQUIRE(x_T && z_obj && x_out && coef_dev && te_dev, "sampler_run_tc_dev: null pointer");
+  GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc_dev: bad sizes");
+  GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc_dev: bad scheduler");
+  if (n == 0) return GLDM_OK;
+  p.mode = 0; p.n = n; p.gpo = grasps_per_obj; p.x_in = x_T; p.z_cond = z_obj; p.te = te_dev;
+  p.n_steps = n_steps; p.coef = coef_dev; p.sched_kind = sched_kind; p.clip = clip_sample;
+  p.noise = noise; p.seed = seed; p.x_out = x_out; p.x_all = x_all;
+  return launch_tc(p, (cudaStream_t)stream);
+}
+
 extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
                                         const int* t, const float* z_cond, int n, float* eps, void* stream) {
   TcParams p = {};

@@ -127,6 +127,24 @@ class PackedResNet:
         self.device = dev
         self.L = L
         self._tc_pack = None
+        self._tc_tables = {}
+
+    def tc_tables(self, timesteps, coef):
+        """Device-resident scheduler coefficients and time-embedding table of a schedule (cached per schedule)."""
+        key = (tuple(int(t) for t in timesteps), coef.data_ptr(), coef._version)
+        ent = self._tc_tables.get(key)
+        if ent is None:
+            dev = self.device
+            with torch.cuda.device(dev):
+                ts = torch.tensor(key[0], dtype=torch.int32, device=dev)
+                cf = coef.detach().to(device=dev, dtype=torch.float32).contiguous()
+                te = torch.empty((len(key[0]), self.cfg.emb_dim), device=dev, dtype=torch.float32)
+                _lib.call("gldm_time_embed_table", ctypes.byref(self.cfg), self.raw.data_ptr(), ts.data_ptr(), len(key[0]),
+                          te.data_ptr(), _stream(dev))
+            if len(self._tc_tables) > 8:
+                self._tc_tables.clear()
+            ent = self._tc_tables[key] = (cf, te)
+        return ent
 
     def tc_pack(self):
         """bf16 UMMA weight images for the tensor-core kernels (built on first use)."""
@@ -210,11 +228,15 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
         tail = (n, int(grasps_per_obj), n_steps, ctypes.cast(ts, ctypes.c_void_p), cf.data_ptr(), int(sched_kind),
                 int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
                 out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
-        pack = pk.tc_pack() if precision == "bf16" else None      # built before the timed section
+        if precision == "bf16":                                   # built / cached before the timed section
+            pack = pk.tc_pack()
+            cf_dev, te_dev = pk.tc_tables(timesteps, coef)
         tok = SECTIONS.start("sampler", dev)
         if precision == "bf16":
-            _lib.call("gldm_sampler_run_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pack.data_ptr(), xin.data_ptr(),
-                      zc.data_ptr(), *tail)
+            _lib.call("gldm_sampler_run_tc_dev", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pack.data_ptr(), xin.data_ptr(),
+                      zc.data_ptr(), n, int(grasps_per_obj), n_steps, cf_dev.data_ptr(), te_dev.data_ptr(), int(sched_kind),
+                      int(bool(clip_sample)), nz.data_ptr() if nz is not None else None, int(seed) & (2 ** 64 - 1),
+                      out.data_ptr(), x_all.data_ptr() if x_all is not None else None, _stream(dev))
         else:
             _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
                       zc.data_ptr(), *tail)

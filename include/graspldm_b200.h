@@ -188,6 +188,14 @@ int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, const void* 
                         const float* z_obj, int n, int grasps_per_obj, int n_steps, const int* timesteps_host,
                         const float* coef_host, int sched_kind, int clip_sample, const float* noise,
                         unsigned long long seed, float* x_out, float* x_all, void* stream);
+/* Same sampler with device-resident tables (no per-call allocation or host copy): coef_dev f32[n_steps,8],
+ * te_dev f32[n_steps,emb] produced once per schedule by gldm_time_embed_table(timesteps_dev i32[n_steps]). */
+int gldm_time_embed_table(const GldmResNetCfg* cfg, const float* raw, const int* timesteps_dev, int count,
+                          float* te_dev, void* stream);
+int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x_T,
+                            const float* z_obj, int n, int grasps_per_obj, int n_steps, const float* coef_dev,
+                            const float* te_dev, int sched_kind, int clip_sample, const float* noise,
+                            unsigned long long seed, float* x_out, float* x_all, void* stream);
 int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
                              const int* t, const float* z_cond, int n, float* eps, void* stream);
 /* ConditionalGraspPoseDecoder.forward on the tensor cores (same contract as gldm_decoder_forward_f32); cfg is the
