@@ -188,8 +188,10 @@ static int check_tc_cfg(const GldmResNetCfg* c) {
 // weight packing: fp32 matrix -> bf16 UMMA image [mtile][tap][kblock][128 rows x SWB bytes] (swizzled)
 // element (m, tap, k) of the source is src[(row0 + m) * (cin * taps) + k * taps + tap]
 // ------------------------------------------------------------------------------------------------
+// block order: tile-major [t][tap][kb], or - when `interleave` - [tap][kb][t] so that the two UMMA issuers, which own
+// the even / odd output tiles, walk the weight stream side by side
 __global__ void pack_image_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int rows_valid, int row0,
-                                  int cin, int taps, int mtiles, int kpt, int a_swb, int standardize) {
+                                  int cin, int taps, int mtiles, int kpt, int a_swb, int standardize, int interleave) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= mtiles * 128) return;
   const bool valid = m < rows_valid;
@@ -213,7 +215,8 @@ __global__ void pack_image_kernel(const float* __restrict__ src, uint8_t* __rest
       const int kb = k / epr, kk = k % epr;
       uint32_t off = (a_swb == 128) ? swz_off<128>(mr, kk >> 3) : (a_swb == 64) ? swz_off<64>(mr, kk >> 3)
                                                                                 : swz_off<32>(mr, kk >> 3);
-      const size_t blk = ((size_t)(t * taps + tap) * nkb + kb) * 128 * a_swb;
+      const size_t bi = interleave ? ((size_t)(tap * nkb + kb) * mtiles + t) : ((size_t)(t * taps + tap) * nkb + kb);
+      const size_t blk = bi * 128 * a_swb;
       *reinterpret_cast<__nv_bfloat16*>(dst + blk + off + (kk & 7) * 2) = __float2bfloat16(v);
     }
 }
@@ -550,9 +553,9 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
   for (int i = tid; i < n_jobs * (int)(sizeof(TcJob) / 4); i += NTHREADS)
     reinterpret_cast<uint32_t*>(s_jobs)[i] = reinterpret_cast<const uint32_t*>(p.jobs)[i];
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }   // released by both issuers
     mbar_init(b_ready, NCOMPUTE / 32);
-    mbar_init(acc_ready, 1);
+    mbar_init(acc_ready, 2);
     fence_barrier_init();
   }
   if (wid == 0) tmem_alloc<512>(tmem_slot);
@@ -607,14 +610,18 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
   //      walk.  The kernel is laid out for a small per-step instruction stream (one generic epilogue, one driver);
   //      it is otherwise instruction-fetch bound.
   const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
-  const bool is_driver = wid_u == 7;       // UMMA issuer
-  const bool is_producer = wid_u == 6;     // weight ring producer (a different scheduler partition than the issuer)
+  // two UMMA issuers (even / odd output tiles of the multi-tile jobs) and the weight ring producer sit in three
+  // different scheduler partitions; each issuer is the highest-numbered warp of its partition
+  const bool is_driver = wid_u == 7 || wid_u == 5;
+  const uint32_t my_owner = wid_u == 5 ? 1u : 0u;
+  const bool is_producer = wid_u == 6;
   uint2* chunk_tab = reinterpret_cast<uint2*>(smem + T::SM_CHUNKS);
   uint4* ops = reinterpret_cast<uint4*>(smem + T::SM_OPS);
   uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + T::SM_OPBEG);
   uint16_t* chunk_end = op_begin + MAXJOBS + 2;      // one past the last weight chunk of every job (index in the step)
   // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
-  //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA)
+  //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA),
+  //            20 owner (which of the two issuer warps executes it; both walk every op for the ring bookkeeping)
   if (tid == 0) {
     const uint32_t ring_a = smem_u32(smem + T::SM_RING), b_base = smem_u32(smem + T::SM_B);
     const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
@@ -643,14 +650,17 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
           emit(f_hi, smem_u32(smem + T::SM_U), T_FILM + f * 16, f_swb >> 5, 0u, 1u, f_bytes);
       };
       if (ffirst) emit_film();
-      for (uint32_t t = 0; t < job.mtiles; ++t)
-        for (uint32_t tap = 0; tap < job.taps; ++tap)
-          for (uint32_t kb = 0; kb < nkb; ++kb) {
-            const uint32_t tsel = job.taps == 3 ? tap : 1u;
-            const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
-                                             : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
-            emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
-          }
+      const uint32_t nblk = job.mtiles * job.taps * nkb;
+      for (uint32_t bi = 0; bi < nblk; ++bi) {
+        uint32_t t, tap, kb;
+        if (job.mtiles >= 2) { t = bi % job.mtiles; kb = (bi / job.mtiles) % nkb; tap = bi / (job.mtiles * nkb); }
+        else { t = 0; kb = bi % nkb; tap = bi / nkb; }
+        const uint32_t tsel = job.taps == 3 ? tap : 1u;
+        const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
+                                         : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
+        emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
+        if (job.mtiles >= 2 && (t & 1u)) ops[nops - 1].w |= 1u << 20;      // issued by the second issuer warp
+      }
       if (!ffirst) emit_film();
       chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
       chunk_end[j] = (uint16_t)ncp;
@@ -704,20 +714,28 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
     tc_fence_after();
     if (rec) pr[3] = clock64();
     uint32_t prev_stage = 0;
+    long long twait = 0;
 #pragma unroll 1
     for (uint32_t i = o0; i < o1; ++i) {
-      const uint4 op = ops[i];
+      // lane-0 broadcasts tell ptxas the fields are warp-uniform: the UMMA operands then move to uniform registers
+      // with plain R2UR instead of one ELECT + R2UR.BROADCAST (~25 cycles each, ~25 per block of four UMMAs)
+      uint4 op = ops[i];
+      op.x = __shfl_sync(0xffffffffu, op.x, 0); op.y = __shfl_sync(0xffffffffu, op.y, 0);
+      op.z = __shfl_sync(0xffffffffu, op.z, 0); op.w = __shfl_sync(0xffffffffu, op.w, 0);
       const uint32_t stage = (op.w >> 16) & 7u;
       if (op.w & (1u << 13)) {                       // first block of a weight chunk
         if (!(op.w & (1u << 15))) {
           umma_commit_elect(&empty[prev_stage]);      // the previous chunk of this job is free once its UMMAs retire
         }
+        const long long w0 = rec ? clock64() : 0;
         mbar_wait(&full[stage], (full_par >> stage) & 1u);
+        if (rec) twait += clock64() - w0;
         full_par ^= 1u << stage;
         tc_fence_after();
         prev_stage = stage;
       }
       if (op.w & (1u << 19)) continue;               // ring padding entry
+      if (((op.w >> 20) & 1u) != my_owner) continue;  // the other issuer's tile
       const uint64_t ad = ((uint64_t)op.z << 32) | op.x;
       const uint64_t bd = ((uint64_t)b_hi << 32) | op.y;
       const uint32_t d = tmem_base + (op.w & 0x1FFu), acc = (op.w >> 12) & 1u, ks = (op.w >> 9) & 7u;
@@ -726,7 +744,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
       else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
       else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
     }
-    if (rec) pr[4] = clock64();
+    if (rec) { pr[4] = clock64(); pr[6 + my_owner] = twait; }
     umma_commit_elect(&empty[prev_stage]);
     umma_commit_elect(acc_ready);
     if (rec) pr[5] = clock64();
@@ -1172,7 +1190,7 @@ extern "C" int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* ra
   auto pack_main = [&](const TcJob& j, int src_off, int cout, int cin, int standardize) {
     uint8_t* m = dst + j.a_off + (film_first(j, emb) ? (size_t)j.film_tiles * ftile : 0);
     pack_image_kernel<<<ceil_div(j.mtiles * 128, 8), 256, 0, s>>>(raw + src_off, m, cout, 0, cin, j.taps, j.mtiles, j.kpt,
-                                                                  j.a_swb, standardize);
+                                                                  j.a_swb, standardize, j.mtiles >= 2);
     ++launches;
   };
   auto pack_film = [&](const TcJob& j, int mlp_off, int ch) {
@@ -1183,7 +1201,7 @@ extern "C" int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* ra
         const int row0 = half * ch + t * 128;
         pack_image_kernel<<<ceil_div(128, 8), 256, 0, s>>>(raw + mlp_off, f + (size_t)(half * ct + t) * ftile,
                                                            min(128, ch - t * 128), row0, emb, 1, 1, pad16(emb),
-                                                           swb_for(pad16(emb)), 0);
+                                                           swb_for(pad16(emb)), 0, 0);
         ++launches;
       }
   };

@@ -67,11 +67,11 @@ if prec == "bf16":
     names += ["fin.c1", "fin.c2"]
     print(f"step cycles: {b[321] - b[320]}")
     prev_end = b[320]
-    print("job         epilogue  drv:refill+bwait  mma-issue  commit+refill  acc-wait")
-    tot = [0] * 5
+    print("job         epilogue  drv:refill+bwait  mma-issue  commit+refill  acc-wait  fullwait0 fullwait1")
+    tot = [0] * 7
     for j, nm in enumerate(names):
         w0, w1, d0, d1, d2, d3, wf, we = b[8 * j:8 * j + 8]
-        row = [d0 - prev_end, d1 - d0, d2 - d1, d3 - d2, w1 - w0]
+        row = [d0 - prev_end, d1 - d0, d2 - d1, d3 - d2, w1 - w0, wf, we]
         tot = [a_ + b_ for a_, b_ in zip(tot, row)]
         print(f"{nm:10s} " + " ".join(f"{x:9d}" for x in row))
         prev_end = w1

@@ -7,7 +7,13 @@
 using namespace gldm::tc;
 namespace cg = cooperative_groups;
 
-constexpr int CHUNK = 16384, STAGES = 4;
+#ifndef CHUNK_B
+#define CHUNK_B 16384
+#endif
+#ifndef NSTAGES
+#define NSTAGES 4
+#endif
+constexpr int CHUNK = CHUNK_B, STAGES = NSTAGES;
 
 __device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
   asm volatile(
@@ -93,12 +99,9 @@ void run(const uint8_t* w, int bytes, int passes, int grid) {
 int main() {
   const int bytes = 2 * 1024 * 1024, passes = 100;
   uint8_t* w; cudaMalloc(&w, bytes); cudaMemset(w, 1, bytes);
+  printf("chunk %d x %d stages\n", CHUNK, STAGES);
   run<1>(w, bytes, passes, 1);
-  run<1>(w, bytes, passes, 16);
-  run<1>(w, bytes, passes, 74);
+  run<1>(w, bytes, passes, 80);
   run<1>(w, bytes, passes, 148);
-  run<2>(w, bytes, passes, 148);
-  run<4>(w, bytes, passes, 148);
-  run<8>(w, bytes, passes, 144);
   return 0;
 }
