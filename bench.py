@@ -196,6 +196,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if os.environ.get("GLDM_TC_SETS"):
+        _lib.call("gldm_sampler_tc_set_sets", int(os.environ["GLDM_TC_SETS"]))
     model = _models.build("fpc").to(dev)
     model.set_inference_timesteps(N_STEPS_DDPM)
     model.diffusion_model.rng_mode = "fused"          # noise drawn inside the sampler kernel (Philox4x32-10)
@@ -308,6 +310,10 @@ def main():
     clocks.start()
     l0 = _lib.launch_count()
     if n_streams > 1:
+        # throughput mode: 32 samples per sampler CTA in two interleaved sets (fewer SMs per batch, the UMMA phase of
+        # one set under the epilogue of the other); the sequential latency pass above used the automatic choice
+        if args.precision == "bf16" and not os.environ.get("GLDM_TC_SETS"):
+            _lib.call("gldm_sampler_tc_set_sets", 2)
         total_ms = timed_pipelined(gen_resident, args.steps, args.warmup)
         launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, n_streams)) * args.steps
     else:
@@ -357,6 +363,8 @@ def main():
                    "parallelism": f"objects sharded over {world} rank(s), one final all_gather",
                    "l2": "256 MiB buffer written before every step" + (" (inside the timed region, on the step's stream)" if n_streams > 1 else " (between timed iterations)"),
                    "batches_in_flight": n_streams, "latency_ms_per_batch": lat_ms / args.steps, "precision": args.precision,
+                   "sampler_samples_per_cta": ("32 (two interleaved sets) in the pipelined passes, 16 in the latency pass"
+                                               if (n_streams > 1 and args.precision == "bf16") else "automatic"),
                    "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcs_host.numel() * 4 + n_local * 4 * 4),
                 "d2h_bytes_per_step": int(out_host["grasps"].numel() * 4 + out_host["confidence"].numel() * 4),

@@ -49,6 +49,7 @@ _SIGS = {
     "gldm_decoder_forward_f32": [POINTER(GldmResNetCfg), P, P, c_int, P, P, c_int, c_int, P, P, P],
     "gldm_sampler_tc_pack_bytes": [POINTER(GldmResNetCfg)],
     "gldm_sampler_tc_set_profile": [P],
+    "gldm_sampler_tc_set_sets": [c_int],
     "gldm_sampler_tc_prepare": [POINTER(GldmResNetCfg), P, P, P],
     "gldm_sampler_run_tc": [POINTER(GldmResNetCfg), P, P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
                             c_ulonglong, P, P, P],

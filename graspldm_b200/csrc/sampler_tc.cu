@@ -27,9 +27,13 @@ namespace stc {
 constexpr int NCOL = 64;                   // GEMM columns per CTA = L * NS
 constexpr int BSLABS = 4;                  // up to 256 channels (64 per K block)
 constexpr int CHUNK = 32768;               // weight ring stage (two 16 KB operand blocks)
-constexpr int MAXJOBS = 32, MAXCHUNKS = 192, MAXOPS = 256;
-constexpr uint32_t T_ACC = 0, T_RES = 192, T_FILM = 320;   // TMEM column map (512 allocated)
-constexpr int NCOMPUTE = 256, NTHREADS = 256;   // warp 6 also produces the weight ring, warp 7 also issues the UMMAs
+constexpr int MAXJOBS = 32, MAXCHUNKS = 224, MAXOPS = 400;
+// TMEM column map of one sample set (256 columns): accumulator tiles 0..2, the FiLM tiles alias tile 2 (the only
+// 3-tile job, to_qkv, has none), residual stream tile 0.  Residual tile 1 (channels 128..255, final block only) lives
+// in shared memory as bf16.
+constexpr uint32_t T_ACC = 0, T_FILM = 128, T_RES = 192, T_SET = 256;
+constexpr int NCOMPUTE = 256;                  // epilogue warps 0..7
+constexpr int NTHREADS = 384;                  // + warp 8 weight-ring producer, warps 9 / 10 UMMA issuers, warp 11 idle
 }  // namespace stc
 
 // Two instantiations of the same machine:
@@ -38,30 +42,32 @@ constexpr int NCOMPUTE = 256, NTHREADS = 256;   // warp 6 also produces the weig
 //   L = 16 : grasp decoder trunk (ResNet1D, R/models/grasp_vae.py:401-436).  4 samples per CTA, column = sample * 16 +
 //            position; a one-position shift is not a whole 8-row swizzle group, so the epilogue writes three shifted
 //            copies of the operand instead (one per tap); embedding width 64.
-template <int L_>
+template <int L_, int NSETS_>
 struct Tr {
-  static constexpr int L = L_, NS = stc::NCOL / L_;
+  static constexpr int L = L_, NS = stc::NCOL / L_, NSETS = NSETS_;
   static constexpr int EMB = (L_ == 4) ? 16 : 64;
   static constexpr int HALO = (L_ == 4) ? 16 : 0;
   static constexpr int BROWS = stc::NCOL + 2 * HALO;
   static constexpr int SLAB = BROWS * 128;                       // bytes per 64-channel K block of the B operand
   static constexpr int COPIES = (L_ == 4) ? 1 : 3;               // operand copies (one per tap for L = 16)
-  static constexpr int STAGES = (L_ == 4) ? 4 : 2;               // weight ring depth (x 32 KB)
+  static constexpr int B_BYTES = COPIES * stc::BSLABS * SLAB;    // operand buffer of one sample set
+  static constexpr int STAGES = (L_ == 4 && NSETS_ == 1) ? 4 : 2;   // weight ring depth (x 32 KB)
   static constexpr int SCR = (L_ == 4) ? 256 : 576;              // per-warp scratch floats
-  // shared memory map (bytes, from a 1024-aligned base)
+  // shared memory map (bytes, from a 1024-aligned base); per-set regions are NSETS consecutive copies
   static constexpr int SM_B = 0;
-  static constexpr int SM_U = SM_B + COPIES * stc::BSLABS * SLAB;   // FiLM operand (u): 16 rows x 128 B
-  static constexpr int SM_RING = SM_U + 2048;
-  static constexpr int SM_SCR = SM_RING + STAGES * stc::CHUNK;
+  static constexpr int SM_U = SM_B + NSETS * B_BYTES;               // FiLM operand (u): 16 rows x 128 B per set
+  static constexpr int SM_RING = SM_U + NSETS * 2048;
+  static constexpr int SM_RES1 = SM_RING + STAGES * stc::CHUNK;     // residual tile 1: [32 values][256 threads] bf16 per set
+  static constexpr int SM_SCR = SM_RES1 + NSETS * 16384;
   static constexpr int SM_XCH = SM_SCR + 8 * SCR * 4;               // cross-warp exchange 2 WG x 4 warps x 64 floats
-  static constexpr int SM_INEMB = SM_XCH + 2 * 4 * 64 * 4;          // in_emb [NS][3][EMB] floats = 3072
-  static constexpr int SM_X = SM_INEMB + NS * 3 * EMB * 4;          // state / trunk input [NS][L] floats = 256
-  static constexpr int SM_BAR = SM_X + NS * L * 4;                  // mbarriers
+  static constexpr int SM_INEMB = SM_XCH + 2 * 4 * 64 * 4;          // in_emb [NS][3][EMB] floats = 3072 per set
+  static constexpr int SM_X = SM_INEMB + NSETS * 3072;              // state / trunk input [NS][L] floats = 256 per set
+  static constexpr int SM_BAR = SM_X + NSETS * 256;                 // mbarriers
   static constexpr int SM_CHUNKS = SM_BAR + 256;                    // weight chunk table {pack offset, bytes}
   static constexpr int SM_JOBS = SM_CHUNKS + stc::MAXCHUNKS * 8;    // job table copy
   static constexpr int SM_OPS = SM_JOBS + stc::MAXJOBS * 48;        // UMMA op table, 16 bytes per block of <= 4 UMMAs
-  static constexpr int SM_OPBEG = SM_OPS + stc::MAXOPS * 16;        // first op / last chunk of every job
-  static constexpr int SM_TOTAL = SM_OPBEG + (stc::MAXJOBS + 2) * 4 + 16;
+  static constexpr int SM_OPBEG = SM_OPS + stc::MAXOPS * 16;        // first op of every (job, set)
+  static constexpr int SM_TOTAL = SM_OPBEG + (2 * stc::MAXJOBS + 2) * 2 + 16;
 };
 
 // epilogue recipe of a job (what the epilogue warps do with its accumulator)
@@ -292,6 +298,7 @@ struct Ctx {
   uint32_t tmem;        // TMEM base with this warp's lane quarter in the lane field
   int lane, q, g, ch;   // lane, quarter (warp & 3), warp-group (sample half), channel within a 128-tile
   uint8_t* smem;
+  uint8_t* bbase;       // B operand buffer of the current sample set
   float* scr;           // per-warp scratch (256 floats)
   float* xch;           // per-warp-group exchange (4 warps x 64 floats)
   uint32_t xoff[8];     // swizzled 16-byte-chunk offset (+ element offset) of this thread's channel for row&7 = j
@@ -351,17 +358,17 @@ __device__ __forceinline__ void tm_store32(const Ctx& c, uint32_t col, const flo
 template <int L>
 __device__ __forceinline__ void write_b(const Ctx& c, int t, const float (&v)[32], bool valid) {
   if (!valid) return;
-  using T = Tr<L>;
+  using T = Tr<L, 1>;
   const int chan = t * 128 + c.ch;
   if (L == 4) {
-    uint8_t* base = c.smem + T::SM_B + (chan >> 6) * T::SLAB + (T::HALO + c.g * 8) * 128;
+    uint8_t* base = c.bbase + (chan >> 6) * T::SLAB + (T::HALO + c.g * 8) * 128;
 #pragma unroll
     for (int l = 0; l < 4; ++l)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<__nv_bfloat16*>(base + (l * 16 + j) * 128 + c.xoff[j]) = __float2bfloat16(v[l * 8 + j]);
   } else {
-    uint8_t* base = c.smem + T::SM_B + (chan >> 6) * T::SLAB + (c.g * 32) * 128;
+    uint8_t* base = c.bbase + (chan >> 6) * T::SLAB + (c.g * 32) * 128;
     constexpr int COPY = stc::BSLABS * T::SLAB;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -522,25 +529,23 @@ __device__ __forceinline__ void ln_stats(const Ctx& c, int ch_total, const float
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int L>
+template <int L, int NSETS>
 __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __grid_constant__ TcParams p) {
   using namespace stc;
-  using T = Tr<L>;
+  using T = Tr<L, NSETS>;
   constexpr int NS = T::NS, EMB = T::EMB, STAGES = T::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::SM_BAR);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + 4;            // [STAGES]
-  uint64_t* b_ready = bars + 8;
-  uint64_t* acc_ready = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* s_inemb = reinterpret_cast<float*>(smem + T::SM_INEMB);
-  float* s_x = reinterpret_cast<float*>(smem + T::SM_X);
+  uint64_t* b_ready = bars + 8;          // [NSETS]
+  uint64_t* acc_ready = bars + 10;       // [NSETS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   TcJob* s_jobs = reinterpret_cast<TcJob*>(smem + T::SM_JOBS);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int s0 = blockIdx.x * NS;
+  const int cta_s0 = blockIdx.x * NS * NSETS;      // first sample of this CTA; set k holds samples cta_s0 + k*NS ...
   const GldmResNetCfg& cfg = p.cfg;
   const ResNetLayout& lay = p.lay;
   const float* W = p.W;
@@ -554,566 +559,590 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
     reinterpret_cast<uint32_t*>(s_jobs)[i] = reinterpret_cast<const uint32_t*>(p.jobs)[i];
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }   // released by both issuers
-    mbar_init(b_ready, NCOMPUTE / 32);
-    mbar_init(acc_ready, 2);
+    for (int k = 0; k < NSETS; ++k) { mbar_init(&b_ready[k], NCOMPUTE / 32); mbar_init(&acc_ready[k], 2); }
     fence_barrier_init();
   }
   if (wid == 0) tmem_alloc<512>(tmem_slot);
   // conditioning embedding SiLU(Linear(z_cond))  (resnets.py:531-533,596), once per launch
-  for (int idx = tid; idx < NS * R * EMB; idx += NTHREADS) {
-    const int e = idx % EMB, r = (idx / EMB) % R, s = idx / (EMB * R);
+  for (int idx = tid; idx < NSETS * NS * R * EMB; idx += NTHREADS) {
+    const int e = idx % EMB, r = (idx / EMB) % R, s = idx / (EMB * R);     // s: sample within the CTA
     float a = 0.f;
-    if (s0 + s < p.n) {
-      const int obj = (s0 + s) / p.gpo;
+    if (cta_s0 + s < p.n) {
+      const int obj = (cta_s0 + s) / p.gpo;
       const float* z = p.z_cond + ((size_t)obj * R + r) * cfg.cond_dim;
       const float* w = W + lay.in_w + (size_t)e * cfg.cond_dim;
       a = __ldg(W + lay.in_b + e);
       for (int j = 0; j < cfg.cond_dim; ++j) a = fmaf(__ldg(w + j), __ldg(z + j), a);
       a = a / (1.0f + expf(-a));
     }
-    s_inemb[(s * 3 + r) * EMB + e] = a;
+    reinterpret_cast<float*>(smem + T::SM_INEMB + (s / NS) * 3072)[((s % NS) * 3 + r) * EMB + e] = a;
   }
-  if (tid < NS * L) {
-    const int s = tid / L, l = tid % L;
+  if (tid < NSETS * NS * L) {
+    const int s = tid / L, l = tid % L;                                    // s: sample within the CTA
     float v = 0.f;
-    if (s0 + s < p.n) {
+    if (cta_s0 + s < p.n) {
       if (L == 4) {
-        v = __ldg(p.x_in + (size_t)(s0 + s) * L + l);
+        v = __ldg(p.x_in + (size_t)(cta_s0 + s) * L + l);
       } else {   // decoder in_layer: Linear(D -> L)   (grasp_vae.py:419)
         v = __ldg(p.head + L * p.D + l);
-        for (int d = 0; d < p.D; ++d) v = fmaf(__ldg(p.head + l * p.D + d), __ldg(p.x_in + (size_t)(s0 + s) * p.D + d), v);
+        for (int d = 0; d < p.D; ++d) v = fmaf(__ldg(p.head + l * p.D + d), __ldg(p.x_in + (size_t)(cta_s0 + s) * p.D + d), v);
       }
     }
-    s_x[tid] = v;
-    if (L == 4 && p.mode == 0 && p.x_all && s0 + s < p.n) p.x_all[(size_t)(s0 + s) * L + l] = v;
+    reinterpret_cast<float*>(smem + T::SM_X + (s / NS) * 256)[(s % NS) * L + l] = v;
+    if (L == 4 && p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
+  }
+  // ---- weight chunk table and UMMA op table of one step: for every job, for every sample set (the order in which
+  //      the epilogue warps hand operands over).  The ring stage of a chunk is a static function of its position.
+  uint2* chunk_tab = reinterpret_cast<uint2*>(smem + T::SM_CHUNKS);
+  uint4* ops = reinterpret_cast<uint4*>(smem + T::SM_OPS);
+  uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + T::SM_OPBEG);   // index = job * NSETS + set
+  // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
+  //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA),
+  //            20 owner (which of the two issuer warps executes it; both walk every op for the ring bookkeeping)
+  if (tid == 0) {
+    const uint32_t ring_a = smem_u32(smem + T::SM_RING);
+    const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
+    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
+    uint32_t nops = 0, chunk_base = 0, ncp = 0;
+    for (int j = 0; j < n_jobs; ++j)
+      for (int set = 0; set < NSETS; ++set) {
+        const TcJob& job = p.jobs[j];
+        const uint32_t b_base = smem_u32(smem + T::SM_B + set * T::B_BYTES), u_base = smem_u32(smem + T::SM_U + set * 2048);
+        for (uint32_t off = 0; off < job.bytes; off += CHUNK)
+          chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, job.bytes - off));
+        op_begin[j * NSETS + set] = (uint16_t)nops;
+        const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+        const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
+                              ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
+        uint32_t off = 0;
+        auto emit = [&](uint32_t hi, uint32_t b_addr, uint32_t col, uint32_t ks, uint32_t acc, uint32_t film, uint32_t bytes) {
+          const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
+          const uint32_t a_addr = ring_a + stage * CHUNK + (off % CHUNK);
+          const uint32_t w = (col + set * T_SET) | (ks << 9) | (acc << 12) | ((off % CHUNK == 0 ? 1u : 0u) << 13) |
+                             (film << 14) | ((off == 0 ? 1u : 0u) << 15) | (stage << 16);
+          ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
+          off += bytes;
+        };
+        const bool ffirst = job.film_tiles && f_bytes > blk;      // blocks in descending size (see film_first)
+        auto emit_film = [&]() {
+          for (uint32_t f = 0; f < job.film_tiles; ++f) emit(f_hi, u_base, T_FILM + f * 16, f_swb >> 5, 0u, 1u, f_bytes);
+        };
+        if (ffirst) emit_film();
+        const uint32_t nblk = job.mtiles * job.taps * nkb;
+        for (uint32_t bi = 0; bi < nblk; ++bi) {
+          uint32_t t, tap, kb;
+          if (job.mtiles >= 2) { t = bi % job.mtiles; kb = (bi / job.mtiles) % nkb; tap = bi / (job.mtiles * nkb); }
+          else { t = 0; kb = bi % nkb; tap = bi / nkb; }
+          const uint32_t tsel = job.taps == 3 ? tap : 1u;
+          const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
+                                           : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
+          emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
+          if (job.mtiles >= 2 && (t & 1u)) ops[nops - 1].w |= 1u << 20;      // issued by the second issuer warp
+        }
+        if (!ffirst) emit_film();
+        chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
+      }
+    // a step must span a whole number of ring revolutions: pad with 16-byte dummy chunks consumed by no-op entries
+    // of the last (job, set)
+    while (ncp % STAGES) {
+      ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
+      chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
+    }
+    op_begin[n_jobs * NSETS] = (uint16_t)nops;
+    op_begin[n_jobs * NSETS + 1] = (uint16_t)ncp;      // chunks per step
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  Ctx c;
-  c.lane = lane; c.q = wid & 3; c.g = wid >> 2; c.ch = c.q * 32 + lane;
-  c.tmem = tmem_base + ((uint32_t)(c.q * 32) << 16);
-  c.smem = smem;
-  c.scr = reinterpret_cast<float*>(smem + T::SM_SCR) + wid * T::SCR;
-  c.xch = reinterpret_cast<float*>(smem + T::SM_XCH) + c.g * 256;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) c.xoff[j] = ((uint32_t)((((c.ch & 63) >> 3) ^ j) << 4)) + (c.ch & 7) * 2;
-  constexpr int NSW = NS / 2;          // samples per warp-group
-  const int sgl = c.g * NSW;           // first sample of this warp-group inside the CTA
-
-  // ---- driver (warp 7) and producer (warp 6): warp-uniform control flow, single instructions issued by one elected
-  //      lane.  Everything address-like is precomputed once into a per-step op table in shared memory (the ring
-  //      stage of a weight chunk is a static function of its position in the step), so the issue loop is a table
-  //      walk.  The kernel is laid out for a small per-step instruction stream (one generic epilogue, one driver);
-  //      it is otherwise instruction-fetch bound.
+  const uint32_t cps = op_begin[n_jobs * NSETS + 1];
   const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
-  // two UMMA issuers (even / odd output tiles of the multi-tile jobs) and the weight ring producer sit in three
-  // different scheduler partitions; each issuer is the highest-numbered warp of its partition
-  const bool is_driver = wid_u == 7 || wid_u == 5;
-  const uint32_t my_owner = wid_u == 5 ? 1u : 0u;
-  const bool is_producer = wid_u == 6;
-  uint2* chunk_tab = reinterpret_cast<uint2*>(smem + T::SM_CHUNKS);
-  uint4* ops = reinterpret_cast<uint4*>(smem + T::SM_OPS);
-  uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + T::SM_OPBEG);
-  uint16_t* chunk_end = op_begin + MAXJOBS + 2;      // one past the last weight chunk of every job (index in the step)
-  // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
-  //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA),
-  //            20 owner (which of the two issuer warps executes it; both walk every op for the ring bookkeeping)
-  if (tid == 0) {
-    const uint32_t ring_a = smem_u32(smem + T::SM_RING), b_base = smem_u32(smem + T::SM_B);
-    const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
-    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
-    uint32_t nops = 0, chunk_base = 0, ncp = 0;
-    for (int j = 0; j < n_jobs; ++j) {
-      const TcJob& job = p.jobs[j];
-      for (uint32_t off = 0; off < job.bytes; off += CHUNK)
-        chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, job.bytes - off));
-      op_begin[j] = (uint16_t)nops;
-      const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
-      const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
-                            ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
-      uint32_t off = 0;
-      auto emit = [&](uint32_t hi, uint32_t b_addr, uint32_t col, uint32_t ks, uint32_t acc, uint32_t film, uint32_t bytes) {
-        const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
-        const uint32_t a_addr = ring_a + stage * CHUNK + (off % CHUNK);
-        const uint32_t w = col | (ks << 9) | (acc << 12) | ((off % CHUNK == 0 ? 1u : 0u) << 13) | (film << 14) |
-                           ((off == 0 ? 1u : 0u) << 15) | (stage << 16);
-        ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
-        off += bytes;
-      };
-      const bool ffirst = job.film_tiles && f_bytes > blk;      // blocks in descending size (see film_first)
-      auto emit_film = [&]() {
-        for (uint32_t f = 0; f < job.film_tiles; ++f)
-          emit(f_hi, smem_u32(smem + T::SM_U), T_FILM + f * 16, f_swb >> 5, 0u, 1u, f_bytes);
-      };
-      if (ffirst) emit_film();
-      const uint32_t nblk = job.mtiles * job.taps * nkb;
-      for (uint32_t bi = 0; bi < nblk; ++bi) {
-        uint32_t t, tap, kb;
-        if (job.mtiles >= 2) { t = bi % job.mtiles; kb = (bi / job.mtiles) % nkb; tap = bi / (job.mtiles * nkb); }
-        else { t = 0; kb = bi % nkb; tap = bi / nkb; }
-        const uint32_t tsel = job.taps == 3 ? tap : 1u;
-        const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
-                                         : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
-        emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
-        if (job.mtiles >= 2 && (t & 1u)) ops[nops - 1].w |= 1u << 20;      // issued by the second issuer warp
-      }
-      if (!ffirst) emit_film();
-      chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
-      chunk_end[j] = (uint16_t)ncp;
-    }
-    // the ring stage of a chunk is (index within the step) % STAGES, so a step must span a whole number of ring
-    // revolutions: pad with 16-byte dummy chunks consumed by no-op entries of the last job
-    while (ncp % STAGES) {
-      ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
-      chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
-    }
-    chunk_end[n_jobs - 1] = (uint16_t)ncp;
-    op_begin[n_jobs] = (uint16_t)nops;
-    chunk_end[n_jobs] = (uint16_t)ncp;      // chunks per step
-  }
-  __syncthreads();
-  const uint32_t cps = chunk_end[n_jobs];
-  // producer state (warp 6): position in the chunk stream and per-stage bit masks
-  uint32_t ld_idx = 0, ld_step = 0, ld_used = 0, ld_par = 0;
-  // called by the producer warp at the hand-off of job j of step `step`: loads every chunk this job still needs
-  // (waiting for ring stages to be released by the issuer) and prefetches later chunks into stages that are free
-  auto produce = [&](int step, int j) {
-    const uint32_t must_end = chunk_end[j];
+  if (wid_u >= 8) {
+  // register re-distribution (per 4-warp group): the service warps need few registers, the epilogue warps many
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (wid_u == 8) {
+    // =========================== weight ring producer (dedicated warp) ===========================
+    uint32_t used = 0, par = 0;
 #pragma unroll 1
-    while (ld_step < (uint32_t)n_steps) {
-      const bool must = ld_step < (uint32_t)step || (ld_step == (uint32_t)step && ld_idx < must_end);
-      const uint32_t s = ld_idx % STAGES;
-      if ((ld_used >> s) & 1u) {
-        const uint32_t par = ((ld_par >> s) & 1u) ^ 1u;
-        if (must) mbar_wait(&empty[s], par);
-        else if (!mbar_test(&empty[s], par)) break;
+    for (int step = 0; step < n_steps; ++step)
+#pragma unroll 1
+      for (uint32_t ci = 0; ci < cps; ++ci) {
+        const uint32_t s = ci % STAGES;
+        if ((used >> s) & 1u) mbar_wait(&empty[s], ((par >> s) & 1u) ^ 1u);
+        used |= 1u << s;
+        par ^= 1u << s;
+        const uint2 e = chunk_tab[ci];
+        bulk_g2s_elect(smem + T::SM_RING + s * CHUNK, p.pack + e.x, e.y, &full[s]);
       }
-      ld_used |= 1u << s;
-      ld_par ^= 1u << s;
-      const uint2 e = chunk_tab[ld_idx];
-      bulk_g2s_elect(smem + T::SM_RING + s * CHUNK, p.pack + e.x, e.y, &full[s]);
-      if (++ld_idx == cps) { ld_idx = 0; ++ld_step; }
-    }
-  };
-  uint32_t full_par = 0;   // issuer state (warp 7): per-stage phase parity of the full barriers
-  uint32_t jobn = 0;       // jobs handed off so far (parity of b_ready / acc_ready)
-  int prof_step = -1;
-
-  auto drive_job = [&](int j) {
+  } else if (wid_u == 9 || wid_u == 10) {
+    // =========================== UMMA issuers (dedicated warps; even / odd output tiles) ===========================
+    const uint32_t my_owner = wid_u == 10 ? 1u : 0u;
     const uint32_t idesc64 = idesc_bf16(128, NCOL), idesc16 = idesc_bf16(128, 16);
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
-    const bool rec = p.prof && blockIdx.x == 0 && prof_step == 1 && lane == 0;
-    long long* pr = p.prof + 8 * j;
-    if (rec) pr[2] = clock64();
-    const uint32_t o0 = op_begin[j], o1 = op_begin[j + 1];
-    mbar_wait(b_ready, jobn & 1);
-    tc_fence_after();
-    if (rec) pr[3] = clock64();
-    uint32_t prev_stage = 0;
-    long long twait = 0;
+    uint32_t full_par = 0, jobn = 0;
 #pragma unroll 1
-    for (uint32_t i = o0; i < o1; ++i) {
-      // lane-0 broadcasts tell ptxas the fields are warp-uniform: the UMMA operands then move to uniform registers
-      // with plain R2UR instead of one ELECT + R2UR.BROADCAST (~25 cycles each, ~25 per block of four UMMAs)
-      uint4 op = ops[i];
-      op.x = __shfl_sync(0xffffffffu, op.x, 0); op.y = __shfl_sync(0xffffffffu, op.y, 0);
-      op.z = __shfl_sync(0xffffffffu, op.z, 0); op.w = __shfl_sync(0xffffffffu, op.w, 0);
-      const uint32_t stage = (op.w >> 16) & 7u;
-      if (op.w & (1u << 13)) {                       // first block of a weight chunk
-        if (!(op.w & (1u << 15))) {
-          umma_commit_elect(&empty[prev_stage]);      // the previous chunk of this job is free once its UMMAs retire
-        }
-        const long long w0 = rec ? clock64() : 0;
-        mbar_wait(&full[stage], (full_par >> stage) & 1u);
-        if (rec) twait += clock64() - w0;
-        full_par ^= 1u << stage;
-        tc_fence_after();
-        prev_stage = stage;
-      }
-      if (op.w & (1u << 19)) continue;               // ring padding entry
-      if (((op.w >> 20) & 1u) != my_owner) continue;  // the other issuer's tile
-      const uint64_t ad = ((uint64_t)op.z << 32) | op.x;
-      const uint64_t bd = ((uint64_t)b_hi << 32) | op.y;
-      const uint32_t d = tmem_base + (op.w & 0x1FFu), acc = (op.w >> 12) & 1u, ks = (op.w >> 9) & 7u;
-      const uint32_t idesc = (op.w & (1u << 14)) ? idesc16 : idesc64;
-      if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
-      else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
-      else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
-    }
-    if (rec) { pr[4] = clock64(); pr[6 + my_owner] = twait; }
-    umma_commit_elect(&empty[prev_stage]);
-    umma_commit_elect(acc_ready);
-    if (rec) pr[5] = clock64();
-  };
-
+    for (int step = 0; step < n_steps; ++step)
 #pragma unroll 1
-  for (int step = 0; step < n_steps; ++step) {
-    prof_step = step;
-    if (p.prof && blockIdx.x == 0 && tid == 0 && (step == 1 || step == 2)) p.prof[320 + step - 1] = clock64();
-    // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16), one (s, e) per thread
-    {
-      const int s = tid / EMB, e = tid % EMB;
-      float te = 0.f;
-      if (L == 4) {
-        const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
-        te = __ldg(p.te + (size_t)ti * EMB + e);
-      }
-      float a = 0.f;
-      for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
-      *reinterpret_cast<__nv_bfloat16*>(smem + T::SM_U + swz_off<128>(s, e >> 3) + (e & 7) * 2) = __float2bfloat16(a);
-    }
-    // ---- init_conv: Conv1d(1 -> ch0, k7, p3) on the state -> residual stream tile 0 and B operand
-    {
-      const int c0 = cfg.ch[0];
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      if (c.ch < c0) {
-        float w7[7];
-#pragma unroll
-        for (int t = 0; t < 7; ++t) w7[t] = __ldg(W + lay.init_w + c.ch * 7 + t);
-        const float b = __ldg(W + lay.init_b + c.ch);
-        if (L == 4) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float xs[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-              float a = b;
-#pragma unroll
-              for (int t = 0; t < 7; ++t) {
-                const int ll = l + t - 3;
-                if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
-              }
-              v[l * 8 + j] = a;
+      for (int j = 0; j < n_jobs; ++j, ++jobn)
+#pragma unroll 1
+        for (int set = 0; set < NSETS; ++set) {
+          const uint32_t o0 = op_begin[j * NSETS + set], o1 = op_begin[j * NSETS + set + 1];
+          const bool rec = p.prof && blockIdx.x == 0 && step == 1 && lane == 0 && set == 0;
+          long long* pr = p.prof + 8 * j;
+          if (rec) pr[2] = clock64();
+          mbar_wait(&b_ready[set], jobn & 1);
+          tc_fence_after();
+          if (rec) pr[3] = clock64();
+          uint32_t prev_stage = 0;
+#pragma unroll 1
+          for (uint32_t i = o0; i < o1; ++i) {
+            uint4 op = ops[i];
+            op.x = __shfl_sync(0xffffffffu, op.x, 0); op.y = __shfl_sync(0xffffffffu, op.y, 0);
+            op.z = __shfl_sync(0xffffffffu, op.z, 0); op.w = __shfl_sync(0xffffffffu, op.w, 0);
+            const uint32_t stage = (op.w >> 16) & 7u;
+            if (op.w & (1u << 13)) {                       // first block of a weight chunk
+              if (!(op.w & (1u << 15))) umma_commit_elect(&empty[prev_stage]);   // previous chunk free once its UMMAs retire
+              mbar_wait(&full[stage], (full_par >> stage) & 1u);
+              full_par ^= 1u << stage;
+              tc_fence_after();
+              prev_stage = stage;
             }
+            if (op.w & (1u << 19)) continue;               // ring padding entry
+            if (((op.w >> 20) & 1u) != my_owner) continue;  // the other issuer's tile
+            const uint64_t ad = ((uint64_t)op.z << 32) | op.x;
+            const uint64_t bd = ((uint64_t)b_hi << 32) | op.y;
+            const uint32_t d = tmem_base + (op.w & 0x1FFu), acc = (op.w >> 12) & 1u, ks = (op.w >> 9) & 7u;
+            const uint32_t idesc = (op.w & (1u << 14)) ? idesc16 : idesc64;
+            if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
+            else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
+            else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
           }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            float xs[16];
-#pragma unroll
-            for (int l = 0; l < 16; ++l) xs[l] = s_x[(sgl + jj) * 16 + l];
-#pragma unroll
-            for (int l = 0; l < 16; ++l) {
-              float a = b;
-#pragma unroll
-              for (int t = 0; t < 7; ++t) {
-                const int ll = l + t - 3;
-                if (ll >= 0 && ll < 16) a = fmaf(w7[t], xs[ll], a);
-              }
-              v[jj * 16 + l] = a;
-            }
-          }
+          if (rec) pr[4] = clock64();
+          umma_commit_elect(&empty[prev_stage]);
+          umma_commit_elect(&acc_ready[set]);
+          if (rec) pr[5] = clock64();
         }
-      }
-      tm_store32<L>(c, T_RES, v);
-      write_b<L>(c, 0, v, c.ch < c0);
-    }
+  }
+  } else {
+    // =========================== epilogue warps ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    Ctx c;
+    c.lane = lane; c.q = wid & 3; c.g = wid >> 2; c.ch = c.q * 32 + lane;
+    c.smem = smem;
+    c.scr = reinterpret_cast<float*>(smem + T::SM_SCR) + wid * T::SCR;
+    c.xch = reinterpret_cast<float*>(smem + T::SM_XCH) + c.g * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c.xoff[j] = ((uint32_t)((((c.ch & 63) >> 3) ^ j) << 4)) + (c.ch & 7) * 2;
+    constexpr int NSW = NS / 2;          // samples per warp-group
+    const int sgl = c.g * NSW;           // first sample of this warp-group inside a set
+    uint32_t jobn = 0;                   // hand-offs per set so far (parity of b_ready / acc_ready)
+    int prof_step = -1;
 
-#pragma unroll 1
-    for (int j = 0; j < n_jobs; ++j) {
-      const TcJob job = s_jobs[j];
-      // ---- hand the operand of job j to the tensor core (one arrival per warp), driver issues its UMMAs
+    // select the sample set the following code works on
+    float* s_inemb = nullptr;
+    float* s_x = nullptr;
+    __nv_bfloat16* s_res1 = nullptr;
+    int s0 = 0;
+    auto select_set = [&](int set) {
+      c.tmem = tmem_base + (uint32_t)set * T_SET + ((uint32_t)(c.q * 32) << 16);
+      c.bbase = smem + T::SM_B + set * T::B_BYTES;
+      s_inemb = reinterpret_cast<float*>(smem + T::SM_INEMB + set * 3072);
+      s_x = reinterpret_cast<float*>(smem + T::SM_X + set * 256);
+      s_res1 = reinterpret_cast<__nv_bfloat16*>(smem + T::SM_RES1 + set * 16384);
+      s0 = cta_s0 + set * NS;
+    };
+    auto handoff = [&](int set) {        // operand of the next job of `set` is complete: one arrival per warp
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_ready);
-      if (is_driver) drive_job(j);
-      if (is_producer) produce(step, j);
-      // ---- per-channel parameters of this job, fetched while the UMMAs run
-      const int flags = job.flags, ch = job.ch, nt = job.mtiles;
-      float pbias[2], pgam[2], pbet[2], pcs[2], pch[2], pg[2], pg2[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int chan = t * 128 + c.ch;
-        const bool valid = t < nt && chan < ch && !(flags & E_ATTN);
-        pbias[t] = (valid && job.o_bias >= 0) ? __ldg(W + job.o_bias + chan) : 0.f;
-        pgam[t] = (valid && job.o_gamma >= 0) ? __ldg(W + job.o_gamma + chan) : 0.f;
-        pbet[t] = (valid && job.o_beta >= 0) ? __ldg(W + job.o_beta + chan) : 0.f;
-        pcs[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + chan) + (float)R : 0.f;
-        pch[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + ch + chan) : 0.f;
-        pg[t] = (valid && job.o_g >= 0) ? __ldg(W + job.o_g + chan) : 0.f;
-        pg2[t] = (valid && job.o_g2 >= 0) ? __ldg(W + job.o_g2 + chan) : 0.f;
-      }
-      // ---- wait for the accumulator
-      {
-        const bool rec = p.prof && blockIdx.x == 0 && tid == 0 && prof_step == 1;
-        const long long t0 = rec ? clock64() : 0;
-        mbar_wait(acc_ready, jobn & 1);
-        if (rec) { p.prof[8 * j] = t0; p.prof[8 * j + 1] = clock64(); }
-        ++jobn;
-        tc_fence_after();
-      }
-      if (flags & E_ATTN) {
-        // ======== linear attention (resnets.py:211-235): qkv -> core -> operand of to_out.  Warp = head, lane = d.
-        float kk[32], e[32];
-        tm_load32<L>(c, T_ACC + 1 * NCOL, kk);
-        if (L == 4) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {   // softmax over the 4 positions (dim=-1)
-            const float m = fmaxf(fmaxf(kk[jj], kk[8 + jj]), fmaxf(kk[16 + jj], kk[24 + jj]));
-            float sum = 0.f;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) { kk[l * 8 + jj] = __expf(kk[l * 8 + jj] - m); sum += kk[l * 8 + jj]; }
-            const float inv = __fdividef(1.0f, sum);
-#pragma unroll
-            for (int l = 0; l < 4; ++l) kk[l * 8 + jj] *= inv;
-          }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {   // softmax over the 16 positions
-            float m = kk[jj * 16];
-#pragma unroll
-            for (int l = 1; l < 16; ++l) m = fmaxf(m, kk[jj * 16 + l]);
-            float sum = 0.f;
-#pragma unroll
-            for (int l = 0; l < 16; ++l) { kk[jj * 16 + l] = __expf(kk[jj * 16 + l] - m); sum += kk[jj * 16 + l]; }
-            const float inv = __fdividef(1.0f, sum);
-#pragma unroll
-            for (int l = 0; l < 16; ++l) kk[jj * 16 + l] *= inv;
-          }
-        }
-        tm_load32<L>(c, T_ACC + 0 * NCOL, e);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = __expf(fminf(e[i], 80.f));   // softmax over d: normalised by Z below
-        // lane sums over d: A[s][n'][n] = sum_d k[n'][s] e[n][s], Z[n][s] = sum_d e[n][s]
-        constexpr int ZOFF = (L == 4) ? 128 : 512;
-        if (L == 4) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            float pr[32];
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1)
-#pragma unroll
-                for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
-            c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
-          }
-        } else {
+      if (lane == 0) mbar_arrive(&b_ready[set]);
+    };
+
 #pragma unroll 1
-          for (int b = 0; b < 16; ++b) {        // sample b >> 3, rows n' = 2 (b & 7) + {0, 1}, all 16 columns n
-            const int jj = b >> 3, n1 = 2 * (b & 7);
-            float k0 = 0.f, k1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {      // select k[jj][n1], k[jj][n1 + 1] without dynamic register indexing
-              k0 = (i == jj * 16 + n1) ? kk[i] : k0;
-              k1 = (i == jj * 16 + n1 + 1) ? kk[i] : k1;
-            }
-            float pr[32];
-#pragma unroll
-            for (int n = 0; n < 16; ++n) {
-              const float en = jj ? e[16 + n] : e[n];
-              pr[n] = k0 * en;
-              pr[16 + n] = k1 * en;
-            }
-            c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);    // A[jj][n1 + (lane >> 4)][lane & 15]
-          }
-        }
+    for (int step = 0; step < n_steps; ++step) {
+      prof_step = step;
+      if (p.prof && blockIdx.x == 0 && tid == 0 && (step == 1 || step == 2)) p.prof[320 + step - 1] = clock64();
+#pragma unroll 1
+      for (int set = 0; set < NSETS; ++set) {
+        select_set(set);
+        // ---- u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e])  -> FiLM GEMM operand (bf16), one (s, e) per thread
         {
-          float z[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) z[i] = e[i];
-          c.scr[ZOFF + lane] = reduce_scatter32(z, lane);
-        }
-        __syncwarp();
-        float vv[32], o[32];
-        tm_load32<L>(c, T_ACC + 2 * NCOL, vv);
-        if (L == 4) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float A[16];
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (jj >> 1) * 32 + (jj & 1) * 16 + i);
-              A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
-            }
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-              float acc = 0.f;
-#pragma unroll
-              for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + jj], A[n1 * 4 + n], acc);
-              const float zinv = __fdividef(0.17677669529663687f, c.scr[ZOFF + n * 8 + jj]);   // scale 32^-0.5 / Z
-              o[n * 8 + jj] = acc * zinv;
-            }
+          const int s = tid / EMB, e = tid % EMB;
+          float te = 0.f;
+          if (L == 4) {
+            const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
+            te = __ldg(p.te + (size_t)ti * EMB + e);
           }
-        } else {
+          float a = 0.f;
+          for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
+          *reinterpret_cast<__nv_bfloat16*>(smem + T::SM_U + set * 2048 + swz_off<128>(s, e >> 3) + (e & 7) * 2) =
+              __float2bfloat16(a);
+        }
+        // ---- init_conv: Conv1d(1 -> ch0, k7, p3) on the state -> residual stream tile 0 and B operand
+        {
+          const int c0 = cfg.ch[0];
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          if (c.ch < c0) {
+            float w7[7];
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
+            for (int t = 0; t < 7; ++t) w7[t] = __ldg(W + lay.init_w + c.ch * 7 + t);
+            const float b = __ldg(W + lay.init_b + c.ch);
+            if (L == 4) {
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-              const float vn = vv[jj * 16 + n1];
-              const float* Ar = c.scr + (jj * 8 + (n1 >> 1)) * 32 + (n1 & 1) * 16;     // A[jj][n1][0..15]
+              for (int j = 0; j < 8; ++j) {
+                float xs[4];
 #pragma unroll
-              for (int n = 0; n < 16; n += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(Ar + n);
-                o[jj * 16 + n] = fmaf(vn, t4.x, o[jj * 16 + n]);
-                o[jj * 16 + n + 1] = fmaf(vn, t4.y, o[jj * 16 + n + 1]);
-                o[jj * 16 + n + 2] = fmaf(vn, t4.z, o[jj * 16 + n + 2]);
-                o[jj * 16 + n + 3] = fmaf(vn, t4.w, o[jj * 16 + n + 3]);
+                for (int l = 0; l < 4; ++l) xs[l] = s_x[(sgl + j) * 4 + l];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                  float a = b;
+#pragma unroll
+                  for (int t = 0; t < 7; ++t) {
+                    const int ll = l + t - 3;
+                    if (ll >= 0 && ll < 4) a = fmaf(w7[t], xs[ll], a);
+                  }
+                  v[l * 8 + j] = a;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                float xs[16];
+#pragma unroll
+                for (int l = 0; l < 16; ++l) xs[l] = s_x[(sgl + jj) * 16 + l];
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                  float a = b;
+#pragma unroll
+                  for (int t = 0; t < 7; ++t) {
+                    const int ll = l + t - 3;
+                    if (ll >= 0 && ll < 16) a = fmaf(w7[t], xs[ll], a);
+                  }
+                  v[jj * 16 + l] = a;
+                }
               }
             }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= __fdividef(0.17677669529663687f, c.scr[ZOFF + i]);
+          }
+          tm_store32<L>(c, T_RES, v);
+          write_b<L>(c, 0, v, c.ch < c0);
         }
-        __syncwarp();
-        write_b<L>(c, 0, o, true);
-      } else {
-        // ======== generic epilogue: bias, GroupNorm / LayerNorm, FiLM, SiLU, residual, PreNorm, operand write
-        float fc_part[32];
-        if (flags & E_FINAL) {
+        handoff(set);
+      }
+
+#pragma unroll 1
+      for (int j = 0; j < n_jobs; ++j, ++jobn) {
+        const TcJob job = s_jobs[j];
+        // ---- per-channel parameters of this job (shared by the sample sets), fetched while the UMMAs run
+        const int flags = job.flags, ch = job.ch, nt = job.mtiles;
+        float pbias[2], pgam[2], pbet[2], pcs[2], pch[2], pg[2], pg2[2];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) fc_part[i] = 0.f;
+        for (int t = 0; t < 2; ++t) {
+          const int chan = t * 128 + c.ch;
+          const bool valid = t < nt && chan < ch && !(flags & E_ATTN);
+          pbias[t] = (valid && job.o_bias >= 0) ? __ldg(W + job.o_bias + chan) : 0.f;
+          pgam[t] = (valid && job.o_gamma >= 0) ? __ldg(W + job.o_gamma + chan) : 0.f;
+          pbet[t] = (valid && job.o_beta >= 0) ? __ldg(W + job.o_beta + chan) : 0.f;
+          pcs[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + chan) + (float)R : 0.f;
+          pch[t] = (valid && job.o_mlpb >= 0) ? (float)R * __ldg(W + job.o_mlpb + ch + chan) : 0.f;
+          pg[t] = (valid && job.o_g >= 0) ? __ldg(W + job.o_g + chan) : 0.f;
+          pg2[t] = (valid && job.o_g2 >= 0) ? __ldg(W + job.o_g2 + chan) : 0.f;
         }
 #pragma unroll 1
-        for (int t = 0; t < nt; ++t) {
-          const bool valid = t * 128 + c.ch < ch;
-          const float bias = t ? pbias[1] : pbias[0], gam = t ? pgam[1] : pgam[0], bet = t ? pbet[1] : pbet[0];
-          const float cs = t ? pcs[1] : pcs[0], chh = t ? pch[1] : pch[0], g1 = t ? pg[1] : pg[0], g2 = t ? pg2[1] : pg2[0];
-          uint32_t rv[32], rr[32], rs8[8], rh8[8];
-          tm_issue32<L>(c, T_ACC + t * NCOL, rv);
-          if (flags & E_ADDRES) tm_issue32<L>(c, T_RES + t * NCOL, rr);
-          if (flags & E_FILM) {      // FiLM tile columns = samples: 8 per warp-group (L = 4) or all 4 of the CTA (L = 16)
-            tm_issue8(c, T_FILM + t * 16 + (L == 4 ? c.g * 8 : 0), rs8);
-            tm_issue8(c, T_FILM + (nt + t) * 16 + (L == 4 ? c.g * 8 : 0), rh8);
+        for (int set = 0; set < NSETS; ++set) {
+          select_set(set);
+          // ---- wait for the accumulator of (job, set); the tensor core meanwhile works on the other set
+          {
+            const bool rec = p.prof && blockIdx.x == 0 && tid == 0 && prof_step == 1 && set == 0;
+            const long long t0 = rec ? clock64() : 0;
+            mbar_wait(&acc_ready[set], jobn & 1);
+            if (rec) { p.prof[8 * j] = t0; p.prof[8 * j + 1] = clock64(); }
+            tc_fence_after();
           }
-          tm_wait();
-          float v[32];
-          tm_use(rv, v);
+          if (flags & E_ATTN) {
+            // ======== linear attention (resnets.py:211-235): qkv -> core -> operand of to_out.  Warp = head, lane = d.
+            float kk[32], e[32];
+            tm_load32<L>(c, T_ACC + 1 * NCOL, kk);
+            if (L == 4) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += bias;
-          if (flags & E_GN) {
-            float mean[8], rstd[8];
-            gn_stats_dispatch<L>(c, ch, v, mean, rstd);
-            float fs[8], fh[8];
-            if (flags & E_FILM) {
-              tm_use(rs8, fs);
-              tm_use(rh8, fh);
-              if (L == 16) {      // this warp-group's two samples are columns 2g, 2g + 1
-                fs[0] = c.g ? fs[2] : fs[0]; fs[1] = c.g ? fs[3] : fs[1];
-                fh[0] = c.g ? fh[2] : fh[0]; fh[1] = c.g ? fh[3] : fh[1];
+              for (int jj = 0; jj < 8; ++jj) {   // softmax over the 4 positions (dim=-1)
+                const float m = fmaxf(fmaxf(kk[jj], kk[8 + jj]), fmaxf(kk[16 + jj], kk[24 + jj]));
+                float sum = 0.f;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) { kk[l * 8 + jj] = __expf(kk[l * 8 + jj] - m); sum += kk[l * 8 + jj]; }
+                const float inv = __fdividef(1.0f, sum);
+#pragma unroll
+                for (int l = 0; l < 4; ++l) kk[l * 8 + jj] *= inv;
               }
-            }
-#pragma unroll
-            for (int jj = 0; jj < NSW; ++jj) {
-              const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
-              const float sc = (flags & E_FILM) ? fs[jj] + cs : 1.f, sh = (flags & E_FILM) ? fh[jj] + chh : 0.f;
-#pragma unroll
-              for (int l = 0; l < L; ++l) {
-                const int i = (L == 4) ? l * 8 + jj : jj * 16 + l;
-                v[i] = fmaf(fmaf(v[i], a, b), sc, sh);
-              }
-            }
-          }
-          if (flags & E_SILU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
-          }
-          if (flags & E_LN) {
-            float mr[32], rs[32];
-            ln_stats(c, ch, v, mr, rs);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g1;
-          }
-          if (flags & E_ADDRES) {
-            float res[32];
-            tm_use(rr, res);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += res[i];
-          }
-          if (!valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-          if (flags & E_STORERES) tm_store32<L>(c, T_RES + t * NCOL, v);
-          if (flags & E_LNNEXT) {
-            float mr[32], rs[32];
-            ln_stats(c, ch, v, mr, rs);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g2;
-          }
-          if (flags & E_FINAL) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(g2, v[i], fc_part[i]);
-          } else {
-            write_b<L>(c, t, v, valid);
-          }
-        }
-        if (flags & E_FINAL) {
-          // ======== final_conv (1x1 -> 1 channel) + scheduler update (L = 4) / trunk output (L = 16)
-          const float part = reduce_scatter32(fc_part, lane);     // lane r: value r of this warp's 32 channels
-          c.xch[c.q * 64 + lane] = part;
-          wg_sync(c.g);
-          if (c.q == 0) {
-            float eps = __ldg(W + lay.fc_b);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
-            if (L == 16) {
-              s_x[sgl * 16 + lane] = eps;                         // value index jj*16 + l
             } else {
-              const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
-              const bool ok = s0 + s < p.n;
-              if (p.mode == 0) {
-                const float* cf = p.coef + (size_t)step * 8;
-                const float x = s_x[s * 4 + l];
-                float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
-                if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-                float prev;
-                if (p.sched_kind == GLDM_SCHED_DDPM) {
-                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
-                  const float sg = __ldg(cf + 4);
-                  if (sg > 0.f && ok) {
-                    const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
-                                            : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
-                    prev = __fadd_rn(prev, __fmul_rn(sg, z));
-                  }
-                } else {
-                  prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
-                }
-                s_x[s * 4 + l] = prev;
-                if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
-              } else {
-                s_x[s * 4 + l] = eps;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {   // softmax over the 16 positions
+                float m = kk[jj * 16];
+#pragma unroll
+                for (int l = 1; l < 16; ++l) m = fmaxf(m, kk[jj * 16 + l]);
+                float sum = 0.f;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) { kk[jj * 16 + l] = __expf(kk[jj * 16 + l] - m); sum += kk[jj * 16 + l]; }
+                const float inv = __fdividef(1.0f, sum);
+#pragma unroll
+                for (int l = 0; l < 16; ++l) kk[jj * 16 + l] *= inv;
               }
             }
+            tm_load32<L>(c, T_ACC + 0 * NCOL, e);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = __expf(fminf(e[i], 80.f));   // softmax over d: normalised by Z below
+            // lane sums over d: A[s][n'][n] = sum_d k[n'][s] e[n][s], Z[n][s] = sum_d e[n][s]
+            constexpr int ZOFF = (L == 4) ? 128 : 512;
+            if (L == 4) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                float pr[32];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                  for (int n1 = 0; n1 < 4; ++n1)
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) pr[jj * 16 + n1 * 4 + n] = kk[n1 * 8 + 2 * b + jj] * e[n * 8 + 2 * b + jj];
+                c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);
+              }
+            } else {
+#pragma unroll 1
+              for (int b = 0; b < 16; ++b) {        // sample b >> 3, rows n' = 2 (b & 7) + {0, 1}, all 16 columns n
+                const int jj = b >> 3, n1 = 2 * (b & 7);
+                float k0 = 0.f, k1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {      // select k[jj][n1], k[jj][n1 + 1] without dynamic register indexing
+                  k0 = (i == jj * 16 + n1) ? kk[i] : k0;
+                  k1 = (i == jj * 16 + n1 + 1) ? kk[i] : k1;
+                }
+                float pr[32];
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {
+                  const float en = jj ? e[16 + n] : e[n];
+                  pr[n] = k0 * en;
+                  pr[16 + n] = k1 * en;
+                }
+                c.scr[b * 32 + lane] = reduce_scatter32(pr, lane);    // A[jj][n1 + (lane >> 4)][lane & 15]
+              }
+            }
+            {
+              float z[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) z[i] = e[i];
+              c.scr[ZOFF + lane] = reduce_scatter32(z, lane);
+            }
+            __syncwarp();
+            float vv[32], o[32];
+            tm_load32<L>(c, T_ACC + 2 * NCOL, vv);
+            if (L == 4) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                float A[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(c.scr + (jj >> 1) * 32 + (jj & 1) * 16 + i);
+                  A[i] = t4.x; A[i + 1] = t4.y; A[i + 2] = t4.z; A[i + 3] = t4.w;
+                }
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  float acc = 0.f;
+#pragma unroll
+                  for (int n1 = 0; n1 < 4; ++n1) acc = fmaf(vv[n1 * 8 + jj], A[n1 * 4 + n], acc);
+                  const float zinv = __fdividef(0.17677669529663687f, c.scr[ZOFF + n * 8 + jj]);   // scale 32^-0.5 / Z
+                  o[n * 8 + jj] = acc * zinv;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                  const float vn = vv[jj * 16 + n1];
+                  const float* Ar = c.scr + (jj * 8 + (n1 >> 1)) * 32 + (n1 & 1) * 16;     // A[jj][n1][0..15]
+#pragma unroll
+                  for (int n = 0; n < 16; n += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(Ar + n);
+                    o[jj * 16 + n] = fmaf(vn, t4.x, o[jj * 16 + n]);
+                    o[jj * 16 + n + 1] = fmaf(vn, t4.y, o[jj * 16 + n + 1]);
+                    o[jj * 16 + n + 2] = fmaf(vn, t4.z, o[jj * 16 + n + 2]);
+                    o[jj * 16 + n + 3] = fmaf(vn, t4.w, o[jj * 16 + n + 3]);
+                  }
+                }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= __fdividef(0.17677669529663687f, c.scr[ZOFF + i]);
+            }
+            __syncwarp();
+            write_b<L>(c, 0, o, true);
+      } else {
+            // ======== generic epilogue: bias, GroupNorm / LayerNorm, FiLM, SiLU, residual, PreNorm, operand write
+            float fc_part[32];
+            if (flags & E_FINAL) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) fc_part[i] = 0.f;
+            }
+#pragma unroll 1
+            for (int t = 0; t < nt; ++t) {
+              const bool valid = t * 128 + c.ch < ch;
+              const float bias = t ? pbias[1] : pbias[0], gam = t ? pgam[1] : pgam[0], bet = t ? pbet[1] : pbet[0];
+              const float cs = t ? pcs[1] : pcs[0], chh = t ? pch[1] : pch[0], g1 = t ? pg[1] : pg[0], g2 = t ? pg2[1] : pg2[0];
+              uint32_t rv[32], rr[32], rs8[8], rh8[8];
+              tm_issue32<L>(c, T_ACC + t * NCOL, rv);
+              if ((flags & E_ADDRES) && t == 0) tm_issue32<L>(c, T_RES, rr);
+              if (flags & E_FILM) {      // FiLM tile columns = samples: 8 per warp-group (L = 4) or all 4 of the CTA (L = 16)
+                tm_issue8(c, T_FILM + t * 16 + (L == 4 ? c.g * 8 : 0), rs8);
+                tm_issue8(c, T_FILM + (nt + t) * 16 + (L == 4 ? c.g * 8 : 0), rh8);
+              }
+              tm_wait();
+              float v[32];
+              tm_use(rv, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += bias;
+              if (flags & E_GN) {
+                float mean[8], rstd[8];
+                gn_stats_dispatch<L>(c, ch, v, mean, rstd);
+                float fs[8], fh[8];
+                if (flags & E_FILM) {
+                  tm_use(rs8, fs);
+                  tm_use(rh8, fh);
+                  if (L == 16) {      // this warp-group's two samples are columns 2g, 2g + 1
+                    fs[0] = c.g ? fs[2] : fs[0]; fs[1] = c.g ? fs[3] : fs[1];
+                    fh[0] = c.g ? fh[2] : fh[0]; fh[1] = c.g ? fh[3] : fh[1];
+                  }
+                }
+#pragma unroll
+                for (int jj = 0; jj < NSW; ++jj) {
+                  const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+                  const float sc = (flags & E_FILM) ? fs[jj] + cs : 1.f, sh = (flags & E_FILM) ? fh[jj] + chh : 0.f;
+#pragma unroll
+                  for (int l = 0; l < L; ++l) {
+                    const int i = (L == 4) ? l * 8 + jj : jj * 16 + l;
+                    v[i] = fmaf(fmaf(v[i], a, b), sc, sh);
+                  }
+                }
+              }
+              if (flags & E_SILU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+              }
+              if (flags & E_LN) {
+                float mr[32], rs[32];
+                ln_stats(c, ch, v, mr, rs);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g1;
+              }
+              if (flags & E_ADDRES) {
+                if (t == 0) {
+                  float res[32];
+                  tm_use(rr, res);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] += res[i];
+                } else {               // channels 128..255 (final block only): bf16 copy in shared memory
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(s_res1[i * 256 + tid]);
+                }
+              }
+              if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+              }
+              if (flags & E_STORERES) {
+                if (t == 0) {
+                  tm_store32<L>(c, T_RES, v);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) s_res1[i * 256 + tid] = __float2bfloat16(v[i]);
+                }
+              }
+              if (flags & E_LNNEXT) {
+                float mr[32], rs[32];
+                ln_stats(c, ch, v, mr, rs);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g2;
+              }
+              if (flags & E_FINAL) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(g2, v[i], fc_part[i]);
+              } else {
+                write_b<L>(c, t, v, valid);
+              }
+            }
+            if (flags & E_FINAL) {
+              // ======== final_conv (1x1 -> 1 channel) + scheduler update (L = 4) / trunk output (L = 16)
+              const float part = reduce_scatter32(fc_part, lane);     // lane r: value r of this warp's 32 channels
+              c.xch[c.q * 64 + lane] = part;
+              wg_sync(c.g);
+              if (c.q == 0) {
+                float eps = __ldg(W + lay.fc_b);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
+                if (L == 16) {
+                  s_x[sgl * 16 + lane] = eps;                         // value index jj*16 + l
+                } else {
+                  const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+                  const bool ok = s0 + s < p.n;
+                  if (p.mode == 0) {
+                    const float* cf = p.coef + (size_t)step * 8;
+                    const float x = s_x[s * 4 + l];
+                    float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
+                    if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+                    float prev;
+                    if (p.sched_kind == GLDM_SCHED_DDPM) {
+                      prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), x));
+                      const float sg = __ldg(cf + 4);
+                      if (sg > 0.f && ok) {
+                        const float z = p.noise ? __ldg(p.noise + ((size_t)step * p.n + s0 + s) * L + l)
+                                                : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)step, (unsigned)l);
+                        prev = __fadd_rn(prev, __fmul_rn(sg, z));
+                      }
+                    } else {
+                      prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
+                    }
+                    s_x[s * 4 + l] = prev;
+                    if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
+                  } else {
+                    s_x[s * 4 + l] = eps;
+                  }
+                }
+              }
+              wg_sync(c.g);
+            }
           }
-          wg_sync(c.g);
+          if (j + 1 < n_jobs) handoff(set);        // operand of job j+1 written: the issuers take over for this set
         }
       }
     }
-  }
-  // ---- outputs
-  wg_sync(c.g);
-  if (L == 4) {
-    if (c.q == 0) {
-      const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
-      if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
-    }
-  } else {
-    // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430)
-    const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
-    const int tl = tid & 127;
-    if (tl < NSW * 7) {
-      const int jj = tl / 7, o = tl - jj * 7, s = sgl + jj;
-      if (s0 + s < p.n) {
-        const float* x = s_x + s * 16;
-        if (o < 6) {
-          float a = __ldg(hw + 6 * L + o);
-          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
-          p.tmrp[(size_t)(s0 + s) * 6 + o] = a;
-        } else {
-          float a = __ldg(hw + 6 * L + 6 + L);
-          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
-          p.logit[s0 + s] = a;
+    // ---- outputs
+#pragma unroll 1
+    for (int set = 0; set < NSETS; ++set) {
+      select_set(set);
+      wg_sync(c.g);
+      if (L == 4) {
+        if (c.q == 0) {
+          const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+          if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
+        }
+      } else {
+        // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430)
+        const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
+        const int tl = tid & 127;
+        if (tl < NSW * 7) {
+          const int jj = tl / 7, o = tl - jj * 7, s = sgl + jj;
+          if (s0 + s < p.n) {
+            const float* x = s_x + s * 16;
+            if (o < 6) {
+              float a = __ldg(hw + 6 * L + o);
+              for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
+              p.tmrp[(size_t)(s0 + s) * 6 + o] = a;
+            } else {
+              float a = __ldg(hw + 6 * L + 6 + L);
+              for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
+              p.logit[s0 + s] = a;
+            }
+          }
         }
       }
     }
@@ -1138,21 +1167,29 @@ static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, cons
 
 static long long* g_tc_prof = nullptr;
 
-template <int L>
+template <int L, int NSETS>
 static int launch_tc_l(TcParams& p, cudaStream_t s) {
   static bool attr = false;
-  const int smem = Tr<L>::SM_TOTAL + 1024;
+  using T = Tr<L, NSETS>;
+  const int smem = T::SM_TOTAL + 1024;
+  static_assert(T::SM_TOTAL + 1024 <= 232448, "shared memory budget");
   if (!attr) {
-    cudaFuncSetAttribute(resnet_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(resnet_tc_kernel<L, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  resnet_tc_kernel<L><<<ceil_div(p.n, Tr<L>::NS), stc::NTHREADS, smem, s>>>(p);
+  resnet_tc_kernel<L, NSETS><<<ceil_div(p.n, T::NS * NSETS), stc::NTHREADS, smem, s>>>(p);
   return check_launch(L == 4 ? "resnet_tc_kernel<4>" : "resnet_tc_kernel<16>");
 }
 
+// sample sets per CTA: 0 = automatic.  Two sets (32 samples per CTA, the UMMA phase of one set overlaps the epilogue
+// of the other) pay off once the batch no longer fits one wave of single-set CTAs.
+static int g_tc_sets = 0;
+
 static int launch_tc(TcParams& p, cudaStream_t s) {
   p.prof = g_tc_prof;
-  return p.cfg.L == 4 ? launch_tc_l<4>(p, s) : launch_tc_l<16>(p, s);
+  if (p.cfg.L != 4) return launch_tc_l<16, 1>(p, s);
+  const bool two = g_tc_sets == 2 || (g_tc_sets == 0 && p.n > 16 * kNumSMs);
+  return two ? launch_tc_l<4, 2>(p, s) : launch_tc_l<4, 1>(p, s);
 }
 
 }  // namespace gldm
@@ -1161,6 +1198,15 @@ using namespace gldm;
 
 extern "C" int gldm_sampler_tc_set_profile(long long* dev_buf) {
   g_tc_prof = dev_buf;
+  return GLDM_OK;
+}
+
+extern "C" int gldm_sampler_tc_set_sets(int sets) {
+  if (sets < 0 || sets > 2) {
+    set_error("sampler_tc_set_sets: 0 (automatic), 1 or 2");
+    return GLDM_EINVAL;
+  }
+  g_tc_sets = sets;
   return GLDM_OK;
 }
 

@@ -179,6 +179,9 @@ int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, co
  * the bf16 UMMA weight images produced once by gldm_sampler_tc_prepare (gldm_sampler_tc_pack_bytes bytes,
  * 1024-byte aligned).  Supported: the fpc latent denoiser family (L = 4, emb 16, time conditioned) and the grasp
  * decoder trunk (L = 16, emb 64), 4 stages of width <= 128, final width <= 256; anything else returns GLDM_ENOSUP. */
+/* sample sets per sampler CTA: 0 = automatic (two sets of 16 samples once the batch exceeds one wave of 16-sample
+ * CTAs: the tensor-core phase of one set then overlaps the epilogue of the other), 1 or 2 to force */
+int gldm_sampler_tc_set_sets(int sets);
 long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg);
 /* development aid: when dev_buf != NULL (>= 512 int64 on the device) CTA 0 stamps clock64() around every
  * accumulator wait of its second denoising step; NULL (default) disables it */

@@ -166,3 +166,26 @@ def test_full_size_properties_config2_bf16(cuda):
     da = _rot_angle_deg(a["grasps"][..., :3, :3], f["grasps"][..., :3, :3]).max().item()
     print(f"[config 2, bf16 vs fp32 path] max translation diff {dt * 1e3:.3f} mm, max rotation diff {da:.3f} deg")
     assert dt < 1e-3 and da < 2.0
+
+
+def test_sampler_two_sets_per_cta_matches_one_set(cuda):
+    """32 samples per CTA in two interleaved sets (tensor-core phase of one set under the epilogue of the other) must
+    reproduce the single-set kernel bit for bit: the per-sample arithmetic is identical."""
+    from graspldm_b200 import _lib
+    m = _models.build("fpc").to(cuda)
+    m.set_inference_timesteps(10)
+    gen = torch.Generator().manual_seed(9)
+    n_obj, G_ = 5, 21                    # 105 samples: 4 CTAs of 32 with a ragged tail / 7 CTAs of 16
+    z = torch.randn(n_obj, 3, 64, generator=gen).to(cuda)
+    x_T = torch.randn(n_obj * G_, 1, 4, generator=gen).to(cuda)
+    noise = torch.randn(10, n_obj * G_, 1, 4, generator=gen).to(cuda)
+    outs = []
+    try:
+        for sets in (1, 2):
+            _lib.call("gldm_sampler_tc_set_sets", sets)
+            x0, allx = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
+                                                grasps_per_object=G_, precision="bf16")
+            outs.append((x0.clone(), allx[5].clone()))
+    finally:
+        _lib.call("gldm_sampler_tc_set_sets", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -15,6 +15,9 @@ import _models  # noqa: E402
 from graspldm_b200.inference import InferenceLDM, default_metas  # noqa: E402
 
 dev = torch.device("cuda:0")
+if os.environ.get("GLDM_TC_SETS"):
+    from graspldm_b200 import _lib as _l
+    _l.call("gldm_sampler_tc_set_sets", int(os.environ["GLDM_TC_SETS"]))
 PEAK = 1392.3e12   # measured sustained bf16 (MEASURED_PEAKS.json)
 
 

@@ -14,6 +14,9 @@ dev = torch.device("cuda:0")
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 n_obj = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 G = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+if os.environ.get("GLDM_TC_SETS"):
+    from graspldm_b200 import _lib as _l
+    _l.call("gldm_sampler_tc_set_sets", int(os.environ["GLDM_TC_SETS"]))
 model = _models.build("fpc").to(dev)
 model.set_inference_timesteps(100)
 model.diffusion_model.rng_mode = "fused"
