@@ -18,7 +18,9 @@ using namespace tc;
 
 namespace c3 {
 constexpr int A_BYTES = 16384;              // 128 voxels x 64 channels bf16
-constexpr int STAGES = 4;
+constexpr int W_BYTES = 16384;              // one weight block in the pack
+constexpr int W_SLOT = 12288;               // shared-memory slot of a weight block: rows 0..95 (co <= 96), 16384 otherwise
+constexpr int STAGES = 3;                   // 3 x 28 KB: two CTAs per SM overlap each other's load latency and epilogue
 constexpr int NTHREADS = 192;
 }  // namespace c3
 
@@ -39,12 +41,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-__global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+template <int WSLOT>
+__global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                     const __grid_constant__ Conv3dTcParams p) {
   using namespace c3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * A_BYTES);
+  constexpr int STAGE_BYTES = A_BYTES + WSLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;
@@ -77,8 +81,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc_kernel(const __grid
       if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full[s], A_BYTES + p.w_rows_bytes);
-        tma_load_2d(smem + (2 * s) * A_BYTES, &xmap, kb * 64, (int)(row0 + shift), &full[s]);
-        bulk_g2s(smem + (2 * s + 1) * A_BYTES, p.w_img + (size_t)it * A_BYTES, p.w_rows_bytes, &full[s]);
+        tma_load_2d(smem + s * STAGE_BYTES, &xmap, kb * 64, (int)(row0 + shift), &full[s]);
+        bulk_g2s(smem + s * STAGE_BYTES + A_BYTES, p.w_img + (size_t)it * W_BYTES, p.w_rows_bytes, &full[s]);
       }
       __syncwarp();
     }
@@ -93,8 +97,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc_kernel(const __grid
       const int kb = it % p.k_blocks;
       mbar_wait(&full[s], (it / STAGES) & 1);
       tc_fence_after();
-      const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s) * A_BYTES) >> 4));
-      const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s + 1) * A_BYTES) >> 4));
+      const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE_BYTES) >> 4));
+      const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE_BYTES + A_BYTES) >> 4));
       const int ks = (kb == p.k_blocks - 1) ? p.ksteps_last : 4;
       const uint32_t acc = it != 0;
       if (ks == 4) umma_bf16_block_elect<4>(tmem, ad, bd, idesc, acc);
@@ -253,11 +257,15 @@ extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float*
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
   static bool attr = false;
-  const int smem = c3::STAGES * 2 * c3::A_BYTES + 1024 + 256;
+  const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 256;
+  const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 256;
   if (!attr) {
-    cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(conv3d_tc_kernel<c3::W_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
+    cudaFuncSetAttribute(conv3d_tc_kernel<c3::W_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     attr = true;
   }
-  conv3d_tc_kernel<<<(unsigned)((rows + 127) / 128), c3::NTHREADS, smem, s>>>(map, p);
+  const unsigned grid = (unsigned)((rows + 127) / 128);
+  if (p.w_rows_bytes <= c3::W_SLOT) conv3d_tc_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem_small, s>>>(map, p);
+  else conv3d_tc_kernel<c3::W_BYTES><<<grid, c3::NTHREADS, smem_big, s>>>(map, p);
   return check_launch("conv3d_tc_kernel");
 }
