@@ -334,7 +334,7 @@ def main():
     dec_ms = sum(sections.get("decoder", [0.0])) / max(1, len(sections.get("decoder", [])))
     samp_flops = n_local * N_STEPS_DDPM * F_DENOISER_PER_SAMPLE_STEP
     achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
-    kname = ("sampler_tc_kernel (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
+    kname = ("resnet_tc_kernel<4> (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
              else "resnet_kernel<4> (fp32 SIMT persistent 100-step sampler, one launch per batch)")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_tc_sampler_traffic.json")
@@ -346,7 +346,7 @@ def main():
                 "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
                 "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); decoder, voxelize / devoxelize, norms on fp32 SIMT kernels"
+                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm / SE and the 3->48 Conv3d on fp32 SIMT kernels; kernel_ms and sections_ms come from the sequential latency pass"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:
