@@ -68,6 +68,8 @@ _SIGS = {
     "gldm_conv3d_k3_tc": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "gldm_decoder_forward_tc": [POINTER(GldmResNetCfg), P, P, P, c_int, P, P, c_int, c_int, P, P, P],
     "gldm_pose_postprocess": [P, P, P, P, c_int, P, P, P, P],
+    "gldm_pose_postprocess_rows": [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
+    "gldm_normalize_clouds": [P, P, P, P, c_int, c_int, P, P, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})
 _RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong,

@@ -711,56 +711,3 @@ extern "C" int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* p
   p.tmrp = tmrp; p.logit = logit;
   return launch_resnet(p, (cudaStream_t)stream);
 }
-
-// pose post-processing: un-normalise, MRP -> quaternion -> rotation matrix -> 4x4, sigmoid
-namespace gldm {
-__global__ void pose_post_kernel(const float* __restrict__ tmrp, const float* __restrict__ logit,
-                                 const float* __restrict__ gmean, const float* __restrict__ gstd, int n,
-                                 float* __restrict__ gt, float* __restrict__ Hm, float* __restrict__ conf) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float g[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    g[j] = __fadd_rn(__fmul_rn(tmrp[(size_t)i * 6 + j], gstd[j]), gmean[j]);   // tools/inference.py:91-94
-    if (gt) gt[(size_t)i * 6 + j] = g[j];
-  }
-  if (Hm) {
-    // rotations.py:218-252 (mrp_to_quat) and :171-215 (quat_to_rotmat), same operator order
-    const float m0 = g[3], m1 = g[4], m2 = g[5];
-    const float magsq = __fadd_rn(__fadd_rn(__fmul_rn(m0, m0), __fmul_rn(m1, m1)), __fmul_rn(m2, m2));
-    const float den = __fadd_rn(1.0f, magsq);
-    const float x = __fdiv_rn(__fmul_rn(2.0f, m0), den), y = __fdiv_rn(__fmul_rn(2.0f, m1), den),
-                z = __fdiv_rn(__fmul_rn(2.0f, m2), den), w = __fdiv_rn(__fsub_rn(1.0f, magsq), den);
-    const float x2 = __fmul_rn(x, x), y2 = __fmul_rn(y, y), z2 = __fmul_rn(z, z), w2 = __fmul_rn(w, w);
-    const float xy = __fmul_rn(x, y), zw = __fmul_rn(z, w), xz = __fmul_rn(x, z), yw = __fmul_rn(y, w),
-                yz = __fmul_rn(y, z), xw = __fmul_rn(x, w);
-    float* o = Hm + (size_t)i * 16;
-    o[0] = __fadd_rn(__fsub_rn(__fsub_rn(x2, y2), z2), w2);
-    o[1] = __fmul_rn(2.0f, __fsub_rn(xy, zw));
-    o[2] = __fmul_rn(2.0f, __fadd_rn(xz, yw));
-    o[3] = g[0];
-    o[4] = __fmul_rn(2.0f, __fadd_rn(xy, zw));
-    o[5] = __fadd_rn(__fsub_rn(__fadd_rn(-x2, y2), z2), w2);
-    o[6] = __fmul_rn(2.0f, __fsub_rn(yz, xw));
-    o[7] = g[1];
-    o[8] = __fmul_rn(2.0f, __fsub_rn(xz, yw));
-    o[9] = __fmul_rn(2.0f, __fadd_rn(yz, xw));
-    o[10] = __fadd_rn(__fadd_rn(__fsub_rn(-x2, y2), z2), w2);
-    o[11] = g[2];
-    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
-  }
-  if (conf && logit) conf[i] = 1.0f / (1.0f + expf(-logit[i]));
-}
-}  // namespace gldm
-
-extern "C" int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean,
-                                     const float* grasp_std, int n, float* grasp_tmrp, float* H, float* conf,
-                                     void* stream) {
-  GLDM_REQUIRE(tmrp && grasp_mean && grasp_std, "pose_postprocess: null pointer");
-  GLDM_REQUIRE(n >= 0, "pose_postprocess: bad n");
-  if (n == 0) return GLDM_OK;
-  pose_post_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(tmrp, logit, grasp_mean, grasp_std, n,
-                                                                      grasp_tmrp, H, conf);
-  return check_launch("pose_post_kernel");
-}

@@ -284,23 +284,42 @@ def _flatten_nopad(tensors, device):
     return torch.cat([t.detach().to(device=device, dtype=torch.float32).reshape(-1) for t in tensors]).contiguous()
 
 
-def pose_postprocess(tmrp, logit, grasp_mean, grasp_std):
-    """tmrp [n,6], logit [n,1] -> (grasp_tmrp [n,6], H [n,4,4], confidence [n,1])"""
+def pose_postprocess(tmrp, logit, grasp_mean, grasp_std, grasps_per_obj=None):
+    """tmrp [n,6], logit [n,1] -> (grasp_tmrp [n,6], H [n,4,4], confidence [n,1]).
+    grasp_mean / grasp_std: one shared row ([6] or [1,6]) or one row per object ([n / grasps_per_obj, 6])."""
     _require_cuda(tmrp, "tmrp")
     n = tmrp.shape[0]
     dev = tmrp.device
     with torch.cuda.device(dev):
         t = tmrp.contiguous().float()
         lg = logit.contiguous().float()
-        gm = grasp_mean.to(dev).reshape(-1).contiguous().float()
-        gs = grasp_std.to(dev).reshape(-1).contiguous().float()
-        assert gm.numel() == 6 and gs.numel() == 6, "per-batch grasp statistics must be shared (shape [6])"
+        gm = grasp_mean.to(dev).reshape(-1, 6).contiguous().float()
+        gs = grasp_std.to(dev).reshape(-1, 6).contiguous().float()
+        gpo = int(grasps_per_obj) if grasps_per_obj else max(n, 1)
         gt = torch.empty((n, 6), device=dev, dtype=torch.float32)
         H = torch.empty((n, 4, 4), device=dev, dtype=torch.float32)
         conf = torch.empty((n, 1), device=dev, dtype=torch.float32)
-        _lib.call("gldm_pose_postprocess", t.data_ptr(), lg.data_ptr(), gm.data_ptr(), gs.data_ptr(), n, gt.data_ptr(),
-                  H.data_ptr(), conf.data_ptr(), _stream(dev))
+        _lib.call("gldm_pose_postprocess_rows", t.data_ptr(), lg.data_ptr(), gm.data_ptr(), gs.data_ptr(), n, gpo,
+                  gm.shape[0], gs.shape[0], gt.data_ptr(), H.data_ptr(), conf.data_ptr(), _stream(dev))
     return gt, H, conf
+
+
+def normalize_clouds(pc, pc_shift, pc_scale, grasp_shift):
+    """pc [b,n,3] raw -> (pc_norm [b,n,3], pc_mean [b,3], grasp_mean [b,6]); inference_base.py:182-212."""
+    _require_cuda(pc, "pc")
+    dev = pc.device
+    b, n, _ = pc.shape
+    with torch.cuda.device(dev):
+        src = pc.contiguous().float()
+        f = lambda v: v.to(dev).reshape(-1).contiguous().float()
+        ps, pscale, gsh = f(pc_shift), f(pc_scale), f(grasp_shift)
+        assert ps.numel() == 3 and pscale.numel() == 3 and gsh.numel() == 6
+        out = torch.empty_like(src)
+        pm = torch.empty((b, 3), device=dev, dtype=torch.float32)
+        gm = torch.empty((b, 6), device=dev, dtype=torch.float32)
+        _lib.call("gldm_normalize_clouds", src.data_ptr(), ps.data_ptr(), pscale.data_ptr(), gsh.data_ptr(), b, n,
+                  out.data_ptr(), pm.data_ptr(), gm.data_ptr(), _stream(dev))
+    return out, pm, gm
 
 
 def _conv3d(x, w_f32, w_img, bias, B, ci, co, r, y, st):

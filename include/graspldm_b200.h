@@ -236,6 +236,20 @@ int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int 
  * tmrp f32[n,6], logit f32[n], grasp_mean/std f32[6] -> grasp_tmrp f32[n,6], H f32[n,4,4], conf f32[n] */
 int gldm_pose_postprocess(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,
                           int n, float* grasp_tmrp, float* H, float* conf, void* stream);
+/* Same with per-object statistics, as the reference's datasets and normalize_input produce them
+ * (R/grasp_ldm/dataset/acronym/acronym_pointclouds.py:232-243, R/tools/inference.py:581-589): grasp i belongs to object
+ * i / grasps_per_obj; grasp_mean f32[mean_rows,6], grasp_std f32[std_rows,6], rows = 1 (shared) or n / grasps_per_obj. */
+int gldm_pose_postprocess_rows(const float* tmrp, const float* logit, const float* grasp_mean, const float* grasp_std,
+                               int n, int grasps_per_obj, int mean_rows, int std_rows, float* grasp_tmrp, float* H,
+                               float* conf, void* stream);
+
+/* Raw-cloud normalisation (R/grasp_ldm/inference/inference_base.py:182-212, R/tools/inference.py:570-591):
+ * pc f32[b,n,3]; pc_shift, pc_scale f32[3]; grasp_shift f32[6] (may be NULL when grasp_mean is NULL).
+ * pc_out[b,n,3] = (pc - mean_n(pc) - pc_shift) / pc_scale; pc_mean[b,3] = pc_shift + mean_n(pc) (metas["pc_mean"]);
+ * grasp_mean[b,6] = grasp_shift with the cloud mean added to the translation part (metas["grasp_mean"]).
+ * pc_out must not alias pc (the reference centres its argument in place; this entry leaves it untouched). */
+int gldm_normalize_clouds(const float* pc, const float* pc_shift, const float* pc_scale, const float* grasp_shift, int b,
+                          int n, float* pc_out, float* pc_mean, float* grasp_mean, void* stream);
 
 #ifdef __cplusplus
 }

@@ -257,3 +257,21 @@ def postprocess(tmrp, logits, xyz, metas, num_pcs, num_grasps):
     return dict(grasps=tmrp_to_H(g), grasp_tmrp=g,
                 confidence=torch.sigmoid(logits.view(num_pcs, num_grasps, 1)),
                 pc=xyz * metas["pc_std"].unsqueeze(-2) + metas["pc_mean"].unsqueeze(-2))
+
+
+def normalize_input(pc, pc_shift, pc_scale, grasp_shift, grasp_scale):
+    """Inference.normalize_input, R/grasp_ldm/inference/inference_base.py:182-212 (metas layout of
+    R/tools/inference.py:581-589 for batches): centre on the cloud mean, dataset shift / scale, and the statistics that
+    undo it.  The argument is left untouched and `grasp_shift` is not accumulated (the reference does both in place)."""
+    assert pc.ndim in (2, 3)
+    pc_mean = torch.mean(pc, dim=-2)
+    c = pc - (pc_mean.unsqueeze(1) if pc.ndim == 3 else pc_mean)
+    c = (c - pc_shift) / pc_scale
+    grasp_mean = grasp_shift.clone() if pc.ndim == 2 else grasp_shift.unsqueeze(0).repeat(pc.shape[0], 1)
+    grasp_mean[..., :3] += pc_mean
+    batched = pc.ndim == 3
+    metas = dict(pc_mean=pc_shift + pc_mean, pc_std=pc_scale.unsqueeze(0) if batched else pc_scale,
+                 grasp_mean=grasp_mean, grasp_std=grasp_scale.unsqueeze(0) if batched else grasp_scale,
+                 use_dataset_statistics=False)
+    return c, metas
+

@@ -111,6 +111,65 @@ def synthetic_clouds(B, N=1024, seed=1234, dist="S"):
     return torch.randn(B, N, 3, generator=g) * 0.7
 
 
+def reference_functions(path, names):
+    """Compile selected top-level functions / methods of a reference file without importing the module (inference_base.py
+    imports models/builder.py -> trimesh, absent here).  The code that runs is the reference's own, read from R at
+    generation time; nothing is copied into this repository."""
+    import ast
+    tree = ast.parse(open(path).read())
+    out = {}
+    ns = {"torch": torch, "Tensor": torch.Tensor, "np": np}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in out:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), ns)
+            out[node.name] = ns[node.name]
+    return out
+
+
+def normalize_golden():
+    """normalize_input -> (fixed model outputs) -> unnormalize_grasps -> tmrp_to_H on raw, un-centred clouds:
+    inference_base.py:61-84, 103-130, 182-212."""
+    fn = reference_functions(f"{REF}/grasp_ldm/inference/inference_base.py",
+                             ("set_normalization_params", "normalize_input", "unnormalize_grasps", "unnormalize_pc"))
+    norm = types.SimpleNamespace(pc_shift=[0.01, -0.02, 0.005], grasp_shift=[0.01, -0.02, 0.005, 0.1, -0.05, 0.2],
+                                 translation_scale=0.05, rotation_scale=0.5)
+    g = torch.Generator().manual_seed(21)
+    raw = synthetic_clouds(3, seed=77, dist="S") * 0.05 + torch.tensor([[[0.4, -0.2, 0.9]], [[-1.5, 0.3, 0.05]], [[0.0, 2.0, -0.7]]])
+    tmrp = torch.randn(3, 4, 6, generator=g)
+    out = {}
+    # single cloud [N,3]: inference_base.py (its in-place `grasp_mean[..., :3] += pc_mean` only broadcasts for one cloud)
+    self = types.SimpleNamespace(device="cpu")
+    fn["set_normalization_params"](self, norm)
+    scale6 = self._INPUT_GRASP_SCALE.clone()
+    pcn, metas = fn["normalize_input"](self, raw[1].clone())
+    res = {"single": (pcn, metas, tmrp[1])}
+    # batch [B,N,3]: tools/inference.py:570-591 (InferenceLDM.normalize_input), whose PC_MEAN / PC_STD / GRASP_MEAN /
+    # GRASP_STD attributes are the same four constants
+    fb = reference_functions(f"{REF}/tools/inference.py", ("normalize_input",))
+    selfb = types.SimpleNamespace(PC_MEAN=torch.tensor(norm.pc_shift), PC_STD=torch.ones(3) * norm.translation_scale,
+                                  GRASP_MEAN=torch.tensor(norm.grasp_shift), GRASP_STD=scale6)
+    pcb, metab = fb["normalize_input"](selfb, raw.clone())
+    res["batch"] = (pcb, metab, tmrp)
+    for tag, (pcn, metas, t) in res.items():
+        out[f"{tag}_pc"] = pcn.numpy()
+        for k in ("pc_mean", "pc_std", "grasp_mean", "grasp_std"):
+            out[f"{tag}_{k}"] = metas[k].numpy()
+        tm = {k: v for k, v in metas.items() if isinstance(v, torch.Tensor)}
+        if tag == "single":
+            tm = {k: v.unsqueeze(0) for k, v in tm.items()}
+            gu = fn["unnormalize_grasps"](t.unsqueeze(0), tm)[0]
+        else:
+            gu = fn["unnormalize_grasps"](t, tm)
+        out[f"{tag}_grasp_tmrp"] = gu.numpy()
+        out[f"{tag}_H"] = tmrp_to_H(gu).numpy()
+        out[f"{tag}_pc_unnorm"] = fn["unnormalize_pc"](pcn, metas).numpy()
+    np.savez_compressed(f"{HERE}/normalize_input.npz", raw=raw.numpy(), tmrp=tmrp.numpy(),
+                        pc_shift=np.array(norm.pc_shift, np.float32), grasp_shift=np.array(norm.grasp_shift, np.float32),
+                        translation_scale=np.float32(norm.translation_scale), rotation_scale=np.float32(norm.rotation_scale),
+                        **out)
+
+
 def manifest(sd):
     out = {}
     for k, v in sd.items():
@@ -179,6 +238,7 @@ def main():
                                 grasp_tmrp=np_(g_un), H=np_(H))
     with open(f"{HERE}/state_dict_manifest.json", "w") as f:
         json.dump(man, f, indent=0, sort_keys=True)
+    normalize_golden()
     print("golden fixtures written to", HERE)
 
 

@@ -179,3 +179,53 @@ def test_fused_rng_is_standard_normal(fpc, cuda):
     assert abs((zz ** 3).mean().item()) < 0.05 and abs((zz ** 4).mean().item() - 3.0) < 0.15
     m.diffusion_model.rng_mode = "reference"
     m.diffusion_model.noise_scheduler.num_inference_steps = None
+
+
+def test_normalize_input_and_per_object_postprocessing(fpc, cuda):
+    """raw clouds in, world-frame grasps out (inference_base.py:161-212, tools/inference.py:570-666)."""
+    from graspldm_b200.inference import InferenceLDM, InferenceVAE
+    from graspldm_b200 import engine
+    m, vae_sd, _ = fpc
+    g = np.load(os.path.join(G, "normalize_input.npz"))
+    norm = dict(pc_shift=g["pc_shift"].tolist(), grasp_shift=g["grasp_shift"].tolist(),
+                translation_scale=float(g["translation_scale"]), rotation_scale=float(g["rotation_scale"]))
+    inf = InferenceVAE(m.vae_model, device=cuda, norm_config=norm)
+    raw = torch.from_numpy(g["raw"])
+    for tag, pc in (("single", raw[1]), ("batch", raw)):
+        before = pc.clone()
+        pcn, metas = inf.normalize_input(pc)
+        assert torch.equal(pc, before)                                        # caller's tensor untouched
+        # the cloud mean is an fp64 reduction here, an fp32 cascade sum in torch.mean: 1 ulp of the mean (~1e-7 m)
+        np.testing.assert_allclose(pcn.cpu().numpy(), g[f"{tag}_pc"], rtol=0, atol=2e-5)
+        for k in ("pc_mean", "pc_std", "grasp_mean", "grasp_std"):
+            assert tuple(metas[k].shape) == g[f"{tag}_{k}"].shape, k
+            np.testing.assert_allclose(metas[k].cpu().numpy(), g[f"{tag}_{k}"], rtol=0, atol=3e-7)
+    # per-object un-normalisation + pose kernel on the reference's statistics: exact fp32
+    tm = torch.from_numpy(g["tmrp"]).to(cuda).reshape(12, 6)
+    gt, H, _ = engine.pose_postprocess(tm, torch.zeros(12, 1, device=cuda), torch.from_numpy(g["batch_grasp_mean"]),
+                                       torch.from_numpy(g["batch_grasp_std"]), grasps_per_obj=4)
+    np.testing.assert_array_equal(gt.cpu().numpy().reshape(3, 4, 6), g["batch_grasp_tmrp"])
+    np.testing.assert_allclose(H.cpu().numpy().reshape(3, 4, 4, 4), g["batch_H"], rtol=1e-6, atol=1e-7)
+    with pytest.raises(RuntimeError):
+        engine.pose_postprocess(tm, torch.zeros(12, 1, device=cuda), torch.zeros(2, 6), torch.ones(1, 6), grasps_per_obj=4)
+    # raw clouds end to end: same grasps as normalise-by-hand + generate_grasps, translated by each cloud's mean
+    z_h = torch.randn(12, 4, generator=torch.Generator().manual_seed(3)).to(cuda)
+    res = inf.generate_on_pointcloud(raw, num_grasps=4, z_h=z_h)
+    pcn, metas = M.normalize_input(raw, torch.from_numpy(g["pc_shift"]), torch.ones(3) * norm["translation_scale"],
+                                   torch.from_numpy(g["grasp_shift"]),
+                                   torch.cat((torch.ones(3) * norm["translation_scale"], torch.ones(3) * norm["rotation_scale"])))
+    with torch.no_grad():
+        tmw, lgw = M.generate_grasps_vae(vae_sd, pcn, 4, z_h.cpu())
+    want = M.postprocess(tmw, lgw, pcn, metas, 3, 4)
+    np.testing.assert_allclose(res["grasp_tmrp"].cpu().numpy(), want["grasp_tmrp"].numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(res["grasps"].cpu().numpy(), want["grasps"].numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(res["pc"].cpu().numpy(), g["raw"], rtol=0, atol=1e-6)
+    # LDM wrapper: same entry point, per-object statistics, intermediate steps for a single cloud
+    m.set_inference_timesteps(10)
+    ldm = InferenceLDM(m, device=cuda, norm_config=norm)
+    out = ldm.infer_on_pointcloud(raw[0], num_grasps=4, return_intermediate=True)
+    assert out["grasps"].shape == (1, 4, 4, 4) and len(out["all_steps_grasps"]) == 50
+    torch.testing.assert_close(out["all_steps_grasps"][-1], out["grasps"][0], rtol=0, atol=0)
+    centre = out["grasps"][0, :, :3, 3].mean(0).cpu()
+    assert (centre - raw[0].mean(0)).abs().max() < 0.5                        # grasps live around the raw cloud
+

@@ -147,3 +147,28 @@ def test_ops_oracle_vs_reference_kernels(gold_ops, name, coords):
         if name == "gauss100":
             assert np.array_equal(di, gold_ops[f"{name}/devox{r}_inds"])
             assert np.array_equal(dw, gold_ops[f"{name}/devox{r}_wgts"])
+
+
+def test_oracle_normalize_input_and_per_object_statistics():
+    """normalize_input / unnormalize_grasps / unnormalize_pc of the reference (inference_base.py:61-84, 182-212 for one
+    cloud; tools/inference.py:570-591 for a batch) on raw, un-centred clouds."""
+    g = np.load(os.path.join(G, "normalize_input.npz"))
+    shift, gshift = torch.from_numpy(g["pc_shift"]), torch.from_numpy(g["grasp_shift"])
+    scale = torch.ones(3) * float(g["translation_scale"])
+    gscale = torch.cat((scale, torch.ones(3) * float(g["rotation_scale"])))
+    raw = torch.from_numpy(g["raw"])
+    for tag, pc, tm in (("single", raw[1], torch.from_numpy(g["tmrp"][1])), ("batch", raw, torch.from_numpy(g["tmrp"]))):
+        before = pc.clone()
+        pcn, metas = M.normalize_input(pc, shift, scale, gshift, gscale)
+        assert torch.equal(pc, before)
+        np.testing.assert_array_equal(pcn.numpy(), g[f"{tag}_pc"])
+        for k in ("pc_mean", "pc_std", "grasp_mean", "grasp_std"):
+            assert metas[k].shape == g[f"{tag}_{k}"].shape, k
+            np.testing.assert_array_equal(metas[k].numpy(), g[f"{tag}_{k}"])
+        if tag == "batch":
+            out = M.postprocess(tm, torch.zeros(12, 1), pcn, metas, 3, 4)
+            np.testing.assert_array_equal(out["grasp_tmrp"].numpy(), g["batch_grasp_tmrp"])
+            np.testing.assert_allclose(out["grasps"].numpy(), g["batch_H"], rtol=1e-6, atol=1e-7)
+            np.testing.assert_array_equal(out["pc"].numpy(), g["batch_pc_unnorm"])
+            np.testing.assert_allclose(out["pc"].numpy(), g["raw"], rtol=0, atol=5e-7)     # round trip to the raw cloud
+
