@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d
                                                                     const __grid_constant__ Conv3dTcParams p) {
   using namespace c3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic (no integer round trip) keeps the shared address space visible to the compiler: LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int STAGE_BYTES = A_BYTES + WSLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;

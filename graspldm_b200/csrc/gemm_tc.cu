@@ -35,7 +35,8 @@ struct GemmTcParams {
 __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   using namespace gtc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic (no integer round trip) keeps the shared address space visible to the compiler: LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * BLOCK);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;

@@ -271,6 +271,18 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the epilogues are issue-slot bound, one instruction per two values
+__device__ __forceinline__ float2 ld2(const float (&v)[32], int i) { return make_float2(v[2 * i], v[2 * i + 1]); }
+__device__ __forceinline__ void st2(float (&v)[32], int i, float2 x) { v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 silu_fast2(float2 x) {
+  const float2 h = __fmul2_rn(x, bc2(0.5f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return __ffma2_rn(h, t, h);
+}
+
 __device__ __forceinline__ void wg_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 // reduce-scatter step: NOUT pairs (i, i + NOUT); lanes with bit `OFF` set keep the upper element
@@ -387,12 +399,16 @@ __device__ __forceinline__ void gn_stats(const Ctx& c, const float (&v)[32], flo
                                          float (&rstd)[8]) {
   float a[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float s = 0.f, q = 0.f;
+  for (int jp = 0; jp < 4; ++jp) {      // sample pair (2jp, 2jp + 1): v[l*8 + 2jp], v[l*8 + 2jp + 1] are register pairs
+    float2 s = ld2(v, jp), q = __fmul2_rn(s, s);
 #pragma unroll
-    for (int l = 0; l < 4; ++l) { s += v[l * 8 + j]; q = fmaf(v[l * 8 + j], v[l * 8 + j], q); }
-    a[j] = s;
-    a[8 + j] = q;
+    for (int l = 1; l < 4; ++l) {
+      const float2 x = ld2(v, l * 4 + jp);
+      s = __fadd2_rn(s, x);
+      q = __ffma2_rn(x, x, q);
+    }
+    a[2 * jp] = s.x; a[2 * jp + 1] = s.y;
+    a[8 + 2 * jp] = q.x; a[8 + 2 * jp + 1] = q.y;
   }
   const int lane = c.lane;
   if (GL == 32) {
@@ -452,11 +468,18 @@ __device__ __forceinline__ void gn_stats(const Ctx& c, const float (&v)[32], flo
 // L = 16 (two samples per warp-group, 16 positions each): statistics over (channels of the group x 16 positions).
 // Groups are cg = c/4 >= 4 consecutive channels: butterfly over min(cg, 32) lanes, + the partner warp for cg = 64.
 __device__ __forceinline__ void gn_stats16(const Ctx& c, int cg, const float (&v)[32], float (&mean)[8], float (&rstd)[8]) {
-  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  float a[4];
 #pragma unroll
-  for (int l = 0; l < 16; ++l) {
-    a[0] += v[l]; a[2] = fmaf(v[l], v[l], a[2]);
-    a[1] += v[16 + l]; a[3] = fmaf(v[16 + l], v[16 + l], a[3]);
+  for (int jj = 0; jj < 2; ++jj) {
+    float2 s = ld2(v, jj * 8), q = __fmul2_rn(s, s);
+#pragma unroll
+    for (int lp = 1; lp < 8; ++lp) {
+      const float2 x = ld2(v, jj * 8 + lp);
+      s = __fadd2_rn(s, x);
+      q = __ffma2_rn(x, x, q);
+    }
+    a[jj] = s.x + s.y;
+    a[2 + jj] = q.x + q.y;
   }
   const int gl = cg < 32 ? cg : 32;
   for (int o = 1; o < gl; o <<= 1) {
@@ -496,12 +519,16 @@ __device__ __forceinline__ void gn_stats_dispatch(const Ctx& c, int ch_total, co
 }
 
 // LayerNorm over the channel axis (one 128-lane tile; lanes >= c hold zeros): per row mean / rstd.
-// All four warps of the warp-group call this; out: mr[32] = mean, rs[32] = rstd for rows l*8 + j.
+// All four warps of the warp-group call this; out: mr[32] = -mean, rs[32] = rstd for rows l*8 + j.
 __device__ __forceinline__ void ln_stats(const Ctx& c, int ch_total, const float (&v)[32], float (&mr)[32],
                                          float (&rs)[32]) {
   float a[32], b[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { a[i] = v[i]; b[i] = v[i] * v[i]; }
+  for (int i = 0; i < 16; ++i) {
+    const float2 x = ld2(v, i);
+    st2(a, i, x);
+    st2(b, i, __fmul2_rn(x, x));
+  }
   const float s = reduce_scatter32(a, c.lane);      // lane r: row r
   const float q = reduce_scatter32(b, c.lane);
   c.xch[c.q * 64 + c.lane] = s;
@@ -513,7 +540,7 @@ __device__ __forceinline__ void ln_stats(const Ctx& c, int ch_total, const float
   const float inv = 1.0f / (float)ch_total;
   const float m = ts * inv;
   const float r = rsqrtf(fmaxf(tq * inv - m * m, 0.f) + 1e-5f);
-  c.scr[c.lane] = m;
+  c.scr[c.lane] = -m;           // callers apply v * (rstd * g) + (-mean) * (rstd * g)
   c.scr[32 + c.lane] = r;
   __syncwarp();
 #pragma unroll
@@ -526,6 +553,18 @@ __device__ __forceinline__ void ln_stats(const Ctx& c, int ch_total, const float
   wg_sync(c.g);     // xch / scr reusable
 }
 
+// v = (v - mean) * rstd * g as one packed FMA per value pair
+__device__ __forceinline__ void ln_apply(const Ctx& c, int ch_total, float g, float (&v)[32]) {
+  float mr[32], rs[32];
+  ln_stats(c, ch_total, v, mr, rs);
+  const float2 g2 = bc2(g);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 A = __fmul2_rn(ld2(rs, i), g2);
+    st2(v, i, __ffma2_rn(ld2(v, i), A, __fmul2_rn(ld2(mr, i), A)));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -535,7 +574,8 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
   using T = Tr<L, NSETS>;
   constexpr int NS = T::NS, EMB = T::EMB, STAGES = T::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic (no integer round trip) keeps the shared address space visible to the compiler: LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::SM_BAR);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + 4;            // [STAGES]
@@ -987,6 +1027,9 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
 #pragma unroll 1
             for (int t = 0; t < nt; ++t) {
               const bool valid = t * 128 + c.ch < ch;
+              // a warp whose 32 channels all lie beyond the layer width has nothing to contribute unless the epilogue
+              // has a warp-group wide reduction (LayerNorm, final conv)
+              if (t * 128 + c.q * 32 >= ch && !(flags & (E_LN | E_LNNEXT | E_FINAL))) continue;
               const float bias = t ? pbias[1] : pbias[0], gam = t ? pgam[1] : pgam[0], bet = t ? pbet[1] : pbet[0];
               const float cs = t ? pcs[1] : pcs[0], chh = t ? pch[1] : pch[0], g1 = t ? pg[1] : pg[0], g2 = t ? pg2[1] : pg2[0];
               uint32_t rv[32], rr[32], rs8[8], rh8[8];
@@ -999,8 +1042,11 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
               tm_wait();
               float v[32];
               tm_use(rv, v);
+              {
+                const float2 b2 = bc2(bias);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += bias;
+                for (int i = 0; i < 16; ++i) st2(v, i, __fadd2_rn(ld2(v, i), b2));
+              }
               if (flags & E_GN) {
                 float mean[8], rstd[8];
                 gn_stats_dispatch<L>(c, ch, v, mean, rstd);
@@ -1013,33 +1059,42 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
                     fh[0] = c.g ? fh[2] : fh[0]; fh[1] = c.g ? fh[3] : fh[1];
                   }
                 }
+                // GroupNorm affine and FiLM folded into one multiply-add per value: v * A + B
+                float A[NSW], Bc[NSW];
 #pragma unroll
                 for (int jj = 0; jj < NSW; ++jj) {
-                  const float a = rstd[jj] * gam, b = bet - mean[jj] * a;
+                  const float a = rstd[jj] * gam, b = fmaf(-mean[jj], a, bet);
                   const float sc = (flags & E_FILM) ? fs[jj] + cs : 1.f, sh = (flags & E_FILM) ? fh[jj] + chh : 0.f;
+                  A[jj] = a * sc;
+                  Bc[jj] = fmaf(b, sc, sh);
+                }
+                if (L == 4) {
 #pragma unroll
-                  for (int l = 0; l < L; ++l) {
-                    const int i = (L == 4) ? l * 8 + jj : jj * 16 + l;
-                    v[i] = fmaf(fmaf(v[i], a, b), sc, sh);
+                  for (int jp = 0; jp < 4; ++jp) {
+                    const float2 A2 = make_float2(A[2 * jp], A[2 * jp + 1]), B2 = make_float2(Bc[2 * jp], Bc[2 * jp + 1]);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) st2(v, l * 4 + jp, __ffma2_rn(ld2(v, l * 4 + jp), A2, B2));
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 2; ++jj) {
+                    const float2 A2 = bc2(A[jj]), B2 = bc2(Bc[jj]);
+#pragma unroll
+                    for (int lp = 0; lp < 8; ++lp) st2(v, jj * 8 + lp, __ffma2_rn(ld2(v, jj * 8 + lp), A2, B2));
                   }
                 }
               }
               if (flags & E_SILU) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+                for (int i = 0; i < 16; ++i) st2(v, i, silu_fast2(ld2(v, i)));
               }
-              if (flags & E_LN) {
-                float mr[32], rs[32];
-                ln_stats(c, ch, v, mr, rs);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g1;
-              }
+              if (flags & E_LN) ln_apply(c, ch, g1, v);
               if (flags & E_ADDRES) {
                 if (t == 0) {
                   float res[32];
                   tm_use(rr, res);
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] += res[i];
+                  for (int i = 0; i < 16; ++i) st2(v, i, __fadd2_rn(ld2(v, i), ld2(res, i)));
                 } else {               // channels 128..255 (final block only): bf16 copy in shared memory
 #pragma unroll
                   for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(s_res1[i * 256 + tid]);
@@ -1057,15 +1112,10 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
                   for (int i = 0; i < 32; ++i) s_res1[i * 256 + tid] = __float2bfloat16(v[i]);
                 }
               }
-              if (flags & E_LNNEXT) {
-                float mr[32], rs[32];
-                ln_stats(c, ch, v, mr, rs);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = (v[i] - mr[i]) * rs[i] * g2;
-              }
+              if (flags & E_LNNEXT) ln_apply(c, ch, g2, v);
               if (flags & E_FINAL) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) fc_part[i] = fmaf(g2, v[i], fc_part[i]);
+                for (int i = 0; i < 16; ++i) st2(fc_part, i, __ffma2_rn(bc2(g2), ld2(v, i), ld2(fc_part, i)));
               } else {
                 write_b<L>(c, t, v, valid);
               }
