@@ -67,6 +67,12 @@ _SIGS = {
     "gldm_conv3d_tc_pack_weight": [P, c_int, c_int, P, P],
     "gldm_conv3d_k3_tc": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "gldm_decoder_forward_tc": [POINTER(GldmResNetCfg), P, P, P, c_int, P, P, c_int, c_int, P, P, P],
+    "gldm_cl_pad": [P, c_int, c_int, c_int, P, P],
+    "gldm_conv3d_k3_f32_cl": [P, P, P, c_int, c_int, c_int, P, c_int, P, P],
+    "gldm_conv3d_tc_cl": [P, P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P],
+    "gldm_gn_swish_cl": [P, c_int, c_int, P, P, P, c_int, c_int, c_int, c_float, P, P],
+    "gldm_se_gate_sum": [P, c_int, P, P, c_int, c_int, c_int, P, P],
+    "gldm_devox_cl": [P, P, c_int, c_int, P, P, c_int, c_int, c_int, c_int, P, P],
     "gldm_pose_postprocess": [P, P, P, P, c_int, P, P, P, P],
     "gldm_pose_postprocess_rows": [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "gldm_normalize_clouds": [P, P, P, P, c_int, c_int, P, P, P, P],

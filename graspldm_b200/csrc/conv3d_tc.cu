@@ -7,7 +7,10 @@
 // 2-D TMA tensor load fetches (SWIZZLE_128B, out-of-range rows read as zero) - no im2col buffer.  The weights are
 // pre-packed UMMA images [tap][K block][128 rows x 128 B] streamed with 1-D bulk copies.  One CTA = 128 padded voxels
 // x all output channels (UMMA M = 128, N = C_out <= 128): warp 0 producer, warp 1 UMMA issuer, warps 2-5 epilogue
-// (bias, drop halo voxels, fp32 store into the reference's [b, c, r^3] layout for GroupNorm / SE / devoxelize).
+// (bias, drop halo voxels).  Two output forms: fp32 in the reference's [b, c, r^3] layout, or - for the fused voxel
+// branch - the same zero-padded channels-last grid the next Conv3d reads (bf16, or fp32 for the devoxelize input)
+// together with the GroupNorm statistics of the result (fp64 atomics per (cloud, group)), so that GroupNorm + Swish
+// becomes one in-place pass (gn_swish_cl_kernel) and devoxelize gathers channels-last rows (devox_cl_kernel).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,6 +34,11 @@ struct Conv3dTcParams {
   int r, co, k_blocks, ksteps_last;   // K blocks of 64 channels per tap; UMMAs (1..4) in the last block
   long long rows;          // b * (r+2)^3
   int w_rows_bytes;        // bytes of a weight block actually needed (co rounded up to 8 rows x 128 B)
+  // channels-last output (out_mode 1: bf16, 2: fp32; 0: the fp32 [b, co, r^3] layout above)
+  int out_mode, out_stride;   // elements per output row (multiple of 16, >= co; channels >= co are written as zero)
+  void* y_cl;                 // [rows][out_stride]; halo rows are never written (they must be zero on entry)
+  double* stats;              // [b][8][2]: sum, sum of squares per GroupNorm group (8 groups), accumulated
+  int batch;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -124,15 +132,74 @@ __global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    if (p.out_mode == 0) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.co; c0 += 16) {
-      uint32_t u[16];
-      tmem_ld16(taddr + c0, u);
-      tmem_ld_wait();
-      if (interior) {
+      for (int c0 = 0; c0 < p.co; c0 += 16) {
+        uint32_t u[16];
+        tmem_ld16(taddr + c0, u);
+        tmem_ld_wait();
+        if (interior) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+        }
+      }
+    } else {
+      // channels-last row of this voxel + GroupNorm partial sums.  The pipeline stages are idle once acc_full fired:
+      // their memory holds the per-thread group partials [128][17].
+      float* part = reinterpret_cast<float*>(smem) + (tid - 64) * 17;
+      const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
+      float gs = 0.f, gq = 0.f;
+      int g = 0, in_g = 0;
+      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
+        float v[16];
+        if (c0 < n_umma) {
+          uint32_t u[16];
+          tmem_ld16(taddr + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < p.co) {
+            gs += v[j];
+            gq = fmaf(v[j], v[j], gq);
+            if (++in_g == cpg) { part[g] = gs; part[8 + g] = gq; ++g; in_g = 0; gs = 0.f; gq = 0.f; }
+          }
+        }
+        if (interior) {
+          if (p.out_mode == 1) {
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
+            dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+        }
+      }
+      __syncwarp();
+      // warp totals of the 16 partials (32 voxels), one fp64 atomic per (group, moment); a warp can straddle two clouds
+      const long long b_last = min(b, (long long)p.batch - 1);
+      const int b_lo = (int)__shfl_sync(0xffffffffu, (int)b_last, 0), b_hi = (int)__shfl_sync(0xffffffffu, (int)b_last, 31);
+      for (int bb = b_lo; bb <= b_hi; ++bb) {
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = (interior && b == bb) ? part[i] : 0.f;
+        rs_step<16, 8>(a, lane); rs_step<8, 4>(a, lane); rs_step<4, 2>(a, lane); rs_step<2, 1>(a, lane);
+        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+        if ((lane & 1) == 0) {
+          const int idx = lane >> 1;       // 0..7: sums of groups 0..7, 8..15: sums of squares
+          atomicAdd(p.stats + ((size_t)bb * 8 + (idx & 7)) * 2 + (idx >> 3), (double)a[0]);
+        }
       }
     }
     tc_fence_before();
@@ -165,6 +232,172 @@ __global__ void __launch_bounds__(256) cl_pad_kernel(const float* __restrict__ x
   }
   *reinterpret_cast<uint4*>(out + (size_t)m * cpad + chunk * 8) =
       make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// GroupNorm(8) + Swish in place on the interior rows of a channels-last padded grid, from the statistics the Conv3d
+// epilogue accumulated (R/../pvcnn/modules/pvconv.py:52-57); optionally the per-channel sums of the result for the
+// SE squeeze (se.py:18-19).  Thread <-> (row lane, 8 channels); a block covers `rpb` padded voxels of one cloud.
+template <bool F32>
+__global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int c, int stride, int r, float eps, double* __restrict__ se_sum,
+                                                          int rpb) {
+  __shared__ float s_red[2048];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int nchunk = stride >> 3, rl = 256 / nchunk;
+  const int chunk = tid % nchunk, rsub = tid / nchunk;
+  const int rp = r + 2, rp2 = rp * rp, P = rp2 * rp, cpg = c >> 3;
+  const double cnt = (double)cpg * r * r * r;
+  float A[8], B[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = chunk * 8 + j;
+    A[j] = 0.f; B[j] = 0.f; acc[j] = 0.f;
+    if (ch < c) {
+      const double* st = stats + ((size_t)b * 8 + ch / cpg) * 2;
+      const double mean = st[0] / cnt;
+      const double var = fmax(st[1] / cnt - mean * mean, 0.0);
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      A[j] = __ldg(gamma + ch) * rstd;
+      B[j] = __ldg(beta + ch) - (float)mean * A[j];
+    }
+  }
+  const bool active = rsub < rl;        // 256 is not a multiple of every chunk count (6, 12 chunks for fp32 rows)
+  const int p_end = active ? min(P, (int)(blockIdx.x + 1) * rpb) : 0;
+  for (int pp = blockIdx.x * rpb + rsub; pp < p_end; pp += rl) {
+    const int x = pp / rp2, yy = (pp / rp) % rp, z = pp % rp;
+    if (x < 1 || x > r || yy < 1 || yy > r || z < 1 || z > r) continue;
+    float v[8];
+    if (F32) {
+      float4* ptr = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ((size_t)b * P + pp) * stride + chunk * 8);
+      const float4 lo = ptr[0], hi = ptr[1];
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(v[j], A[j], B[j]);
+        v[j] = t * (1.0f / (1.0f + expf(-t)));
+        acc[j] += v[j];
+      }
+      ptr[0] = make_float4(v[0], v[1], v[2], v[3]);
+      ptr[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4* ptr = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + ((size_t)b * P + pp) * stride + chunk * 8);
+      const uint4 raw = *ptr;
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[2 * k] = __low2float(h);
+        v[2 * k + 1] = __high2float(h);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(v[j], A[j], B[j]);
+        v[j] = t * (1.0f / (1.0f + expf(-t)));
+        acc[j] += v[j];
+      }
+      *ptr = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+  }
+  if (se_sum) {
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[rsub * stride + chunk * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < c) {
+      float t = 0.f;
+      for (int k = 0; k < rl; ++k) t += s_red[k * stride + tid];
+      atomicAdd(se_sum + (size_t)b * c + tid, (double)t);
+    }
+  }
+}
+
+// SE excite from channel sums: gate = sigmoid(W2 swish(W1 (sum * inv_count)))   (se.py:10-21); one block per cloud
+__global__ void __launch_bounds__(128) se_gate_sum_kernel(const double* __restrict__ sum, float inv_count,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2, int c,
+                                                          int cr, float* __restrict__ gate) {
+  extern __shared__ float s_se[];   // [c] means, [cr] hidden
+  float* s_m = s_se;
+  float* s_h = s_se + c;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < c; k += blockDim.x) s_m[k] = (float)(sum[(size_t)b * c + k] * (double)inv_count);
+  __syncthreads();
+  for (int j = threadIdx.x; j < cr; j += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < c; ++k) a = fmaf(w1[j * c + k], s_m[k], a);
+    s_h[j] = a * (1.0f / (1.0f + expf(-a)));
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < c; o += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < cr; ++k) a = fmaf(w2[o * cr + k], s_h[k], a);
+    gate[(size_t)b * c + o] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// trilinear devoxelize of (grid * gate) + point branch from a channels-last padded grid
+// (R/../pvcnn/modules/functional/src/trilinear_devox/trilinear_devox.cu:20-84 for the corner weights / indices).
+// Thread <-> (point, 8 channels): each corner is one 16- or 32-byte row segment.
+template <bool F32>
+__global__ void __launch_bounds__(128) devox_cl_kernel(const float* __restrict__ coords, const void* __restrict__ grid,
+                                                       const float* __restrict__ gate, const float* __restrict__ point,
+                                                       int c, int stride, int n, int r, float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int rp = r + 2, rp2 = rp * rp, P = rp2 * rp;
+  const float* cb = coords + (size_t)b * 3 * n;
+  const float x = cb[i], y = cb[i + n], z = cb[i + 2 * n];
+  const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+  const float xd1 = x - xl, yd1 = y - yl, zd1 = z - zl;
+  const float xd0 = 1.0f - xd1, yd0 = 1.0f - yd1, zd0 = 1.0f - zd1;
+  float wgt[8];
+  wgt[0] = __fmul_rn(__fmul_rn(xd0, yd0), zd0); wgt[1] = __fmul_rn(__fmul_rn(xd0, yd0), zd1);
+  wgt[2] = __fmul_rn(__fmul_rn(xd0, yd1), zd0); wgt[3] = __fmul_rn(__fmul_rn(xd0, yd1), zd1);
+  wgt[4] = __fmul_rn(__fmul_rn(xd1, yd0), zd0); wgt[5] = __fmul_rn(__fmul_rn(xd1, yd0), zd1);
+  wgt[6] = __fmul_rn(__fmul_rn(xd1, yd1), zd0); wgt[7] = __fmul_rn(__fmul_rn(xd1, yd1), zd1);
+  const int xh = xd1 > 0 ? rp2 : 0, yh = yd1 > 0 ? rp : 0, zh = zd1 > 0 ? 1 : 0;
+  int id[8];
+  id[0] = ((int)xl + 1) * rp2 + ((int)yl + 1) * rp + ((int)zl + 1);
+  id[1] = id[0] + zh; id[2] = id[0] + yh; id[3] = id[2] + zh;
+  id[4] = id[0] + xh; id[5] = id[4] + zh; id[6] = id[4] + yh; id[7] = id[6] + zh;
+  const int c0 = blockIdx.y * 8;
+  float g[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = (gate && c0 + j < c) ? __ldg(gate + (size_t)b * c + c0 + j) : 1.f;
+  const int order[8] = {1, 0, 2, 3, 4, 5, 6, 7};     // accumulation order of the fp32 kernel (devox_gate_add_kernel)
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int k = order[kk];
+    float f[8];
+    if (F32) {
+      const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grid) + ((size_t)b * P + id[k]) * stride + c0);
+      const float4 lo = __ldg(ptr), hi = __ldg(ptr + 1);
+      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+    } else {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(grid) + ((size_t)b * P + id[k]) * stride + c0));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+        f[2 * q] = __low2float(h);
+        f[2 * q + 1] = __high2float(h);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = __fmul_rn(f[j], g[j]);
+      acc[j] = kk == 0 ? __fmul_rn(wgt[k], t) : __fmaf_rn(wgt[k], t, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (c0 + j < c) {
+      const size_t o = ((size_t)b * c + c0 + j) * n + i;
+      out[o] = acc[j] + (point ? point[o] : 0.f);
+    }
+  }
 }
 
 // Conv3d weight fp32 [co][ci][27] -> images [27][k_blocks][128 rows x 128 B] (rows = output channels)
@@ -220,19 +453,10 @@ extern "C" int gldm_conv3d_tc_pack_weight(const float* w, int co, int ci, void* 
   return check_launch("conv3d_weight_image_kernel");
 }
 
-/* x f32[b,ci,r^3] -> y f32[b,co,r^3]; scratch: gldm_conv3d_tc_grid_bytes(b, ci, r) bytes (256-byte aligned) */
-extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r,
-                                 void* scratch, float* y, void* stream) {
-  GLDM_REQUIRE(x && w_img && y && scratch, "conv3d_k3_tc: null pointer");
-  GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_k3_tc: need 16 <= ci, co <= 128");
-  if (b == 0) return GLDM_OK;
-  cudaStream_t s = (cudaStream_t)stream;
+static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias, int b, int ci, int co, int r, float* y,
+                         int out_mode, int out_stride, void* y_cl, double* stats, cudaStream_t s) {
   const int cpad = ((ci + 63) / 64) * 64, kb = cpad / 64;
   const long long P = (long long)(r + 2) * (r + 2) * (r + 2), rows = (long long)b * P;
-  cl_pad_kernel<<<dim3((unsigned)((rows + 255) / 256), cpad / 8), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(scratch), ci,
-                                                                               cpad, r, rows);
-  int rc = check_launch("cl_pad_kernel");
-  if (rc) return rc;
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("conv3d_k3_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -243,7 +467,7 @@ extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float*
   const cuuint64_t gstride[1] = {(cuuint64_t)cpad * 2};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scratch, gdim, gstride, box, estr,
+  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_cl), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
@@ -257,6 +481,7 @@ extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float*
   p.ksteps_last = (last_valid + 15) / 16;
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
+  p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b;
   static bool attr = false;
   const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 256;
   const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 256;
@@ -269,4 +494,80 @@ extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float*
   if (p.w_rows_bytes <= c3::W_SLOT) conv3d_tc_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem_small, s>>>(map, p);
   else conv3d_tc_kernel<c3::W_BYTES><<<grid, c3::NTHREADS, smem_big, s>>>(map, p);
   return check_launch("conv3d_tc_kernel");
+}
+
+static int launch_cl_pad(const float* x, int b, int c, int r, void* out, cudaStream_t s) {
+  const int cpad = ((c + 63) / 64) * 64;
+  const long long P = (long long)(r + 2) * (r + 2) * (r + 2), rows = (long long)b * P;
+  cl_pad_kernel<<<dim3((unsigned)((rows + 255) / 256), cpad / 8), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(out), c, cpad,
+                                                                               r, rows);
+  return check_launch("cl_pad_kernel");
+}
+
+/* x f32[b,ci,r^3] -> y f32[b,co,r^3]; scratch: gldm_conv3d_tc_grid_bytes(b, ci, r) bytes (256-byte aligned) */
+extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r,
+                                 void* scratch, float* y, void* stream) {
+  GLDM_REQUIRE(x && w_img && y && scratch, "conv3d_k3_tc: null pointer");
+  GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_k3_tc: need 16 <= ci, co <= 128");
+  if (b == 0) return GLDM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_cl_pad(x, b, ci, r, scratch, s);
+  if (rc) return rc;
+  return launch_conv3d(scratch, w_img, bias, b, ci, co, r, y, 0, 0, nullptr, nullptr, s);
+}
+
+extern "C" int gldm_cl_pad(const float* x, int b, int c, int r, void* out_cl, void* stream) {
+  GLDM_REQUIRE(x && out_cl, "cl_pad: null pointer");
+  GLDM_REQUIRE(b >= 0 && c > 0 && r > 0, "cl_pad: bad sizes");
+  if (b == 0) return GLDM_OK;
+  return launch_cl_pad(x, b, c, r, out_cl, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const float* bias, int b, int ci, int co, int r,
+                                 void* y_cl, int out_fp32, int out_stride, double* stats, void* stream) {
+  GLDM_REQUIRE(x_cl && w_img && y_cl && stats, "conv3d_tc_cl: null pointer");
+  GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_tc_cl: need 16 <= ci, co <= 128");
+  GLDM_REQUIRE(co % 8 == 0, "conv3d_tc_cl: GroupNorm(8) statistics need co % 8 == 0");
+  GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc_cl: out_stride must be a multiple of 16 in [co, 128]");
+  if (b == 0) return GLDM_OK;
+  return launch_conv3d(x_cl, w_img, bias, b, ci, co, r, nullptr, out_fp32 ? 2 : 1, out_stride, y_cl, stats,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const double* stats, const float* gamma,
+                                const float* beta, int b, int c, int r, float eps, double* se_sum, void* stream) {
+  GLDM_REQUIRE(y_cl && stats && gamma && beta, "gn_swish_cl: null pointer");
+  GLDM_REQUIRE(b >= 0 && c > 0 && c % 8 == 0 && c <= 128 && r > 0, "gn_swish_cl: bad sizes");
+  GLDM_REQUIRE(stride >= c && stride % 8 == 0 && stride <= 128, "gn_swish_cl: bad row stride");
+  if (b == 0) return GLDM_OK;
+  const int P = (r + 2) * (r + 2) * (r + 2);
+  int rpb = 1024;                                  // padded voxels per block: keep >= 4 blocks per SM in flight
+  while (rpb > 128 && (long long)((P + rpb - 1) / rpb) * b < 592) rpb >>= 1;
+  dim3 grid((P + rpb - 1) / rpb, b);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (is_fp32) gn_swish_cl_kernel<true><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, se_sum, rpb);
+  else gn_swish_cl_kernel<false><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, se_sum, rpb);
+  return check_launch("gn_swish_cl_kernel");
+}
+
+extern "C" int gldm_se_gate_sum(const double* sum, int count, const float* w1, const float* w2, int b, int c, int cr,
+                                float* gate, void* stream) {
+  GLDM_REQUIRE(sum && w1 && w2 && gate, "se_gate_sum: null pointer");
+  GLDM_REQUIRE(b >= 0 && c > 0 && cr > 0 && count > 0, "se_gate_sum: bad sizes");
+  if (b == 0) return GLDM_OK;
+  se_gate_sum_kernel<<<b, 128, sizeof(float) * (c + cr), (cudaStream_t)stream>>>(sum, 1.0f / (float)count, w1, w2, c, cr, gate);
+  return check_launch("se_gate_sum_kernel");
+}
+
+extern "C" int gldm_devox_cl(const float* coords, const void* grid_cl, int is_fp32, int stride, const float* gate,
+                             const float* point, int b, int c, int n, int r, float* out, void* stream) {
+  GLDM_REQUIRE(coords && grid_cl && out, "devox_cl: null pointer");
+  GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "devox_cl: bad sizes");
+  GLDM_REQUIRE(stride % 8 == 0 && stride >= ((c + 7) / 8) * 8, "devox_cl: bad row stride");
+  if (b == 0) return GLDM_OK;
+  dim3 g(ceil_div(n, 128), ceil_div(c, 8), b);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (is_fp32) devox_cl_kernel<true><<<g, 128, 0, s>>>(coords, grid_cl, gate, point, c, stride, n, r, out);
+  else devox_cl_kernel<false><<<g, 128, 0, s>>>(coords, grid_cl, gate, point, c, stride, n, r, out);
+  return check_launch("devox_cl_kernel");
 }

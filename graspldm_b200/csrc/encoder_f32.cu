@@ -8,6 +8,8 @@
 //   SE excite                                         se.py:14-19
 //   trilinear devoxelize x gate + point branch        pvconv.py:79-83, trilinear_devox.cu:21-105
 //   Linear over the point axis                        pc_encoders.py:76-79
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gldm {
@@ -168,10 +170,15 @@ __global__ void __launch_bounds__(256) pw_small_co_kernel(const float* __restric
 // Conv3d k3 p1: implicit GEMM, tile = 256 consecutive voxels x 48 output channels, one input channel
 // (27 taps) staged per iteration.  w is pre-permuted to [ci][27][co].
 // ------------------------------------------------------------------------------------------------
+// CL = true (fused voxel branch, co == 48, GroupNorm(8)): the result goes to the zero-padded channels-last bf16 grid
+// [b * (r+2)^3][y_stride] the tensor-core Conv3d reads, and the GroupNorm statistics are accumulated on the way (a warp
+// owns exactly the 6 channels of one group): stats f64[b][8][2] += (sum, sum of squares).
 constexpr int C3_VT = 256, C3_CT = 48;
+template <bool CL>
 __global__ void __launch_bounds__(256) conv3d_k3_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int ci, int co, int r,
-                                                        float* __restrict__ y) {
+                                                        float* __restrict__ y, __nv_bfloat16* __restrict__ y_cl,
+                                                        int y_stride, double* __restrict__ stats) {
   __shared__ __align__(16) float As[27][C3_VT];
   __shared__ __align__(16) float Ws[27][C3_CT];
   const int b = blockIdx.z, co0 = blockIdx.y * C3_CT, v0 = blockIdx.x * C3_VT;
@@ -220,6 +227,38 @@ __global__ void __launch_bounds__(256) conv3d_k3_kernel(const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
+  }
+  if (CL) {
+    const int rp = r + 2;
+    float gs = 0.f, gq = 0.f;
+    float bz[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bz[j] = bias ? __ldg(bias + cg * 6 + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = v0 + (i >> 2) * 128 + vg * 4 + (i & 3);
+      if (v >= r3) continue;
+      const int vx = v / r2, vy = (v / r) % r, vz = v % r;
+      float o[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        o[j] = acc[i][j] + bz[j];
+        gs += o[j];
+        gq = fmaf(o[j], o[j], gq);
+      }
+      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(
+          y_cl + ((size_t)b * rp * rp * rp + ((size_t)(vx + 1) * rp + (vy + 1)) * rp + (vz + 1)) * y_stride + cg * 6);
+      dst[0] = __floats2bfloat162_rn(o[0], o[1]);
+      dst[1] = __floats2bfloat162_rn(o[2], o[3]);
+      dst[2] = __floats2bfloat162_rn(o[4], o[5]);
+    }
+    gs = warp_sum(gs);
+    gq = warp_sum(gq);
+    if (vg == 0) {
+      atomicAdd(stats + ((size_t)b * 8 + cg) * 2, (double)gs);
+      atomicAdd(stats + ((size_t)b * 8 + cg) * 2 + 1, (double)gq);
+    }
+    return;
   }
   float* yb = y + (size_t)b * co * r3;
 #pragma unroll
@@ -402,7 +441,19 @@ extern "C" int gldm_conv3d_k3_f32(const float* x, const float* w, const float* b
   GLDM_REQUIRE(b >= 0 && ci > 0 && co > 0 && r > 0, "conv3d_k3_f32: bad sizes");
   if (b == 0) return GLDM_OK;
   dim3 grid(ceil_div(r * r * r, C3_VT), ceil_div(co, C3_CT), b);
-  conv3d_k3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, ci, co, r, y);
+  conv3d_k3_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, ci, co, r, y, nullptr, 0, nullptr);
+  return check_launch("conv3d_k3_kernel");
+}
+
+extern "C" int gldm_conv3d_k3_f32_cl(const float* x, const float* w, const float* bias, int b, int ci, int r, void* y_cl,
+                                     int y_stride, double* stats, void* stream) {
+  GLDM_REQUIRE(x && w && y_cl && stats, "conv3d_k3_f32_cl: null pointer");
+  GLDM_REQUIRE(b >= 0 && ci > 0 && r > 0, "conv3d_k3_f32_cl: bad sizes");
+  GLDM_REQUIRE(y_stride >= C3_CT && y_stride % 8 == 0, "conv3d_k3_f32_cl: bad row stride");
+  if (b == 0) return GLDM_OK;
+  dim3 grid(ceil_div(r * r * r, C3_VT), 1, b);
+  conv3d_k3_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, ci, C3_CT, r, nullptr,
+                                                                 reinterpret_cast<__nv_bfloat16*>(y_cl), y_stride, stats);
   return check_launch("conv3d_k3_kernel");
 }
 

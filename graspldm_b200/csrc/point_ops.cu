@@ -260,14 +260,18 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
   short* s_tail = reinterpret_cast<short*>(s_cnt + ((r3 + 1) & ~1));
   short* s_next = s_tail + ((r3 + 1) & ~1);
   int* s_vox = reinterpret_cast<int*>(s_next + ((n + 1) & ~1));
-  const float* fb = feat + (size_t)b * c * n;
-  float* ob = out + (size_t)b * c * r3;
+  // blockIdx.y owns a slice of the channels (the point binning is cheap and repeated per slice); slice 0 also writes
+  // the per-point / per-voxel side outputs
+  const int cs = (c + gridDim.y - 1) / gridDim.y, ch_lo = blockIdx.y * cs, ch_n = max(0, min(c, ch_lo + cs) - ch_lo);
+  const bool side = blockIdx.y == 0;
+  const float* fb = feat + ((size_t)b * c + ch_lo) * n;
+  float* ob = out + ((size_t)b * c + ch_lo) * r3;
 
   for (int i = tid; i < r3; i += nthreads) { s_cnt[i] = 0; s_tail[i] = -1; }
   for (int i = tid; i < n; i += nthreads) s_next[i] = -1;
   // zero the output grid (the reference relies on torch::zeros); 128-bit stores when aligned
   {
-    size_t tot = (size_t)c * r3;
+    size_t tot = (size_t)ch_n * r3;
     if ((tot & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       for (size_t i = tid; i < tot / 4; i += nthreads) reinterpret_cast<float4*>(ob)[i] = z;
@@ -309,9 +313,9 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
         float x = __fsub_rn(cf[i + a * n], s_mean[a]);
         x = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);               // (x + 1) / 2.0
         x = fminf(fmaxf(__fmul_rn(x, rf), 0.f), hi);             // clamp(x * r, 0, r-1)
-        norm_out[((size_t)b * 3 + a) * n + i] = x;
+        if (side) norm_out[((size_t)b * 3 + a) * n + i] = x;
         v3[a] = (int)rintf(x);                                   // torch.round: half to even
-        if (vox_out) vox_out[((size_t)b * 3 + a) * n + i] = v3[a];
+        if (vox_out && side) vox_out[((size_t)b * 3 + a) * n + i] = v3[a];
       }
       s_vox[i] = v3[0] * r2 + v3[1] * r + v3[2];
     }
@@ -345,9 +349,9 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
       __syncthreads();
     }
   }
-  if (ind_out)
+  if (ind_out && side)
     for (int i = tid; i < n; i += nthreads) ind_out[(size_t)b * n + i] = s_vox[i];
-  if (cnt_out)
+  if (cnt_out && side)
     for (int i = tid; i < r3; i += nthreads) cnt_out[(size_t)b * r3 + i] = s_cnt[i];
   __syncthreads();
   // Phase C: item (ch, i) with i a list head (the first point of its voxel, i.e. no point links to it).
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
     if (nx >= 0) atomicOr(&s_vox[nx], 0x40000000);               // successor is not a head
   }
   __syncthreads();
-  const int items = c * n;
+  const int items = ch_n * n;
   for (int it = tid; it < items; it += nthreads) {
     const int ch = it / n, i = it - ch * n;
     const int vv = s_vox[i];
@@ -597,20 +601,21 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   const size_t r3 = (size_t)r * r * r;
   size_t smem = 2 * ((r3 + 1) & ~(size_t)1) * 2 + (((size_t)n + 1) & ~(size_t)1) * 2 + (size_t)n * 4;
   int threads = min(512, ceil_div(n, 32) * 32);
+  const int slices = min(8, ceil_div(c, 8));      // channel slices per cloud: more CTAs than clouds for wide features
   if (fused) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(voxelize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
     }
-    voxelize_kernel<true><<<b, threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
+    voxelize_kernel<true><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
   } else {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(voxelize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
     }
-    voxelize_kernel<false><<<b, threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
+    voxelize_kernel<false><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
   }
   return check_launch("voxelize_kernel");
 }

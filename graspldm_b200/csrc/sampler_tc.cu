@@ -285,17 +285,6 @@ __device__ __forceinline__ float2 silu_fast2(float2 x) {
 
 __device__ __forceinline__ void wg_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-// reduce-scatter step: NOUT pairs (i, i + NOUT); lanes with bit `OFF` set keep the upper element
-template <int OFF, int NOUT, int NV>
-__device__ __forceinline__ void rs_step(float (&a)[NV], int lane) {
-  const bool hi = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < NOUT; ++i) {
-    const float send = hi ? a[i] : a[i + NOUT];
-    const float keep = hi ? a[i + NOUT] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-  }
-}
 // sum of a[idx] over the 32 lanes lands in lane idx (a[0])
 __device__ __forceinline__ float reduce_scatter32(float (&a)[32], int lane) {
   rs_step<16, 16>(a, lane);

@@ -234,5 +234,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// reduce-scatter step: NOUT pairs (i, i + NOUT); lanes with bit `OFF` set keep the upper element
+template <int OFF, int NOUT, int NV>
+__device__ __forceinline__ void rs_step(float (&a)[NV], int lane) {
+  const bool hi = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < NOUT; ++i) {
+    const float send = hi ? a[i] : a[i + NOUT];
+    const float keep = hi ? a[i + NOUT] : a[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+
 }  // namespace tc
 }  // namespace gldm

@@ -498,6 +498,71 @@ def encoder_forward(enc, xyz, max_clouds_per_pass=256, precision="fp32"):
     return out.squeeze(1) if out.shape[-2] == 1 else out
 
 
+def _cl_grid(pk, dev, tag, rows, stride, dtype):
+    """Zero-initialised padded channels-last grid, cached per (stream, shape): the kernels never write halo rows, so the
+    zeros survive from call to call; the stream key keeps concurrently running passes (bench --streams) apart."""
+    cache = pk.__dict__.setdefault("_cl_cache", {})
+    key = (tag, torch.cuda.current_stream(dev).cuda_stream, dev.index, rows, stride, dtype)
+    buf = cache.get(key)
+    if buf is None:
+        buf = torch.zeros((rows, stride), device=dev, dtype=dtype)
+        assert buf.data_ptr() % 256 == 0
+        cache[key] = buf
+    return buf
+
+
+def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
+    """Voxel branch of one PVConv on the fused channels-last path: voxelize -> Conv3d -> GN+Swish -> Conv3d -> GN+Swish
+    (+SE squeeze) -> SE gate -> devoxelize(+ point branch).  Returns the fused point features [B, co, N]."""
+    r, ci, co = blk["r"], blk["cin"], blk["cout"]
+    assert blk["groups"] == 8 and co % 8 == 0
+    w1_img, w2_img = pk.tc_conv_weights()[bi]
+    r3, P = r ** 3, (r + 2) ** 3
+    rows = B * P
+    grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
+    norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
+    _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(), norm.data_ptr(),
+              None, st)
+    stats = torch.zeros((2, B, 8, 2), device=dev, dtype=torch.float64)
+    se_sum = torch.zeros((B, co), device=dev, dtype=torch.float64)
+    cpad_o = -(-co // 64) * 64
+    if w1_img is not None:
+        x_cl = _cl_grid(pk, dev, ("x", bi), rows, -(-ci // 64) * 64, torch.bfloat16)
+        _lib.call("gldm_cl_pad", grid.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
+        y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
+        _lib.call("gldm_conv3d_tc_cl", x_cl.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r, y1.data_ptr(),
+                  0, cpad_o, stats[0].data_ptr(), st)
+        _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
+                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, st)
+    elif co == 48:       # 3-channel input: strict-fp32 SIMT Conv3d straight into the channels-last form + statistics
+        y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
+        _lib.call("gldm_conv3d_k3_f32_cl", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, r,
+                  y1.data_ptr(), cpad_o, stats[0].data_ptr(), st)
+        _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
+                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, st)
+    else:
+        t = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
+        _lib.call("gldm_conv3d_k3_f32", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, co, r,
+                  t.data_ptr(), st)
+        _lib.call("gldm_groupnorm_swish_f32", t.data_ptr(), blk["g1w"].data_ptr(), blk["g1b"].data_ptr(), B, co, r3,
+                  blk["groups"], blk["eps1"], None, st)
+        y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
+        _lib.call("gldm_cl_pad", t.data_ptr(), B, co, r, y1.data_ptr(), st)
+    y2 = _cl_grid(pk, dev, ("y2", bi), rows, co, torch.float32)
+    _lib.call("gldm_conv3d_tc_cl", y1.data_ptr(), w2_img.data_ptr(), blk["b2"].data_ptr(), B, co, co, r, y2.data_ptr(), 1, co,
+              stats[1].data_ptr(), st)
+    _lib.call("gldm_gn_swish_cl", y2.data_ptr(), 1, co, stats[1].data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(),
+              B, co, r, blk["eps2"], se_sum.data_ptr(), st)
+    gate = torch.empty((B, co), device=dev, dtype=torch.float32)
+    _lib.call("gldm_se_gate_sum", se_sum.data_ptr(), r3, blk["se1"].data_ptr(), blk["se2"].data_ptr(), B, co,
+              blk["se1"].shape[0], gate.data_ptr(), st)
+    pt = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
+    fused = torch.empty((B, co, N), device=dev, dtype=torch.float32)
+    _lib.call("gldm_devox_cl", norm.data_ptr(), y2.data_ptr(), 1, co, gate.data_ptr(), pt.data_ptr(), B, co, N, r,
+              fused.data_ptr(), st)
+    return fused
+
+
 def _encoder_pass(pk, xyz, precision="fp32"):
     dev = xyz.device
     st = _stream(dev)
@@ -506,7 +571,10 @@ def _encoder_pass(pk, xyz, precision="fp32"):
         feats = xyz.float().transpose(1, 2).contiguous()       # [B,3,N] (layout only)
         coords = feats
         for bi, blk in enumerate(pk.blocks):
-            if blk["kind"] == "pvconv":
+            if blk["kind"] == "pvconv" and precision == "bf16" and pk.tc_conv_weights()[bi][1] is not None \
+                    and blk["groups"] == 8 and blk["cout"] % 16 == 0:
+                feats = _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev)
+            elif blk["kind"] == "pvconv":
                 r, ci, co = blk["r"], blk["cin"], blk["cout"]
                 tcw = pk.tc_conv_weights()[bi] if precision == "bf16" else (None, None)
                 r3 = r ** 3

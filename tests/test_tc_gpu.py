@@ -189,3 +189,98 @@ def test_sampler_two_sets_per_cta_matches_one_set(cuda):
     finally:
         _lib.call("gldm_sampler_tc_set_sets", 0)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("B,ci,co,r", [(3, 48, 48, 24), (2, 48, 96, 12), (5, 96, 96, 12)])
+def test_fused_voxel_branch_ops(cuda, B, ci, co, r):
+    """Channels-last Conv3d (+ GroupNorm statistics) -> GroupNorm + Swish in place (+ SE squeeze) -> SE gate ->
+    devoxelize, op by op against torch on the same bf16-rounded operands (pvconv.py:48-67, se.py:10-21)."""
+    import torch.nn.functional as F
+    from graspldm_b200 import _lib
+    from graspldm_b200.engine import _aligned_bytes, _stream
+    gen = torch.Generator().manual_seed(100 * ci + co + r)
+    P, r3, n = (r + 2) ** 3, r ** 3, 500
+    x = torch.randn(B, ci, r3, generator=gen).to(cuda)
+    w = (torch.randn(co, ci, 3, 3, 3, generator=gen) / (27 * ci) ** 0.5).to(cuda)
+    bias, gamma, beta = (torch.randn(co, generator=gen).to(cuda) * s + o for s, o in ((0.3, 0.1), (0.2, 1.0), (0.2, 0.0)))
+    st = _stream(cuda)
+    img = _aligned_bytes(_lib.lib().gldm_conv3d_tc_weight_bytes(ci), cuda)
+    _lib.call("gldm_conv3d_tc_pack_weight", w.contiguous().data_ptr(), co, ci, img.data_ptr(), st)
+    cpad_i, cpad_o = -(-ci // 64) * 64, -(-co // 64) * 64
+    x_cl = torch.zeros((B * P, cpad_i), device=cuda, dtype=torch.bfloat16)
+    _lib.call("gldm_cl_pad", x.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
+    xb, wb = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    want = F.conv3d(xb.view(B, ci, r, r, r), wb, bias, padding=1)                       # fp32 on bf16-rounded operands
+    interior = lambda t: t.view(B, r + 2, r + 2, r + 2, -1)[:, 1:-1, 1:-1, 1:-1]        # [B,r,r,r,C] view of a padded grid
+    cl = lambda t: t.permute(0, 2, 3, 4, 1)                                             # [B,C,r,r,r] -> [B,r,r,r,C]
+    for fp32_out in (0, 1):
+        stride = co if fp32_out else cpad_o
+        y = torch.zeros((B * P, stride), device=cuda, dtype=torch.float32 if fp32_out else torch.bfloat16)
+        stats = torch.zeros((B, 8, 2), device=cuda, dtype=torch.float64)
+        _lib.call("gldm_conv3d_tc_cl", x_cl.data_ptr(), img.data_ptr(), bias.data_ptr(), B, ci, co, r, y.data_ptr(), fp32_out,
+                  stride, stats.data_ptr(), st)
+        got = interior(y)[..., :co].float()
+        tol = dict(rtol=2e-3, atol=2e-3) if fp32_out else dict(rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(got, cl(want), **tol)
+        full = y.view(B, r + 2, r + 2, r + 2, stride).float()
+        assert full[:, 0].abs().max() == 0 and full[:, :, :, -1].abs().max() == 0       # halo rows untouched
+        assert stride == co or full[..., co:].abs().max() == 0                          # padding channels written as zero
+        g = want.view(B, 8, -1).double()
+        torch.testing.assert_close(stats[..., 0], g.sum(-1), rtol=1e-3, atol=0.5)
+        torch.testing.assert_close(stats[..., 1], (g * g).sum(-1), rtol=2e-3, atol=0.5)
+        # GroupNorm + Swish in place, from the kernel's own statistics, against torch on the kernel's own conv output
+        raw = got.permute(0, 4, 1, 2, 3).contiguous()
+        se_sum = torch.zeros((B, co), device=cuda, dtype=torch.float64)
+        _lib.call("gldm_gn_swish_cl", y.data_ptr(), fp32_out, stride, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, co,
+                  r, 1e-5, se_sum.data_ptr(), st)
+        act = F.silu(F.group_norm(want if fp32_out else raw, 8, gamma, beta, 1e-5))
+        got_act = interior(y)[..., :co].float()
+        torch.testing.assert_close(got_act, cl(act), **(dict(rtol=5e-3, atol=5e-3) if fp32_out else dict(rtol=2e-2, atol=2e-2)))
+        # the SE sums are taken before the bf16 rounding of the stored grid
+        torch.testing.assert_close(se_sum.float() / r3, got_act.mean((1, 2, 3)), rtol=1e-4, atol=1e-5 if fp32_out else 5e-4)
+        full = y.view(B, r + 2, r + 2, r + 2, stride).float()
+        assert full[:, 0].abs().max() == 0 and full[:, :, 0].abs().max() == 0
+    # fp32 grid (y, activated) -> SE gate + devoxelize: same operation order as the fp32 kernels => bit-equal
+    cr = max(co // 8, 1)
+    w1, w2 = torch.randn(cr, co, generator=gen).to(cuda) * 0.2, torch.randn(co, cr, generator=gen).to(cuda) * 0.2
+    gate = torch.empty((B, co), device=cuda)
+    _lib.call("gldm_se_gate_sum", se_sum.data_ptr(), r3, w1.data_ptr(), w2.data_ptr(), B, co, cr, gate.data_ptr(), st)
+    mean = (se_sum / r3).float()
+    torch.testing.assert_close(gate, torch.sigmoid(F.silu(mean @ w1.t()) @ w2.t()), rtol=1e-5, atol=1e-6)
+    coords = (torch.rand(B, 3, n, generator=gen) * (r - 1)).to(cuda)
+    coords[0, :, :4] = torch.tensor([[0.0, r - 1.0, 3.0, 0.5], [0.0, r - 1.0, 2.0, 7.0], [0.0, r - 1.0, 1.0, r - 1.0]], device=cuda)
+    point = torch.randn(B, co, n, generator=gen).to(cuda)
+    out = torch.empty((B, co, n), device=cuda)
+    _lib.call("gldm_devox_cl", coords.data_ptr(), y.data_ptr(), 1, co, gate.data_ptr(), point.data_ptr(), B, co, n, r,
+              out.data_ptr(), st)
+    grid = interior(y).permute(0, 4, 1, 2, 3).reshape(B, co, r3).contiguous()
+    ref = torch.empty((B, co, n), device=cuda)
+    _lib.call("gldm_devox_gate_add_f32", coords.data_ptr(), grid.data_ptr(), gate.data_ptr(), point.data_ptr(), B, co, n, r,
+              ref.data_ptr(), st)
+    assert torch.equal(out, ref)
+
+
+def test_first_conv3d_channels_last(cuda):
+    """3 -> 48 SIMT Conv3d writing the padded channels-last bf16 grid + GroupNorm statistics (pvconv.py:50-52)."""
+    import torch.nn.functional as F
+    from graspldm_b200 import _lib
+    from graspldm_b200.engine import _stream
+    gen = torch.Generator().manual_seed(5)
+    B, ci, co, r = 3, 3, 48, 24
+    P, r3 = (r + 2) ** 3, r ** 3
+    x = torch.randn(B, ci, r3, generator=gen).to(cuda)
+    w = (torch.randn(co, ci, 3, 3, 3, generator=gen) / 9).to(cuda)
+    bias = torch.randn(co, generator=gen).to(cuda) * 0.2
+    wp = w.permute(1, 2, 3, 4, 0).reshape(ci, 27, co).contiguous()
+    y = torch.zeros((B * P, 64), device=cuda, dtype=torch.bfloat16)
+    stats = torch.zeros((B, 8, 2), device=cuda, dtype=torch.float64)
+    _lib.call("gldm_conv3d_k3_f32_cl", x.data_ptr(), wp.data_ptr(), bias.data_ptr(), B, ci, r, y.data_ptr(), 64,
+              stats.data_ptr(), _stream(cuda))
+    want = F.conv3d(x.view(B, ci, r, r, r), w, bias, padding=1)
+    full = y.view(B, r + 2, r + 2, r + 2, 64).float()
+    got = full[:, 1:-1, 1:-1, 1:-1, :co]
+    torch.testing.assert_close(got, want.permute(0, 2, 3, 4, 1), rtol=8e-3, atol=8e-3)      # bf16 storage
+    assert full[..., co:].abs().max() == 0 and full[:, 0].abs().max() == 0 and full[:, :, -1].abs().max() == 0
+    g = want.view(B, 8, -1).double()
+    torch.testing.assert_close(stats[..., 0], g.sum(-1), rtol=1e-4, atol=0.05)
+    torch.testing.assert_close(stats[..., 1], (g * g).sum(-1), rtol=1e-4, atol=0.05)

@@ -7,6 +7,10 @@ import _models
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1280
 prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+sets = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+if sets:
+    from graspldm_b200 import _lib
+    _lib.call("gldm_sampler_tc_set_sets", sets)
 dev = torch.device("cuda:0")
 model = _models.build("fpc").to(dev)
 model.set_inference_timesteps(steps)
