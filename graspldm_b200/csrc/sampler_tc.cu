@@ -175,11 +175,11 @@ static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes
 static int check_tc_cfg(const GldmResNetCfg* c) {
   int rc = check_cfg(c);
   if (rc) return rc;
-  const bool denoiser = c->L == 4 && c->emb_dim == 16 && c->time_cond;
-  const bool decoder = c->L == 16 && c->emb_dim == 64 && !c->time_cond;
-  if (!((denoiser || decoder) && c->n_stages == 4 && c->groups == 4 && c->cond_ch <= 3 && c->cond_dim <= 1024)) {
-    set_error("resnet_tc: this build covers the fpc latent denoiser (L=4, emb 16, time conditioned) and the grasp "
-              "decoder trunk (L=16, emb 64), 4 stages, 4 groups");
+  const bool l4 = c->L == 4 && c->emb_dim == 16 && c->time_cond;     // fpc latent denoiser
+  const bool l16 = c->L == 16 && c->emb_dim == 64;                    // ppc latent denoiser, grasp decoder trunk
+  if (!((l4 || l16) && c->n_stages == 4 && c->groups == 4 && c->cond_ch <= 3 && c->cond_dim <= 1024)) {
+    set_error("resnet_tc: this build covers the latent denoisers (L=4 / emb 16, L=16 / emb 64, time conditioned) and the "
+              "grasp decoder trunk (L=16, emb 64), 4 stages, 4 groups");
     return GLDM_ENOSUP;
   }
   for (int s = 0; s < c->n_stages; ++s)
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
     const int s = tid / L, l = tid % L;                                    // s: sample within the CTA
     float v = 0.f;
     if (cta_s0 + s < p.n) {
-      if (L == 4) {
+      if (p.mode != 2) {   // denoiser: the latent itself
         v = __ldg(p.x_in + (size_t)(cta_s0 + s) * L + l);
       } else {   // decoder in_layer: Linear(D -> L)   (grasp_vae.py:419)
         v = __ldg(p.head + L * p.D + l);
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
       }
     }
     reinterpret_cast<float*>(smem + T::SM_X + (s / NS) * 256)[(s % NS) * L + l] = v;
-    if (L == 4 && p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
+    if (p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
   }
   // ---- weight chunk table and UMMA op table of one step: for every job, for every sample set (the order in which
   //      the epilogue warps hand operands over).  The ring stage of a chunk is a static function of its position.
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
         {
           const int s = tid / EMB, e = tid % EMB;
           float te = 0.f;
-          if (L == 4) {
+          if (cfg.time_cond) {
             const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
             te = __ldg(p.te + (size_t)ti * EMB + e);
           }
@@ -1118,14 +1118,13 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
                 float eps = __ldg(W + lay.fc_b);
 #pragma unroll
                 for (int w = 0; w < 4; ++w) eps += c.xch[w * 64 + lane];
-                if (L == 16) {
-                  s_x[sgl * 16 + lane] = eps;                         // value index jj*16 + l
-                } else {
-                  const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
+                {
+                  // value index of this lane: l*8 + jj (L = 4) or jj*16 + l (L = 16)
+                  const int l = (L == 4) ? lane >> 3 : lane & 15, jj = (L == 4) ? lane & 7 : lane >> 4, s = sgl + jj;
                   const bool ok = s0 + s < p.n;
                   if (p.mode == 0) {
                     const float* cf = p.coef + (size_t)step * 8;
-                    const float x = s_x[s * 4 + l];
+                    const float x = s_x[s * L + l];
                     float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
                     if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
                     float prev;
@@ -1140,10 +1139,10 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
                     } else {
                       prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
                     }
-                    s_x[s * 4 + l] = prev;
+                    s_x[s * L + l] = prev;
                     if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + s0 + s) * L + l] = prev;
                   } else {
-                    s_x[s * 4 + l] = eps;
+                    s_x[s * L + l] = eps;       // network output: denoiser eps (mode 1) / decoder trunk features (mode 2)
                   }
                 }
               }
@@ -1159,10 +1158,10 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
     for (int set = 0; set < NSETS; ++set) {
       select_set(set);
       wg_sync(c.g);
-      if (L == 4) {
+      if (p.mode != 2) {
         if (c.q == 0) {
-          const int l = lane >> 3, jj = lane & 7, s = sgl + jj;
-          if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * 4 + l];
+          const int l = (L == 4) ? lane >> 3 : lane & 15, jj = (L == 4) ? lane & 7 : lane >> 4, s = sgl + jj;
+          if (s0 + s < p.n) p.x_out[(size_t)(s0 + s) * L + l] = s_x[s * L + l];
         }
       } else {
         // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430)
@@ -1335,7 +1334,7 @@ extern "C" int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, c
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
-  GLDM_REQUIRE(cfg->L == 4, "sampler_run_tc: the sampler needs the denoiser configuration (L = 4)");
+  GLDM_REQUIRE(cfg->time_cond, "sampler_run_tc: the sampler needs a time-conditioned denoiser configuration");
   GLDM_REQUIRE(x_T && z_obj && x_out && timesteps_host && coef_host, "sampler_run_tc: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc: bad sizes");
   GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc: bad scheduler");
@@ -1382,7 +1381,7 @@ extern "C" int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* ra
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
-  GLDM_REQUIRE(cfg->L == 4, "sampler_run_tc_dev: the sampler needs the denoiser configuration (L = 4)");
+  GLDM_REQUIRE(cfg->time_cond, "sampler_run_tc_dev: the sampler needs a time-conditioned denoiser configuration");
   GLDM_REQUIRE(x_T && z_obj && x_out && coef_dev && te_dev, "sampler_run_tc_dev: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc_dev: bad sizes");
   GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc_dev: bad scheduler");
@@ -1398,7 +1397,7 @@ extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* r
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
-  GLDM_REQUIRE(cfg->L == 4, "denoiser_forward_tc: needs the denoiser configuration (L = 4)");
+  GLDM_REQUIRE(cfg->time_cond, "denoiser_forward_tc: needs a time-conditioned denoiser configuration");
   GLDM_REQUIRE(x && t && z_cond && eps, "denoiser_forward_tc: null pointer");
   GLDM_REQUIRE(n >= 0, "denoiser_forward_tc: bad n");
   if (n == 0) return GLDM_OK;
@@ -1421,7 +1420,7 @@ extern "C" int gldm_decoder_forward_tc(const GldmResNetCfg* cfg, const float* ra
   TcParams p = {};
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
-  GLDM_REQUIRE(cfg->L == 16, "decoder_forward_tc: needs the decoder trunk configuration (L = 16)");
+  GLDM_REQUIRE(cfg->L == 16 && !cfg->time_cond, "decoder_forward_tc: needs the decoder trunk configuration (L = 16)");
   GLDM_REQUIRE(head && z_h && z_obj && tmrp && logit, "decoder_forward_tc: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && D > 0 && D <= 64, "decoder_forward_tc: bad sizes");
   if (n == 0) return GLDM_OK;

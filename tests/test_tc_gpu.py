@@ -38,22 +38,24 @@ def test_denoiser_forward_bf16(fpc, cuda, B):
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=5e-2)
 
 
-@pytest.mark.parametrize("kind,steps", [("ddpm", 10), ("ddim", 5), ("ddpm", 100)])
-def test_sampler_bf16_tracks_fp32(cuda, kind, steps):
-    m = _models.build("fpc", scheduler=kind).to(cuda)
+@pytest.mark.parametrize("name,kind,steps", [("fpc", "ddpm", 10), ("fpc", "ddim", 5), ("fpc", "ddpm", 100),
+                                             ("ppc", "ddpm", 10), ("ppc", "ddim", 5)])
+def test_sampler_bf16_tracks_fp32(cuda, name, kind, steps):
+    m = _models.build(name, scheduler=kind).to(cuda)
     m.set_inference_timesteps(steps)
     gen = torch.Generator().manual_seed(5)
     n_obj, G_ = 3, 7
-    z = torch.randn(n_obj, 3, 64, generator=gen).to(cuda)
-    x_T = torch.randn(n_obj * G_, 1, 4, generator=gen).to(cuda)
-    noise = torch.randn(steps, n_obj * G_, 1, 4, generator=gen).to(cuda)
+    D, Dc = (4, 64) if name == "fpc" else (16, 256)
+    z = torch.randn(n_obj, 3, Dc, generator=gen).to(cuda)
+    x_T = torch.randn(n_obj * G_, 1, D, generator=gen).to(cuda)
+    noise = torch.randn(steps, n_obj * G_, 1, D, generator=gen).to(cuda)
     a, alla = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
                                        grasps_per_object=G_)
     b, allb = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
                                        grasps_per_object=G_, precision="bf16")
     assert len(allb) == steps + 1 and torch.equal(allb[0], x_T) and torch.equal(allb[-1], b)
     err = (a - b).abs().max().item()
-    print(f"[{kind}{steps}] bf16 vs fp32 latents after {steps} steps: max|diff| {err:.3e}")
+    print(f"[{name} {kind}{steps}] bf16 vs fp32 latents after {steps} steps: max|diff| {err:.3e}")
     # the recurrence damps eps errors (x0 coefficient of the posterior mean is O(1e-2) per step)
     np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=3e-2, atol=3e-2)
 
@@ -284,3 +286,14 @@ def test_first_conv3d_channels_last(cuda):
     g = want.view(B, 8, -1).double()
     torch.testing.assert_close(stats[..., 0], g.sum(-1), rtol=1e-4, atol=0.05)
     torch.testing.assert_close(stats[..., 1], (g * g).sum(-1), rtol=1e-4, atol=0.05)
+
+
+def test_ppc_denoiser_forward_bf16_vs_reference_fixture(cuda):
+    """ppc latent denoiser (16 positions, time conditioned, embedding width 64) on the tensor-core kernel, against the
+    fixture of the reference module (resnets.py:558-616)."""
+    g = np.load(os.path.join(G, "dense_ppc.npz"))
+    m = _models.build("ppc").to(cuda)
+    t = lambda k: torch.from_numpy(g[k]).to(cuda)
+    got = m.diffusion_model.model(t("x"), time=t("t"), z_cond=t("z_cond"), precision="bf16").cpu().numpy()
+    print(f"[ppc] bf16 denoiser vs reference fixture: max|err| {np.abs(got - g['eps']).max():.3e}, max|eps| {np.abs(g['eps']).max():.3f}")
+    np.testing.assert_allclose(got, g["eps"], rtol=5e-2, atol=5e-2)
