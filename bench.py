@@ -345,8 +345,11 @@ def main():
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
                 "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
+                # the same FLOPs over the whole pipelined timed region (which also holds the encoder / decoder kernels
+                # of the batches in flight): a lower bound on what the sampler kernel sustains across the GPU
+                "achieved_timed_region": samp_flops * args.steps / (total_ms * 1e-3) / 1e12,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm / SE and the 3->48 Conv3d on fp32 SIMT kernels; kernel_ms and sections_ms come from the sequential latency pass"
+                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE and the 3->48 Conv3d on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (16 samples per sampler CTA, 80 CTAs)"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:

@@ -56,7 +56,7 @@ def ldm(name, sched, steps, n_obj, grasps, prec="bf16"):
 
 
 print("# Other BASELINE.json configurations on one B200 (bf16 tensor-core path unless noted)\n")
-print("One batch at a time on one stream (no pipelining), inputs resident in HBM, CUDA events, in-kernel Philox noise.\n")
+print("`python tools/bench_configs.py`.  One batch at a time on one stream (no pipelining; the sampler picks one or two sample sets per CTA from the batch size), inputs resident in HBM, CUDA events, in-kernel Philox noise.  \"fraction of peak\" = algorithmic FLOPs (SURVEY.md 8d) / time / 1392.3 TFLOP/s (measured sustained bf16).\n")
 print("| config | workload | ms / batch | grasps/s (clouds/s) | fraction of sustained bf16 peak |")
 print("|---|---|---:|---:|---:|")
 ms, r, f = ldm("fpc", "ddpm", 100, 1, 20)
@@ -71,6 +71,8 @@ for steps in (10, 50):
 for n_obj in (16, 64, 256):
     ms, r, f = ldm("fpc", "ddpm", 100, n_obj, 256)
     print(f"| 5 | LDM 100 DDPM steps, {n_obj} objects x 256 grasps | {ms:.2f} | {r:,.0f} | {f:.4f} |")
+ms, r, f = ldm("ppc", "ddpm", 100, 64, 20)
+print(f"| 4-like | ppc LDM (16-position latent) 100 DDPM steps, 64 objects x 20 grasps | {ms:.2f} | {r:,.0f} | - |")
 # config 4: encoder only, partial-point-cloud config, 4096 clouds
 m = _models.build("ppc").to(dev)
 set_precision(m, "bf16")
