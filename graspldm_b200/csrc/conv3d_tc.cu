@@ -507,7 +507,7 @@ static int launch_cl_pad(const float* x, int b, int c, int r, void* out, cudaStr
 /* x f32[b,ci,r^3] -> y f32[b,co,r^3]; scratch: gldm_conv3d_tc_grid_bytes(b, ci, r) bytes (256-byte aligned) */
 extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r,
                                  void* scratch, float* y, void* stream) {
-  GLDM_REQUIRE(x && w_img && y && scratch, "conv3d_k3_tc: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && w_img && y && scratch), "conv3d_k3_tc: null pointer");
   GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_k3_tc: need 16 <= ci, co <= 128");
   if (b == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -517,7 +517,7 @@ extern "C" int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float*
 }
 
 extern "C" int gldm_cl_pad(const float* x, int b, int c, int r, void* out_cl, void* stream) {
-  GLDM_REQUIRE(x && out_cl, "cl_pad: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && out_cl), "cl_pad: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && r > 0, "cl_pad: bad sizes");
   if (b == 0) return GLDM_OK;
   return launch_cl_pad(x, b, c, r, out_cl, (cudaStream_t)stream);
@@ -525,7 +525,7 @@ extern "C" int gldm_cl_pad(const float* x, int b, int c, int r, void* out_cl, vo
 
 extern "C" int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const float* bias, int b, int ci, int co, int r,
                                  void* y_cl, int out_fp32, int out_stride, double* stats, void* stream) {
-  GLDM_REQUIRE(x_cl && w_img && y_cl && stats, "conv3d_tc_cl: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x_cl && w_img && y_cl && stats), "conv3d_tc_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_tc_cl: need 16 <= ci, co <= 128");
   GLDM_REQUIRE(co % 8 == 0, "conv3d_tc_cl: GroupNorm(8) statistics need co % 8 == 0");
   GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc_cl: out_stride must be a multiple of 16 in [co, 128]");
@@ -536,7 +536,7 @@ extern "C" int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const floa
 
 extern "C" int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const double* stats, const float* gamma,
                                 const float* beta, int b, int c, int r, float eps, double* se_sum, void* stream) {
-  GLDM_REQUIRE(y_cl && stats && gamma && beta, "gn_swish_cl: null pointer");
+  GLDM_REQUIRE(b <= 0 || (y_cl && stats && gamma && beta), "gn_swish_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && c % 8 == 0 && c <= 128 && r > 0, "gn_swish_cl: bad sizes");
   GLDM_REQUIRE(stride >= c && stride % 8 == 0 && stride <= 128, "gn_swish_cl: bad row stride");
   if (b == 0) return GLDM_OK;
@@ -552,7 +552,7 @@ extern "C" int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const doubl
 
 extern "C" int gldm_se_gate_sum(const double* sum, int count, const float* w1, const float* w2, int b, int c, int cr,
                                 float* gate, void* stream) {
-  GLDM_REQUIRE(sum && w1 && w2 && gate, "se_gate_sum: null pointer");
+  GLDM_REQUIRE(b <= 0 || (sum && w1 && w2 && gate), "se_gate_sum: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && cr > 0 && count > 0, "se_gate_sum: bad sizes");
   if (b == 0) return GLDM_OK;
   se_gate_sum_kernel<<<b, 128, sizeof(float) * (c + cr), (cudaStream_t)stream>>>(sum, 1.0f / (float)count, w1, w2, c, cr, gate);
@@ -561,7 +561,7 @@ extern "C" int gldm_se_gate_sum(const double* sum, int count, const float* w1, c
 
 extern "C" int gldm_devox_cl(const float* coords, const void* grid_cl, int is_fp32, int stride, const float* gate,
                              const float* point, int b, int c, int n, int r, float* out, void* stream) {
-  GLDM_REQUIRE(coords && grid_cl && out, "devox_cl: null pointer");
+  GLDM_REQUIRE(b <= 0 || (coords && grid_cl && out), "devox_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "devox_cl: bad sizes");
   GLDM_REQUIRE(stride % 8 == 0 && stride >= ((c + 7) / 8) * 8, "devox_cl: bad row stride");
   if (b == 0) return GLDM_OK;

@@ -414,7 +414,7 @@ using namespace gldm;
 extern "C" int gldm_pointwise_conv_f32(const float* x, const float* w, const float* scale, const float* shift,
                                        const float* add, int b, int ci, int co, int n, int act, float* y,
                                        void* stream) {
-  GLDM_REQUIRE(x && w && y, "pointwise_conv_f32: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && w && y), "pointwise_conv_f32: null pointer");
   GLDM_REQUIRE(b >= 0 && ci > 0 && co > 0 && n > 0, "pointwise_conv_f32: bad sizes");
   GLDM_REQUIRE(act == 0 || act == 1, "pointwise_conv_f32: act must be 0 or 1");
   if (b == 0) return GLDM_OK;
@@ -437,7 +437,7 @@ extern "C" int gldm_pointwise_conv_f32(const float* x, const float* w, const flo
 
 extern "C" int gldm_conv3d_k3_f32(const float* x, const float* w, const float* bias, int b, int ci, int co, int r,
                                   float* y, void* stream) {
-  GLDM_REQUIRE(x && w && y, "conv3d_k3_f32: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && w && y), "conv3d_k3_f32: null pointer");
   GLDM_REQUIRE(b >= 0 && ci > 0 && co > 0 && r > 0, "conv3d_k3_f32: bad sizes");
   if (b == 0) return GLDM_OK;
   dim3 grid(ceil_div(r * r * r, C3_VT), ceil_div(co, C3_CT), b);
@@ -447,7 +447,7 @@ extern "C" int gldm_conv3d_k3_f32(const float* x, const float* w, const float* b
 
 extern "C" int gldm_conv3d_k3_f32_cl(const float* x, const float* w, const float* bias, int b, int ci, int r, void* y_cl,
                                      int y_stride, double* stats, void* stream) {
-  GLDM_REQUIRE(x && w && y_cl && stats, "conv3d_k3_f32_cl: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && w && y_cl && stats), "conv3d_k3_f32_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && ci > 0 && r > 0, "conv3d_k3_f32_cl: bad sizes");
   GLDM_REQUIRE(y_stride >= C3_CT && y_stride % 8 == 0, "conv3d_k3_f32_cl: bad row stride");
   if (b == 0) return GLDM_OK;
@@ -459,7 +459,7 @@ extern "C" int gldm_conv3d_k3_f32_cl(const float* x, const float* w, const float
 
 extern "C" int gldm_groupnorm_swish_f32(float* x, const float* gamma, const float* beta, int b, int c, int s,
                                         int groups, float eps, float* se_mean, void* stream) {
-  GLDM_REQUIRE(x && gamma && beta, "groupnorm_swish_f32: null pointer");
+  GLDM_REQUIRE(b <= 0 || (x && gamma && beta), "groupnorm_swish_f32: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && s > 0 && groups > 0 && c % groups == 0, "groupnorm_swish_f32: bad sizes");
   if (b == 0) return GLDM_OK;
   groupnorm_swish_kernel<<<dim3(groups, b), 512, 0, (cudaStream_t)stream>>>(x, gamma, beta, c, s, groups, eps,
@@ -469,7 +469,7 @@ extern "C" int gldm_groupnorm_swish_f32(float* x, const float* gamma, const floa
 
 extern "C" int gldm_se_gate_f32(const float* mean, const float* w1, const float* w2, int b, int c, int cr,
                                 float* gate, void* stream) {
-  GLDM_REQUIRE(mean && w1 && w2 && gate, "se_gate_f32: null pointer");
+  GLDM_REQUIRE(b <= 0 || (mean && w1 && w2 && gate), "se_gate_f32: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && cr > 0, "se_gate_f32: bad sizes");
   if (b == 0) return GLDM_OK;
   se_gate_kernel<<<b, 128, sizeof(float) * cr, (cudaStream_t)stream>>>(mean, w1, w2, c, cr, gate);
@@ -478,7 +478,7 @@ extern "C" int gldm_se_gate_f32(const float* mean, const float* w1, const float*
 
 extern "C" int gldm_devox_gate_add_f32(const float* coords, const float* grid, const float* gate,
                                        const float* point, int b, int c, int n, int r, float* out, void* stream) {
-  GLDM_REQUIRE(coords && grid && out, "devox_gate_add_f32: null pointer");
+  GLDM_REQUIRE(b <= 0 || (coords && grid && out), "devox_gate_add_f32: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "devox_gate_add_f32: bad sizes");
   if (b == 0) return GLDM_OK;
   dim3 g(ceil_div(n, 128), ceil_div(c, 8), b);

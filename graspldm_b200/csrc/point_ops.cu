@@ -482,7 +482,7 @@ using namespace gldm;
 
 extern "C" int gldm_furthest_point_sampling(const float* coords, int b, int n, int m, int* indices,
                                             void* stream) {
-  GLDM_REQUIRE(coords && indices, "furthest_point_sampling: null pointer");
+  GLDM_REQUIRE(b <= 0 || m <= 0 || (coords && indices), "furthest_point_sampling: null pointer");
   GLDM_REQUIRE(b >= 0 && n > 0 && m >= 0, "furthest_point_sampling: bad sizes b=%d n=%d m=%d", b, n, m);
   GLDM_REQUIRE(n < (1 << 22), "furthest_point_sampling: n=%d exceeds 2^22", n);
   if (b == 0 || m == 0) return GLDM_OK;
@@ -506,7 +506,7 @@ extern "C" int gldm_furthest_point_sampling(const float* coords, int b, int n, i
 
 extern "C" int gldm_ball_query(const float* centers, const float* points, int b, int n, int m, float radius,
                                int u, int* neighbors, void* stream) {
-  GLDM_REQUIRE(centers && points && neighbors, "ball_query: null pointer");
+  GLDM_REQUIRE(b <= 0 || (centers && points && neighbors), "ball_query: null pointer");
   GLDM_REQUIRE(b >= 0 && n > 0 && m > 0 && u > 0, "ball_query: bad sizes");
   if (b == 0) return GLDM_OK;
   float r2 = radius * radius;   // ball_query.cpp:24 (float multiply)
@@ -527,7 +527,7 @@ static int launch_group_gather(const float* feat, const int* idx, int b, int c, 
 
 extern "C" int gldm_grouping_forward(const float* features, const int* indices, int b, int c, int n, int m,
                                      int u, float* out, void* stream) {
-  GLDM_REQUIRE(features && indices && out, "grouping_forward: null pointer");
+  GLDM_REQUIRE(b <= 0 || (features && indices && out), "grouping_forward: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && m > 0 && u > 0, "grouping_forward: bad sizes");
   if (b == 0) return GLDM_OK;
   return launch_group_gather(features, indices, b, c, n, m * u, out, (cudaStream_t)stream, "grouping_kernel");
@@ -535,7 +535,7 @@ extern "C" int gldm_grouping_forward(const float* features, const int* indices, 
 
 extern "C" int gldm_gather_features_forward(const float* features, const int* indices, int b, int c, int n,
                                             int m, float* out, void* stream) {
-  GLDM_REQUIRE(features && indices && out, "gather_features_forward: null pointer");
+  GLDM_REQUIRE(b <= 0 || (features && indices && out), "gather_features_forward: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && m > 0, "gather_features_forward: bad sizes");
   if (b == 0) return GLDM_OK;
   return launch_group_gather(features, indices, b, c, n, m, out, (cudaStream_t)stream, "gather_kernel");
@@ -569,7 +569,7 @@ extern "C" int gldm_gather_features_backward(const float* grad_y, const int* ind
 extern "C" int gldm_three_nn_interpolate_forward(const float* points, const float* centers, const float* feats,
                                                  int b, int c, int m, int n, float* out, int* idx, float* w,
                                                  void* stream) {
-  GLDM_REQUIRE(points && centers && feats && out && idx && w, "three_nn_interpolate_forward: null pointer");
+  GLDM_REQUIRE(b <= 0 || (points && centers && feats && out && idx && w), "three_nn_interpolate_forward: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && m > 0 && n > 0, "three_nn_interpolate_forward: bad sizes");
   if (b == 0) return GLDM_OK;
   dim3 grid(ceil_div(n, 128), b);
@@ -593,7 +593,7 @@ extern "C" int gldm_three_nn_interpolate_backward(const float* grad_y, const int
 
 static int launch_voxelize(bool fused, const float* feat, const void* coords, int b, int c, int n, int r,
                            float* out, int* ind, int* cnt, float* norm, int* vox, cudaStream_t s) {
-  GLDM_REQUIRE(feat && coords && out, "voxelize: null pointer");
+  GLDM_REQUIRE(b <= 0 || (feat && coords && out), "voxelize: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "voxelize: bad sizes b=%d c=%d n=%d r=%d", b, c, n, r);
   GLDM_REQUIRE(n <= kVoxMaxPoints, "voxelize: n=%d > %d points per cloud not supported", n, kVoxMaxPoints);
   GLDM_REQUIRE(r <= 36, "voxelize: resolution %d > 36 not supported (shared-memory voxel table)", r);
@@ -645,7 +645,7 @@ extern "C" int gldm_avg_voxelize_backward(const float* grad_y, const int* ind, c
 extern "C" int gldm_trilinear_devoxelize_forward(const float* coords, const float* features, int b, int c,
                                                  int n, int r, int is_training, float* outs, int* inds,
                                                  float* wgts, void* stream) {
-  GLDM_REQUIRE(coords && features && outs, "trilinear_devoxelize_forward: null pointer");
+  GLDM_REQUIRE(b <= 0 || (coords && features && outs), "trilinear_devoxelize_forward: null pointer");
   GLDM_REQUIRE(!is_training || (inds && wgts), "trilinear_devoxelize_forward: training needs inds/wgts");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "trilinear_devoxelize_forward: bad sizes");
   if (b == 0) return GLDM_OK;

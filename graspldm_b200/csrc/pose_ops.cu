@@ -105,7 +105,7 @@ using namespace gldm;
 extern "C" int gldm_normalize_clouds(const float* pc, const float* pc_shift, const float* pc_scale,
                                      const float* grasp_shift, int b, int n, float* pc_out, float* pc_mean,
                                      float* grasp_mean, void* stream) {
-  GLDM_REQUIRE(pc && pc_shift && pc_scale && pc_out, "normalize_clouds: null pointer");
+  GLDM_REQUIRE(b <= 0 || (pc && pc_shift && pc_scale && pc_out), "normalize_clouds: null pointer");
   GLDM_REQUIRE(grasp_shift || !grasp_mean, "normalize_clouds: grasp_mean needs grasp_shift");
   GLDM_REQUIRE(b >= 0 && n > 0, "normalize_clouds: bad sizes");
   if (b == 0) return GLDM_OK;
@@ -117,7 +117,7 @@ extern "C" int gldm_normalize_clouds(const float* pc, const float* pc_shift, con
 extern "C" int gldm_pose_postprocess_rows(const float* tmrp, const float* logit, const float* grasp_mean,
                                           const float* grasp_std, int n, int grasps_per_obj, int mean_rows,
                                           int std_rows, float* grasp_tmrp, float* H, float* conf, void* stream) {
-  GLDM_REQUIRE(tmrp && grasp_mean && grasp_std, "pose_postprocess: null pointer");
+  GLDM_REQUIRE(n <= 0 || (tmrp && grasp_mean && grasp_std), "pose_postprocess: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0, "pose_postprocess: bad n");
   GLDM_REQUIRE(n % grasps_per_obj == 0, "pose_postprocess: n is not a multiple of grasps_per_obj");
   const int n_obj = n / grasps_per_obj;

@@ -1335,7 +1335,7 @@ extern "C" int gldm_sampler_run_tc(const GldmResNetCfg* cfg, const float* raw, c
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
   GLDM_REQUIRE(cfg->time_cond, "sampler_run_tc: the sampler needs a time-conditioned denoiser configuration");
-  GLDM_REQUIRE(x_T && z_obj && x_out && timesteps_host && coef_host, "sampler_run_tc: null pointer");
+  GLDM_REQUIRE(n <= 0 || (x_T && z_obj && x_out && timesteps_host && coef_host), "sampler_run_tc: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc: bad sizes");
   GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc: bad scheduler");
   if (n == 0) return GLDM_OK;
@@ -1382,7 +1382,7 @@ extern "C" int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* ra
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
   GLDM_REQUIRE(cfg->time_cond, "sampler_run_tc_dev: the sampler needs a time-conditioned denoiser configuration");
-  GLDM_REQUIRE(x_T && z_obj && x_out && coef_dev && te_dev, "sampler_run_tc_dev: null pointer");
+  GLDM_REQUIRE(n <= 0 || (x_T && z_obj && x_out && coef_dev && te_dev), "sampler_run_tc_dev: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && n_steps > 0, "sampler_run_tc_dev: bad sizes");
   GLDM_REQUIRE(sched_kind == GLDM_SCHED_DDPM || sched_kind == GLDM_SCHED_DDIM, "sampler_run_tc_dev: bad scheduler");
   if (n == 0) return GLDM_OK;
@@ -1398,7 +1398,7 @@ extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* r
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
   GLDM_REQUIRE(cfg->time_cond, "denoiser_forward_tc: needs a time-conditioned denoiser configuration");
-  GLDM_REQUIRE(x && t && z_cond && eps, "denoiser_forward_tc: null pointer");
+  GLDM_REQUIRE(n <= 0 || (x && t && z_cond && eps), "denoiser_forward_tc: null pointer");
   GLDM_REQUIRE(n >= 0, "denoiser_forward_tc: bad n");
   if (n == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1421,7 +1421,7 @@ extern "C" int gldm_decoder_forward_tc(const GldmResNetCfg* cfg, const float* ra
   int rc = fill_tc(p, cfg, raw, pack);
   if (rc) return rc;
   GLDM_REQUIRE(cfg->L == 16 && !cfg->time_cond, "decoder_forward_tc: needs the decoder trunk configuration (L = 16)");
-  GLDM_REQUIRE(head && z_h && z_obj && tmrp && logit, "decoder_forward_tc: null pointer");
+  GLDM_REQUIRE(n <= 0 || (head && z_h && z_obj && tmrp && logit), "decoder_forward_tc: null pointer");
   GLDM_REQUIRE(n >= 0 && grasps_per_obj > 0 && D > 0 && D <= 64, "decoder_forward_tc: bad sizes");
   if (n == 0) return GLDM_OK;
   p.mode = 2; p.n = n; p.gpo = grasps_per_obj; p.x_in = z_h; p.z_cond = z_obj; p.n_steps = 1;
