@@ -50,6 +50,7 @@ _SIGS = {
     "gldm_sampler_tc_pack_bytes": [POINTER(GldmResNetCfg)],
     "gldm_sampler_tc_set_profile": [P],
     "gldm_sampler_tc_set_sets": [c_int],
+    "gldm_sampler_tc_set_rows": [c_int],
     "gldm_sampler_tc_prepare": [POINTER(GldmResNetCfg), P, P, P],
     "gldm_sampler_run_tc": [POINTER(GldmResNetCfg), P, P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
                             c_ulonglong, P, P, P],
@@ -103,6 +104,9 @@ def lib():
             fn = getattr(L, name)   # AttributeError if the ABI and the header disagree
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, c_int)
+        # development switches (sampler kernel variants); the defaults are chosen in csrc/sampler_tc.cu
+        if os.environ.get("GLDM_TC_ROWS"):
+            L.gldm_sampler_tc_set_rows(int(os.environ["GLDM_TC_ROWS"]))
         _lib = L
     return _lib
 

@@ -1190,6 +1190,8 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
   if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 
+#include "sampler_rows.cuh"
+
 static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, const void* pack) {
   int rc = check_tc_cfg(cfg);
   if (rc) return rc;
@@ -1223,8 +1225,28 @@ static int launch_tc_l(TcParams& p, cudaStream_t s) {
 // of the other) pay off once the batch no longer fits one wave of single-set CTAs.
 static int g_tc_sets = 0;
 
+// row-major kernel (sampler_rows.cuh): 0 = off, 1 = on where the configuration allows it
+static int g_tc_rows = 0;
+
+static bool rows_supported(const GldmResNetCfg& c) {
+  return c.L == 4 && c.emb_dim == 16 && c.time_cond && c.n_stages == 4 && c.groups == 4 && c.ch[0] == 4 && c.ch[1] == 32 &&
+         c.ch[2] == 64 && c.ch[3] == 128 && c.ch[4] == 256;
+}
+
+static int launch_rows(TcParams& p, cudaStream_t s) {
+  static bool attr = false;
+  const int smem = rows::SM_TOTAL + 1024;
+  if (!attr) {
+    cudaFuncSetAttribute(rows::resnet_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  rows::resnet_rows_kernel<<<ceil_div(p.n, rows::NS), rows::NTHREADS, smem, s>>>(p);
+  return check_launch("resnet_rows_kernel");
+}
+
 static int launch_tc(TcParams& p, cudaStream_t s) {
   p.prof = g_tc_prof;
+  if (g_tc_rows && p.mode != 2 && rows_supported(p.cfg)) return launch_rows(p, s);
   if (p.cfg.L != 4) return launch_tc_l<16, 1>(p, s);
   const bool two = g_tc_sets == 2 || (g_tc_sets == 0 && p.n > 16 * kNumSMs);
   return two ? launch_tc_l<4, 2>(p, s) : launch_tc_l<4, 1>(p, s);
@@ -1245,6 +1267,11 @@ extern "C" int gldm_sampler_tc_set_sets(int sets) {
     return GLDM_EINVAL;
   }
   g_tc_sets = sets;
+  return GLDM_OK;
+}
+
+extern "C" int gldm_sampler_tc_set_rows(int on) {
+  g_tc_rows = on ? 1 : 0;
   return GLDM_OK;
 }
 
