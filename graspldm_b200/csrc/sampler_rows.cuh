@@ -76,6 +76,21 @@ __device__ __forceinline__ void ld_cols(const Ep& e, uint32_t col, float (&v)[NV
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(r[i]);
 }
+// asynchronous forms: issue the loads of a chunk back to back, one tcgen05.wait::ld, then convert
+template <int NV>
+__device__ __forceinline__ void ld_issue(const Ep& e, uint32_t col, uint32_t (&r)[NV]) {
+  if (NV == 8) tmem_ld8(e.tmem + col, *reinterpret_cast<uint32_t(*)[8]>(&r));
+  else tmem_ld4(e.tmem + col, *reinterpret_cast<uint32_t(*)[4]>(&r));
+}
+template <int NV>
+__device__ __forceinline__ void ld_use(const uint32_t (&r)[NV], float (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint32_t x = r[i];
+    asm volatile("" : "+r"(x));     // ordered after the tcgen05.wait::ld (volatile asm keeps program order)
+    v[i] = __uint_as_float(x);
+  }
+}
 template <int NV>
 __device__ __forceinline__ void st_cols(const Ep& e, uint32_t col, const float (&v)[NV]) {
   uint32_t r[NV];
@@ -279,28 +294,55 @@ __device__ __forceinline__ float generic_epilogue(const Ep& e, int flags, int ch
   return dot;
 }
 
-// one swizzled 16-byte chunk (4 floats) of an exchange row: 32 floats per row, chunk j of sample s at j ^ (s & 7)
-__device__ __forceinline__ float4* xrow(uint8_t* base, int pos, int s, int j) {
-  return reinterpret_cast<float4*>(base + (32 + pos * 32 + s) * 128 + ((j ^ (s & 7)) << 4));
+// exchange rows of the attention: bf16, 32 values = four 16-byte chunks per row; region 0 / 1 use complementary halves
+// of the 8 swizzled 16-byte slots of a 128-byte operand row (slot = chunk ^ (sample & 7), region 1 flips bit 2), so a
+// warp's 512-byte access always spreads over all 32 banks
+__device__ __forceinline__ uint4* xslot(uint8_t* base, int region, int pos, int s, int j) {
+  return reinterpret_cast<uint4*>(base + (32 + pos * 32 + s) * 128 + (((j ^ (s & 7)) ^ (region << 2)) << 4));
 }
-
-// linear attention core (resnets.py:211-235) on the q | k | v accumulator; warp-group = head, thread = (position, sample).
-// out[e][n] = sum_n' (sum_d q[d][n] k[d][n']) v[e][n'] with q soft-maxed over d (* 32^-0.5) and k over the positions.
-__device__ __forceinline__ void attention_epilogue(const Ep& e) {
-  uint8_t* X = e.smem + SM_A + e.g * SLAB;        // the idle operand slab of this head: rows 32..159 (halo untouched)
-  const int h = e.g, n = e.pos, s = e.s;
-  float qs[32], kv[32];
+__device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float t[8];
-    ld_cols<8>(e, T_ACC + h * 32 + i * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) qs[i * 8 + j] = t[j];
-    ld_cols<8>(e, T_ACC + 128 + h * 32 + i * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) kv[i * 8 + j] = t[j];
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(h);
+    f[2 * i + 1] = __high2float(h);
   }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// linear attention core (resnets.py:211-235) on the q | k | v accumulator; warp-group = head, thread = (position n, sample).
+//   out[e][n] = sum_n' A[n][n'] v[e][n'],  A[n][n'] = sum_d q^[d][n] k^[d][n'],
+//   q^ = softmax over d of q (* 32^-0.5),  k^ = softmax over the 4 positions of k.
+// The four threads of a (sample, head) split the work by quarters of the 32-wide head dimension instead of each doing
+// everything for its own position: thread t takes d in [8t, 8t+8) for all positions (partial A, 16 values) and later
+// e in [8t, 8t+8) for all positions.  Rows travel through the idle operand slab of the head as bf16 (q^, k, v: every
+// thread of a sample sees the same rounded values, so the soft-max over positions stays consistent); the partial A's
+// as fp32.
+__device__ __forceinline__ void attention_epilogue(const Ep& e) {
+  uint8_t* X = e.smem + SM_A + e.g * SLAB;        // rows 32..159 of this head's slab (the halo rows are not touched)
+  const int h = e.g, t = e.pos, s = e.s;
   {
+    float qs[32], kv[32];
+    uint32_t rq[4][8], rk[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ld_issue<8>(e, T_ACC + h * 32 + i * 8, rq[i]);
+      ld_issue<8>(e, T_ACC + 128 + h * 32 + i * 8, rk[i]);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float tmp[8];
+      ld_use<8>(rq[i], tmp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qs[i * 8 + j] = tmp[j];
+      ld_use<8>(rk[i], tmp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kv[i * 8 + j] = tmp[j];
+    }
     float m = qs[0];
 #pragma unroll
     for (int d = 1; d < 32; ++d) m = fmaxf(m, qs[d]);
@@ -310,80 +352,92 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
     const float sc = __fdividef(0.17677669529663687f, sum);
 #pragma unroll
     for (int d = 0; d < 32; ++d) qs[d] *= sc;
-  }
-  // raw k of this row -> exchange
 #pragma unroll
-  for (int j = 0; j < 8; ++j) *xrow(X, n, s, j) = make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+    for (int j = 0; j < 4; ++j) {
+      *xslot(X, 0, t, s, j) = pack8(&qs[8 * j]);      // q^ of this position
+      *xslot(X, 1, t, s, j) = pack8(&kv[8 * j]);      // raw k of this position
+    }
+  }
   bar_wg(h);
-  // e = exp(k - max over positions)
+  float Ap[16];                                       // partial A[n][n'] over this thread's quarter of d
+  {
+    float q[4][8], k[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 m = make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-#pragma unroll
-    for (int p = 1; p < 4; ++p) {
-      const float4 o = *xrow(X, (n + p) & 3, s, j);
-      m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); m.z = fmaxf(m.z, o.z); m.w = fmaxf(m.w, o.w);
+    for (int pp = 0; pp < 4; ++pp) {
+      unpack8(*xslot(X, 0, pp, s, t), q[pp]);
+      unpack8(*xslot(X, 1, pp, s, t), k[pp]);
     }
-    kv[4 * j] = __expf(kv[4 * j] - m.x); kv[4 * j + 1] = __expf(kv[4 * j + 1] - m.y);
-    kv[4 * j + 2] = __expf(kv[4 * j + 2] - m.z); kv[4 * j + 3] = __expf(kv[4 * j + 3] - m.w);
-  }
-  bar_wg(h);                                       // every raw row has been read
 #pragma unroll
-  for (int j = 0; j < 8; ++j) *xrow(X, n, s, j) = make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+    for (int i = 0; i < 8; ++i) {
+      const float m = fmaxf(fmaxf(k[0][i], k[1][i]), fmaxf(k[2][i], k[3][i]));
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) k[pp][i] = __expf(k[pp][i] - m);
+      const float zi = __fdividef(1.0f, (k[0][i] + k[1][i]) + (k[2][i] + k[3][i]));
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) k[pp][i] *= zi;
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int n1 = 0; n1 < 4; ++n1) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = fmaf(q[n][i], k[n1][i], a);
+        Ap[n * 4 + n1] = a;
+      }
+  }
+  bar_wg(h);                                          // every q^ / k row has been read
+  {
+    uint32_t rv[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_issue<8>(e, T_ACC + 256 + h * 32 + i * 8, rv[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(xslot(X, 0, t, s, j)) = make_float4(Ap[4 * j], Ap[4 * j + 1], Ap[4 * j + 2], Ap[4 * j + 3]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float tmp[8];
+      ld_use<8>(rv[i], tmp);
+      *xslot(X, 1, t, s, i) = pack8(tmp);             // v of this position
+    }
+  }
   bar_wg(h);
-  // qz = q / Z, Z = sum over positions of e
+  float o[4][8];                                      // out[e in quarter t][position n]
+  {
+    float A[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 z = make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+    for (int j = 0; j < 4; ++j) {
+      float4 acc = *reinterpret_cast<const float4*>(xslot(X, 0, 0, s, j));
 #pragma unroll
-    for (int p = 1; p < 4; ++p) {
-      const float4 o = *xrow(X, (n + p) & 3, s, j);
-      z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
+      for (int pp = 1; pp < 4; ++pp) {
+        const float4 x = *reinterpret_cast<const float4*>(xslot(X, 0, pp, s, j));
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+      A[4 * j] = acc.x; A[4 * j + 1] = acc.y; A[4 * j + 2] = acc.z; A[4 * j + 3] = acc.w;
     }
-    qs[4 * j] = __fdividef(qs[4 * j], z.x); qs[4 * j + 1] = __fdividef(qs[4 * j + 1], z.y);
-    qs[4 * j + 2] = __fdividef(qs[4 * j + 2], z.z); qs[4 * j + 3] = __fdividef(qs[4 * j + 3], z.w);
+    float v[4][8];
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) unpack8(*xslot(X, 1, pp, s, t), v[pp]);
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = A[n * 4] * v[0][i];
+#pragma unroll
+        for (int n1 = 1; n1 < 4; ++n1) a = fmaf(A[n * 4 + n1], v[n1][i], a);
+        o[n][i] = a;
+      }
   }
-  float A[4];
+  bar_all();                                          // the exchange rows become operand rows again
+  // channels 32h + 8t .. + 8 of the four rows (n, s)
+  {
+    const int chan = h * 32 + t * 8;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    float a = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 o = *xrow(X, p, s, j);
-      a = fmaf(qs[4 * j], o.x, a); a = fmaf(qs[4 * j + 1], o.y, a);
-      a = fmaf(qs[4 * j + 2], o.z, a); a = fmaf(qs[4 * j + 3], o.w, a);
+    for (int n = 0; n < 4; ++n) {
+      const int R = 32 + n * 32 + s;
+      *reinterpret_cast<uint4*>(e.smem + SM_A + (chan >> 6) * SLAB + R * 128 + ((((chan & 63) >> 3) ^ (R & 7)) << 4)) = pack8(o[n]);
     }
-    A[p] = a;
-  }
-  // v rows
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t[8];
-    ld_cols<8>(e, T_ACC + 256 + h * 32 + i * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) kv[i * 8 + j] = t[j];
-  }
-  bar_wg(h);                                       // every e row has been read
-#pragma unroll
-  for (int j = 0; j < 8; ++j) *xrow(X, n, s, j) = make_float4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
-  bar_wg(h);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const float4 t = *xrow(X, p, s, j);
-      o.x = fmaf(A[p], t.x, o.x); o.y = fmaf(A[p], t.y, o.y); o.z = fmaf(A[p], t.z, o.z); o.w = fmaf(A[p], t.w, o.w);
-    }
-    kv[4 * j] = o.x; kv[4 * j + 1] = o.y; kv[4 * j + 2] = o.z; kv[4 * j + 3] = o.w;
-  }
-  bar_all();                                       // the exchange rows become operand rows again
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = kv[i * 8 + j];
-    st_operand<8>(e, h * 32 + i * 8, t);
   }
 }
 
@@ -566,7 +620,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
           par ^= 1u << s;
           const uint2 c = chunk_tab[ci];
           bulk_g2s_elect(smem + SM_RING + s * CHUNK, p.pack + c.x, c.y, &full[s]);
-          if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[2] = ((long long)step << 32) | ci; __threadfence_system(); }
+
         }
     } else if (wid_u == 17) {
       // =========================== UMMA issuer ===========================
@@ -577,10 +631,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
 #pragma unroll 1
         for (int j = 0; j < n_rj; ++j, ++jobn) {
           const uint32_t o0 = op_begin[j], o_end = op_begin[j + 1];      // the last job also walks the ring padding
-          if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[0] = ((long long)step << 32) | (j << 8) | 1; __threadfence_system(); }
           mbar_wait(b_ready, jobn & 1);
           tc_fence_after();
-          if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[0] = ((long long)step << 32) | (j << 8) | 2; __threadfence_system(); }
           uint32_t prev_stage = 0;
 #pragma unroll 1
           for (uint32_t i = o0; i < o_end; ++i) {
@@ -678,12 +730,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
             s_par[6 * 256 + i] = job.o_g2 >= 0 ? __ldg(W + job.o_g2 + cc) : 0.f;
           }
         }
-        if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[1] = ((long long)step << 32) | (j << 8) | 1; __threadfence_system(); }
+        const bool rec = p.prof && blockIdx.x == 0 && tid == 0 && step == 1;
+        if (rec) p.prof[64 + 8 * j] = clock64();
         mbar_wait(acc_ready, jobn & 1);
         tc_fence_after();
-        if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[1] = ((long long)step << 32) | (j << 8) | 2; __threadfence_system(); }
+        if (rec) p.prof[64 + 8 * j + 1] = clock64();
         bar_all();
-        if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[1] = ((long long)step << 32) | (j << 8) | 3; __threadfence_system(); }
+        if (rec) p.prof[64 + 8 * j + 2] = clock64();
         if (p.prof && blockIdx.x == 0 && p.prof[8] == (long long)j + 1 && step == 0) {
           // development aid: raw TMEM image [128 rows][512 columns] of CTA 0 when job j's accumulator is ready
           float* dump = reinterpret_cast<float*>(p.prof + 16);
@@ -737,7 +790,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
             bar_all();
           }
         }
-        if (p.prof && blockIdx.x == 0 && tid == 0) { p.prof[1] = ((long long)step << 32) | (j << 8) | 4; __threadfence_system(); }
+        if (rec) p.prof[64 + 8 * j + 6] = clock64();
         if (j + 1 < n_rj) handoff();
       }
     }
