@@ -105,7 +105,7 @@ def lib():
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, c_int)
         # development switches (sampler kernel variants); the defaults are chosen in csrc/sampler_tc.cu
-        if os.environ.get("GLDM_TC_ROWS"):
+        if os.environ.get("GLDM_TC_ROWS") is not None:
             L.gldm_sampler_tc_set_rows(int(os.environ["GLDM_TC_ROWS"]))
         _lib = L
     return _lib

@@ -1225,8 +1225,8 @@ static int launch_tc_l(TcParams& p, cudaStream_t s) {
 // of the other) pay off once the batch no longer fits one wave of single-set CTAs.
 static int g_tc_sets = 0;
 
-// row-major kernel (sampler_rows.cuh): 0 = off, 1 = on where the configuration allows it
-static int g_tc_rows = 0;
+// row-major kernel (sampler_rows.cuh): 1 = on where the configuration allows it (default), 0 = channel-major kernel
+static int g_tc_rows = 1;
 
 static bool rows_supported(const GldmResNetCfg& c) {
   return c.L == 4 && c.emb_dim == 16 && c.time_cond && c.n_stages == 4 && c.groups == 4 && c.ch[0] == 4 && c.ch[1] == 32 &&

@@ -183,6 +183,7 @@ def test_sampler_two_sets_per_cta_matches_one_set(cuda):
     noise = torch.randn(10, n_obj * G_, 1, 4, generator=gen).to(cuda)
     outs = []
     try:
+        _lib.call("gldm_sampler_tc_set_rows", 0)          # the channel-major kernel (default for this model: row-major)
         for sets in (1, 2):
             _lib.call("gldm_sampler_tc_set_sets", sets)
             x0, allx = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
@@ -190,7 +191,17 @@ def test_sampler_two_sets_per_cta_matches_one_set(cuda):
             outs.append((x0.clone(), allx[5].clone()))
     finally:
         _lib.call("gldm_sampler_tc_set_sets", 0)
+        _lib.call("gldm_sampler_tc_set_rows", 1)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # the row-major kernel (activations as the M operand, 32 samples per CTA) against the channel-major one: same network,
+    # different summation orders and bf16 rounding points -> bf16-level agreement; and it is deterministic
+    r0, rall = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
+                                        grasps_per_object=G_, precision="bf16")
+    r1, _ = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, x_T=x_T, noise=noise, grasps_per_object=G_,
+                                     precision="bf16")
+    assert torch.equal(r0, r1) and len(rall) == 11
+    print(f"row-major vs channel-major sampler after 10 steps: max|diff| {(r0 - outs[0][0]).abs().max().item():.3e}")
+    np.testing.assert_allclose(r0.cpu().numpy(), outs[0][0].cpu().numpy(), rtol=3e-2, atol=3e-2)
 
 
 @pytest.mark.parametrize("B,ci,co,r", [(3, 48, 48, 24), (2, 48, 96, 12), (5, 96, 96, 12)])
