@@ -314,6 +314,8 @@ def main():
         # one set under the epilogue of the other); the sequential latency pass above used the automatic choice
         if args.precision == "bf16" and not os.environ.get("GLDM_TC_SETS"):
             _lib.call("gldm_sampler_tc_set_sets", 2)
+        if args.precision == "bf16" and os.environ.get("GLDM_TC_ROWS") is None:
+            _lib.call("gldm_sampler_tc_set_rows", 1)     # throughput mode: the row-major sampler kernel (32 samples per CTA)
         total_ms = timed_pipelined(gen_resident, args.steps, args.warmup)
         launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, n_streams)) * args.steps
     else:
@@ -334,7 +336,7 @@ def main():
     dec_ms = sum(sections.get("decoder", [0.0])) / max(1, len(sections.get("decoder", [])))
     samp_flops = n_local * N_STEPS_DDPM * F_DENOISER_PER_SAMPLE_STEP
     achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
-    kname = ("resnet_rows_kernel (tcgen05 persistent 100-step sampler, activations as the M = 128 operand, one launch per batch)" if args.precision == "bf16"
+    kname = ("resnet_tc_kernel<4,1> in the latency pass / resnet_rows_kernel in the pipelined passes (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
              else "resnet_kernel<4> (fp32 SIMT persistent 100-step sampler, one launch per batch)")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_tc_sampler_traffic.json")
@@ -349,7 +351,7 @@ def main():
                 # of the batches in flight): a lower bound on what the sampler kernel sustains across the GPU
                 "achieved_timed_region": samp_flops * args.steps / (total_ms * 1e-3) / 1e12,
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE and the 3->48 Conv3d on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (32 samples per sampler CTA: 40 CTAs on 148 SMs at this batch size)"
+                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE and the 3->48 Conv3d on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (channel-major sampler kernel, 16 samples per CTA, 80 CTAs; the pipelined passes use the row-major kernel, 32 samples per CTA)"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:
@@ -366,8 +368,8 @@ def main():
                    "parallelism": f"objects sharded over {world} rank(s), one final all_gather",
                    "l2": "256 MiB buffer written before every step" + (" (inside the timed region, on the step's stream)" if n_streams > 1 else " (between timed iterations)"),
                    "batches_in_flight": n_streams, "latency_ms_per_batch": lat_ms / args.steps, "precision": args.precision,
-                   "sampler_samples_per_cta": ("32 (row-major tcgen05 kernel: rows = 4 positions x 32 samples)"
-                                               if args.precision == "bf16" else "8 (fp32 SIMT kernel)"),
+                   "sampler_samples_per_cta": ("32 (row-major tcgen05 kernel: rows = 4 positions x 32 samples) in the pipelined passes, 16 (channel-major kernel, 80 CTAs) in the latency pass"
+                                               if (n_streams > 1 and args.precision == "bf16") else "automatic"),
                    "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcs_host.numel() * 4 + n_local * 4 * 4),
                 "d2h_bytes_per_step": int(out_host["grasps"].numel() * 4 + out_host["confidence"].numel() * 4),

@@ -1225,8 +1225,10 @@ static int launch_tc_l(TcParams& p, cudaStream_t s) {
 // of the other) pay off once the batch no longer fits one wave of single-set CTAs.
 static int g_tc_sets = 0;
 
-// row-major kernel (sampler_rows.cuh): 1 = on where the configuration allows it (default), 0 = channel-major kernel
-static int g_tc_rows = 1;
+// row-major kernel (sampler_rows.cuh): 1 = on where the configuration allows it, 0 = channel-major kernel, -1 (default)
+// = by batch size: the row-major kernel has the better throughput per SM (32 samples per CTA), the channel-major one
+// spreads a small batch over twice as many SMs (16 samples per CTA) and finishes it sooner
+static int g_tc_rows = -1;
 
 static bool rows_supported(const GldmResNetCfg& c) {
   return c.L == 4 && c.emb_dim == 16 && c.time_cond && c.n_stages == 4 && c.groups == 4 && c.ch[0] == 4 && c.ch[1] == 32 &&
@@ -1246,7 +1248,8 @@ static int launch_rows(TcParams& p, cudaStream_t s) {
 
 static int launch_tc(TcParams& p, cudaStream_t s) {
   p.prof = g_tc_prof;
-  if (g_tc_rows && p.mode != 2 && rows_supported(p.cfg)) return launch_rows(p, s);
+  const bool want_rows = g_tc_rows == 1 || (g_tc_rows < 0 && p.n > 16 * kNumSMs);
+  if (want_rows && p.mode != 2 && rows_supported(p.cfg)) return launch_rows(p, s);
   if (p.cfg.L != 4) return launch_tc_l<16, 1>(p, s);
   const bool two = g_tc_sets == 2 || (g_tc_sets == 0 && p.n > 16 * kNumSMs);
   return two ? launch_tc_l<4, 2>(p, s) : launch_tc_l<4, 1>(p, s);
@@ -1271,7 +1274,7 @@ extern "C" int gldm_sampler_tc_set_sets(int sets) {
 }
 
 extern "C" int gldm_sampler_tc_set_rows(int on) {
-  g_tc_rows = on ? 1 : 0;
+  g_tc_rows = on < 0 ? -1 : on ? 1 : 0;
   return GLDM_OK;
 }
 

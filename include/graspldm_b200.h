@@ -182,8 +182,9 @@ int gldm_decoder_forward_f32(const GldmResNetCfg* cfg, const float* prepared, co
 /* sample sets per sampler CTA: 0 = automatic (two sets of 16 samples once the batch exceeds one wave of 16-sample
  * CTAs: the tensor-core phase of one set then overlaps the epilogue of the other), 1 or 2 to force */
 int gldm_sampler_tc_set_sets(int sets);
-/* 1 (default): the fpc latent denoiser runs on the row-major kernel (activations as the M = 128 operand, 32 samples per
- * CTA); 0: on the channel-major kernel (weights as the M operand), which also serves the ppc denoiser and the decoder */
+/* Kernel choice for the fpc latent denoiser: 1 = row-major kernel (activations as the M = 128 operand, 32 samples per
+ * CTA: best throughput per SM), 0 = channel-major kernel (weights as the M operand, 16 or 32 samples per CTA; it also
+ * serves the ppc denoiser and the decoder), -1 (default) = by batch size (row-major above one wave of 16-sample CTAs) */
 int gldm_sampler_tc_set_rows(int on);
 long long gldm_sampler_tc_pack_bytes(const GldmResNetCfg* cfg);
 /* development aid: when dev_buf != NULL (>= 512 int64 on the device) CTA 0 stamps clock64() around every

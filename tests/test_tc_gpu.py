@@ -193,12 +193,15 @@ def test_sampler_two_sets_per_cta_matches_one_set(cuda):
         _lib.call("gldm_sampler_tc_set_sets", 0)
         _lib.call("gldm_sampler_tc_set_rows", 1)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    # the row-major kernel (activations as the M operand, 32 samples per CTA) against the channel-major one: same network,
-    # different summation orders and bf16 rounding points -> bf16-level agreement; and it is deterministic
-    r0, rall = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
-                                        grasps_per_object=G_, precision="bf16")
-    r1, _ = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, x_T=x_T, noise=noise, grasps_per_object=G_,
-                                     precision="bf16")
+    try:
+        # the row-major kernel (activations as the M operand, 32 samples per CTA) against the channel-major one: same
+        # network, different summation orders and bf16 rounding points -> bf16-level agreement; and it is deterministic
+        r0, rall = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
+                                            grasps_per_object=G_, precision="bf16")
+        r1, _ = m.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, x_T=x_T, noise=noise, grasps_per_object=G_,
+                                         precision="bf16")
+    finally:
+        _lib.call("gldm_sampler_tc_set_rows", -1)         # back to the automatic choice
     assert torch.equal(r0, r1) and len(rall) == 11
     print(f"row-major vs channel-major sampler after 10 steps: max|diff| {(r0 - outs[0][0]).abs().max().item():.3e}")
     np.testing.assert_allclose(r0.cpu().numpy(), outs[0][0].cpu().numpy(), rtol=3e-2, atol=3e-2)
@@ -308,3 +311,59 @@ def test_ppc_denoiser_forward_bf16_vs_reference_fixture(cuda):
     got = m.diffusion_model.model(t("x"), time=t("t"), z_cond=t("z_cond"), precision="bf16").cpu().numpy()
     print(f"[ppc] bf16 denoiser vs reference fixture: max|err| {np.abs(got - g['eps']).max():.3e}, max|eps| {np.abs(g['eps']).max():.3f}")
     np.testing.assert_allclose(got, g["eps"], rtol=5e-2, atol=5e-2)
+
+
+@pytest.fixture
+def row_major(cuda):
+    """Force the row-major sampler kernel (the automatic choice takes it only above one wave of 16-sample CTAs)."""
+    from graspldm_b200 import _lib
+    _lib.call("gldm_sampler_tc_set_rows", 1)
+    yield
+    _lib.call("gldm_sampler_tc_set_rows", -1)
+
+
+def test_row_major_kernel_parity(fpc, cuda, row_major):
+    """The row-major tcgen05 sampler kernel (csrc/sampler_rows.cuh) on its own: single evaluation against the oracle,
+    full DDPM / DDIM trajectories against the fp32 path, end to end against the reference fixture."""
+    from graspldm_b200.inference import InferenceLDM, default_metas
+    m, vae, ddm = fpc
+    for B in (1, 37, 70):                                    # partially filled CTAs of 32 samples
+        gen = torch.Generator().manual_seed(11 + B)
+        x, zc = torch.randn(B, 1, 4, generator=gen), torch.randn(B, 3, 64, generator=gen)
+        tt = torch.randint(0, 1000, (B,), generator=gen)
+        with torch.no_grad():
+            want = M.denoiser_forward(ddm, "diffusion_model.model.", x, tt, zc)
+        got = m.diffusion_model.model(x.to(cuda), time=tt.to(cuda), z_cond=zc.to(cuda), precision="bf16").cpu()
+        print(f"[rows B={B}] denoiser max|err| vs oracle {(got - want).abs().max().item():.3e}")
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-2, atol=5e-2)
+    for kind, steps in (("ddpm", 100), ("ddim", 5)):
+        mm = _models.build("fpc", scheduler=kind).to(cuda)
+        mm.set_inference_timesteps(steps)
+        gen = torch.Generator().manual_seed(5)
+        n_obj, G_ = 3, 15
+        z = torch.randn(n_obj, 3, 64, generator=gen).to(cuda)
+        x_T = torch.randn(n_obj * G_, 1, 4, generator=gen).to(cuda)
+        noise = torch.randn(steps, n_obj * G_, 1, 4, generator=gen).to(cuda)
+        a, _ = mm.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, x_T=x_T, noise=noise, grasps_per_object=G_)
+        b, allb = mm.diffusion_model.sample(z_cond=z, batch_size=n_obj * G_, return_all=True, x_T=x_T, noise=noise,
+                                            grasps_per_object=G_, precision="bf16")
+        assert len(allb) == steps + 1 and torch.equal(allb[0], x_T) and torch.equal(allb[-1], b)
+        print(f"[rows {kind}{steps}] bf16 vs fp32 latents: max|diff| {(a - b).abs().max().item():.3e}")
+        np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=3e-2, atol=3e-2)
+        # a sample's latent does not depend on its CTA neighbours
+        b2, _ = mm.diffusion_model.sample(z_cond=z[:1], batch_size=G_, x_T=x_T[:G_], noise=noise[:, :G_].contiguous(),
+                                          grasps_per_object=G_, precision="bf16")
+        assert torch.equal(b2, b[:G_])
+    g = np.load(os.path.join(G, "ldm_fpc_ddpm100.npz"))
+    mm = _models.build("fpc").to(cuda)
+    mm.set_inference_timesteps(100)
+    _set_precision(mm, "bf16")
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S")
+    out = InferenceLDM(mm, device=cuda).generate_grasps(xyz, default_metas(2), num_grasps=3,
+                                                        x_T=torch.from_numpy(g["x_T"]).to(cuda),
+                                                        noise=torch.from_numpy(g["noise"]).to(cuda))
+    want = M.postprocess(torch.from_numpy(g["tmrp"]), torch.from_numpy(g["logit"]), xyz, default_metas(2), 2, 3)
+    dt = (out["grasps"].cpu()[..., :3, 3] - want["grasps"][..., :3, 3]).norm(dim=-1).max().item()
+    da = _rot_angle_deg(out["grasps"].cpu()[..., :3, :3], want["grasps"][..., :3, :3]).max().item()
+    print(f"[rows e2e] max translation error {dt * 1e3:.3f} mm, max rotation error {da:.3f} deg")
+    assert dt < 1e-3 and da < 2.0
