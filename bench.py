@@ -306,6 +306,13 @@ def main():
 
     # pass 1 (sequential, one batch at a time): per-batch latency and the per-section / per-kernel durations
     lat_ms, sections = timed(gen_resident, args.steps, args.warmup, sections=True)
+    # the sampler kernel of the pipelined passes (row-major, 32 samples per CTA), timed alone the same way
+    rows_ms = None
+    if n_streams > 1 and args.precision == "bf16" and os.environ.get("GLDM_TC_ROWS") is None:
+        _lib.call("gldm_sampler_tc_set_rows", 1)
+        _, sec_rows = timed(gen_resident, max(3, args.steps // 2), 2, sections=True)
+        _lib.call("gldm_sampler_tc_set_rows", -1)
+        rows_ms = sum(sec_rows.get("sampler", [0.0])) / max(1, len(sec_rows.get("sampler", [])))
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = _lib.launch_count()
@@ -350,6 +357,11 @@ def main():
                 # the same FLOPs over the whole pipelined timed region (which also holds the encoder / decoder kernels
                 # of the batches in flight): a lower bound on what the sampler kernel sustains across the GPU
                 "achieved_timed_region": samp_flops * args.steps / (total_ms * 1e-3) / 1e12,
+                # the row-major kernel of the pipelined passes alone: one batch = ceil(samples / 32) CTAs, one per SM
+                "pipelined_kernel": (None if not rows_ms else {
+                    "name": "resnet_rows_kernel", "kernel_ms": rows_ms, "ctas": -(-n_local // 32), "sms": 148,
+                    "achieved": samp_flops / (rows_ms * 1e-3) / 1e12,
+                    "frac_of_peak_of_occupied_sms": samp_flops / (rows_ms * 1e-3) / 1e12 / (pk["tflops_sustained"] * min(1.0, -(-n_local // 32) / 148))}),
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
                 "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE and the 3->48 Conv3d on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (channel-major sampler kernel, 16 samples per CTA, 80 CTAs; the pipelined passes use the row-major kernel, 32 samples per CTA)"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
