@@ -176,10 +176,23 @@ def main():
                     help="batches in flight: consecutive steps are issued round-robin on this many CUDA streams, so the "
                          "encoder / decoder of one batch fill the SMs the persistent sampler of another leaves idle")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: whatever native libraries print there (NCCL's version banner ...) goes to
+    # stderr instead; file descriptor 1 is restored for the final line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
@@ -388,7 +401,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
