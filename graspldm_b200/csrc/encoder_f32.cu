@@ -234,23 +234,33 @@ __global__ void __launch_bounds__(256) conv3d_k3_kernel(const float* __restrict_
     float bz[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) bz[j] = bias ? __ldg(bias + cg * 6 + j) : 0.f;
+    // stage the [256 voxels][48 channels] bf16 tile in shared memory (the tap buffer is free now) so that the grid rows
+    // are written as whole 16-byte pieces instead of 4-byte scatters
+    __syncthreads();
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(&As[0][0]);      // [256][48]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int v = v0 + (i >> 2) * 128 + vg * 4 + (i & 3);
-      if (v >= r3) continue;
-      const int vx = v / r2, vy = (v / r) % r, vz = v % r;
+      const int vl = (i >> 2) * 128 + vg * 4 + (i & 3);
+      const bool ok = v0 + vl < r3;
       float o[6];
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         o[j] = acc[i][j] + bz[j];
-        gs += o[j];
-        gq = fmaf(o[j], o[j], gq);
+        if (ok) { gs += o[j]; gq = fmaf(o[j], o[j], gq); }
       }
-      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(
-          y_cl + ((size_t)b * rp * rp * rp + ((size_t)(vx + 1) * rp + (vy + 1)) * rp + (vz + 1)) * y_stride + cg * 6);
+      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(tile + vl * 48 + cg * 6);
       dst[0] = __floats2bfloat162_rn(o[0], o[1]);
       dst[1] = __floats2bfloat162_rn(o[2], o[3]);
       dst[2] = __floats2bfloat162_rn(o[4], o[5]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 256 * 6; idx += 256) {
+      const int vl = idx / 6, piece = idx - vl * 6, v = v0 + vl;
+      if (v >= r3) continue;
+      const int vx = v / r2, vy = (v / r) % r, vz = v % r;
+      const uint4 val = *reinterpret_cast<const uint4*>(tile + vl * 48 + piece * 8);
+      *reinterpret_cast<uint4*>(y_cl + ((size_t)b * rp * rp * rp + ((size_t)(vx + 1) * rp + (vy + 1)) * rp + (vz + 1)) * y_stride +
+                                piece * 8) = val;
     }
     gs = warp_sum(gs);
     gq = warp_sum(gq);
