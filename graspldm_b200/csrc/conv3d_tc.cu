@@ -12,6 +12,7 @@
 // together with the GroupNorm statistics of the result (fp64 atomics per (cloud, group)), so that GroupNorm + Swish
 // becomes one in-place pass (gn_swish_cl_kernel) and devoxelize gathers channels-last rows (devox_cl_kernel).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -47,6 +48,105 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// epilogue warps (2..5) of both kernel variants: thread <-> padded voxel row; halo voxels and rows past the end are dropped
+__device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t* smem, uint32_t tmem, uint64_t* acc_full,
+                                                long long row0, int tid, int lane, int wid) {
+  const int rp = p.r + 2, rp2 = rp * rp;
+  {
+    const int q = wid & 3;
+    const long long m = row0 + q * 32 + lane;
+    const int P = rp2 * rp;
+    const long long b = m / P;
+    const int pp = (int)(m - b * P);
+    const int x = pp / rp2, yy = (pp / rp) % rp, z = pp % rp;
+    const bool interior = m < p.rows && x >= 1 && x <= p.r && yy >= 1 && yy <= p.r && z >= 1 && z <= p.r;
+    const int r3 = p.r * p.r * p.r;
+    const int v = ((x - 1) * p.r + (yy - 1)) * p.r + (z - 1);
+    float* yb = p.y + ((size_t)b * p.co) * r3 + v;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    if (p.out_mode == 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.co; c0 += 16) {
+        uint32_t u[16];
+        tmem_ld16(taddr + c0, u);
+        tmem_ld_wait();
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+        }
+      }
+    } else {
+      // channels-last row of this voxel + GroupNorm partial sums.  The pipeline stages are idle once acc_full fired:
+      // their memory holds the per-thread group partials [128][17].
+      float* part = reinterpret_cast<float*>(smem) + (tid - 64) * 17;
+      const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
+      float gs = 0.f, gq = 0.f;
+      int g = 0, in_g = 0;
+      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
+        float v[16];
+        if (c0 < n_umma) {
+          uint32_t u[16];
+          tmem_ld16(taddr + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < p.co) {
+            gs += v[j];
+            gq = fmaf(v[j], v[j], gq);
+            if (++in_g == cpg) { part[g] = gs; part[8 + g] = gq; ++g; in_g = 0; gs = 0.f; gq = 0.f; }
+          }
+        }
+        if (interior) {
+          if (p.out_mode == 1) {
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
+            dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+        }
+      }
+      __syncwarp();
+      // warp totals of the 16 partials (32 voxels) per cloud slot (the 128 rows of a CTA touch at most two clouds:
+      // slot 0 = the cloud of its first row, slot 1 = the next one), then a fixed-order sum over the 4 epilogue warps:
+      // the statistics are bit-reproducible (no atomics); conv_stats_finalize_kernel adds the CTAs of a cloud in order
+      float* wtot = reinterpret_cast<float*>(smem) + 128 * 17;          // [4 warps][2 slots][16]
+      const int b0 = (int)(row0 / P);
+      for (int slot = 0; slot < 2; ++slot) {
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = (interior && b == b0 + slot) ? part[i] : 0.f;
+        rs_step<16, 8>(a, lane); rs_step<8, 4>(a, lane); rs_step<4, 2>(a, lane); rs_step<2, 1>(a, lane);
+        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+        if ((lane & 1) == 0) wtot[(q * 2 + slot) * 16 + (lane >> 1)] = a[0];   // index 0..7 sums, 8..15 sums of squares
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0) {
+        const int slot = lane >> 4, idx = lane & 15;
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t += (double)wtot[(w * 2 + slot) * 16 + idx];
+        p.stats[((size_t)blockIdx.x * 2 + slot) * 16 + idx] = t;          // p.stats = per-CTA partials here
+      }
+    }
+    tc_fence_before();
+  }
 }
 
 template <int WSLOT>
@@ -118,91 +218,97 @@ __global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d
     }
     umma_commit_elect(acc_full);
   } else {
-    // ---- epilogue: thread <-> padded voxel row; halo voxels and rows past the end are dropped
-    const int q = wid & 3;
-    const long long m = row0 + q * 32 + lane;
-    const int P = rp2 * rp;
-    const long long b = m / P;
-    const int pp = (int)(m - b * P);
-    const int x = pp / rp2, yy = (pp / rp) % rp, z = pp % rp;
-    const bool interior = m < p.rows && x >= 1 && x <= p.r && yy >= 1 && yy <= p.r && z >= 1 && z <= p.r;
-    const int r3 = p.r * p.r * p.r;
-    const int v = ((x - 1) * p.r + (yy - 1)) * p.r + (z - 1);
-    float* yb = p.y + ((size_t)b * p.co) * r3 + v;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-    if (p.out_mode == 0) {
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
+  }
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<128>(tmem);
+}
+
+// Variant that fetches the A rows once per (dx, dy): the three dz taps of a filter column are the same rows shifted by one,
+// so one 136-row TMA box serves three UMMA groups whose A descriptor starts 0 / 128 / 256 bytes into the tile (the
+// 128-byte swizzle is a function of the absolute shared-memory address bits, so a descriptor start that is not a
+// multiple of the 8-row swizzle atom needs nothing else - measured on the B200: with the matrix-base-offset field set to
+// the row phase (bo_mode 1) the results are wrong, with the field left 0 (bo_mode 2, the default) they are exact).
+// A traffic drops 3x; a stage is one A tile + three weight blocks.
+namespace c3 {
+constexpr int A3_ROWS = 136, A3_BYTES = 18432;      // 136 x 128 B = 17408, slot rounded to 1024
+constexpr int STAGES3 = 2;
+}
+template <int WSLOT>
+__global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc3_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                     const __grid_constant__ Conv3dTcParams p, int bo_mode) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int STAGE_BYTES = A3_BYTES + 3 * WSLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES3 * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES3;
+  uint64_t* acc_full = bars + 2 * STAGES3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES3 + 1);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const long long row0 = (long long)blockIdx.x * 128;
+  const int rp = p.r + 2, rp2 = rp * rp;
+  const int n_it = 9 * p.k_blocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES3; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.co; c0 += 16) {
-        uint32_t u[16];
-        tmem_ld16(taddr + c0, u);
-        tmem_ld_wait();
-        if (interior) {
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES3, round = it / STAGES3;
+      const int col = it / p.k_blocks, kb = it - col * p.k_blocks;       // col = dx*3 + dy
+      const int shift = (col / 3 - 1) * rp2 + (col % 3 - 1) * rp - 1;     // row of the dz = -1 tap
+      if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full[s], A3_ROWS * 128 + 3 * p.w_rows_bytes);
+        tma_load_2d(smem + s * STAGE_BYTES, &xmap, kb * 64, (int)(row0 + shift), &full[s]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-        }
-      }
-    } else {
-      // channels-last row of this voxel + GroupNorm partial sums.  The pipeline stages are idle once acc_full fired:
-      // their memory holds the per-thread group partials [128][17].
-      float* part = reinterpret_cast<float*>(smem) + (tid - 64) * 17;
-      const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
-      float gs = 0.f, gq = 0.f;
-      int g = 0, in_g = 0;
-      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
-        float v[16];
-        if (c0 < n_umma) {
-          uint32_t u[16];
-          tmem_ld16(taddr + c0, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) : 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < p.co) {
-            gs += v[j];
-            gq = fmaf(v[j], v[j], gq);
-            if (++in_g == cpg) { part[g] = gs; part[8 + g] = gq; ++g; in_g = 0; gs = 0.f; gq = 0.f; }
-          }
-        }
-        if (interior) {
-          if (p.out_mode == 1) {
-            uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
-            dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          }
-        }
+        for (int dz = 0; dz < 3; ++dz)
+          bulk_g2s(smem + s * STAGE_BYTES + A3_BYTES + dz * WSLOT,
+                   p.w_img + ((size_t)(col * 3 + dz) * p.k_blocks + kb) * W_BYTES, p.w_rows_bytes, &full[s]);
       }
       __syncwarp();
-      // warp totals of the 16 partials (32 voxels), one fp64 atomic per (group, moment); a warp can straddle two clouds
-      const long long b_last = min(b, (long long)p.batch - 1);
-      const int b_lo = (int)__shfl_sync(0xffffffffu, (int)b_last, 0), b_hi = (int)__shfl_sync(0xffffffffu, (int)b_last, 31);
-      for (int bb = b_lo; bb <= b_hi; ++bb) {
-        float a[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = (interior && b == bb) ? part[i] : 0.f;
-        rs_step<16, 8>(a, lane); rs_step<8, 4>(a, lane); rs_step<4, 2>(a, lane); rs_step<2, 1>(a, lane);
-        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-        if ((lane & 1) == 0) {
-          const int idx = lane >> 1;       // 0..7: sums of groups 0..7, 8..15: sums of squares
-          atomicAdd(p.stats + ((size_t)bb * 8 + (idx & 7)) * 2 + (idx >> 3), (double)a[0]);
-        }
-      }
     }
-    tc_fence_before();
+  } else if (wid == 1) {
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const uint32_t base = smem_u32(smem);
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES3;
+      const int kb = it % p.k_blocks;
+      mbar_wait(&full[s], (it / STAGES3) & 1);
+      tc_fence_after();
+      const int ks = (kb == p.k_blocks - 1) ? p.ksteps_last : 4;
+#pragma unroll 1
+      for (int dz = 0; dz < 3; ++dz) {
+        const uint32_t a_addr = base + s * STAGE_BYTES + dz * 128;
+        const uint32_t a_hi = hi | (bo_mode == 1 ? ((uint32_t)dz << 17) : 0u);      // descriptor bits [49,52)
+        const uint64_t ad = ((uint64_t)a_hi << 32) | (0x10000u | (a_addr >> 4));
+        const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE_BYTES + A3_BYTES + dz * WSLOT) >> 4));
+        const uint32_t acc = (it != 0 || dz != 0) ? 1u : 0u;
+        if (ks == 4) umma_bf16_block_elect<4>(tmem, ad, bd, idesc, acc);
+        else if (ks == 3) { umma_bf16_block_elect<2>(tmem, ad, bd, idesc, acc); umma_bf16_block_elect<1>(tmem, ad + 4, bd + 4, idesc, 1u); }
+        else if (ks == 2) umma_bf16_block_elect<2>(tmem, ad, bd, idesc, acc);
+        else umma_bf16_block_elect<1>(tmem, ad, bd, idesc, acc);
+      }
+      umma_commit_elect(&empty[s]);
+    }
+    umma_commit_elect(acc_full);
+  } else {
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
   }
   __syncthreads();
   if (wid == 1) tmem_dealloc<128>(tmem);
@@ -232,6 +338,30 @@ __global__ void __launch_bounds__(256) cl_pad_kernel(const float* __restrict__ x
   }
   *reinterpret_cast<uint4*>(out + (size_t)m * cpad + chunk * 8) =
       make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// stats[b][g][moment] = sum over the CTAs covering cloud b of their slot partials, in CTA order (deterministic)
+__global__ void conv_stats_finalize_kernel(const double* __restrict__ part, int P, long long rows, double* __restrict__ stats) {
+  const int b = blockIdx.x, idx = threadIdx.x;       // 16 threads: 0..7 sums, 8..15 sums of squares
+  const long long r_lo = (long long)b * P, r_hi = r_lo + P - 1;
+  const long long c_lo = r_lo / 128, c_hi = r_hi / 128;
+  double t = 0.0;
+  for (long long c = c_lo; c <= c_hi; ++c) {
+    const int slot = b - (int)((c * 128) / P);
+    t += part[((size_t)c * 2 + slot) * 16 + idx];
+  }
+  (void)rows;
+  stats[((size_t)b * 8 + (idx & 7)) * 2 + (idx >> 3)] = t;
+}
+// the same for per-block partials laid out [b][nblk][16] (SIMT first conv) and [b][nblk][c] (SE squeeze sums)
+__global__ void block_partials_finalize_kernel(const double* __restrict__ part, int nblk, int width, int remap,
+                                               double* __restrict__ out) {
+  const int b = blockIdx.x, i = threadIdx.x;
+  if (i >= width) return;
+  double t = 0.0;
+  for (int k = 0; k < nblk; ++k) t += part[((size_t)b * nblk + k) * width + i];
+  if (remap) out[((size_t)b * 8 + (i & 7)) * 2 + (i >> 3)] = t;      // [16] -> stats[b][group][moment]
+  else out[(size_t)b * width + i] = t;
 }
 
 // GroupNorm(8) + Swish in place on the interior rows of a channels-last padded grid, from the statistics the Conv3d
@@ -308,7 +438,7 @@ __global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, 
     if (tid < c) {
       float t = 0.f;
       for (int k = 0; k < rl; ++k) t += s_red[k * stride + tid];
-      atomicAdd(se_sum + (size_t)b * c + tid, (double)t);
+      se_sum[((size_t)b * gridDim.x + blockIdx.x) * c + tid] = (double)t;     // per-block partial (summed in order later)
     }
   }
 }
@@ -491,6 +621,28 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
     attr = true;
   }
   const unsigned grid = (unsigned)((rows + 127) / 128);
+  // one A tile per filter column (conv3d_tc3_kernel) by default; GLDM_CONV3D_TAPS3=0 selects the one-tile-per-tap kernel
+  static int taps3 = -1;
+  if (taps3 < 0) { const char* ev = getenv("GLDM_CONV3D_TAPS3"); taps3 = ev ? atoi(ev) : 2; }
+  if (taps3 > 0 && p.w_rows_bytes <= c3::W_SLOT) {
+    CUtensorMap map3;
+    const cuuint32_t box3[2] = {64, (cuuint32_t)c3::A3_ROWS};
+    const CUresult cr3 = enc(&map3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_cl), gdim, gstride, box3, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr3 != CUDA_SUCCESS) {
+      set_error("conv3d_k3_tc: cuTensorMapEncodeTiled (136-row box) failed (%d)", (int)cr3);
+      return GLDM_ECUDA;
+    }
+    const int smem3 = c3::STAGES3 * (c3::A3_BYTES + 3 * c3::W_SLOT) + 1024 + 256;
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(conv3d_tc3_kernel<c3::W_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+      attr3 = true;
+    }
+    conv3d_tc3_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem3, s>>>(map3, p, taps3);
+    return check_launch("conv3d_tc3_kernel");
+  }
   if (p.w_rows_bytes <= c3::W_SLOT) conv3d_tc_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem_small, s>>>(map, p);
   else conv3d_tc_kernel<c3::W_BYTES><<<grid, c3::NTHREADS, smem_big, s>>>(map, p);
   return check_launch("conv3d_tc_kernel");
@@ -523,31 +675,66 @@ extern "C" int gldm_cl_pad(const float* x, int b, int c, int r, void* out_cl, vo
   return launch_cl_pad(x, b, c, r, out_cl, (cudaStream_t)stream);
 }
 
+static int gn_blocks(int b, int r, int* rpb_out) {
+  const int P = (r + 2) * (r + 2) * (r + 2);
+  int rpb = 1024;                                  // padded voxels per block: keep >= 4 blocks per SM in flight
+  while (rpb > 128 && (long long)((P + rpb - 1) / rpb) * b < 592) rpb >>= 1;
+  if (rpb_out) *rpb_out = rpb;
+  return (P + rpb - 1) / rpb;
+}
+
+extern "C" long long gldm_voxel_ws_bytes(int b, int c, int r) {
+  if (b < 0 || c <= 0 || r <= 0) return -1;
+  const long long P = (long long)(r + 2) * (r + 2) * (r + 2);
+  const long long n_cta = (b * P + 127) / 128, nblk = ((long long)r * r * r + 255) / 256;
+  long long d = n_cta * 32;
+  if ((long long)b * nblk * 16 > d) d = (long long)b * nblk * 16;
+  const long long se = (long long)b * gn_blocks(b > 0 ? b : 1, r, nullptr) * c;
+  if (se > d) d = se;
+  return d * 8 + 256;
+}
+
 extern "C" int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const float* bias, int b, int ci, int co, int r,
-                                 void* y_cl, int out_fp32, int out_stride, double* stats, void* stream) {
-  GLDM_REQUIRE(b <= 0 || (x_cl && w_img && y_cl && stats), "conv3d_tc_cl: null pointer");
+                                 void* y_cl, int out_fp32, int out_stride, double* stats, void* ws, void* stream) {
+  GLDM_REQUIRE(b <= 0 || (x_cl && w_img && y_cl && stats && ws), "conv3d_tc_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && ci >= 16 && co > 0 && co <= 128 && r > 0, "conv3d_tc_cl: need 16 <= ci, co <= 128");
   GLDM_REQUIRE(co % 8 == 0, "conv3d_tc_cl: GroupNorm(8) statistics need co % 8 == 0");
   GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc_cl: out_stride must be a multiple of 16 in [co, 128]");
   if (b == 0) return GLDM_OK;
-  return launch_conv3d(x_cl, w_img, bias, b, ci, co, r, nullptr, out_fp32 ? 2 : 1, out_stride, y_cl, stats,
-                       (cudaStream_t)stream);
+  int rc = launch_conv3d(x_cl, w_img, bias, b, ci, co, r, nullptr, out_fp32 ? 2 : 1, out_stride, y_cl,
+                         reinterpret_cast<double*>(ws), (cudaStream_t)stream);
+  if (rc) return rc;
+  const int P = (r + 2) * (r + 2) * (r + 2);
+  conv_stats_finalize_kernel<<<b, 16, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(ws), P, (long long)b * P, stats);
+  return check_launch("conv_stats_finalize_kernel");
 }
 
 extern "C" int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const double* stats, const float* gamma,
-                                const float* beta, int b, int c, int r, float eps, double* se_sum, void* stream) {
+                                const float* beta, int b, int c, int r, float eps, double* se_sum, void* ws, void* stream) {
   GLDM_REQUIRE(b <= 0 || (y_cl && stats && gamma && beta), "gn_swish_cl: null pointer");
+  GLDM_REQUIRE(b <= 0 || !se_sum || ws, "gn_swish_cl: the SE sums need the workspace");
   GLDM_REQUIRE(b >= 0 && c > 0 && c % 8 == 0 && c <= 128 && r > 0, "gn_swish_cl: bad sizes");
   GLDM_REQUIRE(stride >= c && stride % 8 == 0 && stride <= 128, "gn_swish_cl: bad row stride");
   if (b == 0) return GLDM_OK;
-  const int P = (r + 2) * (r + 2) * (r + 2);
-  int rpb = 1024;                                  // padded voxels per block: keep >= 4 blocks per SM in flight
-  while (rpb > 128 && (long long)((P + rpb - 1) / rpb) * b < 592) rpb >>= 1;
-  dim3 grid((P + rpb - 1) / rpb, b);
+  int rpb;
+  const int gx = gn_blocks(b, r, &rpb);
+  dim3 grid(gx, b);
   cudaStream_t s = (cudaStream_t)stream;
-  if (is_fp32) gn_swish_cl_kernel<true><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, se_sum, rpb);
-  else gn_swish_cl_kernel<false><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, se_sum, rpb);
-  return check_launch("gn_swish_cl_kernel");
+  double* part = se_sum ? reinterpret_cast<double*>(ws) : nullptr;
+  if (is_fp32) gn_swish_cl_kernel<true><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, part, rpb);
+  else gn_swish_cl_kernel<false><<<grid, 256, 0, s>>>(y_cl, stats, gamma, beta, c, stride, r, eps, part, rpb);
+  int rc = check_launch("gn_swish_cl_kernel");
+  if (rc || !se_sum) return rc;
+  block_partials_finalize_kernel<<<b, 128, 0, s>>>(part, gx, c, 0, se_sum);
+  return check_launch("block_partials_finalize_kernel");
+}
+
+extern "C" int gldm_block_partials_to_stats(const double* part, int b, int nblk, double* stats, void* stream) {
+  GLDM_REQUIRE(b <= 0 || (part && stats), "block_partials_to_stats: null pointer");
+  GLDM_REQUIRE(b >= 0 && nblk > 0, "block_partials_to_stats: bad sizes");
+  if (b == 0) return GLDM_OK;
+  block_partials_finalize_kernel<<<b, 16, 0, (cudaStream_t)stream>>>(part, nblk, 16, 1, stats);
+  return check_launch("block_partials_finalize_kernel");
 }
 
 extern "C" int gldm_se_gate_sum(const double* sum, int count, const float* w1, const float* w2, int b, int c, int cr,

@@ -264,9 +264,10 @@ __global__ void __launch_bounds__(256) conv3d_k3_kernel(const float* __restrict_
     }
     gs = warp_sum(gs);
     gq = warp_sum(gq);
-    if (vg == 0) {
-      atomicAdd(stats + ((size_t)b * 8 + cg) * 2, (double)gs);
-      atomicAdd(stats + ((size_t)b * 8 + cg) * 2 + 1, (double)gq);
+    if (vg == 0) {      // per-block partials [b][block][16] (0..7 sums, 8..15 sums of squares): no atomics, summed in order later
+      double* dst = stats + ((size_t)b * gridDim.x + blockIdx.x) * 16;
+      dst[cg] = (double)gs;
+      dst[8 + cg] = (double)gq;
     }
     return;
   }
@@ -455,16 +456,21 @@ extern "C" int gldm_conv3d_k3_f32(const float* x, const float* w, const float* b
   return check_launch("conv3d_k3_kernel");
 }
 
+extern "C" int gldm_block_partials_to_stats(const double* part, int b, int nblk, double* stats, void* stream);
+
 extern "C" int gldm_conv3d_k3_f32_cl(const float* x, const float* w, const float* bias, int b, int ci, int r, void* y_cl,
-                                     int y_stride, double* stats, void* stream) {
-  GLDM_REQUIRE(b <= 0 || (x && w && y_cl && stats), "conv3d_k3_f32_cl: null pointer");
+                                     int y_stride, double* stats, void* ws, void* stream) {
+  GLDM_REQUIRE(b <= 0 || (x && w && y_cl && stats && ws), "conv3d_k3_f32_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && ci > 0 && r > 0, "conv3d_k3_f32_cl: bad sizes");
   GLDM_REQUIRE(y_stride >= C3_CT && y_stride % 8 == 0, "conv3d_k3_f32_cl: bad row stride");
   if (b == 0) return GLDM_OK;
   dim3 grid(ceil_div(r * r * r, C3_VT), 1, b);
   conv3d_k3_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, ci, C3_CT, r, nullptr,
-                                                                 reinterpret_cast<__nv_bfloat16*>(y_cl), y_stride, stats);
-  return check_launch("conv3d_k3_kernel");
+                                                                 reinterpret_cast<__nv_bfloat16*>(y_cl), y_stride,
+                                                                 reinterpret_cast<double*>(ws));
+  int rc = check_launch("conv3d_k3_kernel");
+  if (rc) return rc;
+  return gldm_block_partials_to_stats(reinterpret_cast<const double*>(ws), b, (int)grid.x, stats, stream);
 }
 
 extern "C" int gldm_groupnorm_swish_f32(float* x, const float* gamma, const float* beta, int b, int c, int s,

@@ -523,23 +523,25 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
     norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
     _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(), norm.data_ptr(),
               None, st)
-    stats = torch.zeros((2, B, 8, 2), device=dev, dtype=torch.float64)
-    se_sum = torch.zeros((B, co), device=dev, dtype=torch.float64)
+    stats = torch.empty((2, B, 8, 2), device=dev, dtype=torch.float64)
+    se_sum = torch.empty((B, co), device=dev, dtype=torch.float64)
+    # workspace of the bit-reproducible (atomic-free) statistics: per-block partials, added in a fixed order
+    ws = _cl_grid(pk, dev, ("ws", bi), 1, (_lib.lib().gldm_voxel_ws_bytes(B, max(ci, co), r) + 7) // 8, torch.float64)
     cpad_o = -(-co // 64) * 64
     if w1_img is not None:
         x_cl = _cl_grid(pk, dev, ("x", bi), rows, -(-ci // 64) * 64, torch.bfloat16)
         _lib.call("gldm_cl_pad", grid.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
         _lib.call("gldm_conv3d_tc_cl", x_cl.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r, y1.data_ptr(),
-                  0, cpad_o, stats[0].data_ptr(), st)
+                  0, cpad_o, stats[0].data_ptr(), ws.data_ptr(), st)
         _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
-                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, st)
+                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, None, st)
     elif co == 48:       # 3-channel input: strict-fp32 SIMT Conv3d straight into the channels-last form + statistics
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
         _lib.call("gldm_conv3d_k3_f32_cl", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, r,
-                  y1.data_ptr(), cpad_o, stats[0].data_ptr(), st)
+                  y1.data_ptr(), cpad_o, stats[0].data_ptr(), ws.data_ptr(), st)
         _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
-                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, st)
+                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, None, st)
     else:
         t = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
         _lib.call("gldm_conv3d_k3_f32", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, co, r,
@@ -550,9 +552,9 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
         _lib.call("gldm_cl_pad", t.data_ptr(), B, co, r, y1.data_ptr(), st)
     y2 = _cl_grid(pk, dev, ("y2", bi), rows, co, torch.float32)
     _lib.call("gldm_conv3d_tc_cl", y1.data_ptr(), w2_img.data_ptr(), blk["b2"].data_ptr(), B, co, co, r, y2.data_ptr(), 1, co,
-              stats[1].data_ptr(), st)
+              stats[1].data_ptr(), ws.data_ptr(), st)
     _lib.call("gldm_gn_swish_cl", y2.data_ptr(), 1, co, stats[1].data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(),
-              B, co, r, blk["eps2"], se_sum.data_ptr(), st)
+              B, co, r, blk["eps2"], se_sum.data_ptr(), ws.data_ptr(), st)
     gate = torch.empty((B, co), device=dev, dtype=torch.float32)
     _lib.call("gldm_se_gate_sum", se_sum.data_ptr(), r3, blk["se1"].data_ptr(), blk["se2"].data_ptr(), B, co,
               blk["se1"].shape[0], gate.data_ptr(), st)

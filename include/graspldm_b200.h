@@ -242,19 +242,23 @@ int gldm_conv3d_k3_tc(const float* x, const void* w_img, const float* bias, int 
  * are never written and must be zero on entry.
  *   gldm_cl_pad:        x f32[b,c,r^3] -> bf16 padded grid (stride = c rounded up to 64), halo rows written as zero
  *   gldm_conv3d_tc_cl:  padded bf16 grid -> padded grid y_cl (+ bias) and GroupNorm(8) statistics
- *                       stats f64[b][8][2] += (sum, sum of squares) per group (zero it before the call)
- *   gldm_gn_swish_cl:   GroupNorm(8) + Swish in place from those statistics; se_sum f64[b][c] += channel sums (or NULL)
+ *                       stats f64[b][8][2] = (sum, sum of squares) per group
+ *   gldm_gn_swish_cl:   GroupNorm(8) + Swish in place from those statistics; se_sum f64[b][c] = channel sums (or NULL)
+ * All sums are bit-reproducible: blocks write partials into the workspace `ws` (gldm_voxel_ws_bytes(b, c, r) bytes,
+ * 256-byte aligned, contents irrelevant on entry) and a second small kernel adds them in a fixed order - no atomics.
  *   gldm_se_gate_sum:   gate f32[b][c] = sigmoid(W2 swish(W1 (se_sum / count)))
  *   gldm_devox_cl:      out f32[b,c,n] = trilinear(grid * gate)(coords f32[b,3,n] in voxel units) + point f32[b,c,n] */
 int gldm_cl_pad(const float* x, int b, int c, int r, void* out_cl, void* stream);
 /* strict-fp32 SIMT Conv3d k3 p1 for few input channels (the 3 -> 48 first layer) writing the padded bf16 grid
  * y_cl [b * (r+2)^3][y_stride] (+ bias) and the GroupNorm(8) statistics of its 48 output channels; w f32[ci][27][48] */
 int gldm_conv3d_k3_f32_cl(const float* x, const float* w, const float* bias, int b, int ci, int r, void* y_cl,
-                          int y_stride, double* stats, void* stream);
+                          int y_stride, double* stats, void* ws, void* stream);
+long long gldm_voxel_ws_bytes(int b, int c, int r);
 int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const float* bias, int b, int ci, int co, int r, void* y_cl,
-                      int out_fp32, int out_stride, double* stats, void* stream);
+                      int out_fp32, int out_stride, double* stats, void* ws, void* stream);
 int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const double* stats, const float* gamma, const float* beta, int b,
-                     int c, int r, float eps, double* se_sum, void* stream);
+                     int c, int r, float eps, double* se_sum, void* ws, void* stream);
+int gldm_block_partials_to_stats(const double* part, int b, int nblk, double* stats, void* stream);
 int gldm_se_gate_sum(const double* sum, int count, const float* w1, const float* w2, int b, int c, int cr, float* gate,
                      void* stream);
 int gldm_devox_cl(const float* coords, const void* grid_cl, int is_fp32, int stride, const float* gate, const float* point,

@@ -98,8 +98,11 @@ def test_encoder_batch_independence_and_single_cloud(cuda, precision):
     z5 = m.vae_model.encode_pc(xyz)
     z1 = m.vae_model.encode_pc(xyz[3:4])
     assert z5.shape == (5, 3, 64) and z1.shape == (1, 3, 64)
-    # fp32 path: bit-identical; bf16 path: the GroupNorm statistics are fp64 atomics whose order may differ
+    # the statistics of the fused voxel branch are summed per cloud in an order that depends on where the cloud's rows
+    # fall in the 128-row tiles of the batch, so a cloud encoded alone can differ in the last bits (and, rarely, by one
+    # bf16 rounding flip of a voxel activation) from the same cloud inside a batch; run to run everything is bit-equal
     if precision == "fp32":
         assert torch.equal(z1[0], z5[3])
     else:
-        torch.testing.assert_close(z1[0], z5[3], rtol=0, atol=2e-6)
+        torch.testing.assert_close(z1[0], z5[3], rtol=0, atol=1e-5)
+        assert torch.equal(m.vae_model.encode_pc(xyz), z5)
