@@ -345,10 +345,17 @@ __global__ void conv_stats_finalize_kernel(const double* __restrict__ part, int 
   const int b = blockIdx.x, idx = threadIdx.x;       // 16 threads: 0..7 sums, 8..15 sums of squares
   const long long r_lo = (long long)b * P, r_hi = r_lo + P - 1;
   const long long c_lo = r_lo / 128, c_hi = r_hi / 128;
+  // same order as a plain loop, but eight independent loads in flight at a time
   double t = 0.0;
-  for (long long c = c_lo; c <= c_hi; ++c) {
-    const int slot = b - (int)((c * 128) / P);
-    t += part[((size_t)c * 2 + slot) * 16 + idx];
+  for (long long c = c_lo; c <= c_hi; c += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long cc = c + u;
+      v[u] = cc <= c_hi ? part[((size_t)cc * 2 + (b - (int)((cc * 128) / P))) * 16 + idx] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += v[u];
   }
   (void)rows;
   stats[((size_t)b * 8 + (idx & 7)) * 2 + (idx >> 3)] = t;
@@ -359,7 +366,13 @@ __global__ void block_partials_finalize_kernel(const double* __restrict__ part, 
   const int b = blockIdx.x, i = threadIdx.x;
   if (i >= width) return;
   double t = 0.0;
-  for (int k = 0; k < nblk; ++k) t += part[((size_t)b * nblk + k) * width + i];
+  for (int k = 0; k < nblk; k += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = k + u < nblk ? part[((size_t)b * nblk + k + u) * width + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += v[u];
+  }
   if (remap) out[((size_t)b * 8 + (i & 7)) * 2 + (i >> 3)] = t;      // [16] -> stats[b][group][moment]
   else out[(size_t)b * width + i] = t;
 }
