@@ -46,6 +46,7 @@ _SIGS = {
     "gldm_sampler_run_f32": [POINTER(GldmResNetCfg), P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
                              c_ulonglong, P, P, P],
     "gldm_denoiser_forward_f32": [POINTER(GldmResNetCfg), P, P, P, P, c_int, P, P],
+    "gldm_denoiser_forward_f32_ftime": [POINTER(GldmResNetCfg), P, P, P, P, c_int, P, P],
     "gldm_decoder_forward_f32": [POINTER(GldmResNetCfg), P, P, c_int, P, P, c_int, c_int, P, P, P],
     "gldm_sampler_tc_pack_bytes": [POINTER(GldmResNetCfg)],
     "gldm_sampler_tc_set_profile": [P],
@@ -58,6 +59,7 @@ _SIGS = {
     "gldm_sampler_run_tc_dev": [POINTER(GldmResNetCfg), P, P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P,
                                 c_ulonglong, P, P, P],
     "gldm_denoiser_forward_tc": [POINTER(GldmResNetCfg), P, P, P, P, P, c_int, P, P],
+    "gldm_denoiser_forward_tc_ftime": [POINTER(GldmResNetCfg), P, P, P, P, P, c_int, P, P],
     "gldm_gemm_tc_image_bytes": [c_longlong, c_int],
     "gldm_gemm_tc_pack_weight": [P, c_int, c_int, P, P],
     "gldm_gemm_tc_to_image": [P, c_int, c_int, c_int, P, P],

@@ -75,6 +75,7 @@ struct ResNetParams {
   const float* x_in;       // [n][L] (x_T / x) or z_h [n][D] for the decoder
   const float* z_cond;     // [n_obj][cond_ch][cond_dim]
   const int* t_sample;     // mode 1: per-sample timestep
+  const float* tf_sample;  // mode 1, continuous time (elucidated sampler: c_noise(sigma)); used when non-NULL
   int n_steps;
   const int* timesteps;    // device [n_steps]
   const float* coef;       // device [n_steps][8]
@@ -430,10 +431,9 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
       const int fh = cfg.fourier_half, fd = 2 * fh + 1;
       for (int idx = tid; idx < S * fd; idx += 256) {
         const int s = idx / fd, j = idx - s * fd;
-        int t = 0;
-        if (p.mode == 0) t = p.timesteps[step];
-        else if (s0 + s < p.n) t = p.t_sample[s0 + s];
-        const float tf = (float)t;
+        float tf = 0.f;
+        if (p.mode == 0) tf = (float)p.timesteps[step];
+        else if (s0 + s < p.n) tf = p.tf_sample ? p.tf_sample[s0 + s] : (float)p.t_sample[s0 + s];
         float v = tf;
         if (j > 0) {
           const int i = (j - 1) % fh;
@@ -695,6 +695,19 @@ extern "C" int gldm_denoiser_forward_f32(const GldmResNetCfg* cfg, const float* 
   GLDM_REQUIRE(x && z_cond && eps && (t || !cfg->time_cond), "denoiser_forward: null pointer");
   GLDM_REQUIRE(n >= 0, "denoiser_forward: bad n");
   p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.t_sample = t; p.x_out = eps;
+  return launch_resnet(p, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_denoiser_forward_f32_ftime(const GldmResNetCfg* cfg, const float* prepared, const float* x,
+                                               const float* t, const float* z_cond, int n, float* eps, void* stream) {
+  ResNetParams p = {};
+  int rc = fill_common(p, cfg, prepared);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->time_cond, "denoiser_forward_ftime: needs a time-conditioned configuration");
+  GLDM_REQUIRE(n <= 0 || (x && z_cond && eps && t), "denoiser_forward_ftime: null pointer");
+  GLDM_REQUIRE(n >= 0, "denoiser_forward_ftime: bad n");
+  if (n == 0) return GLDM_OK;
+  p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.tf_sample = t; p.x_out = eps;
   return launch_resnet(p, (cudaStream_t)stream);
 }
 

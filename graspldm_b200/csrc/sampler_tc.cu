@@ -229,13 +229,14 @@ __global__ void pack_image_kernel(const float* __restrict__ src, uint8_t* __rest
 
 // time embedding table: te[i][:] = time_mlp(t_i)   (resnets.py:44-56, 517-522); one warp per entry
 __global__ void time_embed_kernel(const float* __restrict__ W, ResNetLayout lay, int fh, int emb,
-                                  const int* __restrict__ ts, int count, float* __restrict__ te) {
+                                  const int* __restrict__ ts, const float* __restrict__ tsf, int count,
+                                  float* __restrict__ te) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= count) return;
   __shared__ float s_f[8][40], s_h[8][64];
   float* f = s_f[threadIdx.x >> 5];
   float* h = s_h[threadIdx.x >> 5];
-  const float tf = (float)ts[i];
+  const float tf = tsf ? tsf[i] : (float)ts[i];      // continuous time for the elucidated sampler
   const int fd = 2 * fh + 1;
   for (int j = lane; j < fd; j += 32) {
     float v = tf;
@@ -1351,8 +1352,9 @@ extern "C" int gldm_sampler_tc_prepare(const GldmResNetCfg* cfg, const float* ra
   return GLDM_OK;
 }
 
-static int run_time_embed(const TcParams& p, const int* ts_dev, int count, float* te, cudaStream_t s) {
-  time_embed_kernel<<<ceil_div(count, 8), 256, 0, s>>>(p.W, p.lay, p.cfg.fourier_half, p.cfg.emb_dim, ts_dev, count, te);
+static int run_time_embed(const TcParams& p, const int* ts_dev, int count, float* te, cudaStream_t s,
+                          const float* tsf_dev = nullptr) {
+  time_embed_kernel<<<ceil_div(count, 8), 256, 0, s>>>(p.W, p.lay, p.cfg.fourier_half, p.cfg.emb_dim, ts_dev, tsf_dev, count, te);
   return check_launch("time_embed_kernel");
 }
 
@@ -1439,6 +1441,28 @@ extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* r
   }
   p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.te = d_te; p.n_steps = 1; p.x_out = eps;
   rc = run_time_embed(p, t, n, d_te, s);
+  if (rc == GLDM_OK) rc = launch_tc(p, s);
+  cudaFreeAsync(d_te, s);
+  return rc;
+}
+
+extern "C" int gldm_denoiser_forward_tc_ftime(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
+                                              const float* t, const float* z_cond, int n, float* eps, void* stream) {
+  TcParams p = {};
+  int rc = fill_tc(p, cfg, raw, pack);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->time_cond, "denoiser_forward_tc_ftime: needs a time-conditioned denoiser configuration");
+  GLDM_REQUIRE(n <= 0 || (x && t && z_cond && eps), "denoiser_forward_tc_ftime: null pointer");
+  GLDM_REQUIRE(n >= 0, "denoiser_forward_tc_ftime: bad n");
+  if (n == 0) return GLDM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* d_te = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_te), sizeof(float) * p.cfg.emb_dim * (size_t)n, s) != cudaSuccess) {
+    set_error("denoiser_forward_tc_ftime: cudaMallocAsync failed");
+    return GLDM_ECUDA;
+  }
+  p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.te = d_te; p.n_steps = 1; p.x_out = eps;
+  rc = run_time_embed(p, nullptr, n, d_te, s, t);
   if (rc == GLDM_OK) rc = launch_tc(p, s);
   cudaFreeAsync(d_te, s);
   return rc;

@@ -191,13 +191,15 @@ def resnet_forward(module, x, time, z_cond, precision="fp32"):
         xin = x.reshape(B, L).contiguous().float()
         zc = z_cond.contiguous().float()
         out = torch.empty((B, L), device=dev, dtype=torch.float32)
-        t32 = time.to(device=dev, dtype=torch.int32).contiguous() if time is not None else None
+        ftime = time is not None and torch.is_floating_point(time)      # continuous time (elucidated sampler)
+        t32 = None if time is None else time.to(device=dev, dtype=torch.float32 if ftime else torch.int32).contiguous()
+        sfx = "_ftime" if ftime else ""
         if precision == "bf16":
-            _lib.call("gldm_denoiser_forward_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pk.tc_pack().data_ptr(),
+            _lib.call("gldm_denoiser_forward_tc" + sfx, ctypes.byref(pk.cfg), pk.raw.data_ptr(), pk.tc_pack().data_ptr(),
                       xin.data_ptr(), t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(),
                       _stream(dev))
         else:
-            _lib.call("gldm_denoiser_forward_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
+            _lib.call("gldm_denoiser_forward_f32" + sfx, ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
                       t32.data_ptr() if t32 is not None else None, zc.data_ptr(), B, out.data_ptr(), _stream(dev))
     return out.view(B, 1, L)
 

@@ -166,6 +166,8 @@ int gldm_sampler_run_f32(const GldmResNetCfg* cfg, const float* prepared, const 
  * x f32[n,D], t i32[n], z_cond f32[n,cond_ch,cond_dim] (per sample) -> eps f32[n,D] */
 int gldm_denoiser_forward_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x, const int* t,
                               const float* z_cond, int n, float* eps, void* stream);
+int gldm_denoiser_forward_f32_ftime(const GldmResNetCfg* cfg, const float* prepared, const float* x, const float* t,
+                                    const float* z_cond, int n, float* eps, void* stream);
 /* ConditionalGraspPoseDecoder.forward (R/models/grasp_vae.py:401-436): in_layer -> ResNet1D -> heads.
  * head weights: in_w f32[L,D] in_b[L]  tmrp_w[6,L] tmrp_b[6]  cls_w[1,L] cls_b[1] packed in `head` in
  * that order.  z_h f32[n,D], z_obj f32[n_obj,cond_ch,cond_dim] -> tmrp f32[n,6], logit f32[n,1] */
@@ -205,6 +207,10 @@ int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* raw, const vo
                             unsigned long long seed, float* x_out, float* x_all, void* stream);
 int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
                              const int* t, const float* z_cond, int n, float* eps, void* stream);
+/* the same with continuous per-sample times (elucidated sampler: time = c_noise(sigma) = log(sigma) / 4,
+ * R/grasp_ldm/models/diffusion/elucidated_diffusion.py:120-147) */
+int gldm_denoiser_forward_tc_ftime(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
+                                   const float* t, const float* z_cond, int n, float* eps, void* stream);
 /* ConditionalGraspPoseDecoder.forward on the tensor cores (same contract as gldm_decoder_forward_f32); cfg is the
  * decoder trunk (L = 16, emb 64, not time conditioned), pack from gldm_sampler_tc_prepare with that cfg. */
 int gldm_decoder_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* head, int D,

@@ -275,3 +275,59 @@ def normalize_input(pc, pc_shift, pc_scale, grasp_shift, grasp_scale):
                  use_dataset_statistics=False)
     return c, metas
 
+
+# ----------------------------------------------------------------------------- elucidated sampler
+def edm_sigmas(n, sigma_min=0.002, sigma_max=80.0, rho=7.0):
+    """Karras schedule, R/grasp_ldm/models/diffusion/elucidated_diffusion.py:155-168 (eq. 5), with the trailing 0."""
+    i = torch.arange(n, dtype=torch.float32)
+    s = (sigma_max ** (1 / rho) + i / (n - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+    return torch.cat((s, torch.zeros(1)))
+
+
+def edm_denoise(sd, x, sigma, z_cond, sigma_data=0.5, p="diffusion_model.net."):
+    """Preconditioned network (eq. 7), elucidated_diffusion.py:111-153: c_skip x + c_out F(c_in x; log(sigma)/4)."""
+    sig = torch.full((x.shape[0],), float(sigma))
+    s3 = sig.view(-1, 1, 1)
+    c_in = 1 * (s3 ** 2 + sigma_data ** 2) ** -0.5
+    c_skip = (sigma_data ** 2) / (s3 ** 2 + sigma_data ** 2)
+    c_out = s3 * sigma_data * (sigma_data ** 2 + s3 ** 2) ** -0.5
+    f = denoiser_forward(sd, p, c_in * x, torch.log(sig.clamp(min=1e-20)) * 0.25, z_cond)
+    return c_skip * x + c_out * f
+
+
+def edm_sample_heun(sd, z_cond, x_init, noise, n, p="diffusion_model.net.", S_churn=80, S_tmin=0.05, S_tmax=50, S_noise=1.003):
+    """Stochastic second-order sampler (Algorithm 2 of Karras et al. 2022), elucidated_diffusion.py:179-258."""
+    sig = edm_sigmas(n)
+    x = sig[0] * x_init
+    for i in range(n):
+        s, s_next = float(sig[i]), float(sig[i + 1])
+        gamma = min(S_churn / n, math.sqrt(2) - 1) if S_tmin <= s <= S_tmax else 0.0
+        s_hat = s + gamma * s
+        x_hat = x + math.sqrt(s_hat ** 2 - s ** 2) * (S_noise * noise[i])
+        d = (x_hat - edm_denoise(sd, x_hat, s_hat, z_cond, p=p)) / s_hat
+        x = x_hat + (s_next - s_hat) * d
+        if s_next != 0:
+            d2 = (x - edm_denoise(sd, x, s_next, z_cond, p=p)) / s_next
+            x = x_hat + 0.5 * (s_next - s_hat) * (d + d2)
+    return x
+
+
+def edm_sample_dpmpp(sd, z_cond, x_init, n, p="diffusion_model.net."):
+    """DPM-Solver++(2M), elucidated_diffusion.py:260-315."""
+    sig = edm_sigmas(n)
+    x = sig[0] * x_init
+    prev = None
+    for i in range(n):
+        den = edm_denoise(sd, x, float(sig[i]), z_cond, p=p)
+        t, t_next = -sig[i].log(), -sig[i + 1].log()
+        h = t_next - t
+        if prev is None or sig[i + 1] == 0:
+            dd = den
+        else:
+            r = (t - (-sig[i - 1].log())) / h
+            g = -1 / (2 * r)
+            dd = (1 - g) * den + g * prev
+        x = ((-t_next).exp() / (-t).exp()) * x - (-h).expm1() * dd
+        prev = den
+    return x
+

@@ -170,6 +170,38 @@ def normalize_golden():
                         **out)
 
 
+def edm_golden():
+    """ElucidatedDiffusion.sample_normal / sample_using_dpmpp of the reference (elucidated_diffusion.py:179-315) around the
+    reference denoiser with the seeded fpc weights; the N(0,1) draws are recorded by replaying the global CPU generator."""
+    from grasp_ldm.models.diffusion.elucidated_diffusion import ElucidatedDiffusion
+    cfg = Config.fromfile(CONFIGS["fpc"])
+    torch.manual_seed(0)
+    den = TimeConditionedResNet1D(**dict(cfg.model.ddm.model.args)["model"]["args"]).eval()     # same weights as build_reference_ldm
+    edm = ElucidatedDiffusion(net=den, seq_length=4).eval()
+    g = torch.Generator().manual_seed(33)
+    B, n_heun, n_dpm = 6, 8, 10
+    zc = torch.randn(B, 3, 64, generator=g)
+    out = dict(z_cond=zc.numpy())
+    with torch.no_grad():
+        torch.manual_seed(101)
+        x_init = torch.randn(B, 1, 4)
+        noise = torch.stack([torch.randn(B, 1, 4) for _ in range(n_heun)])
+        torch.manual_seed(101)
+        x, _ = edm.sample(use_dpmpp=False, batch_size=B, z_cond=zc, num_sample_steps=n_heun)
+        out.update(heun_x_init=x_init.numpy(), heun_noise=noise.numpy(), heun_x=x.numpy(), heun_steps=np.int64(n_heun))
+        torch.manual_seed(202)
+        x_init = torch.randn(B, 1, 4)
+        torch.manual_seed(202)
+        x, _ = edm.sample(use_dpmpp=True, batch_size=B, z_cond=zc, num_sample_steps=n_dpm)
+        out.update(dpmpp_x_init=x_init.numpy(), dpmpp_x=x.numpy(), dpmpp_steps=np.int64(n_dpm))
+        # one preconditioned evaluation at a few noise levels
+        xs = torch.randn(B, 1, 4, generator=g)
+        for k, sg in enumerate((80.0, 2.5, 0.05)):
+            out[f"denoise_{k}"] = edm.preconditioned_network_forward(xs * sg, sg, z_cond=zc).numpy()
+        out["denoise_x"] = xs.numpy()
+    np.savez_compressed(f"{HERE}/edm_fpc.npz", **out)
+
+
 def manifest(sd):
     out = {}
     for k, v in sd.items():
@@ -239,6 +271,7 @@ def main():
     with open(f"{HERE}/state_dict_manifest.json", "w") as f:
         json.dump(man, f, indent=0, sort_keys=True)
     normalize_golden()
+    edm_golden()
     print("golden fixtures written to", HERE)
 
 

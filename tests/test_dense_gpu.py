@@ -229,3 +229,40 @@ def test_normalize_input_and_per_object_postprocessing(fpc, cuda):
     centre = out["grasps"][0, :, :3, 3].mean(0).cpu()
     assert (centre - raw[0].mean(0)).abs().max() < 0.5                        # grasps live around the raw cloud
 
+
+
+def test_elucidated_samplers(fpc, cuda):
+    """ElucidatedDiffusion.sample (stochastic Heun and DPM-Solver++ 2M) around the denoiser kernels,
+    against the fixture produced by the reference's own class (elucidated_diffusion.py:126-315)."""
+    from graspldm_b200.edm import ElucidatedDiffusion
+    from graspldm_b200.grasp_ldm import GraspLatentDDM
+    m, vae_sd, _ = fpc
+    g = np.load(os.path.join(G, "edm_fpc.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(cuda)
+    edm = ElucidatedDiffusion(net=m.diffusion_model.model, seq_length=4)
+    torch.testing.assert_close(edm.sample_schedule(8).cpu()[[0, 7, 8]], torch.tensor([80.0, 0.002, 0.0]), rtol=1e-5, atol=0)
+    # bf16: a single preconditioned evaluation is within the usual 5e-2; over the 15 evaluations of the 8-step Heun
+    # sampler the errors add up (the elucidated update has no contraction like the DDPM posterior mean), hence 1.5e-1
+    for prec, tol, tol_s in (("fp32", dict(rtol=1e-3, atol=2e-4), dict(rtol=1e-3, atol=2e-4)),
+                             ("bf16", dict(rtol=5e-2, atol=5e-2), dict(rtol=1.5e-1, atol=1.5e-1))):
+        for k, sg in enumerate((80.0, 2.5, 0.05)):
+            got = edm.preconditioned_network_forward(t("denoise_x") * sg, sg, z_cond=t("z_cond"), precision=prec)
+            np.testing.assert_allclose(got.cpu().numpy(), g[f"denoise_{k}"], **tol)
+        x, allx = edm.sample(use_dpmpp=False, batch_size=6, z_cond=t("z_cond"), num_sample_steps=int(g["heun_steps"]),
+                             return_all=True, x_init=t("heun_x_init"), noise=t("heun_noise"), precision=prec)
+        assert len(allx) == int(g["heun_steps"]) + 1
+        print(f"[edm heun {prec}] max|err| {np.abs(x.cpu().numpy() - g['heun_x']).max():.3e}")
+        np.testing.assert_allclose(x.cpu().numpy(), g["heun_x"], **tol_s)
+        x, _ = edm.sample(use_dpmpp=True, batch_size=6, z_cond=t("z_cond"), num_sample_steps=int(g["dpmpp_steps"]),
+                          x_init=t("dpmpp_x_init"), precision=prec)
+        print(f"[edm dpm++ {prec}] max|err| {np.abs(x.cpu().numpy() - g['dpmpp_x']).max():.3e}")
+        np.testing.assert_allclose(x.cpu().numpy(), g["dpmpp_x"], **tol_s)
+    # the model-level switch of the reference (grasp_ldm.py:59-62, 214-219): elucidated_diffusion=True + use_dpmpp kwarg
+    ldm = GraspLatentDDM(model=m.diffusion_model.model, latent_in_features=4, diffusion_timesteps=1000, diffusion_loss="l2",
+                         elucidated_diffusion=True)
+    ldm.set_vae_model(m.vae_model)
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S").to(cuda)
+    (tm, lg), steps = ldm.generate_grasps(xyz, num_grasps=3, use_dpmpp=True, num_sample_steps=10)
+    assert tm.shape == (6, 6) and lg.shape == (6, 1) and steps == [] and torch.isfinite(tm).all()
+    with pytest.raises(KeyError):
+        ldm.generate_grasps(xyz, num_grasps=3)        # the reference pops `use_dpmpp` unconditionally (:171)

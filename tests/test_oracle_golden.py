@@ -172,3 +172,20 @@ def test_oracle_normalize_input_and_per_object_statistics():
             np.testing.assert_array_equal(out["pc"].numpy(), g["batch_pc_unnorm"])
             np.testing.assert_allclose(out["pc"].numpy(), g["raw"], rtol=0, atol=5e-7)     # round trip to the raw cloud
 
+
+
+def test_oracle_elucidated_samplers(fpc):
+    """Oracle restatement of the elucidated sampler (preconditioning, stochastic Heun, DPM-Solver++ 2M) against the
+    outputs of the reference's own ElucidatedDiffusion around the reference denoiser (tests/golden/make_golden.py)."""
+    _, _, ddm = fpc
+    g = np.load(os.path.join(G, "edm_fpc.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    P = "diffusion_model.model."
+    with torch.no_grad():
+        for k, sg in enumerate((80.0, 2.5, 0.05)):
+            got = M.edm_denoise(ddm, t("denoise_x") * sg, sg, t("z_cond"), p=P)
+            np.testing.assert_allclose(got.numpy(), g[f"denoise_{k}"], rtol=1e-4, atol=2e-5)
+        x = M.edm_sample_heun(ddm, t("z_cond"), t("heun_x_init"), t("heun_noise"), int(g["heun_steps"]), p=P)
+        np.testing.assert_allclose(x.numpy(), g["heun_x"], rtol=1e-3, atol=1e-4)
+        x = M.edm_sample_dpmpp(ddm, t("z_cond"), t("dpmpp_x_init"), int(g["dpmpp_steps"]), p=P)
+        np.testing.assert_allclose(x.numpy(), g["dpmpp_x"], rtol=1e-3, atol=1e-4)
