@@ -242,9 +242,9 @@ def test_elucidated_samplers(fpc, cuda):
     edm = ElucidatedDiffusion(net=m.diffusion_model.model, seq_length=4)
     torch.testing.assert_close(edm.sample_schedule(8).cpu()[[0, 7, 8]], torch.tensor([80.0, 0.002, 0.0]), rtol=1e-5, atol=0)
     # bf16: a single preconditioned evaluation is within the usual 5e-2; over the 15 evaluations of the 8-step Heun
-    # sampler the errors add up (the elucidated update has no contraction like the DDPM posterior mean; measured 8e-2), hence 3e-1
+    # sampler the errors add up (the elucidated update has no contraction like the DDPM posterior mean; measured 7.9e-2 for Heun and 1.2e-2 for DPM-Solver++ on the B200), hence 1.5e-1
     for prec, tol, tol_s in (("fp32", dict(rtol=1e-3, atol=2e-4), dict(rtol=1e-3, atol=2e-4)),
-                             ("bf16", dict(rtol=5e-2, atol=5e-2), dict(rtol=3e-1, atol=3e-1))):
+                             ("bf16", dict(rtol=5e-2, atol=5e-2), dict(rtol=1.5e-1, atol=1.5e-1))):
         for k, sg in enumerate((80.0, 2.5, 0.05)):
             got = edm.preconditioned_network_forward(t("denoise_x") * sg, sg, z_cond=t("z_cond"), precision=prec)
             np.testing.assert_allclose(got.cpu().numpy(), g[f"denoise_{k}"], **tol)
