@@ -202,6 +202,25 @@ def edm_golden():
     np.savez_compressed(f"{HERE}/edm_fpc.npz", **out)
 
 
+def ppc_ldm_golden():
+    """Partial-point-cloud model family (latent 16, conditioning width 256): 10 DDPM steps end to end through the
+    unmodified reference classes, injected noise (same recipe as the fpc LDM fixtures in main())."""
+    nobj, G, nsteps = 2, 3, 10
+    m = build_reference_ldm("ppc", scheduler="ddpm")
+    D = m.diffusion_model.n_dims
+    m.set_inference_timesteps(nsteps)
+    xyz = torch.cat([synthetic_clouds(2, seed=1234, dist="S"), synthetic_clouds(1, seed=99, dist="G")])
+    gg = torch.Generator().manual_seed(42)
+    noise = torch.randn(nsteps, nobj * G, 1, D, generator=gg)
+    m.diffusion_model.noise_scheduler.injected_noise = list(noise)
+    torch.manual_seed(42)
+    x_T = torch.randn((nobj * G, 1, D))
+    torch.manual_seed(42)
+    with torch.no_grad():
+        (tm, lg), _ = m.generate_grasps(xyz[:nobj], num_grasps=G, device="cpu")
+    np.savez_compressed(f"{HERE}/ldm_ppc_ddpm10.npz", x_T=x_T.numpy(), noise=noise.numpy(), tmrp=tm.numpy(), logit=lg.numpy())
+
+
 def manifest(sd):
     out = {}
     for k, v in sd.items():
@@ -272,6 +291,7 @@ def main():
         json.dump(man, f, indent=0, sort_keys=True)
     normalize_golden()
     edm_golden()
+    ppc_ldm_golden()
     print("golden fixtures written to", HERE)
 
 

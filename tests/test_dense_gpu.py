@@ -266,3 +266,22 @@ def test_elucidated_samplers(fpc, cuda):
     assert tm.shape == (6, 6) and lg.shape == (6, 1) and steps == [] and torch.isfinite(tm).all()
     with pytest.raises(KeyError):
         ldm.generate_grasps(xyz, num_grasps=3)        # the reference pops `use_dpmpp` unconditionally (:171)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ppc_ldm_generation_matches_reference_fixture(cuda, precision):
+    """The partial-point-cloud model family end to end (encoder -> 10 DDPM steps on the 16-position latent -> decoder)
+    against the fixture of the unmodified reference classes; bf16 = every tensor-core kernel switched on."""
+    g = np.load(os.path.join(G, "ldm_ppc_ddpm10.npz"))
+    m = _models.build("ppc").to(cuda)
+    m.set_inference_timesteps(10)
+    m.diffusion_model.precision = precision
+    m.vae_model.encoder.pc_encoder.precision = precision
+    m.vae_model.decoder.precision = precision
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S").to(cuda)
+    (tm, lg), _ = m.generate_grasps(xyz, num_grasps=3, x_T=torch.from_numpy(g["x_T"]).to(cuda),
+                                    noise=torch.from_numpy(g["noise"]).to(cuda))
+    print(f"[ppc {precision}] tmrp max|err| {maxerr(tm.cpu(), g['tmrp']):.2e} logit {maxerr(lg.cpu(), g['logit']):.2e}")
+    tol = dict(rtol=1e-3, atol=1e-3) if precision == "fp32" else dict(rtol=3e-2, atol=3e-2)
+    np.testing.assert_allclose(tm.cpu().numpy(), g["tmrp"], **tol)
+    np.testing.assert_allclose(lg.cpu().numpy(), g["logit"], **tol)

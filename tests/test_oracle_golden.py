@@ -189,3 +189,16 @@ def test_oracle_elucidated_samplers(fpc):
         np.testing.assert_allclose(x.numpy(), g["heun_x"], rtol=1e-3, atol=1e-4)
         x = M.edm_sample_dpmpp(ddm, t("z_cond"), t("dpmpp_x_init"), int(g["dpmpp_steps"]), p=P)
         np.testing.assert_allclose(x.numpy(), g["dpmpp_x"], rtol=1e-3, atol=1e-4)
+
+
+def test_oracle_ppc_ldm_generation_vs_reference_loop():
+    """Second model family (partial point clouds: latent 16, conditioning width 256), 10 DDPM steps end to end."""
+    m = _models.build("ppc")
+    vae, ddm = _models.split_state_dicts(m)
+    g = np.load(os.path.join(G, "ldm_ppc_ddpm10.npz"))
+    xyz = _data.synthetic_clouds(2, seed=1234, dist="S")
+    with torch.no_grad():
+        tm, lg = M.generate_grasps_ldm(vae, ddm, xyz, 3, torch.from_numpy(g["x_T"]), noise=torch.from_numpy(g["noise"]),
+                                       num_inference_steps=10, kind="ddpm")
+    np.testing.assert_allclose(tm.numpy(), g["tmrp"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(lg.numpy(), g["logit"], rtol=1e-4, atol=2e-5)
