@@ -376,7 +376,7 @@ def main():
                     "achieved": samp_flops / (rows_ms * 1e-3) / 1e12,
                     "frac_of_peak_of_occupied_sms": samp_flops / (rows_ms * 1e-3) / 1e12 / (pk["tflops_sustained"] * min(1.0, -(-n_local // 32) / 148))}),
                 "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE and the 3->48 Conv3d on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (channel-major sampler kernel, 16 samples per CTA, 80 CTAs; the pipelined passes use the row-major kernel, 32 samples per CTA)"
+                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (channel-major sampler kernel, 16 samples per CTA, 80 CTAs; the pipelined passes use the row-major kernel, 32 samples per CTA)"
                          if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
     if rank != 0:
         if world > 1:

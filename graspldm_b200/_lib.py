@@ -74,6 +74,9 @@ _SIGS = {
     "gldm_conv3d_k3_f32_cl": [P, P, P, c_int, c_int, c_int, P, c_int, P, P, P],
     "gldm_voxel_ws_bytes": [c_int, c_int, c_int],
     "gldm_block_partials_to_stats": [P, c_int, c_int, P, P],
+    "gldm_conv3d_tc16_weight_bytes": [],
+    "gldm_conv3d_tc16_pack_weight": [P, c_int, c_int, P, P],
+    "gldm_conv3d_tc16_cl": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P],
     "gldm_conv3d_tc_cl": [P, P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, P],
     "gldm_gn_swish_cl": [P, c_int, c_int, P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "gldm_se_gate_sum": [P, c_int, P, P, c_int, c_int, c_int, P, P],
@@ -83,7 +86,7 @@ _SIGS = {
     "gldm_normalize_clouds": [P, P, P, P, c_int, c_int, P, P, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})
-_RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong, "gldm_voxel_ws_bytes": c_longlong,
+_RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong, "gldm_voxel_ws_bytes": c_longlong, "gldm_conv3d_tc16_weight_bytes": c_longlong,
              "gldm_resnet_raw_floats": c_longlong, "gldm_sampler_tc_pack_bytes": c_longlong, "gldm_gemm_tc_image_bytes": c_longlong, "gldm_conv3d_tc_weight_bytes": c_longlong,
              "gldm_conv3d_tc_grid_bytes": c_longlong, "gldm_resnet_prepared_floats": c_longlong}
 

@@ -314,6 +314,122 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc3_kernel(const __gri
   if (wid == 1) tmem_dealloc<128>(tmem);
 }
 
+// Narrow-input variant (ci <= 16: the 3 -> 48 first layer): the padded grid has 16 channels (32-byte rows, SWIZZLE_32B),
+// one K = 16 UMMA per tap, A rows again fetched once per filter column.  Weight image: [27 taps][128 rows x 32 B].
+namespace c3 {
+constexpr int A16_BYTES = 5120;             // 136 rows x 32 B = 4352, slot rounded to 1024
+constexpr int W16_SLOT = 4096, W16_BYTES = 4096;
+constexpr int STAGES16 = 4;
+}
+__global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc16_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                      const __grid_constant__ Conv3dTcParams p) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int STAGE_BYTES = A16_BYTES + 3 * W16_SLOT;
+  // (the epilogue reuses the first 9.2 KB of the stage area for its partial sums: 4 stages = 68 KB, enough)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES16 * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES16;
+  uint64_t* acc_full = bars + 2 * STAGES16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES16 + 1);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const long long row0 = (long long)blockIdx.x * 128;
+  const int rp = p.r + 2, rp2 = rp * rp;
+  constexpr int n_it = 9;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES16; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES16, round = it / STAGES16;
+      const int shift = (it / 3 - 1) * rp2 + (it % 3 - 1) * rp - 1;       // row of the dz = -1 tap of column it = dx*3 + dy
+      if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full[s], A3_ROWS * 32 + 3 * p.w_rows_bytes);
+        tma_load_2d(smem + s * STAGE_BYTES, &xmap, 0, (int)(row0 + shift), &full[s]);
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+          bulk_g2s(smem + s * STAGE_BYTES + A16_BYTES + dz * W16_SLOT, p.w_img + (size_t)(it * 3 + dz) * W16_BYTES,
+                   p.w_rows_bytes, &full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (wid == 1) {
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (256u >> 4) | (1u << 14) | ((uint32_t)SW_32 << 29);      // 8-row groups of 32-byte rows
+    const uint32_t base = smem_u32(smem);
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES16;
+      mbar_wait(&full[s], (it / STAGES16) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int dz = 0; dz < 3; ++dz) {
+        const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE_BYTES + dz * 32) >> 4));
+        const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE_BYTES + A16_BYTES + dz * W16_SLOT) >> 4));
+        umma_bf16_block_elect<1>(tmem, ad, bd, idesc, (it != 0 || dz != 0) ? 1u : 0u);
+      }
+      umma_commit_elect(&empty[s]);
+    }
+    umma_commit_elect(acc_full);
+  } else {
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
+  }
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<128>(tmem);
+}
+
+// fp32 [b, c <= 16, r^3] -> bf16 zero-padded grid with 16 channels per row; one thread per padded voxel
+__global__ void __launch_bounds__(256) cl_pad16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int r,
+                                                       long long rows) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int rp = r + 2, rp2 = rp * rp, P = rp2 * rp, r3 = r * r * r;
+  const long long b = m / P;
+  const int pp = (int)(m - b * P);
+  const int xx = pp / rp2, yy = (pp / rp) % rp, zz = pp % rp;
+  const bool interior = xx >= 1 && xx <= r && yy >= 1 && yy <= r && zz >= 1 && zz <= r;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (interior) {
+    const float* xb = x + ((size_t)b * c) * r3 + ((xx - 1) * r + (yy - 1)) * r + (zz - 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < c) v[j] = __ldg(xb + (size_t)j * r3);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 16);
+  dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+// Conv3d weight fp32 [co][ci <= 16][27] -> [27 taps][128 rows x 32 B] (SWIZZLE_32B rows = output channels)
+__global__ void __launch_bounds__(128) conv3d_weight_image16_kernel(const float* __restrict__ w, uint8_t* __restrict__ img, int co,
+                                                                    int ci) {
+  const int row = threadIdx.x, tap = blockIdx.x;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = (row < co && k < ci) ? w[((size_t)row * ci + k) * 27 + tap] : 0.f;
+#pragma unroll
+  for (int chunk = 0; chunk < 2; ++chunk)
+    *reinterpret_cast<uint4*>(img + (size_t)tap * c3::W16_BYTES + swz_off<32>(row, chunk)) =
+        make_uint4(pack_bf16(v[8 * chunk], v[8 * chunk + 1]), pack_bf16(v[8 * chunk + 2], v[8 * chunk + 3]),
+                   pack_bf16(v[8 * chunk + 4], v[8 * chunk + 5]), pack_bf16(v[8 * chunk + 6], v[8 * chunk + 7]));
+}
+
 // fp32 [b, c, r^3] -> bf16 channels-last zero-padded grid [b * (r+2)^3][cpad]; one thread per (padded voxel, 8 channels)
 __global__ void __launch_bounds__(256) cl_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int cpad,
                                                      int r, long long rows) {
@@ -740,6 +856,62 @@ extern "C" int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const doubl
   if (rc || !se_sum) return rc;
   block_partials_finalize_kernel<<<b, 128, 0, s>>>(part, gx, c, 0, se_sum);
   return check_launch("block_partials_finalize_kernel");
+}
+
+/* narrow-input Conv3d (ci <= 16) on the tensor cores, channels-last output + statistics:
+ * w_img: 27 * 4096 bytes from gldm_conv3d_tc16_pack_weight; scratch: b * (r+2)^3 * 32 bytes (256-byte aligned) */
+extern "C" long long gldm_conv3d_tc16_weight_bytes(void) { return 27LL * c3::W16_BYTES; }
+extern "C" int gldm_conv3d_tc16_pack_weight(const float* w, int co, int ci, void* img, void* stream) {
+  GLDM_REQUIRE(w && img, "conv3d_tc16_pack_weight: null pointer");
+  GLDM_REQUIRE(co > 0 && co <= 128 && ci > 0 && ci <= 16, "conv3d_tc16_pack_weight: need ci <= 16, co <= 128");
+  conv3d_weight_image16_kernel<<<27, 128, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<uint8_t*>(img), co, ci);
+  return check_launch("conv3d_weight_image16_kernel");
+}
+extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r,
+                                   void* scratch, void* y_cl, int out_stride, double* stats, void* ws, void* stream) {
+  GLDM_REQUIRE(b <= 0 || (x && w_img && scratch && y_cl && stats && ws), "conv3d_tc16_cl: null pointer");
+  GLDM_REQUIRE(b >= 0 && ci > 0 && ci <= 16 && co > 0 && co <= 128 && co % 8 == 0 && r > 0, "conv3d_tc16_cl: bad sizes");
+  GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc16_cl: bad out_stride");
+  if (b == 0) return GLDM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long P = (long long)(r + 2) * (r + 2) * (r + 2), rows = (long long)b * P;
+  cl_pad16_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(scratch), ci, r, rows);
+  int rc = check_launch("cl_pad16_kernel");
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("conv3d_tc16_cl: cuTensorMapEncodeTiled is not available from the driver");
+    return GLDM_ECUDA;
+  }
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {32};
+  const cuuint32_t box[2] = {16, (cuuint32_t)c3::A3_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scratch, gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv3d_tc16_cl: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return GLDM_ECUDA;
+  }
+  Conv3dTcParams p = {};
+  p.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  p.bias = bias; p.y = nullptr; p.r = r; p.co = co; p.k_blocks = 1; p.ksteps_last = 1;
+  p.rows = rows;
+  p.w_rows_bytes = ((co + 7) / 8) * 256;
+  p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b;
+  const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 256;
+  static bool attr16 = false;
+  if (!attr16) {
+    cudaFuncSetAttribute(conv3d_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+    attr16 = true;
+  }
+  conv3d_tc16_kernel<<<(unsigned)((rows + 127) / 128), c3::NTHREADS, smem16, s>>>(map, p);
+  rc = check_launch("conv3d_tc16_kernel");
+  if (rc) return rc;
+  conv_stats_finalize_kernel<<<b, 16, 0, s>>>(reinterpret_cast<const double*>(ws), (int)P, rows, stats);
+  return check_launch("conv_stats_finalize_kernel");
 }
 
 extern "C" int gldm_block_partials_to_stats(const double* part, int b, int nblk, double* stats, void* stream) {

@@ -5,6 +5,7 @@ device memory, streams and one-time layout work on weights (permutes, BatchNorm 
 There is no CPU path: tensors must live on a CUDA device.
 """
 import ctypes
+import os
 
 import torch
 
@@ -431,6 +432,12 @@ class PackedEncoder:
                             img = _aligned_bytes(_lib.lib().gldm_conv3d_tc_weight_bytes(ci), dev)
                             _lib.call("gldm_conv3d_tc_pack_weight", w.data_ptr(), co, ci, img.data_ptr(), _stream(dev))
                             pair.append(img)
+                        elif ci < 16 and co <= 128 and co % 8 == 0 and os.environ.get("GLDM_CONV3D_TC16", "1") != "0":
+                            # narrow first layer (3 -> 48): K = 16 image, tagged so that the voxel branch picks the kernel
+                            img = _aligned_bytes(_lib.lib().gldm_conv3d_tc16_weight_bytes(), dev)
+                            _lib.call("gldm_conv3d_tc16_pack_weight", w.data_ptr(), co, ci, img.data_ptr(), _stream(dev))
+                            img.narrow_k = True
+                            pair.append(img)
                         else:
                             pair.append(None)
                     out.append(pair)
@@ -530,7 +537,14 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
     # workspace of the bit-reproducible (atomic-free) statistics: per-block partials, added in a fixed order
     ws = _cl_grid(pk, dev, ("ws", bi), 1, (_lib.lib().gldm_voxel_ws_bytes(B, max(ci, co), r) + 7) // 8, torch.float64)
     cpad_o = -(-co // 64) * 64
-    if w1_img is not None:
+    if w1_img is not None and getattr(w1_img, "narrow_k", False):
+        x16 = _cl_grid(pk, dev, ("x16", bi), rows, 16, torch.bfloat16)
+        y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
+        _lib.call("gldm_conv3d_tc16_cl", grid.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r,
+                  x16.data_ptr(), y1.data_ptr(), cpad_o, stats[0].data_ptr(), ws.data_ptr(), st)
+        _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
+                  blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, None, st)
+    elif w1_img is not None:
         x_cl = _cl_grid(pk, dev, ("x", bi), rows, -(-ci // 64) * 64, torch.bfloat16)
         _lib.call("gldm_cl_pad", grid.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
@@ -587,7 +601,8 @@ def _encoder_pass(pk, xyz, precision="fp32"):
                 _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(),
                           norm.data_ptr(), None, st)
                 y1 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
-                _conv3d(grid, blk["w1"], tcw[0], blk["b1"], B, ci, co, r, y1, st)
+                w1_img = None if getattr(tcw[0], "narrow_k", False) else tcw[0]      # (the K = 16 image is for the fused path)
+                _conv3d(grid, blk["w1"], w1_img, blk["b1"], B, ci, co, r, y1, st)
                 _lib.call("gldm_groupnorm_swish_f32", y1.data_ptr(), blk["g1w"].data_ptr(), blk["g1b"].data_ptr(), B, co,
                           r3, blk["groups"], blk["eps1"], None, st)
                 y2 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)

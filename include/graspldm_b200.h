@@ -265,6 +265,13 @@ int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const float* bias, in
 int gldm_gn_swish_cl(void* y_cl, int is_fp32, int stride, const double* stats, const float* gamma, const float* beta, int b,
                      int c, int r, float eps, double* se_sum, void* ws, void* stream);
 int gldm_block_partials_to_stats(const double* part, int b, int nblk, double* stats, void* stream);
+/* narrow-input Conv3d k3 p1 (ci <= 16: the 3 -> 48 first layer) on the tensor cores: x f32[b,ci,r^3] -> padded bf16 grid
+ * y_cl [b * (r+2)^3][out_stride] (+ bias) and its GroupNorm(8) statistics.  w_img: gldm_conv3d_tc16_weight_bytes() bytes
+ * from gldm_conv3d_tc16_pack_weight(w f32[co,ci,3,3,3]); scratch: b * (r+2)^3 * 32 bytes, 256-byte aligned */
+long long gldm_conv3d_tc16_weight_bytes(void);
+int gldm_conv3d_tc16_pack_weight(const float* w, int co, int ci, void* img, void* stream);
+int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r, void* scratch,
+                        void* y_cl, int out_stride, double* stats, void* ws, void* stream);
 int gldm_se_gate_sum(const double* sum, int count, const float* w1, const float* w2, int b, int c, int cr, float* gate,
                      void* stream);
 int gldm_devox_cl(const float* coords, const void* grid_cl, int is_fp32, int stride, const float* gate, const float* point,

@@ -372,3 +372,34 @@ def test_row_major_kernel_parity(fpc, cuda, row_major):
     da = _rot_angle_deg(out["grasps"].cpu()[..., :3, :3], want["grasps"][..., :3, :3]).max().item()
     print(f"[rows e2e] max translation error {dt * 1e3:.3f} mm, max rotation error {da:.3f} deg")
     assert dt < 1e-3 and da < 2.0
+
+
+def test_first_conv3d_tensor_core(cuda):
+    """3 -> 48 Conv3d on the tensor cores (K = 16 rows, SWIZZLE_32B, one A tile per filter column) against torch on the
+    same bf16-rounded operands, incl. the padded channels-last output and the GroupNorm statistics."""
+    import torch.nn.functional as F
+    from graspldm_b200 import _lib
+    from graspldm_b200.engine import _aligned_bytes, _stream
+    gen = torch.Generator().manual_seed(6)
+    B, ci, co, r = 3, 3, 48, 24
+    P, r3 = (r + 2) ** 3, r ** 3
+    x = torch.randn(B, ci, r3, generator=gen).to(cuda)
+    w = (torch.randn(co, ci, 3, 3, 3, generator=gen) / 9).to(cuda)
+    bias = torch.randn(co, generator=gen).to(cuda) * 0.2
+    st = _stream(cuda)
+    img = _aligned_bytes(_lib.lib().gldm_conv3d_tc16_weight_bytes(), cuda)
+    _lib.call("gldm_conv3d_tc16_pack_weight", w.contiguous().data_ptr(), co, ci, img.data_ptr(), st)
+    scratch = torch.empty((B * P, 16), device=cuda, dtype=torch.bfloat16)
+    y = torch.zeros((B * P, 64), device=cuda, dtype=torch.bfloat16)
+    stats = torch.full((B, 8, 2), float("nan"), device=cuda, dtype=torch.float64)
+    ws = torch.empty(_lib.lib().gldm_voxel_ws_bytes(B, co, r) // 8 + 1, device=cuda, dtype=torch.float64)
+    _lib.call("gldm_conv3d_tc16_cl", x.data_ptr(), img.data_ptr(), bias.data_ptr(), B, ci, co, r, scratch.data_ptr(),
+              y.data_ptr(), 64, stats.data_ptr(), ws.data_ptr(), st)
+    want = F.conv3d(x.to(torch.bfloat16).float().view(B, ci, r, r, r), w.to(torch.bfloat16).float(), bias, padding=1)
+    full = y.view(B, r + 2, r + 2, r + 2, 64).float()
+    got = full[:, 1:-1, 1:-1, 1:-1, :co]
+    torch.testing.assert_close(got, want.permute(0, 2, 3, 4, 1), rtol=8e-3, atol=8e-3)      # bf16 storage
+    assert full[..., co:].abs().max() == 0 and full[:, 0].abs().max() == 0 and full[:, :, -1].abs().max() == 0
+    g = want.view(B, 8, -1).double()
+    torch.testing.assert_close(stats[..., 0], g.sum(-1), rtol=1e-4, atol=0.05)
+    torch.testing.assert_close(stats[..., 1], (g * g).sum(-1), rtol=1e-4, atol=0.05)
