@@ -36,7 +36,6 @@ for j, nm in enumerate(names):
     else:
         row = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], gap]
     tot = [x + y for x, y in zip(tot, row)]
-    extra = f"  pf_issue {b[512 + j] - t[2]:6d}" + (f"  first tmem ld {b[64 + 8 * j + 7] - b[512 + j]:6d}" if t[3] else "")
-    print(f"{nm:14s} " + " ".join(f"{x:9d}" for x in row) + extra)
+    print(f"{nm:14s} " + " ".join(f"{x:9d}" for x in row))
     prev = t[6]
 print("total          " + " ".join(f"{x:9d}" for x in tot), "  first..last", b[64 + 8 * (len(names) - 1) + 6] - b[64])
