@@ -2,7 +2,7 @@
 optional TMEM dump at a chosen job, and compare against torch."""
 import os, sys, time
 os.environ["GLDM_TC_ROWS"] = "1"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import torch.nn.functional as F
