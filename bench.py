@@ -166,8 +166,8 @@ def cpu_baseline_sample():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)     # 50 x ~6 ms: the four-deep pipeline's fill / drain is < 3 % of it
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation); fp32: strict-fp32 SIMT parity path")
