@@ -28,8 +28,10 @@ REF = "/root/reference"
 sys.path.insert(0, os.path.join(HERE, "_shims"))
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import ops_np  # noqa: E402
+import _models  # noqa: E402  (trained_like_: shared with the tests so both module trees get identical values)
 
 
 def _install_cpu_backend():
@@ -221,6 +223,56 @@ def ppc_ldm_golden():
     np.savez_compressed(f"{HERE}/ldm_ppc_ddpm10.npz", x_T=x_T.numpy(), noise=noise.numpy(), tmrp=tm.numpy(), logit=lg.numpy())
 
 
+def trained_golden(man):
+    """Checkpoint-like state (tests/_models.py::trained_like_: non-trivial BatchNorm running statistics and affine
+    parameters of every BatchNorm / GroupNorm / LayerNorm) through the unmodified reference classes: single evaluations,
+    encoder, VAE mode, LDM (100 DDPM / 10 DDIM steps) for both model families, and one BASELINE config-2-sized run
+    (64 objects x 20 grasps, 100 DDPM steps) for fpc.  x_T / noise of the config-2 run are not stored: the test re-draws
+    them from the same seeded CPU generators."""
+    np_ = lambda x: x.detach().cpu().numpy()
+    base = json.load(open(f"{HERE}/state_dict_manifest.json")) if not man else man
+    for name in ("fpc", "ppc"):
+        model = _models.trained_like_(build_reference_ldm(name))
+        full = manifest(model.state_dict())
+        man[name + "_trained"] = {k: v for k, v in full.items() if base[name][k]["sha"] != v["sha"]}
+        D = model.diffusion_model.n_dims
+        Dc = 64 if name == "fpc" else 256
+        den, vae = model.diffusion_model.model, model.vae_model
+        d0 = np.load(f"{HERE}/dense_{name}.npz")
+        t = lambda k: torch.from_numpy(d0[k])
+        xyz = torch.cat([synthetic_clouds(2, seed=1234, dist="S"), synthetic_clouds(1, seed=99, dist="G")])
+        nobj, G = 2, 3
+        with torch.no_grad():
+            eps = den(t("x"), time=t("t"), z_cond=t("z_cond"))
+            tmrp, logit = vae.decoder(t("z_h"), t("z_cond"))
+            np.savez_compressed(f"{HERE}/dense_{name}_trained.npz", eps=np_(eps), tmrp=np_(tmrp), logit=np_(logit))
+            np.savez_compressed(f"{HERE}/encoder_{name}_trained.npz", z_pc=np_(vae.encode_pc(xyz)))
+            torch.manual_seed(5)
+            z_h = torch.randn(nobj * G, D)
+            torch.manual_seed(5)
+            tm, lg = vae.generate_grasps(xyz[:nobj], num_grasps=G)
+            np.savez_compressed(f"{HERE}/vae_{name}_trained.npz", z_h=np_(z_h), tmrp=np_(tm), logit=np_(lg))
+            runs = [("ddpm", 100, nobj, G, xyz[:nobj]), ("ddim", 10, nobj, G, xyz[:nobj])]
+            if name == "fpc":
+                runs.append(("ddpm", 100, 64, 20, synthetic_clouds(64, seed=1234, dist="S")))
+            for sched, nsteps, no, ng, clouds in runs:
+                m = _models.trained_like_(build_reference_ldm(name, scheduler=sched))
+                m.set_inference_timesteps(nsteps)
+                gg = torch.Generator().manual_seed(42)
+                noise = torch.randn(nsteps, no * ng, 1, D, generator=gg)
+                m.diffusion_model.noise_scheduler.injected_noise = list(noise)
+                torch.manual_seed(42)
+                x_T = torch.randn((no * ng, 1, D))
+                torch.manual_seed(42)
+                (tm, lg), _ = m.generate_grasps(clouds, num_grasps=ng, device="cpu")
+                if no == 64:
+                    np.savez_compressed(f"{HERE}/ldm_{name}_trained_config2.npz", tmrp=np_(tm), logit=np_(lg))
+                else:
+                    np.savez_compressed(f"{HERE}/ldm_{name}_trained_{sched}{nsteps}.npz", x_T=np_(x_T), noise=np_(noise),
+                                        tmrp=np_(tm), logit=np_(lg))
+    return man
+
+
 def manifest(sd):
     out = {}
     for k, v in sd.items():
@@ -232,6 +284,17 @@ def manifest(sd):
 def main():
     torch.set_num_threads(8)
     np_ = lambda x: x.detach().cpu().numpy()
+    only = set(sys.argv[1:])          # e.g. `make_golden.py trained` regenerates one section
+    if only:
+        if "trained" in only:
+            man = json.load(open(f"{HERE}/state_dict_manifest.json"))
+            man = trained_golden(man)
+            with open(f"{HERE}/state_dict_manifest.json", "w") as f:
+                json.dump(man, f, indent=0, sort_keys=True)
+        for tag, fn in (("normalize", normalize_golden), ("edm", edm_golden), ("ppc_ldm", ppc_ldm_golden)):
+            if tag in only:
+                fn()
+        return
     man = {}
     for name in ("fpc", "ppc"):
         model = build_reference_ldm(name)
@@ -287,6 +350,7 @@ def main():
             H = tmrp_to_H(g_un)
             np.savez_compressed(f"{HERE}/vae_{name}.npz", z_h=np_(z_h), tmrp=np_(tm), logit=np_(lg),
                                 grasp_tmrp=np_(g_un), H=np_(H))
+    man = trained_golden(man)
     with open(f"{HERE}/state_dict_manifest.json", "w") as f:
         json.dump(man, f, indent=0, sort_keys=True)
     normalize_golden()

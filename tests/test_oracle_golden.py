@@ -202,3 +202,53 @@ def test_oracle_ppc_ldm_generation_vs_reference_loop():
                                        num_inference_steps=10, kind="ddpm")
     np.testing.assert_allclose(tm.numpy(), g["tmrp"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(lg.numpy(), g["logit"], rtol=1e-4, atol=2e-5)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# checkpoint-like state: BatchNorm running statistics / every norm's affine parameters away from their init values
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["fpc", "ppc"])
+def test_trained_like_state_matches_the_reference_tree(name):
+    """tests/_models.py::trained_like_ gives the product's module tree the same values it gave the reference's tree when
+    the *_trained fixtures were generated (hashes of every tensor it changed)."""
+    man = json.load(open(os.path.join(G, "state_dict_manifest.json")))[name + "_trained"]
+    sd = _models.build_trained_like(name).state_dict()
+    kinds = {k.rsplit(".", 1)[-1] for k in man}
+    assert {"running_mean", "running_var", "weight", "bias", "g"} <= kinds
+    assert any(".norm.weight" in k and "diffusion_model" in k for k in man) and any("voxel_layers" in k for k in man)
+    base = _models.build(name).state_dict()
+    for k, v in sd.items():
+        a = v.detach().contiguous().numpy()
+        if k in man:
+            assert hashlib.sha256(a.tobytes()).hexdigest()[:16] == man[k]["sha"], k
+            assert not np.array_equal(a, base[k].numpy()), k
+        else:
+            assert np.array_equal(a, base[k].numpy()), k
+
+
+@pytest.mark.parametrize("name", ["fpc", "ppc"])
+def test_oracle_vs_reference_on_trained_like_state(name):
+    vae, ddm = _models.split_state_dicts(_models.build_trained_like(name))
+    g0 = np.load(os.path.join(G, f"dense_{name}.npz"))
+    g = np.load(os.path.join(G, f"dense_{name}_trained.npz"))
+    t = lambda k: torch.from_numpy(g0[k])
+    with torch.no_grad():
+        eps = M.denoiser_forward(ddm, "diffusion_model.model.", t("x"), t("t"), t("z_cond"))
+        tm, lg = M.decoder_forward(vae, "decoder.", t("z_h"), t("z_cond"))
+    assert np.abs(g["eps"] - g0["eps"]).max() > 1e-2          # the fixture does depend on the norm parameters
+    np.testing.assert_allclose(eps.numpy(), g["eps"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(tm.numpy(), g["tmrp"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(lg.numpy(), g["logit"], rtol=1e-5, atol=2e-6)
+    xyz = torch.cat([_data.synthetic_clouds(2, seed=1234, dist="S"), _data.synthetic_clouds(1, seed=99, dist="G")])
+    with torch.no_grad():
+        z = M.pvcnn_encoder_forward(vae, "encoder.pc_encoder.", xyz)
+    want = np.load(os.path.join(G, f"encoder_{name}_trained.npz"))["z_pc"]
+    assert np.abs(want - np.load(os.path.join(G, f"encoder_{name}.npz"))["z_pc"]).max() > 1e-2
+    np.testing.assert_allclose(z.numpy(), want, rtol=1e-4, atol=2e-5)
+    for kind, steps in (("ddpm", 100), ("ddim", 10)):
+        f = np.load(os.path.join(G, f"ldm_{name}_trained_{kind}{steps}.npz"))
+        with torch.no_grad():
+            tm, lg = M.generate_grasps_ldm(vae, ddm, xyz[:2], 3, torch.from_numpy(f["x_T"]), noise=torch.from_numpy(f["noise"]),
+                                           num_inference_steps=steps, kind=kind)
+        np.testing.assert_allclose(tm.numpy(), f["tmrp"], rtol=1e-4, atol=5e-5)
+        np.testing.assert_allclose(lg.numpy(), f["logit"], rtol=1e-4, atol=5e-5)
