@@ -33,6 +33,22 @@ inline int check_launch(const char* what) {
     }                                \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: one opt-in per (kernel, device), checked.
+struct SmemOptIn { unsigned long long done = 0; };   // bit d = already set on device d
+template <typename K>
+inline int opt_in_smem(SmemOptIn& st, K kernel, int bytes, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ((st.done >> dev) & 1ull)) return GLDM_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot opt in to %d bytes of dynamic shared memory on device %d: %s", what, bytes, dev, cudaGetErrorString(e));
+    return GLDM_ECUDA;
+  }
+  if (dev >= 0 && dev < 64) st.done |= 1ull << dev;
+  return GLDM_OK;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

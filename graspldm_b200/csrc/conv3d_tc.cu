@@ -741,14 +741,11 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
   p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b;
-  static bool attr = false;
+  static SmemOptIn attr_s, attr_b;
   const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 256;
   const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 256;
-  if (!attr) {
-    cudaFuncSetAttribute(conv3d_tc_kernel<c3::W_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
-    cudaFuncSetAttribute(conv3d_tc_kernel<c3::W_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
-    attr = true;
-  }
+  if (int rc = opt_in_smem(attr_s, conv3d_tc_kernel<c3::W_SLOT>, smem_small, "conv3d_tc_kernel")) return rc;
+  if (int rc = opt_in_smem(attr_b, conv3d_tc_kernel<c3::W_BYTES>, smem_big, "conv3d_tc_kernel (wide)")) return rc;
   const unsigned grid = (unsigned)((rows + 127) / 128);
   // one A tile per filter column (conv3d_tc3_kernel) by default; GLDM_CONV3D_TAPS3=0 selects the one-tile-per-tap kernel
   static int taps3 = -1;
@@ -764,11 +761,8 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
       return GLDM_ECUDA;
     }
     const int smem3 = c3::STAGES3 * (c3::A3_BYTES + 3 * c3::W_SLOT) + 1024 + 256;
-    static bool attr3 = false;
-    if (!attr3) {
-      cudaFuncSetAttribute(conv3d_tc3_kernel<c3::W_SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
-      attr3 = true;
-    }
+    static SmemOptIn attr3;
+    if (int rc = opt_in_smem(attr3, conv3d_tc3_kernel<c3::W_SLOT>, smem3, "conv3d_tc3_kernel")) return rc;
     conv3d_tc3_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem3, s>>>(map3, p, taps3);
     return check_launch("conv3d_tc3_kernel");
   }
@@ -902,11 +896,8 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
   p.w_rows_bytes = ((co + 7) / 8) * 256;
   p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b;
   const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 256;
-  static bool attr16 = false;
-  if (!attr16) {
-    cudaFuncSetAttribute(conv3d_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
-    attr16 = true;
-  }
+  static SmemOptIn attr16;
+  if (int rc2 = opt_in_smem(attr16, conv3d_tc16_kernel, smem16, "conv3d_tc16_kernel")) return rc2;
   conv3d_tc16_kernel<<<(unsigned)((rows + 127) / 128), c3::NTHREADS, smem16, s>>>(map, p);
   rc = check_launch("conv3d_tc16_kernel");
   if (rc) return rc;

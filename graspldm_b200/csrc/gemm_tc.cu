@@ -238,11 +238,8 @@ extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const floa
   GLDM_REQUIRE(rows >= 0 && rows % 128 == 0, "gemm_tc_run: rows = %lld must be a multiple of 128", rows);
   GLDM_REQUIRE(k > 0 && n_out > 0 && n_out % 128 == 0, "gemm_tc_run: n_out = %d must be a multiple of 128", n_out);
   if (rows == 0) return GLDM_OK;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM);
-    attr = true;
-  }
+  static SmemOptIn attr;
+  if (int rc = opt_in_smem(attr, gemm_tc_kernel, gtc::SMEM, "gemm_tc_kernel")) return rc;
   GemmTcParams p;
   p.a_img = reinterpret_cast<const uint8_t*>(a_img);
   p.b_img = reinterpret_cast<const uint8_t*>(w_img);

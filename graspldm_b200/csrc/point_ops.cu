@@ -603,18 +603,12 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   int threads = min(512, ceil_div(n, 32) * 32);
   const int slices = min(8, ceil_div(c, 8));      // channel slices per cloud: more CTAs than clouds for wide features
   if (fused) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(voxelize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, voxelize_kernel<true>, 200 * 1024, "voxelize_kernel<fused>")) return rc;
     voxelize_kernel<true><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
   } else {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(voxelize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, voxelize_kernel<false>, 200 * 1024, "voxelize_kernel")) return rc;
     voxelize_kernel<false><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
   }
   return check_launch("voxelize_kernel");

@@ -573,18 +573,12 @@ static size_t resnet_smem_bytes() {
 static int launch_resnet(const ResNetParams& p, cudaStream_t s) {
   if (p.n == 0) return GLDM_OK;
   if (p.cfg.L == 4) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(resnet_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resnet_smem_bytes<4>());
-      attr = true;
-    }
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, resnet_kernel<4>, (int)resnet_smem_bytes<4>(), "resnet_kernel<4>")) return rc;
     resnet_kernel<4><<<ceil_div(p.n, Tile<4>::S), 256, resnet_smem_bytes<4>(), s>>>(p);
   } else {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(resnet_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resnet_smem_bytes<16>());
-      attr = true;
-    }
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, resnet_kernel<16>, (int)resnet_smem_bytes<16>(), "resnet_kernel<16>")) return rc;
     resnet_kernel<16><<<ceil_div(p.n, Tile<16>::S), 256, resnet_smem_bytes<16>(), s>>>(p);
   }
   return check_launch("resnet_kernel");

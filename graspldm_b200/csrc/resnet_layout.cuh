@@ -74,13 +74,13 @@ inline int check_cfg(const GldmResNetCfg* c) {
   GLDM_REQUIRE(c->cond_ch >= 1 && c->cond_ch <= 4, "resnet: cond_ch=%d (<=4)", c->cond_ch);
   GLDM_REQUIRE(c->cond_dim >= 1 && c->cond_dim <= 1024, "resnet: cond_dim=%d", c->cond_dim);
   GLDM_REQUIRE(!c->time_cond || (c->fourier_half >= 1 && c->fourier_half <= 16), "resnet: fourier_half");
+  GLDM_REQUIRE(c->groups >= 1 && c->groups <= 8, "resnet: groups=%d (1..8)", c->groups);
   for (int i = 0; i <= c->n_stages; ++i) {
     const int ch = c->ch[i];
     GLDM_REQUIRE(ch == 4 || ch == 8 || ch == 16 || ch == 32 || ch == 64 || ch == 128 || ch == 256,
                  "resnet: channel width %d not supported (4,8,16,32,64,128,256)", ch);
     GLDM_REQUIRE(ch % c->groups == 0, "resnet: channels %d not divisible by groups %d", ch, c->groups);
   }
-  GLDM_REQUIRE(c->groups >= 1 && c->groups <= 8, "resnet: groups=%d (<=8)", c->groups);
   return GLDM_OK;
 }
 

@@ -1210,14 +1210,11 @@ static long long* g_tc_prof = nullptr;
 
 template <int L, int NSETS>
 static int launch_tc_l(TcParams& p, cudaStream_t s) {
-  static bool attr = false;
+  static SmemOptIn attr;
   using T = Tr<L, NSETS>;
   const int smem = T::SM_TOTAL + 1024;
   static_assert(T::SM_TOTAL + 1024 <= 232448, "shared memory budget");
-  if (!attr) {
-    cudaFuncSetAttribute(resnet_tc_kernel<L, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (int rc = opt_in_smem(attr, resnet_tc_kernel<L, NSETS>, smem, "resnet_tc_kernel")) return rc;
   resnet_tc_kernel<L, NSETS><<<ceil_div(p.n, T::NS * NSETS), stc::NTHREADS, smem, s>>>(p);
   return check_launch(L == 4 ? "resnet_tc_kernel<4>" : "resnet_tc_kernel<16>");
 }
@@ -1237,12 +1234,9 @@ static bool rows_supported(const GldmResNetCfg& c) {
 }
 
 static int launch_rows(TcParams& p, cudaStream_t s) {
-  static bool attr = false;
+  static SmemOptIn attr;
   const int smem = rows::SM_TOTAL + 1024;
-  if (!attr) {
-    cudaFuncSetAttribute(rows::resnet_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (int rc = opt_in_smem(attr, rows::resnet_rows_kernel, smem, "resnet_rows_kernel")) return rc;
   rows::resnet_rows_kernel<<<ceil_div(p.n, rows::NS), rows::NTHREADS, smem, s>>>(p);
   return check_launch("resnet_rows_kernel");
 }

@@ -178,13 +178,22 @@ def _check_precision(precision):
         raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
 
 
+def _cond3d(z):
+    """Conditioning as [B, C, Dc].  A 2-D latent [B, Dc] (PVCNNEncoder with out_channels=1 squeezes its output,
+    pc_encoders.py:113-114) is the single-channel case of the multi-channel FiLM (resnets.py:163-175)."""
+    if z.ndim == 2:
+        return z.unsqueeze(1)
+    if z.ndim != 3:
+        raise RuntimeError(f"conditioning latent must be [B, Dc] or [B, C, Dc], got {tuple(z.shape)}")
+    return z
+
+
 def resnet_forward(module, x, time, z_cond, precision="fp32"):
     """One network evaluation: x [B,1,L], time int[B] or None, z_cond [B,C,Dc] -> [B,1,L]."""
     _check_precision(precision)
     _require_cuda(x, "x")
     _require_cuda(z_cond, "z_cond")
-    if z_cond.ndim != 3:
-        raise NotImplementedError("conditioning must be [B, C, Dc] (multi-channel FiLM)")
+    z_cond = _cond3d(z_cond)
     B, _, L = x.shape
     pk = packed_resnet(module, L, z_cond.shape[1])
     dev = x.device
@@ -213,6 +222,7 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
     _require_cuda(x_T, "x_T")
     _require_cuda(z_obj, "z_cond")
     n, _, D = x_T.shape
+    z_obj = _cond3d(z_obj)
     pk = packed_resnet(denoiser, D, z_obj.shape[1])
     dev = x_T.device
     n_steps = len(timesteps)
@@ -253,6 +263,7 @@ def decoder_forward(decoder, z_h, z_obj, grasps_per_obj, precision="fp32"):
     _require_cuda(z_h, "z_h")
     _require_cuda(z_obj, "cond")
     n, D = z_h.shape
+    z_obj = _cond3d(z_obj)
     net = decoder.net
     L = decoder.feature_resolution
     pk = packed_resnet(net, L, z_obj.shape[1])
@@ -507,17 +518,32 @@ def encoder_forward(enc, xyz, max_clouds_per_pass=256, precision="fp32"):
     return out.squeeze(1) if out.shape[-2] == 1 else out
 
 
+_CL_CACHE_MAX = 64      # buffers kept per encoder (tag x stream); least recently used ones are dropped beyond that
+
+
 def _cl_grid(pk, dev, tag, rows, stride, dtype):
-    """Zero-initialised padded channels-last grid, cached per (stream, shape): the kernels never write halo rows, so the
-    zeros survive from call to call; the stream key keeps concurrently running passes (bench --streams) apart."""
+    """Zero-initialised padded channels-last grid, cached per (tag, stream): the kernels never write halo rows or padding
+    channels with anything but zero, so the zeros survive from call to call; the stream key keeps concurrently running
+    passes (bench --streams) apart.  One buffer per key, sized for the LARGEST batch seen: a smaller batch uses a prefix
+    (its halo rows are the same rows, still zero), a larger one replaces the buffer.  Bounded (LRU) - see clear_cl_cache."""
     cache = pk.__dict__.setdefault("_cl_cache", {})
-    key = (tag, torch.cuda.current_stream(dev).cuda_stream, dev.index, rows, stride, dtype)
-    buf = cache.get(key)
-    if buf is None:
-        buf = torch.zeros((rows, stride), device=dev, dtype=dtype)
+    key = (tag, torch.cuda.current_stream(dev).cuda_stream, dev.index, stride if rows > 1 else 0, dtype)
+    need = rows * stride
+    buf = cache.pop(key, None)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(need, device=dev, dtype=dtype)
         assert buf.data_ptr() % 256 == 0
-        cache[key] = buf
-    return buf
+    cache[key] = buf                              # (re)inserted last = most recently used
+    while len(cache) > _CL_CACHE_MAX:
+        cache.pop(next(iter(cache)))
+    return buf[:need].view(rows, stride)
+
+
+def clear_cl_cache(enc):
+    """Release the cached channels-last grids of an encoder (they are re-created, zeroed, on the next bf16 pass)."""
+    ent = enc.__dict__.get("_gldm_pack")
+    if ent is not None:
+        ent[1].__dict__.pop("_cl_cache", None)
 
 
 def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):

@@ -109,8 +109,13 @@ class InferenceLDM(_InferenceBase):
     def generate_grasps(self, pc, metas, num_grasps=10, cls_cond=None, return_intermediate=False, **kwargs):
         batch_pcs = (pc.unsqueeze(0) if pc.ndim == 2 else pc).to(self.device, non_blocking=True)
         metas = {k: v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in metas.items()}
-        if self.fast_sampler == "DDIM":
+        if self.fast_sampler == "DDIM":                          # tools/inference.py:605-609
             self.model.set_inference_timesteps(self.num_inference_steps)
+        elif self.fast_sampler == "DPMPP":                       # elucidated models: DPM-Solver++ with the configured steps
+            kwargs["use_dpmpp"] = True
+            kwargs["num_sample_steps"] = self.num_inference_steps
+        elif getattr(self.model, "is_elucidated_diffusion", False):
+            kwargs.setdefault("use_dpmpp", False)                # the reference's sample() pops the key unconditionally
         final_grasps, step_grasps = self.model.generate_grasps(xyz=batch_pcs, num_grasps=num_grasps, metas=metas,
                                                                return_intermediate=return_intermediate, **kwargs)
         out = self._finish(final_grasps, batch_pcs, metas, num_grasps)
