@@ -17,54 +17,70 @@
 // the 4 positions of a sample (4 warps of a warp-group), LayerNorm / final-conv sums over the 4 warp-groups of a row,
 // and the k / v rows of the other 3 positions in the linear attention (through the idle operand buffer).
 //
-// TMEM columns: [0,256) accumulator (q | k | v = [0,384) for the attention job), FiLM scale [128,256) and shift
-// [256,384) (FiLM layers are <= 128 wide; the 256-wide first conv of the final block runs as two 128-column halves),
-// [384,512) residual stream: fp32 for widths <= 128, packed bf16 pairs for the 256-wide final block.
+// FiLM is hoisted out of the sample loop: the conditioning embedding depends only on (object, step), so a prologue
+// kernel (film_table_kernel, sampler_tc.cu) writes one [A | B] vector pair per FiLM layer and (object, step) - GroupNorm
+// affine and FiLM folded into one multiply-add - and the epilogue reads it through L1 (prefetched while the UMMAs run).
+// No FiLM UMMAs, no per-step operand rebuild, no FiLM columns in TMEM.
+//
+// Layers of 32 / 64 / 128 channels (8 / 16 / 32 channels per thread) keep their accumulator row in REGISTERS between
+// the statistics and the apply pass: TMEM is read once per element (TMEM read bandwidth, 64 B/cycle/SM, is the wall of
+// this epilogue).  The 256-wide final block (64 channels per thread) and the 4-channel first stage use the two-pass form.
+//
+// TMEM columns: [0,256) accumulator (q | k | v = [0,384) for the attention job), [384,512) residual stream: fp32 for
+// widths <= 128, packed bf16 pairs for the 256-wide final block.
 #pragma once
 
 namespace rows {
 constexpr int NS = 32;                          // samples per CTA
 constexpr int NEPI = 512;                       // 16 epilogue warps
-constexpr int NTHREADS = 640;                   // + producer, issuer, two idle register donors
+constexpr int NTHREADS = 640;                   // + producer, issuer, two idle register donors (warps are allocated in fours)
 constexpr int SLAB = 192 * 128;                 // 64 channels x (32 halo + 128 + 32 halo) rows
 constexpr int CHUNK = stc::CHUNK, STAGES = 2;
 constexpr int MAXRJ = 40, MAXOPS = 400, MAXCHUNKS = 256;
-constexpr uint32_t T_ACC = 0, T_FS = 128, T_FH = 256, T_RES = 384;
+constexpr uint32_t T_ACC = 0, T_RES = 384;
 // shared memory map (from a 1024-aligned base)
 constexpr int SM_A = 0;
-constexpr int SM_U = SM_A + 4 * SLAB;                     // FiLM operand u: 128 rows x 128 B (K = 16 used)
-constexpr int SM_RING = SM_U + 128 * 128;
-constexpr int SM_PAR = SM_RING + STAGES * CHUNK;          // per-job channel parameters [7][256] floats
-constexpr int SM_XG = SM_PAR + 7 * 256 * 4;               // GroupNorm exchange [4 groups][4 positions][32] float2
+constexpr int SM_RING = SM_A + 4 * SLAB;
+constexpr int PAR_FLOATS = 5120;                          // every per-channel parameter of the network, resident for all steps
+constexpr int SM_PAR = SM_RING + STAGES * CHUNK;
+constexpr int SM_PTAB = SM_PAR + PAR_FLOATS * 4;          // [MAXRJ][5] int16: offsets of a job's bias, gamma, beta, g1, g2 (-1: none)
+constexpr int SM_JD = SM_PTAB + MAXRJ * 5 * 2 + 16;       // [MAXRJ] uint4 job descriptors read by the epilogue warps
+constexpr int SM_XG = SM_JD + MAXRJ * 16;                 // GroupNorm exchange [4 groups][4 positions][32] float2
 constexpr int SM_XL = SM_XG + 4 * 4 * 32 * 8;             // row exchange [128 rows][4 warp-groups] float2
-constexpr int SM_INEMB = SM_XL + 128 * 4 * 8;             // [32][3][16] floats
-constexpr int SM_X = SM_INEMB + 32 * 3 * 16 * 4;          // state [32][4]
+constexpr int SM_X = SM_XL + 128 * 4 * 8;                 // state [32][4]
 constexpr int SM_BAR = SM_X + 32 * 4 * 4;
 constexpr int SM_CHUNKS = SM_BAR + 256;
-constexpr int SM_RJ = SM_CHUNKS + MAXCHUNKS * 8;          // row-job table
-constexpr int SM_OPS = SM_RJ + MAXRJ * 8;
+constexpr int SM_OPS = SM_CHUNKS + MAXCHUNKS * 8;
 constexpr int SM_OPBEG = SM_OPS + MAXOPS * 16;
 constexpr int SM_TOTAL = SM_OPBEG + (MAXRJ + 2) * 2 + 16;
 static_assert(SM_TOTAL + 1024 <= 232448, "shared memory budget");
 
-// kind 0: a whole layer.  The 256-wide FiLM layer (first conv of the final block) does not fit TMEM next to its FiLM
-// vectors (256 + 2 * 256 columns) and its epilogue overwrites the operand it is computed from, so it runs as five
-// row-jobs: kind 1 = the convolution (N = 256) + GroupNorm, normalised values kept in the accumulator columns;
-// kind 2 / 3 (h = 0, 1) = FiLM scale / shift of channel half h into columns [256, 384), applied in place; kind 3 ends
-// with SiLU and writes the operand.
-struct RJob { int16_t job; int8_t kind, h; int16_t ch, wgs; };
-constexpr int E_INPLACE = 0x4000;      // internal: GroupNorm result back into the accumulator columns, nothing else
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int NV>
+__device__ __forceinline__ void ld_film(const float* f, float (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(f + i));
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+}
 
 __device__ __forceinline__ void bar_wg(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
+// job-start barrier: the 16 epilogue warps PARK here (a hardware barrier takes no issue slots) until the waiter warp, the
+// only one that polls the accumulator mbarrier, arrives.  512 threads spinning on mbarrier.try_wait took 22 % of all
+// issued instructions and starved the UMMA issuer warp of issue slots.
+__device__ __forceinline__ void bar_job_sync() { asm volatile("bar.sync 6, 544;" ::: "memory"); }
+__device__ __forceinline__ void bar_job_arrive() { asm volatile("bar.arrive 6, 544;" ::: "memory"); }
 
+// per-thread epilogue state, kept small: the epilogue warps run at the register limit
 struct Ep {
   uint32_t tmem;        // TMEM base + this warp's lane quarter
   int g, pos, s, row;   // warp-group, position, sample (lane), row = pos * 32 + s
   uint8_t* smem;
-  const float* par;     // staged channel parameters [7][256]: bias, gamma, beta, film scale bias (+1), film shift bias, g1, g2
-  float2* xg;
-  float2* xl;
+  uint32_t po[3];       // this job's channel parameters (float offsets into SM_PAR): bias | gamma << 16, beta | g1 << 16, g2
+  __device__ __forceinline__ float2* xg() const { return reinterpret_cast<float2*>(smem + SM_XG); }
+  __device__ __forceinline__ float2* xl() const { return reinterpret_cast<float2*>(smem + SM_XL); }
 };
 
 template <int NV>
@@ -101,7 +117,8 @@ __device__ __forceinline__ void st_cols(const Ep& e, uint32_t col, const float (
 }
 template <int NV>
 __device__ __forceinline__ void ld_par(const Ep& e, int k, int c, float (&v)[NV]) {
-  const float* p = e.par + k * 256 + c;
+  const uint32_t off = (k & 1) ? e.po[k >> 1] >> 16 : e.po[k >> 1] & 0xffffu;
+  const float* p = reinterpret_cast<const float*>(e.smem + SM_PAR) + off + c;
 #pragma unroll
   for (int i = 0; i < NV; i += 4) {
     const float4 t = *reinterpret_cast<const float4*>(p + i);
@@ -143,155 +160,310 @@ __device__ __forceinline__ void st_operand(const Ep& e, int chan, const float (&
   }
 }
 
-// generic layer epilogue.  NV = 8: warp-group g owns channels [g*cw, (g+1)*cw), cw = ch / wgs >= 8, one GroupNorm group;
-// NV = 4: the 4-channel first stage, warp-group 0 owns all 4 channels = 4 GroupNorm groups of one channel.
-// Returns the final-conv partial dot product (E_FINAL) of this thread's channels.
-template <int NV>
-__device__ __forceinline__ float generic_epilogue(const Ep& e, int flags, int ch, int ch_total, int ch_off, int wgs) {
-  const bool active = e.g < wgs;
-  const int cw = (NV == 8) ? ch / wgs : 4;
-  const int c_lo = (NV == 8) ? e.g * cw : 0, c_hi = c_lo + cw;
-  const bool packed = ch_total > 128;
-  float mean[NV == 4 ? 4 : 1], rstd[NV == 4 ? 4 : 1];
-  float lmean = 0.f, lrstd = 1.f;
-  // ---- pass 1: statistics of (acc + bias)
-  if (flags & (E_GN | E_LN)) {
-    float s[NV == 4 ? 4 : 1], q[NV == 4 ? 4 : 1];
+// 4-channel first stage: warp-group 0 alone, a thread holds the 4 channels of its row = 4 GroupNorm groups of one channel
+// (statistics over the 4 positions of the sample); LayerNorm over the 4 channels is in-thread.  Static register indexing.
+__device__ __forceinline__ void narrow_epilogue(const Ep& e, int flags, const float* film) {
+  if (e.g != 0) return;
+  float x[4], a[4], b[4];
+  ld_cols<4>(e, T_ACC, x);
+  ld_par<4>(e, 0, 0, b);
 #pragma unroll
-    for (int i = 0; i < (NV == 4 ? 4 : 1); ++i) { s[i] = 0.f; q[i] = 0.f; }
-    if (active) {
-      for (int c = c_lo; c < c_hi; c += NV) {
-        float x[NV], b[NV];
-        ld_cols<NV>(e, T_ACC + c, x);
-        ld_par<NV>(e, 0, c, b);
+  for (int i = 0; i < 4; ++i) x[i] += b[i];
+  if (flags & E_GN) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const float t = x[j] + b[j];
-          const int gi = (NV == 4 && (flags & E_GN)) ? j : 0;
-          s[gi] += t;
-          q[gi] = fmaf(t, t, q[gi]);
-        }
-      }
-    }
-    if (flags & E_GN) {
-      // sums over the 4 positions of a sample: the 4 warps of this warp-group
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < (NV == 4 ? 4 : 1); ++i) e.xg[((NV == 4 ? i : e.g) * 4 + e.pos) * 32 + e.s] = make_float2(s[i], q[i]);
-      }
-      bar_wg(e.g);
-      if (active) {
-        const float inv = 1.0f / (float)((NV == 4 ? 1 : cw) * 4);
-#pragma unroll
-        for (int i = 0; i < (NV == 4 ? 4 : 1); ++i) {
-          float ts = 0.f, tq = 0.f;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float2 t = e.xg[((NV == 4 ? i : e.g) * 4 + p) * 32 + e.s];
-            ts += t.x; tq += t.y;
-          }
-          const float m = ts * inv;
-          mean[i] = m;
-          rstd[i] = rsqrtf(fmaxf(tq * inv - m * m, 0.f) + 1e-5f);
-        }
-      }
+    for (int i = 0; i < 4; ++i) e.xg()[(i * 4 + e.pos) * 32 + e.s] = make_float2(x[i], x[i] * x[i]);
+    bar_wg(0);
+    if (flags & E_FILM) {
+      ld_film<4>(film, a);
+      ld_film<4>(film + 4, b);
     } else {
-      // channel LayerNorm of the row: sums over the warp-groups
-      e.xl[e.row * 4 + e.g] = active ? make_float2(s[0], q[0]) : make_float2(0.f, 0.f);
-      bar_all();
+      ld_par<4>(e, 1, 0, a);
+      ld_par<4>(e, 2, 0, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       float ts = 0.f, tq = 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) { const float2 t = e.xl[e.row * 4 + w]; ts += t.x; tq += t.y; }
-      const float inv = 1.0f / (float)ch_total;
-      lmean = ts * inv;
-      lrstd = rsqrtf(fmaxf(tq * inv - lmean * lmean, 0.f) + 1e-5f);
-      bar_all();            // xl is reused by E_LNNEXT / E_FINAL below
+      for (int pp = 0; pp < 4; ++pp) { const float2 t = e.xg()[(i * 4 + pp) * 32 + e.s]; ts += t.x; tq += t.y; }
+      const float m = ts * 0.25f, r = rsqrtf(fmaxf(tq * 0.25f - m * m, 0.f) + 1e-5f);
+      x[i] = fmaf(x[i] - m, r * a[i], b[i]);
     }
   }
-  // ---- pass 2
-  float ls = 0.f, lq = 0.f, dot = 0.f;
-  if (active) {
-    for (int c = c_lo; c < c_hi; c += NV) {
-      float v[NV], t0[NV], t1[NV];
-      ld_cols<NV>(e, T_ACC + c, v);
-      ld_par<NV>(e, 0, c, t0);
+  if (flags & E_SILU) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] += t0[j];
+    for (int i = 0; i < 4; i += 2) {
+      const float2 t = silu_fast2(make_float2(x[i], x[i + 1]));
+      x[i] = t.x; x[i + 1] = t.y;
+    }
+  }
+  if (flags & E_LN) {
+    const float m = 0.25f * ((x[0] + x[1]) + (x[2] + x[3]));
+    const float q = 0.25f * (fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
+    const float r = rsqrtf(fmaxf(q - m * m, 0.f) + 1e-5f);
+    ld_par<4>(e, 3, 0, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (x[i] - m) * r * a[i];
+  }
+  if (flags & E_ADDRES) {
+    ld_cols<4>(e, T_RES, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] += b[i];
+  }
+  if (flags & E_STORERES) {
+    st_cols<4>(e, T_RES, x);
+    tmem_st_wait();
+  }
+  if (flags & E_LNNEXT) {       // PreNorm of the attention: operand = LayerNorm(result) * g2
+    const float m = 0.25f * ((x[0] + x[1]) + (x[2] + x[3]));
+    const float q = 0.25f * (fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
+    const float r = rsqrtf(fmaxf(q - m * m, 0.f) + 1e-5f);
+    ld_par<4>(e, 4, 0, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (x[i] - m) * r * a[i];
+  }
+  st_operand<4>(e, 0, x);
+}
+
+// packed fp32 pairs: FADD2 / FMUL2 / FFMA2 do two values per issue slot, and the epilogue is issue bound
+struct F8 { float2 p[4]; };
+__device__ __forceinline__ F8 ld_par8(const Ep& e, int k, int c) {
+  const uint32_t off = (k & 1) ? e.po[k >> 1] >> 16 : e.po[k >> 1] & 0xffffu;
+  const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.smem + SM_PAR) + off + c);
+  const float4 t0 = p[0], t1 = p[1];
+  F8 r;
+  r.p[0] = make_float2(t0.x, t0.y); r.p[1] = make_float2(t0.z, t0.w);
+  r.p[2] = make_float2(t1.x, t1.y); r.p[3] = make_float2(t1.z, t1.w);
+  return r;
+}
+__device__ __forceinline__ F8 ld_film8(const float* f) {
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(f)), t1 = __ldg(reinterpret_cast<const float4*>(f) + 1);
+  F8 r;
+  r.p[0] = make_float2(t0.x, t0.y); r.p[1] = make_float2(t0.z, t0.w);
+  r.p[2] = make_float2(t1.x, t1.y); r.p[3] = make_float2(t1.z, t1.w);
+  return r;
+}
+// 8 accumulator words (after the tcgen05.wait::ld) as four float pairs
+__device__ __forceinline__ void use8(const uint32_t* r, float2 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t a = r[2 * i], b = r[2 * i + 1];
+    asm volatile("" : "+r"(a), "+r"(b));     // ordered after the wait
+    v[i] = make_float2(__uint_as_float(a), __uint_as_float(b));
+  }
+}
+__device__ __forceinline__ void st_operand8(const Ep& e, int chan, const float2 (&v)[4]) {
+  const int R = 32 + e.row;
+  uint8_t* dst = e.smem + SM_A + (chan >> 6) * SLAB + R * 128 + ((((chan & 63) >> 3) ^ (R & 7)) << 4);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y),
+                                              pack_bf16(v[3].x, v[3].y));
+}
+// v = (v - mean) * (rstd * a) + b for 8 channels
+__device__ __forceinline__ void norm8(float2 (&v)[4], const F8& a, const F8& b, float2 nmean, float2 rstd) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __ffma2_rn(__fadd2_rn(v[i], nmean), __fmul2_rn(a.p[i], rstd), b.p[i]);
+}
+__device__ __forceinline__ void silu8(float2 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = silu_fast2(v[i]);
+}
+
+// register-resident layer epilogue: ch = 32 / 64 / 128, this thread's cw = ch / 4 channels ([g * cw, (g+1) * cw) = one
+// GroupNorm group) stay in x[] from the single TMEM read to the operand store; chunks of 8 channels, k < cw / 8.
+__device__ __forceinline__ void reg_epilogue(const Ep& e, int flags, int ch, const float* film, long long* rec) {
+  const int cw = ch >> 2, nk = cw >> 3, c_lo = e.g * cw;
+  float2 x[4][4];
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+  {
+    uint32_t r[32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nk) tmem_ld8(e.tmem + T_ACC + c_lo + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(&r[8 * k]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nk) {
+        const F8 b = ld_par8(e, 0, c_lo + 8 * k);
+        use8(&r[8 * k], x[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[k][i] = __fadd2_rn(x[k][i], b.p[i]);
+          s2 = __fadd2_rn(s2, x[k][i]);
+          q2 = __ffma2_rn(x[k][i], x[k][i], q2);
+        }
+      }
+  }
+  if (rec) rec[3] = clock64();
+  float mean = 0.f, rstd = 1.f;           // GroupNorm of this thread's group, or channel LayerNorm of its row
+  if (flags & (E_GN | E_LN)) {
+    float ts = 0.f, tq = 0.f, inv;
+    if (flags & E_GN) {                   // sums over the 4 positions of a sample: the 4 warps of this warp-group
+      e.xg()[(e.g * 4 + e.pos) * 32 + e.s] = make_float2(s2.x + s2.y, q2.x + q2.y);
+      bar_wg(e.g);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) { const float2 t = e.xg()[(e.g * 4 + pp) * 32 + e.s]; ts += t.x; tq += t.y; }
+      inv = 1.0f / (float)(cw * 4);
+    } else {                              // sums over the 4 warp-groups of a row
+      e.xl()[e.row * 4 + e.g] = make_float2(s2.x + s2.y, q2.x + q2.y);
+      bar_all();
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { const float2 t = e.xl()[e.row * 4 + w]; ts += t.x; tq += t.y; }
+      inv = 1.0f / (float)ch;
+    }
+    mean = ts * inv;
+    rstd = rsqrtf(fmaxf(tq * inv - mean * mean, 0.f) + 1e-5f);
+  }
+  if (rec) rec[4] = clock64();
+  const float2 nmean = make_float2(-mean, -mean), rstd2 = make_float2(rstd, rstd);
+  float2 l2 = make_float2(0.f, 0.f), lq2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nk) {
+      const int c = c_lo + 8 * k;
+      float2(&v)[4] = x[k];
+      uint32_t rr[8];
+      if (flags & E_ADDRES) tmem_ld8(e.tmem + T_RES + c, rr);        // residual chunk in flight under the math below
       if (flags & E_GN) {
-        ld_par<NV>(e, 1, c, t0);
-        ld_par<NV>(e, 2, c, t1);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int gi = NV == 4 ? j : 0;
-          const float a = rstd[gi] * t0[j];
-          v[j] = fmaf(v[j] - mean[gi], a, t1[j]);
-        }
+        if (flags & E_FILM) norm8(v, ld_film8(film + c), ld_film8(film + ch + c), nmean, rstd2);
+        else norm8(v, ld_par8(e, 1, c), ld_par8(e, 2, c), nmean, rstd2);
       }
-      if (flags & E_INPLACE) {
-        st_cols<NV>(e, T_ACC + c, v);
-        continue;
-      }
-      if (flags & E_FILM) {
-        float fs[NV], fh[NV];
-        ld_cols<NV>(e, T_FS + c, fs);
-        ld_cols<NV>(e, T_FH + c, fh);
-        ld_par<NV>(e, 3, c, t0);
-        ld_par<NV>(e, 4, c, t1);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) v[j] = fmaf(v[j], fs[j] + t0[j], fh[j] + t1[j]);
-      }
-      if (flags & E_SILU) {
-#pragma unroll
-        for (int j = 0; j < NV; j += 2) {
-          const float2 r = silu_fast2(make_float2(v[j], v[j + 1]));
-          v[j] = r.x; v[j + 1] = r.y;
-        }
-      }
+      if (flags & E_SILU) silu8(v);
       if (flags & E_LN) {
-        ld_par<NV>(e, 5, c, t0);
+        const F8 g1 = ld_par8(e, 3, c);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) v[j] = (v[j] - lmean) * lrstd * t0[j];
+        for (int i = 0; i < 4; ++i) v[i] = __fmul2_rn(__fadd2_rn(v[i], nmean), __fmul2_rn(g1.p[i], rstd2));
       }
       if (flags & E_ADDRES) {
-        ld_res<NV>(e, packed, ch_off + c, t0);
+        tmem_ld_wait();
+        float2 t[4];
+        use8(rr, t);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) v[j] += t0[j];
+        for (int i = 0; i < 4; ++i) v[i] = __fadd2_rn(v[i], t[i]);
       }
-      if (flags & E_STORERES) st_res<NV>(e, packed, ch_off + c, v);
+      if (flags & E_STORERES) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { w[2 * i] = __float_as_uint(v[i].x); w[2 * i + 1] = __float_as_uint(v[i].y); }
+        tmem_st8(e.tmem + T_RES + c, w);
+      }
       if (flags & E_LNNEXT) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) { ls += v[j]; lq = fmaf(v[j], v[j], lq); }
-      } else if (flags & E_FINAL) {
-        ld_par<NV>(e, 6, c, t0);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) dot = fmaf(t0[j], v[j], dot);
+        for (int i = 0; i < 4; ++i) { l2 = __fadd2_rn(l2, v[i]); lq2 = __ffma2_rn(v[i], v[i], lq2); }
       } else {
-        st_operand<NV>(e, ch_off + c, v);
+        st_operand8(e, c, v);
       }
     }
-    if (flags & (E_STORERES | E_INPLACE)) tmem_st_wait();
   }
-  // ---- pass 3: PreNorm of the attention: operand = LayerNorm(result) * g2, result re-read from the residual stream
+  if (flags & E_STORERES) tmem_st_wait();
+  if (rec) rec[5] = clock64();
   if (flags & E_LNNEXT) {
-    e.xl[e.row * 4 + e.g] = active ? make_float2(ls, lq) : make_float2(0.f, 0.f);
+    // PreNorm of the attention: operand = LayerNorm(result) * g2, the result is still in x[]
+    e.xl()[e.row * 4 + e.g] = make_float2(l2.x + l2.y, lq2.x + lq2.y);
     bar_all();
     float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { const float2 t = e.xl[e.row * 4 + w]; ts += t.x; tq += t.y; }
-    const float inv = 1.0f / (float)ch_total;
+    for (int w = 0; w < 4; ++w) { const float2 t = e.xl()[e.row * 4 + w]; ts += t.x; tq += t.y; }
+    const float inv = 1.0f / (float)ch;
     const float m = ts * inv, r = rsqrtf(fmaxf(tq * inv - m * m, 0.f) + 1e-5f);
-    if (active) {
-      for (int c = c_lo; c < c_hi; c += NV) {
-        float v[NV], g2[NV];
-        ld_res<NV>(e, packed, ch_off + c, v);
-        ld_par<NV>(e, 6, c, g2);
+    const float2 nm = make_float2(-m, -m), r2 = make_float2(r, r);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) v[j] = (v[j] - m) * r * g2[j];
-        st_operand<NV>(e, ch_off + c, v);
+    for (int k = 0; k < 4; ++k)
+      if (k < nk) {
+        const F8 g2 = ld_par8(e, 4, c_lo + 8 * k);
+        float2 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __fmul2_rn(__fadd2_rn(x[k][i], nm), __fmul2_rn(g2.p[i], r2));
+        st_operand8(e, c_lo + 8 * k, o);
+      }
+  }
+}
+
+// 256-wide layers (final block, last stage conv): 64 channels per thread do not fit the register file, so the
+// accumulator is read twice (statistics, apply) - 32 / 16 columns per tcgen05.wait::ld.  Residual stream: packed bf16 pairs.
+// Returns the final-conv partial dot product (E_FINAL) of this thread's channels.
+__device__ __forceinline__ float wide_epilogue(const Ep& e, int flags, const float* film) {
+  constexpr int CH = 256, CW = 64;
+  const int c_lo = e.g * CW;
+  float mean = 0.f, rstd = 1.f;
+  if (flags & E_GN) {
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tmem_ld8(e.tmem + T_ACC + c_lo + 32 * h + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(&r[8 * k]));
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const F8 b = ld_par8(e, 0, c_lo + 32 * h + 8 * k);
+        float2 v[4];
+        use8(&r[8 * k], v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = __fadd2_rn(v[i], b.p[i]);
+          s2 = __fadd2_rn(s2, v[i]);
+          q2 = __ffma2_rn(v[i], v[i], q2);
+        }
+      }
+    }
+    e.xg()[(e.g * 4 + e.pos) * 32 + e.s] = make_float2(s2.x + s2.y, q2.x + q2.y);
+    bar_wg(e.g);
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) { const float2 t = e.xg()[(e.g * 4 + pp) * 32 + e.s]; ts += t.x; tq += t.y; }
+    const float inv = 1.0f / (float)(CW * 4);
+    mean = ts * inv;
+    rstd = rsqrtf(fmaxf(tq * inv - mean * mean, 0.f) + 1e-5f);
+  }
+  const float2 nmean = make_float2(-mean, -mean), rstd2 = make_float2(rstd, rstd);
+  float2 dot2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int c = c_lo; c < c_lo + CW; c += 16) {
+    uint32_t r[16], rr[8];
+    tmem_ld8(e.tmem + T_ACC + c, *reinterpret_cast<uint32_t(*)[8]>(&r[0]));
+    tmem_ld8(e.tmem + T_ACC + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&r[8]));
+    if (flags & E_ADDRES) tmem_ld8(e.tmem + T_RES + (c >> 1), rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int cc = c + 8 * hh;
+      float2 v[4];
+      use8(&r[8 * hh], v);
+      {
+        const F8 b = ld_par8(e, 0, cc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __fadd2_rn(v[i], b.p[i]);
+      }
+      if (flags & E_GN) {
+        if (flags & E_FILM) norm8(v, ld_film8(film + cc), ld_film8(film + CH + cc), nmean, rstd2);
+        else norm8(v, ld_par8(e, 1, cc), ld_par8(e, 2, cc), nmean, rstd2);
+      }
+      if (flags & E_SILU) silu8(v);
+      if (flags & E_ADDRES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t t = rr[4 * hh + i];
+          asm volatile("" : "+r"(t));
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&t);
+          v[i] = __fadd2_rn(v[i], make_float2(__low2float(h2), __high2float(h2)));
+        }
+      }
+      if (flags & E_STORERES) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = pack_bf16(v[i].x, v[i].y);
+        tmem_st4(e.tmem + T_RES + (cc >> 1), w);
+      }
+      if (flags & E_FINAL) {
+        const F8 w = ld_par8(e, 4, cc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dot2 = __ffma2_rn(w.p[i], v[i], dot2);
+      } else {
+        st_operand8(e, cc, v);
       }
     }
   }
-  return dot;
+  if (flags & E_STORERES) tmem_st_wait();
+  return dot2.x + dot2.y;
 }
 
 // exchange rows of the attention: bf16, 32 values = four 16-byte chunks per row; region 0 / 1 use complementary halves
@@ -441,29 +613,6 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
   }
 }
 
-// FiLM rounds of the split 256-wide layer: channel half h (128 channels, 32 per warp-group); FiLM vector in [256, 384)
-__device__ __forceinline__ void film_round(const Ep& e, int kind, int h) {
-  for (int c = e.g * 32; c < e.g * 32 + 32; c += 8) {
-    float v[8], f[8], b[8];
-    ld_cols<8>(e, T_ACC + 128 * h + c, v);
-    ld_cols<8>(e, T_FH + c, f);
-    ld_par<8>(e, kind == 2 ? 3 : 4, c, b);
-    if (kind == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= f[j] + b[j];
-      st_cols<8>(e, T_ACC + 128 * h + c, v);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const float2 r = silu_fast2(make_float2(v[j] + f[j] + b[j], v[j + 1] + f[j + 1] + b[j + 1]));
-        v[j] = r.x; v[j + 1] = r.y;
-      }
-      st_operand<8>(e, 128 * h + c, v);
-    }
-  }
-  if (kind == 2) tmem_st_wait();
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -473,22 +622,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   uint64_t* b_ready = bars + 8;
   uint64_t* acc_ready = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  RJob* rj = reinterpret_cast<RJob*>(smem + SM_RJ);
   uint2* chunk_tab = reinterpret_cast<uint2*>(smem + SM_CHUNKS);
   uint4* ops = reinterpret_cast<uint4*>(smem + SM_OPS);
   uint16_t* op_begin = reinterpret_cast<uint16_t*>(smem + SM_OPBEG);
   float* s_par = reinterpret_cast<float*>(smem + SM_PAR);
-  float* s_inemb = reinterpret_cast<float*>(smem + SM_INEMB);
+  int16_t* s_ptab = reinterpret_cast<int16_t*>(smem + SM_PTAB);
   float* s_x = reinterpret_cast<float*>(smem + SM_X);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int cta_s0 = blockIdx.x * NS;
-  const GldmResNetCfg& cfg = p.cfg;
   const ResNetLayout& lay = p.lay;
   const float* W = p.W;
-  const int R = cfg.cond_ch;
-  constexpr int EMB = 16, L = 4;
+  constexpr int L = 4;
   const int n_steps = (p.mode == 0) ? p.n_steps : 1;
+  const int n_rj = p.n_jobs;
 
   // ---- one-time setup
   for (int i = tid; i < SM_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -499,19 +646,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     fence_barrier_init();
   }
   if (wid == 0) tmem_alloc<512>(tmem_slot);
-  for (int idx = tid; idx < NS * R * EMB; idx += NTHREADS) {
-    const int e = idx % EMB, r = (idx / EMB) % R, s = idx / (EMB * R);
-    float a = 0.f;
-    if (cta_s0 + s < p.n) {
-      const int obj = (cta_s0 + s) / p.gpo;
-      const float* z = p.z_cond + ((size_t)obj * R + r) * cfg.cond_dim;
-      const float* w = W + lay.in_w + (size_t)e * cfg.cond_dim;
-      a = __ldg(W + lay.in_b + e);
-      for (int j = 0; j < cfg.cond_dim; ++j) a = fmaf(__ldg(w + j), __ldg(z + j), a);
-      a = a / (1.0f + expf(-a));
-    }
-    s_inemb[(s * 3 + r) * EMB + e] = a;
-  }
   if (tid < NS * L) {
     const int s = tid / L, l = tid % L;
     float v = 0.f;
@@ -519,81 +653,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     s_x[s * L + l] = v;
     if (p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
   }
-  // ---- row-job, weight-chunk and UMMA op tables of one step
+  // ---- weight-chunk and UMMA op tables of one step (only the convolution / projection blocks of a job's image are
+  // streamed: the FiLM projection tiles behind them belong to the channel-major kernel)
   // op.x / op.y: low words of the A (activation) / B (weight) descriptors; op.z: high word of the B descriptor;
   // op.w: [0,9) TMEM column, [9,12) K steps, 12 accumulate, 13 first use of a ring chunk, 15 first op of the job,
   //       [16,19) ring stage, 19 ring padding, [20,25) N / 16
   if (tid == 0) {
-    const uint32_t ring_a = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A), u_base = smem_u32(smem + SM_U);
-    const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
-    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
-    uint32_t nops = 0, chunk_base = 0, ncp = 0, nrj = 0;
-    for (int j = 0; j < p.n_jobs; ++j) {
+    const uint32_t ring_a = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A);
+    uint32_t nops = 0, chunk_base = 0, ncp = 0;
+    int npar = 0;
+    for (int j = 0; j < n_rj; ++j) {
       const TcJob& job = p.jobs[j];
-      const bool split = job.mtiles == 2 && job.film_tiles;
-      const int n_sub = split ? 5 : 1;
+      {
+        // FiLM layers take their GroupNorm affine from the FiLM table (folded), so gamma / beta are not staged for them
+        const bool film = (job.flags & E_FILM) != 0;
+        const int src[5] = {job.o_bias, film ? -1 : job.o_gamma, film ? -1 : job.o_beta, job.o_g, job.o_g2};
+        for (int k = 0; k < 5; ++k) {
+          const bool use = src[k] >= 0 && !(job.flags & E_ATTN) && npar + job.ch <= PAR_FLOATS;
+          s_ptab[j * 5 + k] = (int16_t)(use ? npar : -1);
+          if (use) npar += (job.ch + 3) & ~3;
+        }
+        // x: flags | ch << 16; y: FiLM offset | g2 << 16; z: bias | gamma << 16; w: beta | g1 << 16 (float offsets in SM_PAR)
+        uint32_t o[5];
+        for (int k = 0; k < 5; ++k) o[k] = (uint32_t)max((int)s_ptab[j * 5 + k], 0);
+        reinterpret_cast<uint4*>(smem + SM_JD)[j] = make_uint4((uint32_t)job.flags | ((uint32_t)job.ch << 16),
+                                                              (uint32_t)max(job.o_film, 0) | (o[4] << 16), o[0] | (o[1] << 16),
+                                                              o[2] | (o[3] << 16));
+      }
       const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
       const uint32_t mb = job.mtiles * job.taps * nkb * blk;            // bytes of the main blocks
       const uint32_t w_hi = ((8u * a_swb) >> 4) | (1u << 14) |
                             ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
-      for (int sub = 0; sub < n_sub; ++sub) {
-        RJob r;
-        r.job = (int16_t)j;
-        r.kind = (int8_t)(!split ? 0 : sub == 0 ? 1 : (sub & 1) ? 2 : 3);
-        r.h = (int8_t)(sub >= 3 ? 1 : 0);
-        r.ch = (int16_t)(r.kind >= 2 ? 128 : job.ch);
-        r.wgs = (int16_t)((job.flags & E_ATTN) ? 4 : job.ch == 4 ? 1 : 4);
-        rj[nrj] = r;
-        // the part of the image this row-job streams
-        const uint32_t s_off = r.kind >= 2 ? mb : 0u, s_bytes = r.kind == 1 ? mb : r.kind >= 2 ? job.bytes - mb : job.bytes;
-        for (uint32_t off = 0; off < s_bytes; off += CHUNK)
-          chunk_tab[ncp++] = make_uint2(job.a_off + s_off + off, min((uint32_t)CHUNK, s_bytes - off));
-        op_begin[nrj] = (uint16_t)nops;
-        const uint32_t n_main = (job.flags & E_ATTN) ? 128u : (uint32_t)((job.ch + 15) & ~15);
-        uint32_t last_chunk = 0xffffffffu;
-        bool first = true;
-        auto emit = [&](uint32_t a_addr, uint32_t off, uint32_t hi, uint32_t col, uint32_t ks, uint32_t acc, uint32_t nn) {
-          const uint32_t ci = chunk_base + off / CHUNK, stage = ci % STAGES;
-          const uint32_t b_addr = ring_a + stage * CHUNK + (off % CHUNK);
-          const uint32_t w = col | (ks << 9) | (acc << 12) | ((ci != last_chunk ? 1u : 0u) << 13) | ((first ? 1u : 0u) << 15) |
-                             (stage << 16) | ((nn >> 4) << 20);
-          ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
-          last_chunk = ci;
-          first = false;
-        };
-        if (r.kind <= 1) {
-          for (uint32_t tap = 0; tap < job.taps; ++tap)
-            for (uint32_t kb = 0; kb < nkb; ++kb) {
-              const uint32_t tsel = job.taps == 3 ? tap : 1u;
-              const uint32_t a_addr = a_base + kb * SLAB + tsel * 32 * 128;
-              const uint32_t boff = (tap * nkb + kb) * job.mtiles * blk;
-              const uint32_t acc = (tap | kb) != 0 ? 1u : 0u;
-              if (job.flags & E_ATTN) {
-                for (uint32_t t = 0; t < 3; ++t) emit(a_addr, boff + t * blk, w_hi, T_ACC + t * 128, a_swb >> 5, acc, 128u);
-              } else {
-                emit(a_addr, boff, w_hi, T_ACC, a_swb >> 5, acc, job.mtiles == 2 ? 256u : n_main);
-              }
-            }
-          if (job.film_tiles && r.kind == 0) {
-            emit(u_base, mb, f_hi, T_FS, f_swb >> 5, 0u, n_main);
-            emit(u_base, mb + f_bytes, f_hi, T_FH, f_swb >> 5, 0u, n_main);
+      for (uint32_t off = 0; off < mb; off += CHUNK) chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, mb - off));
+      op_begin[j] = (uint16_t)nops;
+      const uint32_t n_main = (job.flags & E_ATTN) ? 128u : (uint32_t)((job.ch + 15) & ~15);
+      uint32_t last_chunk = 0xffffffffu;
+      bool first = true;
+      auto emit = [&](uint32_t a_addr, uint32_t off, uint32_t col, uint32_t ks, uint32_t acc, uint32_t nn) {
+        const uint32_t ci = chunk_base + off / CHUNK, stage = ci % STAGES;
+        const uint32_t b_addr = ring_a + stage * CHUNK + (off % CHUNK);
+        const uint32_t w = col | (ks << 9) | (acc << 12) | ((ci != last_chunk ? 1u : 0u) << 13) | ((first ? 1u : 0u) << 15) |
+                           (stage << 16) | ((nn >> 4) << 20);
+        ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), w_hi, w);
+        last_chunk = ci;
+        first = false;
+      };
+      for (uint32_t tap = 0; tap < job.taps; ++tap)
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          const uint32_t tsel = job.taps == 3 ? tap : 1u;
+          const uint32_t a_addr = a_base + kb * SLAB + tsel * 32 * 128;
+          const uint32_t boff = (tap * nkb + kb) * job.mtiles * blk;
+          const uint32_t acc = (tap | kb) != 0 ? 1u : 0u;
+          if (job.flags & E_ATTN) {
+            for (uint32_t t = 0; t < 3; ++t) emit(a_addr, boff + t * blk, T_ACC + t * 128, a_swb >> 5, acc, 128u);
+          } else {
+            emit(a_addr, boff, T_ACC, a_swb >> 5, acc, job.mtiles == 2 ? 256u : n_main);
           }
-        } else {
-          // FiLM tiles of the split layer: [scale 0, scale 1, shift 0, shift 1]; this row-job streams only that part
-          const uint32_t tile = (r.kind == 2 ? 0u : 2u) + (uint32_t)r.h;
-          emit(u_base, tile * f_bytes, f_hi, T_FH, f_swb >> 5, 0u, 128u);
         }
-        chunk_base += (s_bytes + CHUNK - 1) / CHUNK;
-        ++nrj;
-      }
+      chunk_base += (mb + CHUNK - 1) / CHUNK;
     }
     while (ncp % STAGES) {
       ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
       chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
     }
-    op_begin[nrj] = (uint16_t)nops;
+    op_begin[n_rj] = (uint16_t)nops;
     op_begin[MAXRJ] = (uint16_t)ncp;
-    op_begin[MAXRJ + 1] = (uint16_t)nrj;
+  }
+  __syncthreads();
+  // every per-channel parameter of the network, once (step-invariant)
+  for (int j = 0; j < n_rj; ++j) {
+    const TcJob& job = p.jobs[j];
+    const int src[5] = {job.o_bias, job.o_gamma, job.o_beta, job.o_g, job.o_g2};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int o = s_ptab[j * 5 + k];
+      if (o >= 0)
+        for (int i = tid; i < job.ch; i += NTHREADS) s_par[o + i] = __ldg(W + src[k] + i);
+    }
   }
   fence_async_smem();
   tc_fence_before();
@@ -601,7 +737,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cps = op_begin[MAXRJ];
-  const int n_rj = op_begin[MAXRJ + 1];
   const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
   if (wid_u >= 16) {
     // setmaxnreg only redistributes the CTA's own allocation (640 x 96): the 4 service warps give up 64 registers each,
@@ -615,12 +750,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
 #pragma unroll 1
         for (uint32_t ci = 0; ci < cps; ++ci) {
           const uint32_t s = ci % STAGES;
-          if ((used >> s) & 1u) mbar_wait(&empty[s], ((par >> s) & 1u) ^ 1u);
+          if ((used >> s) & 1u)
+            while (!mbar_try_wait(&empty[s], ((par >> s) & 1u) ^ 1u)) __nanosleep(64);     // off the critical path: back off
           used |= 1u << s;
           par ^= 1u << s;
           const uint2 c = chunk_tab[ci];
           bulk_g2s_elect(smem + SM_RING + s * CHUNK, p.pack + c.x, c.y, &full[s]);
-
         }
     } else if (wid_u == 17) {
       // =========================== UMMA issuer ===========================
@@ -659,6 +794,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
           umma_commit_elect(&empty[prev_stage]);
           umma_commit_elect(acc_ready);
         }
+    } else if (wid_u == 18) {
+      // =========================== accumulator waiter ===========================
+      uint32_t jobn = 0;
+#pragma unroll 1
+      for (int step = 0; step < n_steps; ++step)
+#pragma unroll 1
+        for (int j = 0; j < n_rj; ++j, ++jobn) {
+          mbar_wait(acc_ready, jobn & 1);
+          tc_fence_after();
+          tc_fence_before();
+          bar_job_arrive();
+        }
     }
   } else {
     // =========================== epilogue warps ===========================
@@ -667,32 +814,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     e.g = wid >> 2; e.pos = wid & 3; e.s = lane; e.row = e.pos * 32 + lane;
     e.tmem = tmem_base + ((uint32_t)(e.pos * 32) << 16);
     e.smem = smem;
-    e.par = s_par;
-    e.xg = reinterpret_cast<float2*>(smem + SM_XG);
-    e.xl = reinterpret_cast<float2*>(smem + SM_XL);
-    uint32_t jobn = 0;
+    const bool dbg = p.prof != nullptr && blockIdx.x == 0;
     auto handoff = [&]() {
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_ready);
     };
+    // FiLM table row of this thread's sample: (object, step) in the sampler, the sample itself in a single evaluation
+    const int smp = min(cta_s0 + e.s, p.n - 1);
+    const size_t film_row0 = ((p.mode == 0) ? (size_t)(smp / p.gpo) * n_steps : (size_t)smp) * p.film_stride;
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
-      // ---- FiLM operand u[s][e] = sum_r silu(time_emb[e] + in_emb[s][r][e]), replicated over the 4 positions
-      {
-        const int s = tid / EMB, ee = tid % EMB;
-        const int ti = (p.mode == 0) ? step : min(cta_s0 + s, p.n - 1);
-        const float te = __ldg(p.te + (size_t)ti * EMB + ee);
-        float a = 0.f;
-        for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + ee]; a += z / (1.0f + __expf(-z)); }
-        const __nv_bfloat16 hv = __float2bfloat16(a);
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-          const int row = pp * 32 + s;
-          *reinterpret_cast<__nv_bfloat16*>(smem + SM_U + row * 128 + (((ee >> 3) ^ (row & 7)) << 4) + (ee & 7) * 2) = hv;
-        }
-      }
+      const float* film_step = p.film + (film_row0 + (size_t)step * p.film_stride);
       // ---- init_conv: Conv1d(1 -> 4, k7, p3) on the state -> residual stream and operand (warp-group 0: 4 channels)
       if (e.g == 0) {
         float v[4];
@@ -712,32 +846,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
       }
       handoff();
 #pragma unroll 1
-      for (int j = 0; j < n_rj; ++j, ++jobn) {
-        const RJob r = rj[j];
-        const TcJob& job = p.jobs[r.job];
-        const int flags = r.kind == 1 ? (E_GN | E_INPLACE) : job.flags;
-        const int ch = r.ch, ch_total = job.ch, ch_off = r.kind >= 2 ? 128 * r.h : 0;
-        // ---- stage the channel parameters of this job while its UMMAs run
+      for (int j = 0; j < n_rj; ++j) {
+        const uint4 jd = reinterpret_cast<const uint4*>(smem + SM_JD)[j];
+        const int flags = (int)(jd.x & 0xffffu), ch = (int)(jd.x >> 16);
+        const float* film = film_step + (jd.y & 0xffffu);
+        // ---- this job's channel parameters (resident in shared memory); pull its FiLM vectors into L1 while its UMMAs run
         if (!(flags & E_ATTN)) {
-          for (int i = tid; i < ch; i += NEPI) {
-            const int cc = ch_off + i;
-            s_par[0 * 256 + i] = job.o_bias >= 0 ? __ldg(W + job.o_bias + cc) : 0.f;
-            s_par[1 * 256 + i] = job.o_gamma >= 0 ? __ldg(W + job.o_gamma + cc) : 0.f;
-            s_par[2 * 256 + i] = job.o_beta >= 0 ? __ldg(W + job.o_beta + cc) : 0.f;
-            s_par[3 * 256 + i] = job.o_mlpb >= 0 ? (float)R * __ldg(W + job.o_mlpb + cc) + (float)R : 1.f;   // sum_r (scale_r + 1)
-            s_par[4 * 256 + i] = job.o_mlpb >= 0 ? (float)R * __ldg(W + job.o_mlpb + ch_total + cc) : 0.f;
-            s_par[5 * 256 + i] = job.o_g >= 0 ? __ldg(W + job.o_g + cc) : 0.f;
-            s_par[6 * 256 + i] = job.o_g2 >= 0 ? __ldg(W + job.o_g2 + cc) : 0.f;
+          e.po[0] = jd.z; e.po[1] = jd.w; e.po[2] = jd.y >> 16;
+          if (flags & E_FILM) {
+            const int cw = ch >= 32 ? ch >> 2 : 4, c_lo = ch >= 32 ? e.g * cw : 0;
+            prefetch_l1(film + c_lo);
+            prefetch_l1(film + c_lo + cw - 1);
+            prefetch_l1(film + ch + c_lo);
+            prefetch_l1(film + ch + c_lo + cw - 1);
           }
         }
-        const bool rec = p.prof && blockIdx.x == 0 && tid == 0 && step == 1;
+        const bool rec = dbg && tid == 0 && step == 1;
         if (rec) p.prof[64 + 8 * j] = clock64();
-        mbar_wait(acc_ready, jobn & 1);
+        bar_job_sync();
         tc_fence_after();
         if (rec) p.prof[64 + 8 * j + 1] = clock64();
-        bar_all();
         if (rec) p.prof[64 + 8 * j + 2] = clock64();
-        if (p.prof && blockIdx.x == 0 && p.prof[8] == (long long)j + 1 && step == 0) {
+        if (dbg && step == 0 && p.prof[8] == (long long)j + 1) {
           // development aid: raw TMEM image [128 rows][512 columns] of CTA 0 when job j's accumulator is ready
           float* dump = reinterpret_cast<float*>(p.prof + 16);
           for (int c = e.g * 128; c < e.g * 128 + 128; c += 8) {
@@ -749,19 +879,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
         }
         if (flags & E_ATTN) {
           attention_epilogue(e);
-        } else if (r.kind >= 2) {
-          film_round(e, r.kind, r.h);
+        } else if (ch >= 32 && ch <= 128) {
+          reg_epilogue(e, flags, ch, film, rec ? p.prof + 64 + 8 * j : nullptr);
+        } else if (ch == 4) {
+          narrow_epilogue(e, flags, film);
         } else {
-          const float dot = (ch_total == 4) ? generic_epilogue<4>(e, flags, ch, ch_total, ch_off, r.wgs)
-                                            : generic_epilogue<8>(e, flags, ch, ch_total, ch_off, r.wgs);
+          const float dot = wide_epilogue(e, flags, film);
           if (flags & E_FINAL) {
             // ======== final_conv (1x1 -> 1 channel) + scheduler update of x[sample][position]
-            e.xl[e.row * 4 + e.g] = make_float2(dot, 0.f);
+            e.xl()[e.row * 4 + e.g] = make_float2(dot, 0.f);
             bar_all();
             if (e.g == 0) {
               float eps = __ldg(W + lay.fc_b);
 #pragma unroll
-              for (int w = 0; w < 4; ++w) eps += e.xl[e.row * 4 + w].x;
+              for (int w = 0; w < 4; ++w) eps += e.xl()[e.row * 4 + w].x;
               const int l = e.pos, s = e.s;
               const bool ok = cta_s0 + s < p.n;
               if (p.mode == 0) {

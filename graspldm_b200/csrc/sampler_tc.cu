@@ -65,7 +65,7 @@ struct Tr {
   static constexpr int SM_BAR = SM_X + NSETS * 256;                 // mbarriers
   static constexpr int SM_CHUNKS = SM_BAR + 256;                    // weight chunk table {pack offset, bytes}
   static constexpr int SM_JOBS = SM_CHUNKS + stc::MAXCHUNKS * 8;    // job table copy
-  static constexpr int SM_OPS = SM_JOBS + stc::MAXJOBS * 48;        // UMMA op table, 16 bytes per block of <= 4 UMMAs
+  static constexpr int SM_OPS = SM_JOBS + stc::MAXJOBS * 64;        // UMMA op table, 16 bytes per block of <= 4 UMMAs
   static constexpr int SM_OPBEG = SM_OPS + stc::MAXOPS * 16;        // first op of every (job, set)
   static constexpr int SM_TOTAL = SM_OPBEG + (2 * stc::MAXJOBS + 2) * 2 + 16;
 };
@@ -87,7 +87,10 @@ struct TcJob {
   uint16_t mtiles, taps, kpt, a_swb, film_tiles, flags;
   int ch;                                     // valid output channels
   int o_bias, o_gamma, o_beta, o_mlpb, o_g, o_g2;   // float offsets into the raw blob (-1: unused)
+  int o_mlpw;                                 // FiLM projection Linear(emb -> 2 ch) weight [2 ch][emb] (-1: no FiLM)
+  int o_film;                                 // float offset of this layer's [A (ch) | B (ch)] pair in a FiLM table row
 };
+static_assert(sizeof(TcJob) <= 64, "job table slot");
 
 struct TcParams {
   GldmResNetCfg cfg;
@@ -113,6 +116,11 @@ struct TcParams {
   float* tmrp;             // [n][6]
   float* logit;            // [n]
   long long* prof;         // development aid: per-job clock stamps of CTA 0 (NULL in production)
+  // row-major kernel: FiLM hoisted out of the sample loop.  film[(obj * n_steps + step) * film_stride + o_film + ...]
+  // (mode 1: one row per sample) holds, per FiLM layer, A = gamma * S and B = beta * S + H with S / H the summed
+  // multi-channel scale (+1 each) / shift of resnets.py:163-175: GroupNorm affine and FiLM as ONE multiply-add.
+  const float* film;
+  int film_stride;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -132,10 +140,10 @@ static uint32_t main_bytes(const TcJob& j) {
 static bool film_first(const TcJob& j, int emb) { return j.film_tiles && film_tile_bytes(emb) > 128u * j.a_swb; }
 static uint32_t job_bytes(const TcJob& j, int emb) { return main_bytes(j) + (uint32_t)j.film_tiles * film_tile_bytes(emb); }
 
-static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes) {
+static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes, int* film_stride = nullptr) {
   ResNetLayout l;
   make_layout(c, l);
-  int n = 0;
+  int n = 0, film_off = 0, o_mlpw_next = -1;
   uint32_t off = 0;
   auto add = [&](int cout, int cin, int taps, int film_c, uint16_t flags, int o_bias, int o_gamma, int o_beta,
                  int o_mlpb, int o_g, int o_g2) {
@@ -148,12 +156,15 @@ static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes
     j.flags = flags;
     j.ch = cout;
     j.o_bias = o_bias; j.o_gamma = o_gamma; j.o_beta = o_beta; j.o_mlpb = o_mlpb; j.o_g = o_g; j.o_g2 = o_g2;
+    j.o_mlpw = -1; j.o_film = -1;
+    if (film_c) { j.o_mlpw = o_mlpw_next; j.o_film = film_off; film_off += 2 * film_c; }
     j.a_off = off;
     j.bytes = job_bytes(j, c.emb_dim);
     off += (j.bytes + 1023) & ~1023u;
     jobs[n++] = j;
   };
   auto add_rb = [&](const RbOff& o, int ch, uint16_t extra2, int o_g2) {
+    o_mlpw_next = o.mlp_w;
     add(ch, ch, 3, ch, E_GN | E_FILM | E_SILU, o.p1_b, o.n1_w, o.n1_b, o.mlp_b, -1, -1);
     add(ch, ch, 3, 0, (uint16_t)(E_GN | E_SILU | E_ADDRES | extra2), o.p2_b, o.n2_w, o.n2_b, -1, -1, o_g2);
   };
@@ -169,6 +180,7 @@ static int build_jobs(const GldmResNetCfg& c, TcJob* jobs, uint32_t* total_bytes
   const int cl = c.ch[c.n_stages];
   add_rb(l.fin, cl, E_FINAL, l.fc_w);
   *total_bytes = off;
+  if (film_stride) *film_stride = film_off;
   return n;
 }
 
@@ -1193,6 +1205,71 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
 
 #include "sampler_rows.cuh"
 
+// ------------------------------------------------------------------------------------------------
+// FiLM table of the row-major kernel.  The conditioning embedding of a ResnetBlock depends only on (object, step):
+//   latent_emb[r] = time_mlp(t) + SiLU(Linear(z_pc[obj][r]))                      resnets.py:590-603
+//   scale | shift = sum_r Linear(SiLU(latent_emb[r])), x * (scale + R) + shift     resnets.py:163-175, 191-196
+// so one vector per (object, step) serves all grasps of the object (the channel-major kernel rebuilds it per sample
+// and step on the tensor cores).  Folded with the GroupNorm affine of the block: A = gamma * S, B = beta * S + H.
+// One block per object (mode 1: per sample); thread = one FiLM channel, its two projection rows live in registers
+// while the block walks the steps.
+// ------------------------------------------------------------------------------------------------
+struct FilmJobs { int n; int ch[12], o_mlpw[12], o_mlpb[12], o_gamma[12], o_beta[12], o_film[12]; };
+
+template <int EMB>
+__global__ void __launch_bounds__(256) film_table_kernel(const float* __restrict__ W, ResNetLayout lay, FilmJobs fj, int R,
+                                                         int cond_dim, const float* __restrict__ z_cond, int z_div,
+                                                         const float* __restrict__ te, int te_per_block, int n_steps,
+                                                         int stride, float* __restrict__ film) {
+  constexpr int TS = 32;                        // steps per tile
+  __shared__ float s_ie[4 * EMB];
+  __shared__ float s_u[TS][EMB];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int idx = tid; idx < R * EMB; idx += 256) {
+    const int e = idx % EMB, r = idx / EMB;
+    const float* z = z_cond + ((size_t)(b / z_div) * R + r) * cond_dim;
+    const float* w = W + lay.in_w + (size_t)e * cond_dim;
+    float a = __ldg(W + lay.in_b + e);
+    for (int j = 0; j < cond_dim; ++j) a = fmaf(__ldg(w + j), __ldg(z + j), a);
+    s_ie[idx] = a / (1.0f + expf(-a));
+  }
+  int total = 0;
+  for (int j = 0; j < fj.n; ++j) total += fj.ch[j];
+  for (int t0 = 0; t0 < n_steps; t0 += TS) {
+    const int nt = min(TS, n_steps - t0);
+    __syncthreads();
+    for (int idx = tid; idx < nt * EMB; idx += 256) {
+      const int e = idx % EMB, t = idx / EMB;
+      const float tv = __ldg(te + (size_t)(te_per_block ? b : t0 + t) * EMB + e);
+      float a = 0.f;
+      for (int r = 0; r < R; ++r) { const float zz = tv + s_ie[r * EMB + e]; a += zz / (1.0f + __expf(-zz)); }
+      s_u[t][e] = a;
+    }
+    __syncthreads();
+    for (int q = tid; q < total; q += 256) {
+      int j = 0, c = q;
+      while (c >= fj.ch[j]) { c -= fj.ch[j]; ++j; }
+      const int ch = fj.ch[j];
+      float ws[EMB], wh[EMB];
+#pragma unroll
+      for (int e = 0; e < EMB; ++e) {
+        ws[e] = __ldg(W + fj.o_mlpw[j] + (size_t)c * EMB + e);
+        wh[e] = __ldg(W + fj.o_mlpw[j] + (size_t)(ch + c) * EMB + e);
+      }
+      const float bs = (float)R * __ldg(W + fj.o_mlpb[j] + c) + (float)R, bh = (float)R * __ldg(W + fj.o_mlpb[j] + ch + c);
+      const float gamma = __ldg(W + fj.o_gamma[j] + c), beta = __ldg(W + fj.o_beta[j] + c);
+      float* dst = film + ((size_t)b * n_steps + t0) * stride + fj.o_film[j] + c;
+      for (int t = 0; t < nt; ++t) {
+        float S = bs, H = bh;
+#pragma unroll
+        for (int e = 0; e < EMB; ++e) { S = fmaf(ws[e], s_u[t][e], S); H = fmaf(wh[e], s_u[t][e], H); }
+        dst[(size_t)t * stride] = gamma * S;
+        dst[(size_t)t * stride + ch] = fmaf(beta, S, H);
+      }
+    }
+  }
+}
+
 static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, const void* pack) {
   int rc = check_tc_cfg(cfg);
   if (rc) return rc;
@@ -1202,7 +1279,7 @@ static int fill_tc(TcParams& p, const GldmResNetCfg* cfg, const float* raw, cons
   p.W = raw;
   p.pack = reinterpret_cast<const uint8_t*>(pack);
   uint32_t total;
-  p.n_jobs = build_jobs(*cfg, p.jobs, &total);
+  p.n_jobs = build_jobs(*cfg, p.jobs, &total, &p.film_stride);
   return GLDM_OK;
 }
 
@@ -1237,8 +1314,32 @@ static int launch_rows(TcParams& p, cudaStream_t s) {
   static SmemOptIn attr;
   const int smem = rows::SM_TOTAL + 1024;
   if (int rc = opt_in_smem(attr, rows::resnet_rows_kernel, smem, "resnet_rows_kernel")) return rc;
-  rows::resnet_rows_kernel<<<ceil_div(p.n, rows::NS), rows::NTHREADS, smem, s>>>(p);
-  return check_launch("resnet_rows_kernel");
+  // FiLM table: one row per (object, step) in the sampler, one per sample in a single evaluation; stream-ordered scratch
+  FilmJobs fj = {};
+  for (int j = 0; j < p.n_jobs; ++j)
+    if (p.jobs[j].o_film >= 0) {
+      GLDM_REQUIRE(fj.n < 12, "resnet_rows: too many FiLM layers");
+      fj.ch[fj.n] = p.jobs[j].ch; fj.o_mlpw[fj.n] = p.jobs[j].o_mlpw; fj.o_mlpb[fj.n] = p.jobs[j].o_mlpb;
+      fj.o_gamma[fj.n] = p.jobs[j].o_gamma; fj.o_beta[fj.n] = p.jobs[j].o_beta; fj.o_film[fj.n] = p.jobs[j].o_film;
+      ++fj.n;
+    }
+  const int blocks = p.mode == 0 ? ceil_div(p.n, p.gpo) : p.n, steps = p.mode == 0 ? p.n_steps : 1;
+  float* film = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&film), sizeof(float) * (size_t)blocks * steps * p.film_stride, s) != cudaSuccess) {
+    set_error("resnet_rows: cudaMallocAsync of the FiLM table (%lld bytes) failed",
+              (long long)(sizeof(float) * (size_t)blocks * steps * p.film_stride));
+    return GLDM_ECUDA;
+  }
+  film_table_kernel<16><<<blocks, 256, 0, s>>>(p.W, p.lay, fj, p.cfg.cond_ch, p.cfg.cond_dim, p.z_cond, p.mode == 0 ? 1 : p.gpo,
+                                               p.te, p.mode == 0 ? 0 : 1, steps, p.film_stride, film);
+  int rc = check_launch("film_table_kernel");
+  if (rc == GLDM_OK) {
+    p.film = film;
+    rows::resnet_rows_kernel<<<ceil_div(p.n, rows::NS), rows::NTHREADS, smem, s>>>(p);
+    rc = check_launch("resnet_rows_kernel");
+  }
+  cudaFreeAsync(film, s);
+  return rc;
 }
 
 static int launch_tc(TcParams& p, cudaStream_t s) {

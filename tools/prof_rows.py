@@ -24,12 +24,13 @@ b = buf.cpu().tolist()
 names = []
 for st in range(4):
     names += [f"s{st}.rb0.c1", f"s{st}.rb0.c2", f"s{st}.rb1.c1", f"s{st}.rb1.c2", f"s{st}.qkv", f"s{st}.out", f"s{st}.down"]
-names += ["fin.c1 main", "fin.c1 s0", "fin.c1 h0", "fin.c1 s1", "fin.c1 h1", "fin.c2"]
+names += ["fin.c1", "fin.c2"]
 prev = None
 tot = [0] * 7
 print("row-job        wait(umma)  startbar   pass1   exchange   pass2   pass3+commit   gap")
 for j, nm in enumerate(names):
-    t = b[64 + 8 * j: 64 + 8 * j + 7]
+    t = b[64 + 8 * j: 64 + 8 * j + 8]
+    if t[7]: print(f"      (TMEM load + wait: {t[7] - t[2]} cycles)")
     gap = (t[0] - prev) if prev is not None else 0
     if t[3] == 0:
         row = [t[1] - t[0], t[2] - t[1], 0, 0, t[6] - t[2], 0, gap]
