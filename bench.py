@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""Headline benchmark: grasps/sec of full LDM grasp generation (PVCNN encoder + 100 DDPM latent-denoising
-steps + grasp decoder + pose post-processing) on synthetic point clouds - BASELINE.json's metric on its
-config 2 (fpc_1a_latentc3_z4_pc64, 64 objects x 20 grasps per GPU, random-init weights).
+"""Headline benchmark: grasps/sec of full LDM grasp generation (PVCNN encoder + T latent-denoising steps + grasp
+decoder + pose post-processing) on synthetic point clouds - BASELINE.json's metric.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
 
-One "step" = one generation pass over one batch.  `value` is timed with the point clouds resident in HBM;
-`e2e` goes through graspldm_b200.inference.InferenceLDM.generate_grasps with pinned HOST buffers (H2D of
-the clouds and D2H of poses + confidences inside the timed region).  N > 1: one rank per GPU (torchrun),
-objects sharded by rank, no collective on the compute path, one final all_gather of the results
-(weak scaling: 64 objects per GPU).  `--impl reference` times the CPU oracle port (the reference's own
-python cannot travel to the GPU box and its encoder has no CPU path at all, SURVEY.md finding 6) on rank 0.
+--config selects a BASELINE.json configuration (default 2, the one the metric is quoted on):
+  1  fpc VAE-mode generation, 1 cloud x 20 grasps per GPU
+  2  fpc LDM, 100 DDPM steps, 64 objects x 20 grasps per GPU (weak scaling)
+  3  fpc LDM, DDIM --ddim-steps 10|50, 1024 objects x 100 grasps in total, sharded by object (strong scaling)
+  4  ppc encoder only, 4096 clouds per GPU (clouds/s)
+  5  fpc LDM, 100 DDPM steps, --objects O x 256 grasps per GPU (weak scaling; default O = 256)
+
+One "step" = one pass of the path over one batch.  `value` is timed with the point clouds resident in HBM; `e2e` goes
+through graspldm_b200.inference.Inference{LDM,VAE}.generate_grasps (config 4: PVCNNEncoder.forward) with pinned HOST
+buffers (H2D of the clouds and D2H of the results inside the timed region).  N > 1: one rank per GPU (torchrun), objects
+sharded by rank, no collective on the compute path, one final all_gather of the packed results.  `--impl reference` times
+the CPU oracle port (the reference's own python cannot travel to the GPU box and its encoder has no CPU path at all,
+SURVEY.md finding 6) on rank 0, on a bounded sample of the same configuration.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -27,12 +34,55 @@ os.environ.setdefault("TQDM_DISABLE", "1")
 
 import torch  # noqa: E402
 
-N_OBJ, N_GRASPS, N_STEPS_DDPM, N_POINTS = 64, 20, 100, 1024
-METRIC, UNIT = "grasps/sec (LDM 100 steps)", "grasps/s"
+N_POINTS = 1024
 # algorithmic work (SURVEY.md 8d / BASELINE.md section 2), FLOPs
 F_ENCODER_PER_CLOUD = 8.115e9
 F_DENOISER_PER_SAMPLE_STEP = 7.589e6
 F_DECODER_PER_GRASP = 30.70e6
+
+
+def workload(args, world):
+    """The configuration both arms run: everything BASELINE.json fixes, nothing about how either arm executes it."""
+    c = args.config
+    if c == 1:
+        w = dict(id=1, model="fpc", mode="vae", objects_per_gpu=1, grasps=20, T=0, sched=None, scaling="weak",
+                 metric="grasps/sec (VAE mode)", unit="grasps/s",
+                 text="fpc_1a_latentc3_z4_pc64 VAE-mode generation, 1 synthetic point cloud x 20 grasps per GPU (BASELINE.json configs[0])")
+    elif c == 2:
+        w = dict(id=2, model="fpc", mode="ldm", objects_per_gpu=64, grasps=20, T=100, sched="ddpm", scaling="weak",
+                 metric="grasps/sec (LDM 100 steps)", unit="grasps/s",
+                 text="fpc_1a_latentc3_z4_pc64 LDM-mode generation, 100 DDPM steps, 64 objects x 20 grasps per GPU "
+                      "(BASELINE.json configs[1])")
+    elif c == 3:
+        w = dict(id=3, model="fpc", mode="ldm", objects_total=1024, grasps=100, T=args.ddim_steps, sched="ddim", scaling="strong",
+                 metric=f"grasps/sec (LDM DDIM {args.ddim_steps} steps)", unit="grasps/s",
+                 text=f"fpc LDM-mode DDIM {args.ddim_steps}-step sampling, 1024 objects x 100 grasps in total, sharded by object "
+                      "(BASELINE.json configs[2])")
+    elif c == 4:
+        w = dict(id=4, model="ppc", mode="encoder", objects_per_gpu=4096, grasps=0, T=0, sched=None, scaling="weak",
+                 metric="clouds/sec (ppc PVCNN encoder)", unit="clouds/s",
+                 text="partial-point-cloud encoder config, 4096 clouds per GPU, encoder-only throughput (BASELINE.json configs[3])")
+    else:
+        w = dict(id=5, model="fpc", mode="ldm", objects_per_gpu=args.objects, grasps=256, T=100, sched="ddpm", scaling="weak",
+                 metric="grasps/sec (LDM 100 steps)", unit="grasps/s",
+                 text=f"fpc LDM-mode generation, 100 DDPM steps, {args.objects} objects x 256 grasps per GPU "
+                      "(BASELINE.json configs[4], large-batch sweep)")
+    w["objects"] = w["objects_total"] if "objects_total" in w else w["objects_per_gpu"] * world
+    w["config"] = {"workload": w["text"] + ", random-init weights, 1024-point synthetic clouds", "config_id": w["id"],
+                   "objects": w["objects"], "grasps_per_object": w["grasps"], "denoising_steps": w["T"], "scheduler": w["sched"],
+                   "parallelism": f"objects sharded over {world} rank(s), one final all_gather"}
+    return w
+
+
+def units_per_step(w, n_obj):
+    return n_obj if w["mode"] == "encoder" else n_obj * w["grasps"]
+
+
+def flops(w, n_obj):
+    """algorithmic FLOPs of one step over n_obj objects: (encoder, sampler, decoder)"""
+    n = n_obj * w["grasps"]
+    return (n_obj * F_ENCODER_PER_CLOUD, n * w["T"] * F_DENOISER_PER_SAMPLE_STEP if w["mode"] == "ldm" else 0.0,
+            n * F_DECODER_PER_GRASP if w["mode"] != "encoder" else 0.0)
 
 
 def peaks():
@@ -44,8 +94,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  Uses NVML in-process
-    (a light query) and falls back to polling nvidia-smi, which the recipe names."""
+    """SM clock / throttle reasons during the timed regions (B200_PROFILING.md recipe).  Uses NVML in-process (a light
+    query, every 20 ms over all timed passes) and falls back to polling nvidia-smi, which the recipe names."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -87,88 +137,130 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.1 if self.nvml is not None else 0.2)
+            self._halt.wait(0.02 if self.nvml is not None else 0.2)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        pw = [float(r[2]) for r in self.rows]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
-                    samples=len(self.rows), source="nvml" if self.nvml is not None else "nvidia-smi")
+                    samples=len(self.rows), power_w_max=(max(pw) if pw else None),
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle port on the host cores, all threads, bounded sample per step."""
-    if rank != 0:
-        return
+# --------------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle port; test infrastructure used here only as the measured CPU baseline)
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_sample_objects(w):
+    """Objects of the bounded CPU sample: about 32 k sample-steps (16 objects x 20 grasps x 100 steps for config 2)."""
+    if w["mode"] == "ldm":
+        return max(1, min(64, 32000 // max(1, w["grasps"] * w["T"])))
+    return 16
+
+
+def make_cpu_step(w, n_obj):
     import _data
     import _models
     from oracle import model_torch as M
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n_obj = 2
-    model = _models.build("fpc")
+    model = _models.build(w["model"], scheduler=w["sched"] or "ddpm")
     vae_sd, ddm_sd = _models.split_state_dicts(model)
-    pcs = _data.synthetic_clouds(n_obj, seed=1234, dist="S")
+    pcs = _data.synthetic_clouds(n_obj, N_POINTS, seed=1234, dist="S")
     metas = dict(pc_mean=torch.zeros(n_obj, 3), pc_std=torch.full((n_obj, 3), 0.05), grasp_mean=torch.zeros(1, 6),
                  grasp_std=torch.tensor([[.05, .05, .05, .5, .5, .5]]))
+    D = 4 if w["model"] == "fpc" else 16
+    G = w["grasps"]
 
     def one():
         g = torch.Generator().manual_seed(42)
-        x_T = torch.randn(n_obj * N_GRASPS, 1, 4, generator=g)
         with torch.no_grad():
-            tm, lg = M.generate_grasps_ldm(vae_sd, ddm_sd, pcs, N_GRASPS, x_T, num_inference_steps=N_STEPS_DDPM)
-            return M.postprocess(tm, lg, pcs, metas, n_obj, N_GRASPS)
+            if w["mode"] == "encoder":
+                return M.pvcnn_encoder_forward(vae_sd, "encoder.pc_encoder.", pcs)
+            if w["mode"] == "vae":
+                tm, lg = M.generate_grasps_vae(vae_sd, pcs, G, torch.randn(n_obj * G, D, generator=g))
+            else:
+                x_T = torch.randn(n_obj * G, 1, D, generator=g)
+                tm, lg = M.generate_grasps_ldm(vae_sd, ddm_sd, pcs, G, x_T, num_inference_steps=w["T"], kind=w["sched"])
+            return M.postprocess(tm, lg, pcs, metas, n_obj, G)
+    return one
 
-    for _ in range(min(args.warmup, 1)):
+
+def cpu_baseline_sample(w):
+    """Bounded CPU sample of the same workload on the host cores (reported beside the GPU number): warm-up 1, median of
+    3 passes with every host thread, one more pass with 8 threads."""
+    cores = os.cpu_count() or 1
+    n_obj = cpu_sample_objects(w)
+    one = make_cpu_step(w, n_obj)
+    units = units_per_step(w, n_obj)
+    torch.set_num_threads(cores)
+    one()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
         one()
-    steps = max(1, min(args.steps, 3))
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    torch.set_num_threads(min(8, cores))
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    dt = (time.perf_counter() - t0) / steps
-    v = n_obj * N_GRASPS / dt
-    sample = f"{n_obj} objects x {N_GRASPS} grasps, {N_STEPS_DDPM} DDPM steps per step ({steps} steps timed)"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fpc_1a_latentc3_z4_pc64 LDM 100 DDPM steps, CPU oracle port (plain PyTorch fp32 + numpy ops)",
-                   "objects_per_step": n_obj, "grasps_per_object": N_GRASPS},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    one()
+    t8 = time.perf_counter() - t0
+    torch.set_num_threads(cores)
+    return {"value": units / med, "unit": w["unit"], "cores": cores, "kind": "port",
+            "sample": f"{n_obj} objects x {w['grasps']} grasps, {w['T']} steps per pass; warm-up 1, median of 3 passes "
+                      f"({med:.2f} s each) on {cores} threads",
+            "value_8_threads": units / t8, "passes_s": [round(t, 3) for t in ts]}
 
 
-def cpu_baseline_sample():
-    """Bounded CPU sample of the same workload on the host cores (reported beside the GPU number)."""
-    import _data
-    import _models
-    from oracle import model_torch as M
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on the host cores, all threads, a bounded sample of the arm's configuration per step."""
+    if rank != 0:
+        return
+    w = workload(args, world)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_obj = 2
-    model = _models.build("fpc")
-    vae_sd, ddm_sd = _models.split_state_dicts(model)
-    pcs = _data.synthetic_clouds(n_obj, seed=1234, dist="S")
-    g = torch.Generator().manual_seed(42)
-    x_T = torch.randn(n_obj * N_GRASPS, 1, 4, generator=g)
+    n_obj = cpu_sample_objects(w)
+    one = make_cpu_step(w, n_obj)
     t0 = time.perf_counter()
-    with torch.no_grad():
-        M.generate_grasps_ldm(vae_sd, ddm_sd, pcs, N_GRASPS, x_T, num_inference_steps=N_STEPS_DDPM)
-    dt = time.perf_counter() - t0
-    return {"value": n_obj * N_GRASPS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_obj} objects x {N_GRASPS} grasps, {N_STEPS_DDPM} DDPM steps, 1 pass, {dt:.1f} s"}
+    one()                                                   # calibration pass (also the first warm-up step)
+    t1 = time.perf_counter() - t0
+    budget = 240.0                                          # the whole run stays within a few minutes
+    if t1 * (args.steps + args.warmup) > budget and n_obj > 2:
+        n_obj = max(2, int(n_obj * budget / (t1 * (args.steps + args.warmup))))
+        one = make_cpu_step(w, n_obj)
+        one()
+    for _ in range(max(0, args.warmup - 1)):
+        one()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    units = units_per_step(w, n_obj)
+    v = units / dt
+    sample = (f"{n_obj} objects x {w['grasps']} grasps, {w['T']} steps per step ({args.steps} steps timed after {args.warmup} "
+              f"warm-up, median step {statistics.median(ts):.2f} s)")
+    print(json.dumps({
+        "impl": "reference", "metric": w["metric"], "value": v, "unit": w["unit"], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": w["config"],
+        "cpu_baseline": {"value": v, "unit": w["unit"], "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)     # 50 x ~6 ms: the four-deep pipeline's fill / drain is < 3 % of it
+    ap.add_argument("--steps", type=int, default=200)     # config 2: 200 x ~5 ms = a 1 s timed region
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (see the module docstring)")
+    ap.add_argument("--ddim-steps", type=int, default=10, choices=[10, 50], help="config 3: DDIM steps")
+    ap.add_argument("--objects", type=int, default=256, help="config 5: objects per GPU (x 256 grasps)")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation); fp32: strict-fp32 SIMT parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -201,7 +293,7 @@ def main():
     import _data
     import _models
     from graspldm_b200 import _lib, engine, sharding
-    from graspldm_b200.inference import InferenceLDM, default_metas
+    from graspldm_b200.inference import InferenceLDM, InferenceVAE, default_metas
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
@@ -209,79 +301,107 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    w = workload(args, world)
     if os.environ.get("GLDM_TC_SETS"):
         _lib.call("gldm_sampler_tc_set_sets", int(os.environ["GLDM_TC_SETS"]))
-    model = _models.build("fpc").to(dev)
-    model.set_inference_timesteps(N_STEPS_DDPM)
+    model = _models.build(w["model"], scheduler=w["sched"] or "ddpm").to(dev)
+    if w["mode"] == "ldm":
+        model.set_inference_timesteps(w["T"])
     model.diffusion_model.rng_mode = "fused"          # noise drawn inside the sampler kernel (Philox4x32-10)
     model.diffusion_model.precision = args.precision
     model.vae_model.encoder.pc_encoder.precision = args.precision
     model.vae_model.decoder.precision = args.precision
-    inf = InferenceLDM(model, device=dev)
-    n_total = N_OBJ * world                            # weak scaling: 64 objects per GPU
+    inf = InferenceLDM(model, device=dev) if w["mode"] == "ldm" else InferenceVAE(model.vae_model, device=dev)
+    n_total, G = w["objects"], w["grasps"]
     lo, hi = sharding.shard_bounds(n_total, world, rank)
-    pcs_host = _data.synthetic_clouds(hi - lo, N_POINTS, seed=1234 + rank, dist="S").pin_memory()
-    metas = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in default_metas(hi - lo).items()}
+    n_loc = hi - lo
+    counts = sharding.shard_counts(n_total, world)
+    # clouds: distinct up to 256 objects per rank, then repeated (the kernels do not care; host memory does)
+    base = _data.synthetic_clouds(min(n_loc, 256), N_POINTS, seed=1234 + rank, dist="S")
+    pcs_host = base.repeat((n_loc + base.shape[0] - 1) // base.shape[0], 1, 1)[:n_loc].contiguous().pin_memory()
+    metas = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in default_metas(n_loc).items()}
     metas_dev = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in metas.items()}
     pcs_dev = pcs_host.to(dev)
-    counts = sharding.shard_counts(n_total, world)
     n_streams = max(1, args.streams)
-    out_hosts = [{"grasps": torch.empty((hi - lo, N_GRASPS, 4, 4)).pin_memory(),
-                  "confidence": torch.empty((hi - lo, N_GRASPS, 1)).pin_memory()} for _ in range(n_streams)]
-    out_host = out_hosts[0]
+    chunk = 1024 if w["mode"] == "encoder" else max(1, min(n_loc, 131072 // max(1, G)))     # objects per generation call
+    if w["mode"] == "encoder":
+        F_out = 64 if w["model"] == "fpc" else 256
+        out_hosts = [{"z_pc": torch.empty((n_loc, 3, F_out)).pin_memory()} for _ in range(n_streams)]
+    else:
+        out_hosts = [{"grasps": torch.empty((n_loc, G, 4, 4)).pin_memory(),
+                      "confidence": torch.empty((n_loc, G, 1)).pin_memory()} for _ in range(n_streams)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    enc = model.vae_model.encoder.pc_encoder
+
+    def generate(pcs, mt, seed):
+        """the public call(s) of one step over this rank's objects -> dict of per-object results"""
+        outs = []
+        for s in range(0, n_loc, chunk):
+            e = min(n_loc, s + chunk)
+            if w["mode"] == "encoder":
+                outs.append({"z_pc": enc(pcs[s:e].to(dev, non_blocking=True))})
+                continue
+            m = {k: (v[s:e] if isinstance(v, torch.Tensor) and v.shape[0] == n_loc else v) for k, v in mt.items()}
+            kw = dict(seed=seed) if w["mode"] == "ldm" else {}
+            o = inf.generate_grasps(pcs[s:e], m, num_grasps=G, **kw)
+            outs.append({"grasps": o["grasps"], "confidence": o["confidence"]})
+        return outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
 
     def gen_resident(seed):
-        out = inf.generate_grasps(pcs_dev, metas_dev, num_grasps=N_GRASPS, seed=seed)
+        out = generate(pcs_dev, metas_dev, seed)
         if world > 1:
-            out = sharding.gather_results({"grasps": out["grasps"], "confidence": out["confidence"]}, counts)
+            out = sharding.gather_results(out, counts)
         return out
 
     def gen_e2e(seed):
         oh = out_hosts[seed % n_streams]
-        out = inf.generate_grasps(pcs_host, metas, num_grasps=N_GRASPS, seed=seed)   # H2D inside
-        oh["grasps"].copy_(out["grasps"], non_blocking=True)                           # D2H of the result
-        oh["confidence"].copy_(out["confidence"], non_blocking=True)
+        out = generate(pcs_host, metas, seed)                 # H2D inside
+        for k, v in out.items():
+            oh[k].copy_(v, non_blocking=True)                 # D2H of the result
         if world > 1:
-            sharding.gather_results({"grasps": out["grasps"], "confidence": out["confidence"]}, counts)
+            sharding.gather_results(out, counts)
         return out
 
-    def timed(fn, steps, warmup, sections=False):
+    def fence():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, steps, warmup):
+        """sequential pass, one batch at a time: per-batch latency (L2 flushed between iterations, outside the events)"""
         import gc
         for i in range(warmup):
             fn(i)
         gc.collect()
         gc.disable()      # a generational collection inside the timed loop stalls the launching thread for tens of ms
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        fence()
         evs = []
-        engine.SECTIONS.enabled = sections
+        engine.SECTIONS.enabled = True
         engine.SECTIONS.events = []
         for i in range(steps):
-            flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+            flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn(1000 + i)
             b.record()
             evs.append((a, b))
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        fence()
         engine.SECTIONS.enabled = False
         gc.enable()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, engine.SECTIONS.collect()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), engine.SECTIONS.collect()
 
-    def timed_pipelined(fn, steps, warmup):
+    def timed_pipelined(fn, steps, warmup, sections):
         """K steps issued round-robin on n_streams streams; one event pair brackets the whole region.  The L2 flush
-        of every step is inside the timed region here (it runs on the step's own stream)."""
+        of every step is inside the timed region here (it runs on the step's own stream).  With `sections` every
+        encoder / sampler / decoder launch is also bracketed by events on its own stream."""
         import gc
         streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
         main = torch.cuda.current_stream(dev)
@@ -290,10 +410,9 @@ def main():
                 fn(i)
         gc.collect()
         gc.disable()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        fence()
+        engine.SECTIONS.enabled = sections
+        engine.SECTIONS.events = []
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(main)
         for st in streams:
@@ -305,100 +424,93 @@ def main():
         for st in streams:
             main.wait_stream(st)
         b.record(main)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        fence()
+        engine.SECTIONS.enabled = False
         gc.enable()
-        total_ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
+        return max_over_ranks(a.elapsed_time(b)), engine.SECTIONS.collect()
 
-    # pass 1 (sequential, one batch at a time): per-batch latency and the per-section / per-kernel durations
-    lat_ms, sections = timed(gen_resident, args.steps, args.warmup, sections=True)
-    # the sampler kernel of the pipelined passes (row-major, 32 samples per CTA), timed alone the same way
-    rows_ms = None
-    if n_streams > 1 and args.precision == "bf16" and os.environ.get("GLDM_TC_ROWS") is None:
-        _lib.call("gldm_sampler_tc_set_rows", 1)
-        _, sec_rows = timed(gen_resident, max(3, args.steps // 2), 2, sections=True)
-        _lib.call("gldm_sampler_tc_set_rows", -1)
-        rows_ms = sum(sec_rows.get("sampler", [0.0])) / max(1, len(sec_rows.get("sampler", [])))
+    tc = args.precision == "bf16"
+    rows_env = os.environ.get("GLDM_TC_ROWS")
     clocks = ClockSampler(local_rank)
     clocks.start()
+    # pass 1 (sequential, one batch at a time): per-batch latency with the automatic kernel choice
+    lat_steps = max(3, min(args.steps, 20))
+    lat_ms, lat_sections = timed(gen_resident, lat_steps, args.warmup)
+    # pass 2 (the reported value): batches in flight on n_streams streams.  Throughput mode of the sampler: the row-major
+    # tcgen05 kernel (32 samples per CTA) - forced here, the automatic choice takes it only above one wave of CTAs
     l0 = _lib.launch_count()
     if n_streams > 1:
-        # throughput mode: 32 samples per sampler CTA in two interleaved sets (fewer SMs per batch, the UMMA phase of
-        # one set under the epilogue of the other); the sequential latency pass above used the automatic choice
-        if args.precision == "bf16" and not os.environ.get("GLDM_TC_SETS"):
-            _lib.call("gldm_sampler_tc_set_sets", 2)
-        if args.precision == "bf16" and os.environ.get("GLDM_TC_ROWS") is None:
-            _lib.call("gldm_sampler_tc_set_rows", 1)     # throughput mode: the row-major sampler kernel (32 samples per CTA)
-        total_ms = timed_pipelined(gen_resident, args.steps, args.warmup)
+        if tc and rows_env is None:
+            _lib.call("gldm_sampler_tc_set_rows", 1)
+        total_ms, sections = timed_pipelined(gen_resident, args.steps, args.warmup, sections=True)
         launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, n_streams)) * args.steps
+        e2e_ms, _ = timed_pipelined(gen_e2e, args.steps, args.warmup, sections=False)
     else:
-        total_ms, _ = timed(gen_resident, args.steps, args.warmup)
+        total_ms, sections = timed(gen_resident, args.steps, args.warmup)
         launches = (_lib.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+        e2e_ms, _ = timed(gen_e2e, args.steps, args.warmup)
     clk = clocks.finish()
-    e2e_ms = timed_pipelined(gen_e2e, args.steps, args.warmup) if n_streams > 1 else timed(gen_e2e, args.steps, args.warmup)[0]
 
     ms_per_step = total_ms / args.steps
-    grasps_per_step = n_total * N_GRASPS
-    value = grasps_per_step / (ms_per_step * 1e-3)
-    e2e_value = grasps_per_step / (e2e_ms / args.steps * 1e-3)
+    units = units_per_step(w, n_total)
+    value = units / (ms_per_step * 1e-3)
+    e2e_value = units / (e2e_ms / args.steps * 1e-3)
 
     pk = peaks()
-    n_local = (hi - lo) * N_GRASPS
-    samp_ms = sum(sections.get("sampler", [0.0])) / max(1, len(sections.get("sampler", [])))
-    enc_ms = sum(sections.get("encoder", [0.0])) / max(1, len(sections.get("encoder", [])))
-    dec_ms = sum(sections.get("decoder", [0.0])) / max(1, len(sections.get("decoder", [])))
-    samp_flops = n_local * N_STEPS_DDPM * F_DENOISER_PER_SAMPLE_STEP
-    achieved = samp_flops / (samp_ms * 1e-3) / 1e12 if samp_ms > 0 else 0.0
-    kname = ("resnet_tc_kernel<4,1> in the latency pass / resnet_rows_kernel in the pipelined passes (tcgen05 persistent 100-step sampler, one launch per batch)" if args.precision == "bf16"
-             else "resnet_kernel<4> (fp32 SIMT persistent 100-step sampler, one launch per batch)")
+    mean = lambda xs: (sum(xs) / len(xs)) if xs else 0.0
+    f_enc, f_samp, f_dec = flops(w, n_loc)
+    calls = max(1, -(-n_loc // chunk))                    # generation calls (= launches of each section) per step
+    rows_kernel = tc and w["mode"] == "ldm" and w["model"] == "fpc" and (n_streams > 1 and rows_env is None or rows_env == "1"
+                                                                         or chunk * G > 16 * 148)
+    names = {"encoder": ("PVCNN encoder pass: conv3d_tc3_kernel / conv3d_tc16_kernel / gemm_tc_kernel (tcgen05) + SIMT voxel glue"
+                         if tc else "PVCNN encoder pass (fp32 SIMT)"),
+             "sampler": (("rows::resnet_rows_kernel" if rows_kernel else "resnet_tc_kernel<L,NSETS>") +
+                         " (tcgen05 persistent T-step sampler, one launch per call)") if tc else "resnet_kernel<L> (fp32 SIMT persistent sampler)",
+             "decoder": "resnet_tc_kernel<16,1> (tcgen05 grasp decoder)" if tc else "resnet_kernel<16> (fp32 SIMT decoder)"}
+    kernels = []
+    for sec, fl in (("encoder", f_enc), ("sampler", f_samp), ("decoder", f_dec)):
+        ms = mean(sections.get(sec, []))
+        if fl > 0 and ms > 0:
+            tf = fl / calls / (ms * 1e-3) / 1e12
+            kernels.append({"section": sec, "name": names[sec], "ms_in_timed_region": ms, "launches_per_step": calls,
+                            "algorithmic_flops_per_launch": fl / calls, "achieved_tflops": tf, "frac": tf / pk["tflops_sustained"],
+                            "ms_alone": mean(lat_sections.get(sec, []))})
+    dom = max(kernels, key=lambda k: k["ms_in_timed_region"] * k["launches_per_step"])
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_tc_sampler_traffic.json")
-    if args.precision == "bf16" and os.path.exists(tp):
-        t = json.load(open(tp))["sampler_tc_kernel"]          # dram__bytes_read + write of one ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r02_tc_sampler_traffic.json")
+    if dom["section"] == "sampler" and tc and os.path.exists(tp):
+        t = json.load(open(tp))["resnet_rows_kernel"]          # dram__bytes_read + write of one ncu --set full capture
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    roofline = {"bound": "tensor", "kernel": kname,
-                "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
-                "algorithmic_flops_per_launch": samp_flops, "kernel_ms": samp_ms,
-                # the same FLOPs over the whole pipelined timed region (which also holds the encoder / decoder kernels
-                # of the batches in flight): a lower bound on what the sampler kernel sustains across the GPU
-                "achieved_timed_region": samp_flops * args.steps / (total_ms * 1e-3) / 1e12,
-                # the row-major kernel of the pipelined passes alone: one batch = ceil(samples / 32) CTAs, one per SM
-                "pipelined_kernel": (None if not rows_ms else {
-                    "name": "resnet_rows_kernel", "kernel_ms": rows_ms, "ctas": -(-n_local // 32), "sms": 148,
-                    "achieved": samp_flops / (rows_ms * 1e-3) / 1e12,
-                    "frac_of_peak_of_occupied_sms": samp_flops / (rows_ms * 1e-3) / 1e12 / (pk["tflops_sustained"] * min(1.0, -(-n_local // 32) / 148))}),
-                "sections_ms": {"encoder": enc_ms, "sampler": samp_ms, "decoder": dec_ms},
-                "note": ("sampler, decoder, encoder point-wise layers and Conv3d on tcgen05 (bf16 operands, fp32 accumulate); voxelize / devoxelize / GroupNorm+Swish / SE on fp32 SIMT kernels over channels-last grids; kernel_ms and sections_ms come from the sequential latency pass (channel-major sampler kernel, 16 samples per CTA, 80 CTAs; the pipelined passes use the row-major kernel, 32 samples per CTA)"
-                         if args.precision == "bf16" else "strict-fp32 SIMT (FFMA) parity path")}
+    total_flops = f_enc + f_samp + f_dec
+    roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["achieved_tflops"], "peak": pk["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
+                "algorithmic_flops_per_launch": dom["algorithmic_flops_per_launch"], "kernel_ms": dom["ms_in_timed_region"],
+                "how": "CUDA events on the launching stream around every launch of the section INSIDE the timed region; with "
+                       f"{n_streams} batches in flight the kernel shares the GPU with the other batches' kernels, so its duration "
+                       "there is longer than alone (ms_alone: the sequential latency pass)",
+                "kernels": kernels,
+                # all algorithmic FLOPs of a step over the whole timed region: what the GPU sustains end to end
+                "whole_step": {"algorithmic_flops_per_step": total_flops,
+                               "achieved_tflops": total_flops / (ms_per_step * 1e-3) / 1e12,
+                               "frac": total_flops / (ms_per_step * 1e-3) / 1e12 / pk["tflops_sustained"]}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample(w)
+    h2d = pcs_host.numel() * 4 + (n_loc * G * (4 if w["model"] == "fpc" else 16) * 4 if w["mode"] != "encoder" else 0)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "fpc_1a_latentc3_z4_pc64 LDM-mode generation, 100 DDPM steps, 64 objects x 20 grasps per GPU "
-                               "(BASELINE.json configs[1]), random-init weights, 1024-point synthetic clouds",
-                   "objects": n_total, "grasps_per_object": N_GRASPS, "denoising_steps": N_STEPS_DDPM,
-                   "parallelism": f"objects sharded over {world} rank(s), one final all_gather",
-                   "l2": "256 MiB buffer written before every step" + (" (inside the timed region, on the step's stream)" if n_streams > 1 else " (between timed iterations)"),
-                   "batches_in_flight": n_streams, "latency_ms_per_batch": lat_ms / args.steps, "precision": args.precision,
-                   "sampler_samples_per_cta": ("32 (row-major tcgen05 kernel: rows = 4 positions x 32 samples) in the pipelined passes, 16 (channel-major kernel, 80 CTAs) in the latency pass"
-                                               if (n_streams > 1 and args.precision == "bf16") else "automatic"),
-                   "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcs_host.numel() * 4 + n_local * 4 * 4),
-                "d2h_bytes_per_step": int(out_host["grasps"].numel() * 4 + out_host["confidence"].numel() * 4),
-                "ms_per_step": e2e_ms / args.steps},
+        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+        "dtype": "bf16" if tc else "f32", "data": "synthetic", "config": w["config"],
+        "run": {"l2": "256 MiB buffer written before every step" + (" (inside the timed region, on the step's stream)" if n_streams > 1 else " (between timed iterations)"),
+                "batches_in_flight": n_streams, "objects_per_call": chunk, "precision": args.precision,
+                "latency_ms_per_batch": lat_ms / lat_steps,
+                "latency_pass": "one batch at a time, automatic sampler kernel choice (channel-major 16-sample CTAs up to 2368 samples)",
+                "sampler_kernel_timed_region": names["sampler"] if w["mode"] == "ldm" else None,
+                "rng": "in-kernel Philox4x32-10 + Box-Muller (x_T drawn on the host generator as the reference does)"},
+        "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(sum(v.numel() * 4 for v in out_hosts[0].values())), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
     emit(line)
