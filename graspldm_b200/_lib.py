@@ -84,6 +84,8 @@ _SIGS = {
     "gldm_pose_postprocess": [P, P, P, P, c_int, P, P, P, P],
     "gldm_pose_postprocess_rows": [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "gldm_normalize_clouds": [P, P, P, P, c_int, c_int, P, P, P, P],
+    "gldm_sa_mlp_max_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P],
+    "gldm_se_gate_relu_f32": [P, P, P, c_int, c_int, c_int, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})
 _RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong, "gldm_voxel_ws_bytes": c_longlong, "gldm_conv3d_tc16_weight_bytes": c_longlong,

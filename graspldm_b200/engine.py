@@ -380,6 +380,128 @@ def _fold_bn(conv, bn):
     return scale.float().contiguous(), shift.float().contiguous()
 
 
+def pack_point_block(blk):
+    """Kernel-ready constants of one PVCNN point block: a PVConv (pvconv.py:13-84) or a single-layer SharedMLP."""
+    if hasattr(blk, "voxel_layers"):
+        vl = [m for m in blk.voxel_layers if not isinstance(m, torch.nn.Dropout)]      # conv, gn, swish, conv, gn, swish, se
+        c1, g1, c2, g2, se = vl[0], vl[1], vl[3], vl[4], vl[6]
+        pw = blk.point_features.layers
+        assert len(pw) == 3, "PVConv's point branch is a single-layer SharedMLP"
+        sc, sh = _fold_bn(pw[0], pw[1])
+        return dict(
+            kind="pvconv", r=blk.resolution, cin=blk.in_channels, cout=blk.out_channels,
+            normalize=bool(blk.voxelization.normalize), vox_eps=float(blk.voxelization.eps),
+            se_relu=isinstance(se.fc[1], torch.nn.ReLU),
+            w1_raw=c1.weight.detach().float().contiguous(), w2_raw=c2.weight.detach().float().contiguous(),
+            # Conv3d weights [co,ci,3,3,3] -> [ci,27,co] (layout only)
+            w1=c1.weight.detach().permute(1, 2, 3, 4, 0).reshape(c1.in_channels, 27, c1.out_channels).contiguous().float(),
+            b1=c1.bias.detach().float().contiguous(), g1w=g1.weight.detach().float().contiguous(),
+            g1b=g1.bias.detach().float().contiguous(), eps1=float(g1.eps),
+            w2=c2.weight.detach().permute(1, 2, 3, 4, 0).reshape(c2.in_channels, 27, c2.out_channels).contiguous().float(),
+            b2=c2.bias.detach().float().contiguous(), g2w=g2.weight.detach().float().contiguous(),
+            g2b=g2.bias.detach().float().contiguous(), eps2=float(g2.eps), groups=int(g1.num_groups),
+            se1=se.fc[0].weight.detach().float().contiguous(), se2=se.fc[2].weight.detach().float().contiguous(),
+            pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
+            pscale=sc, pshift=sh)
+    pw = blk.layers
+    assert len(pw) == 3, "single-layer SharedMLP block"
+    sc, sh = _fold_bn(pw[0], pw[1])
+    return dict(kind="mlp", cin=pw[0].in_channels, cout=pw[0].out_channels,
+                pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
+                pscale=sc, pshift=sh)
+
+
+def pvconv_forward_f32(blk, feats, coords):
+    """PVConv.forward on the strict-fp32 kernels (pvconv.py:76-84): voxelize -> Conv3d, GroupNorm, Swish (x2) -> SE ->
+    trilinear devoxelize + point branch.  feats [B,Cin,N], coords [B,3,N] -> [B,Cout,N].  `normalize=True`
+    (voxelization.py:19-30, PVCNN2's blocks) takes the per-cloud scaling through a few element-wise device operations and
+    the avg_voxelize operator; `normalize=False` (PVCNN) is one fused kernel."""
+    dev = feats.device
+    st = _stream(dev)
+    B, ci, N = feats.shape
+    r, co = blk["r"], blk["cout"]
+    r3 = r ** 3
+    with torch.cuda.device(dev):
+        feats = feats.contiguous().float()
+        coords = coords.contiguous().float()
+        if blk["normalize"]:
+            nc = coords - coords.mean(2, keepdim=True)
+            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + blk["vox_eps"]) + 0.5
+            norm = torch.clamp(nc * r, 0, r - 1).contiguous()
+            vox = torch.round(norm).to(torch.int32).contiguous()
+            grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
+            ind = torch.empty((B, N), device=dev, dtype=torch.int32)
+            cnt = torch.empty((B, r3), device=dev, dtype=torch.int32)
+            _lib.call("gldm_avg_voxelize_forward", feats.data_ptr(), vox.data_ptr(), B, ci, N, r, grid.data_ptr(),
+                      ind.data_ptr(), cnt.data_ptr(), st)
+        else:
+            grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
+            norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
+            _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(),
+                      norm.data_ptr(), None, st)
+        y1 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
+        _lib.call("gldm_conv3d_k3_f32", grid.data_ptr(), blk["w1"].data_ptr(), blk["b1"].data_ptr(), B, ci, co, r, y1.data_ptr(), st)
+        _lib.call("gldm_groupnorm_swish_f32", y1.data_ptr(), blk["g1w"].data_ptr(), blk["g1b"].data_ptr(), B, co, r3,
+                  blk["groups"], blk["eps1"], None, st)
+        y2 = torch.empty((B, co, r3), device=dev, dtype=torch.float32)
+        _lib.call("gldm_conv3d_k3_f32", y1.data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(), B, co, co, r, y2.data_ptr(), st)
+        se_mean = torch.empty((B, co), device=dev, dtype=torch.float32)
+        _lib.call("gldm_groupnorm_swish_f32", y2.data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(), B, co, r3,
+                  blk["groups"], blk["eps2"], se_mean.data_ptr(), st)
+        gate = torch.empty((B, co), device=dev, dtype=torch.float32)
+        _lib.call("gldm_se_gate_relu_f32" if blk["se_relu"] else "gldm_se_gate_f32", se_mean.data_ptr(), blk["se1"].data_ptr(),
+                  blk["se2"].data_ptr(), B, co, blk["se1"].shape[0], gate.data_ptr(), st)
+        pt = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
+        fused = torch.empty((B, co, N), device=dev, dtype=torch.float32)
+        _lib.call("gldm_devox_gate_add_f32", norm.data_ptr(), y2.data_ptr(), gate.data_ptr(), pt.data_ptr(), B, co, N, r,
+                  fused.data_ptr(), st)
+    return fused
+
+
+def packed_block(module):
+    """pack_point_block cached on the module (rebuilt when its parameters change)."""
+    sig = _signature(module)
+    ent = module.__dict__.get("_gldm_block")
+    if ent is None or ent[0] != sig:
+        _require_cuda(next(module.parameters()), "model parameters")
+        ent = (sig, pack_point_block(module))
+        module.__dict__["_gldm_block"] = ent
+    return ent[1]
+
+
+def sa_group_mlp_max(mlp, coords, centers, feats, idx, include_coords=True):
+    """Fused grouping -> SharedMLP(dim=2) -> max of one PointNetSAModule branch (csrc/set_abstraction.cu).
+    coords [B,3,N], centers [B,3,M], feats [B,C,N] or None, idx i32 [B,M,U] -> [B,C_out,M]."""
+    _require_cuda(coords, "coords")
+    dev = coords.device
+    sig = _signature(mlp)
+    ent = mlp.__dict__.get("_gldm_sa")
+    if ent is None or ent[0] != sig:
+        layers = []
+        for i in range(0, len(mlp.layers), 3):
+            conv, bn = mlp.layers[i], mlp.layers[i + 1]
+            sc, sh = _fold_bn(conv, bn)
+            wt = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).t().contiguous().float()
+            layers.append((wt, sc, sh, conv.out_channels))
+        ent = (sig, layers)
+        mlp.__dict__["_gldm_sa"] = ent
+    layers = ent[1]
+    B, _, N = coords.shape
+    M, U = idx.shape[1], idx.shape[2]
+    C = 0 if feats is None else feats.shape[1]
+    nl = len(layers)
+    widths = (ctypes.c_int * nl)(*[l[3] for l in layers])
+    arr = lambda k: (ctypes.c_void_p * nl)(*[l[k].data_ptr() for l in layers])
+    with torch.cuda.device(dev):
+        out = torch.empty((B, layers[-1][3], M), device=dev, dtype=torch.float32)
+        f = None if feats is None else feats.contiguous().float()
+        _lib.call("gldm_sa_mlp_max_f32", coords.contiguous().data_ptr(), centers.contiguous().data_ptr(),
+                  f.data_ptr() if f is not None else None, idx.contiguous().data_ptr(), B, C, N, M, U, int(include_coords), nl,
+                  ctypes.cast(widths, ctypes.c_void_p), ctypes.cast(arr(0), ctypes.c_void_p), ctypes.cast(arr(1), ctypes.c_void_p),
+                  ctypes.cast(arr(2), ctypes.c_void_p), out.data_ptr(), _stream(dev))
+    return out
+
+
 class PackedEncoder:
     """Device-resident, kernel-ready weights of a PVCNNEncoder."""
 
@@ -387,32 +509,7 @@ class PackedEncoder:
         p0 = next(enc.parameters())
         _require_cuda(p0, "model parameters")
         self.device = p0.device
-        self.blocks = []
-        for blk in enc.pvcnn_modules.point_features:
-            if hasattr(blk, "voxel_layers"):
-                vl = blk.voxel_layers
-                c1, g1, c2, g2, se = vl[0], vl[1], vl[4], vl[5], vl[7]
-                pw = blk.point_features.layers
-                sc, sh = _fold_bn(pw[0], pw[1])
-                self.blocks.append(dict(
-                    kind="pvconv", r=blk.resolution, cin=blk.in_channels, cout=blk.out_channels,
-                    w1_raw=c1.weight.detach().float().contiguous(), w2_raw=c2.weight.detach().float().contiguous(),
-                    # Conv3d weights [co,ci,3,3,3] -> [ci,27,co] (layout only)
-                    w1=c1.weight.detach().permute(1, 2, 3, 4, 0).reshape(c1.in_channels, 27, c1.out_channels).contiguous().float(),
-                    b1=c1.bias.detach().float().contiguous(), g1w=g1.weight.detach().float().contiguous(),
-                    g1b=g1.bias.detach().float().contiguous(), eps1=float(g1.eps),
-                    w2=c2.weight.detach().permute(1, 2, 3, 4, 0).reshape(c2.in_channels, 27, c2.out_channels).contiguous().float(),
-                    b2=c2.bias.detach().float().contiguous(), g2w=g2.weight.detach().float().contiguous(),
-                    g2b=g2.bias.detach().float().contiguous(), eps2=float(g2.eps), groups=int(g1.num_groups),
-                    se1=se.fc[0].weight.detach().float().contiguous(), se2=se.fc[2].weight.detach().float().contiguous(),
-                    pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
-                    pscale=sc, pshift=sh))
-            else:
-                pw = blk.layers
-                sc, sh = _fold_bn(pw[0], pw[1])
-                self.blocks.append(dict(kind="mlp", cin=pw[0].in_channels, cout=pw[0].out_channels,
-                                        pw=pw[0].weight.detach().reshape(pw[0].out_channels, pw[0].in_channels).float().contiguous(),
-                                        pscale=sc, pshift=sh))
+        self.blocks = [pack_point_block(blk) for blk in enc.pvcnn_modules.point_features]
         cd = enc.conv_downscale
         self.wd = cd.weight.detach().reshape(cd.out_channels, cd.in_channels).float().contiguous()
         self.bd = cd.bias.detach().float().contiguous()

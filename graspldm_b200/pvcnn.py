@@ -22,9 +22,7 @@ class Swish(nn.Module):                   # R/../modules.py:5-7 (parameter-free 
 class SE3d(nn.Module):                    # modules/se.py:12-25
     def __init__(self, channel, reduction=8, use_relu=False):
         super().__init__()
-        if use_relu:
-            raise NotImplementedError("with_se_relu is not used by the generation configs")
-        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), Swish(),
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(True) if use_relu else Swish(),
                                 nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
 
 
@@ -70,8 +68,11 @@ class Voxelization(nn.Module):            # modules/voxelization.py:9-35
 
     @torch.no_grad()
     def forward(self, features, coords):
-        if self.normalize:
-            raise NotImplementedError("normalize=True is not used by PVCNN (pvcnn_base.py:49-56 passes False)")
+        if self.normalize:           # voxelization.py:19-30: scale by twice the largest point norm of the cloud
+            nc = coords - coords.mean(2, keepdim=True)
+            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + self.eps) + 0.5
+            norm = torch.clamp(nc * self.r, 0, self.r - 1)
+            return F.avg_voxelize(features, torch.round(norm).to(torch.int32), self.r), norm
         grid, norm = F.voxelize_fused(features, coords, self.r)
         return grid, norm
 
@@ -83,8 +84,8 @@ class PVConv(nn.Module):                  # modules/pvconv.py:13-84
     def __init__(self, in_channels, out_channels, kernel_size, resolution, use_attention=False, dropout=0.1,
                  with_se=False, with_se_relu=False, normalize=True, eps=0):
         super().__init__()
-        if use_attention or kernel_size != 3 or not with_se or normalize:
-            raise NotImplementedError("PVConv is implemented as configured by PVCNN: k=3, SE, no attention, normalize=False")
+        if use_attention or kernel_size != 3 or not with_se:
+            raise NotImplementedError("PVConv is implemented as PVCNN / PVCNN2 configure it: k=3, SE, no voxel attention")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.resolution = kernel_size, resolution
         self.voxelization = Voxelization(resolution, normalize=normalize, eps=eps)
@@ -96,6 +97,14 @@ class PVConv(nn.Module):                  # modules/pvconv.py:13-84
         layers.append(SE3d(out_channels, use_relu=with_se_relu))
         self.voxel_layers = nn.Sequential(*layers)
         self.point_features = SharedMLP(in_channels, out_channels)
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        """(features [B,C,N], coords [B,3,N]) -> (fused [B,C_out,N], coords)   pvconv.py:76-84, strict-fp32 kernels"""
+        features, coords = inputs
+        if self.training:
+            raise NotImplementedError("generation path: call .eval()")
+        return engine.pvconv_forward_f32(engine.packed_block(self), features, coords), coords
 
 
 class BallQuery(nn.Module):               # modules/ball_query.py:9-34
@@ -114,6 +123,30 @@ class BallQuery(nn.Module):               # modules/ball_query.py:9-34
             return nb_coords
         nb = F.grouping(points_features, idx)
         return torch.cat([nb_coords, nb], dim=1) if self.include_coordinates else nb
+
+
+class PointNetAModule(nn.Module):         # modules/pointnet.py:11-50 (global abstraction: MLP over all points, max)
+    def __init__(self, in_channels, out_channels, include_coordinates=True):
+        super().__init__()
+        if not isinstance(out_channels, (list, tuple)):
+            out_channels = [[out_channels]]
+        elif not isinstance(out_channels[0], (list, tuple)):
+            out_channels = [out_channels]
+        mlps, total = [], 0
+        for oc in out_channels:
+            mlps.append(SharedMLP(in_channels + (3 if include_coordinates else 0), oc, dim=1))
+            total += oc[-1]
+        self.include_coordinates, self.out_channels = include_coordinates, total
+        self.mlps = nn.ModuleList(mlps)
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        features, coords = inputs
+        if self.include_coordinates:
+            features = torch.cat([features, coords], dim=1)
+        zero = torch.zeros((coords.size(0), 3, 1), device=coords.device)
+        outs = [mlp(features).max(dim=-1, keepdim=True).values for mlp in self.mlps]
+        return (torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]), zero
 
 
 class PointNetSAModule(nn.Module):        # modules/pointnet.py:53-114
@@ -138,8 +171,17 @@ class PointNetSAModule(nn.Module):        # modules/pointnet.py:53-114
     @torch.no_grad()
     def forward(self, inputs):
         features, coords = inputs
+        """(features [B,C,N] | None, coords [B,3,N]) -> ([B, sum C_out, M], centres [B,3,M]).  FPS and ball query are the
+        bit-exact operator kernels; grouping, the shared MLP and the max over the neighbours are ONE kernel per radius
+        (csrc/set_abstraction.cu): the grouped tensor [B, C+3, M, U] of the reference never reaches HBM."""
+        coords = coords.contiguous()
         centers = F.furthest_point_sample(coords, self.num_centers)
-        outs = [mlp(g(coords, centers, features)).max(dim=-1).values for g, mlp in zip(self.groupers, self.mlps)]
+        outs = []
+        for g, mlp in zip(self.groupers, self.mlps):
+            if mlp.training:
+                raise NotImplementedError("generation path: call .eval() (BatchNorm uses running statistics)")
+            idx = F.ball_query(centers, coords, g.radius, g.num_neighbors)
+            outs.append(engine.sa_group_mlp_max(mlp, coords, centers, features, idx, g.include_coordinates))
         return (torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]), centers
 
 
@@ -185,3 +227,159 @@ class PVCNN(nn.Module):                   # pvcnn_base.py:15-140 (unconditioned,
                 cin = oc
         self.point_features = nn.ModuleList(layers)
         self.is_conditioned = False
+
+    @torch.no_grad()
+    def forward(self, inputs, *, cond=None):
+        """[B, 3+C, N] -> [B, C_out, N]   pvcnn_base.py:114-140 (strict-fp32 kernels, block by block)"""
+        features = inputs[:, :self.in_channels, :].contiguous()
+        coords = features[:, :3, :].contiguous()
+        for blk in self.point_features:
+            features = blk((features, coords))
+            features = features[0] if isinstance(features, tuple) else features
+        return features
+
+
+def _seq_or_single(blocks):
+    return blocks[0] if len(blocks) == 1 else nn.Sequential(*blocks)
+
+
+def create_pointnet2_sa_components(sa_blocks, extra_feature_channels, with_se=False, voxelization_normalize=True, eps=0,
+                                   dropout=0.1, width_multiplier=1, voxel_resolution_multiplier=1):
+    """utils.py:97-185 (embed_dim = 0, no voxel attention): same modules in the same order -> same seeded init / keys."""
+    r, vr = width_multiplier, voxel_resolution_multiplier
+    in_channels = extra_feature_channels + 3
+    sa_layers, sa_in_channels = [], []
+    num_centers = None
+    for c, (conv_configs, sa_configs) in enumerate(sa_blocks):
+        sa_in_channels.append(in_channels)
+        blocks = []
+        if conv_configs is not None:
+            out_channels, num_blocks, voxel_resolution = conv_configs
+            out_channels = int(r * out_channels)
+            for k in range(num_blocks):
+                # utils.py:139-143: past the first SA stage only the FIRST block of a stage is instantiated (the reference
+                # skips the others but still advances the channel count); mirrored for identical keys and arithmetic
+                if c == 0 or k == 0:
+                    if voxel_resolution is None:
+                        blocks.append(SharedMLP(in_channels, out_channels))
+                    else:
+                        blocks.append(PVConv(in_channels, out_channels, kernel_size=3, resolution=int(vr * voxel_resolution),
+                                             dropout=dropout, with_se=with_se, with_se_relu=True, normalize=voxelization_normalize,
+                                             eps=eps))
+                in_channels = out_channels
+            extra_feature_channels = in_channels
+        num_centers, radius, num_neighbors, out_channels = sa_configs
+        oc = [[int(r * c) for c in o] if isinstance(o, (list, tuple)) else int(r * o) for o in out_channels]
+        if num_centers is None:
+            blocks.append(PointNetAModule(in_channels=extra_feature_channels, out_channels=oc, include_coordinates=True))
+        else:
+            blocks.append(PointNetSAModule(num_centers=num_centers, radius=radius, num_neighbors=num_neighbors,
+                                           in_channels=extra_feature_channels, out_channels=oc, include_coordinates=True))
+        in_channels = extra_feature_channels = blocks[-1].out_channels
+        sa_layers.append(_seq_or_single(blocks))
+    return sa_layers, sa_in_channels, in_channels, 1 if num_centers is None else num_centers
+
+
+def create_pointnet2_fp_modules(fp_blocks, in_channels, sa_in_channels, with_se=False, normalize=True, eps=0, dropout=0.1,
+                                width_multiplier=1, voxel_resolution_multiplier=1):
+    """utils.py:188-247"""
+    r, vr = width_multiplier, voxel_resolution_multiplier
+    fp_layers = []
+    for fp_idx, (fp_configs, conv_configs) in enumerate(fp_blocks):
+        blocks = []
+        out_channels = tuple(int(r * oc) for oc in fp_configs)
+        blocks.append(PointNetFPModule(in_channels=in_channels + sa_in_channels[-1 - fp_idx], out_channels=out_channels))
+        in_channels = out_channels[-1]
+        if conv_configs is not None:
+            out_channels, num_blocks, voxel_resolution = conv_configs
+            out_channels = int(r * out_channels)
+            for _ in range(num_blocks):
+                if voxel_resolution is None:
+                    blocks.append(SharedMLP(in_channels, out_channels))
+                else:
+                    blocks.append(PVConv(in_channels, out_channels, kernel_size=3, resolution=int(vr * voxel_resolution),
+                                         dropout=dropout, with_se=with_se, with_se_relu=True, normalize=normalize, eps=eps))
+                in_channels = out_channels
+        fp_layers.append(_seq_or_single(blocks))
+    return fp_layers, in_channels
+
+
+def _run_blocks(module, inputs):
+    """nn.Sequential of tuple-in / tuple-out blocks (the reference chains them the same way)"""
+    if isinstance(module, nn.Sequential):
+        for m in module:
+            inputs = m(inputs)
+        return inputs
+    return module(inputs)
+
+
+class PVCNN2(nn.Module):                  # pvcnn_base.py:180-279
+    sa_blocks = [((32, 1, 32), (1024, 0.1, 32, (32, 64))), ((64, 2, 16), (256, 0.2, 32, (64, 128))),
+                 ((128, 1, 8), (64, 0.4, 32, (128, 256))), (None, (16, 0.8, 32, (256, 256, 512)))]
+    fp_blocks = [((256, 256), (256, 1, 8)), ((256, 256), (256, 1, 8)), ((256, 128), (128, 2, 16)), ((128, 128, 64), (64, 1, 32))]
+
+    def __init__(self, in_channels=3, extra_feature_channels=0, width_multiplier=1, voxel_resolution_multiplier=1,
+                 use_attention=False, dropout=0.1):
+        super().__init__()
+        if use_attention:
+            raise NotImplementedError("voxel attention is not used")
+        self.in_channels = in_channels + extra_feature_channels
+        sa_layers, sa_in_channels, channels_sa_features, _ = create_pointnet2_sa_components(
+            sa_blocks=self.sa_blocks, extra_feature_channels=extra_feature_channels, with_se=True, voxelization_normalize=True,
+            dropout=dropout, width_multiplier=width_multiplier, voxel_resolution_multiplier=voxel_resolution_multiplier)
+        self.sa_layers = nn.ModuleList(sa_layers)
+        sa_in_channels[0] = extra_feature_channels
+        fp_layers, _ = create_pointnet2_fp_modules(
+            fp_blocks=self.fp_blocks, in_channels=channels_sa_features, sa_in_channels=sa_in_channels, with_se=True,
+            width_multiplier=width_multiplier, voxel_resolution_multiplier=voxel_resolution_multiplier)
+        self.fp_layers = nn.ModuleList(fp_layers)
+        self.out_channels = self.fp_layers[-1][-1].out_channels
+
+    @torch.no_grad()
+    def forward(self, inputs, cond=None):
+        if isinstance(inputs, dict):
+            inputs = inputs["features"]
+        coords, features = inputs[:, :3, :].contiguous(), inputs.contiguous()
+        coords_list, in_features_list = [], []
+        for sa in self.sa_layers:
+            in_features_list.append(features)
+            coords_list.append(coords)
+            features, coords = _run_blocks(sa, (features, coords))
+        in_features_list[0] = inputs[:, 3:, :].contiguous()
+        for fp_idx, fp in enumerate(self.fp_layers):
+            features, coords = _run_blocks(fp, (coords_list[-1 - fp_idx], coords, features, in_features_list[-1 - fp_idx]))
+        return features
+
+
+class PointNet2SSG(nn.Module):            # pointnet2.py:13-119
+    sa_blocks = [(None, (512, 0.2, 64, (64, 64, 128))), (None, (128, 0.4, 64, (128, 128, 256))),
+                 (None, (None, None, None, (256, 512, 1024)))]
+    fp_blocks = [((256, 256), None), ((256, 128), None), ((128, 128, 128), None)]
+
+    def __init__(self, num_shapes=0, extra_feature_channels=3, width_multiplier=1, voxel_resolution_multiplier=1):
+        super().__init__()
+        assert extra_feature_channels >= 0
+        self.in_channels = extra_feature_channels + 3
+        self.num_shapes, self.with_one_hot_shape_id = num_shapes, False
+        sa_layers, sa_in_channels, channels_sa_features, _ = create_pointnet2_sa_components(
+            sa_blocks=self.sa_blocks, extra_feature_channels=extra_feature_channels, width_multiplier=width_multiplier)
+        self.sa_layers = nn.ModuleList(sa_layers)
+        fp_layers, _ = create_pointnet2_fp_modules(
+            fp_blocks=self.fp_blocks, in_channels=channels_sa_features, sa_in_channels=sa_in_channels,
+            width_multiplier=width_multiplier, voxel_resolution_multiplier=voxel_resolution_multiplier)
+        self.fp_layers = nn.ModuleList(fp_layers)
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        features = inputs[:, :self.in_channels, :]
+        with_ids = features
+        coords, features = features[:, :3, :].contiguous(), features[:, 3:, :].contiguous()
+        coords_list, in_features_list = [], []
+        for sa in self.sa_layers:
+            in_features_list.append(features)
+            coords_list.append(coords)
+            features, coords = _run_blocks(sa, (features if features.shape[1] > 0 else None, coords))
+        in_features_list[0] = with_ids.contiguous()
+        for fp_idx, fp in enumerate(self.fp_layers):
+            features, coords = _run_blocks(fp, (coords_list[-1 - fp_idx], coords, features, in_features_list[-1 - fp_idx]))
+        return features

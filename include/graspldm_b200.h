@@ -296,6 +296,21 @@ int gldm_pose_postprocess_rows(const float* tmrp, const float* logit, const floa
 int gldm_normalize_clouds(const float* pc, const float* pc_shift, const float* pc_scale, const float* grasp_shift, int b,
                           int n, float* pc_out, float* pc_mean, float* grasp_mean, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Set abstraction (PointNet++ / PVCNN2 side of the operator family), fused
+ * ------------------------------------------------------------------------------------------ */
+/* PointNetSAModule.forward for one radius, after the centre selection   R/../pvcnn/modules/pointnet.py:100-111,
+ * ball_query.py:16-34, shared_mlp.py:18-28: ball-query neighbours idx i32[b,m,u] -> gather (coords - centre | features)
+ * -> n_layers x (1x1 conv, folded BatchNorm scale / shift, ReLU) -> max over the u neighbours -> out f32[b, widths[last], m].
+ * The grouped tensor [b, c+3, m, u] never exists in HBM.  wt[l] = layer weight TRANSPOSED to [c_in][c_out] (device
+ * pointers in HOST arrays of n_layers entries); every width <= 512, c + 3 <= 512. */
+int gldm_sa_mlp_max_f32(const float* coords, const float* centers, const float* feats, const int* idx, int b, int c, int n,
+                        int m, int u, int include_coords, int n_layers, const int* widths, const float* const* wt,
+                        const float* const* scale, const float* const* shift, float* out, void* stream);
+/* SE excite with ReLU (se.py:12-25, use_relu=True): gate f32[b,c] = sigmoid(W2 relu(W1 mean)) */
+int gldm_se_gate_relu_f32(const float* mean, const float* w1, const float* w2, int b, int c, int cr, float* gate,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,6 +173,49 @@ def _pvconv(sd, p, feats, coords, r):
     return torch.from_numpy(dv) + _shared_mlp(sd, p + "point_features.", feats)
 
 
+def _shared_mlp_n(sd, p, x):
+    """Multi-layer SharedMLP over [B,C,N] or [B,C,M,U] (k=1 conv + BatchNorm eval + ReLU per layer), shared_mlp.py:6-35."""
+    i = 0
+    while (p + f"layers.{i}.weight") in sd:
+        w = sd[p + f"layers.{i}.weight"]
+        x = torch.einsum("oc,bc...->bo...", w.reshape(w.shape[0], w.shape[1]), x) + \
+            sd[p + f"layers.{i}.bias"].view((1, -1) + (1,) * (x.ndim - 2))
+        rm, rv = sd[p + f"layers.{i + 1}.running_mean"], sd[p + f"layers.{i + 1}.running_var"]
+        sh = (1, -1) + (1,) * (x.ndim - 2)
+        x = (x - rm.view(sh)) / torch.sqrt(rv.view(sh) + 1e-5) * sd[p + f"layers.{i + 1}.weight"].view(sh) + \
+            sd[p + f"layers.{i + 1}.bias"].view(sh)
+        x = F.relu(x)
+        i += 3
+    return x
+
+
+def sa_module_forward(sd, p, features, coords, num_centers, radii, num_neighbors):
+    """PointNetSAModule.forward, R/.../pvcnn/modules/pointnet.py:100-111 with BallQuery.forward (ball_query.py:16-34):
+    FPS -> per radius (ball query -> group (coords - centre | features) -> SharedMLP(dim=2) -> max over neighbours)."""
+    t = lambda a: torch.from_numpy(a)
+    c = coords.contiguous().numpy()
+    centers = t(ops_np.gather_features_forward(c, ops_np.furthest_point_sampling(c, num_centers)))
+    outs = []
+    for j, (r, u) in enumerate(zip(radii, num_neighbors)):
+        idx = ops_np.ball_query(centers.numpy(), c, r, u)
+        g = t(ops_np.grouping_forward(c, idx)) - centers.unsqueeze(-1)
+        if features is not None:
+            g = torch.cat([g, t(ops_np.grouping_forward(features.contiguous().numpy(), idx))], dim=1)
+        outs.append(_shared_mlp_n(sd, p + f"mlps.{j}.", g).max(dim=-1).values)
+    return (torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]), centers
+
+
+def fp_module_forward(sd, p, points_coords, centers_coords, centers_features, points_features=None):
+    """PointNetFPModule.forward, pointnet.py:122-135: 3-NN inverse-distance interpolation (+ skip features) -> SharedMLP."""
+    out, _, _ = ops_np.three_nearest_neighbors_interpolate_forward(points_coords.contiguous().numpy(),
+                                                                   centers_coords.contiguous().numpy(),
+                                                                   centers_features.contiguous().numpy())
+    x = torch.from_numpy(out)
+    if points_features is not None:
+        x = torch.cat([x, points_features], dim=1)
+    return _shared_mlp_n(sd, p + "mlp.", x)
+
+
 def pvcnn_encoder_forward(sd, p, xyz, resolutions=(24, 12)):
     """PVCNNEncoder.forward, R/models/modules/pc_encoders.py:87-115 over PVCNN.forward
     (R/.../pvcnn/pvcnn_base.py:114-140): xyz [B,N,3] -> z_pc [B,C_out,out_features]."""

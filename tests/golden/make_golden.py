@@ -273,6 +273,58 @@ def trained_golden(man):
     return man
 
 
+def pointnet_golden():
+    """Set-abstraction family (SURVEY.md finding 1: the FPS / ball-query / grouping / 3-NN side of the operator extension is
+    reached through PointNetSAModule / PointNetFPModule, i.e. PVCNN2 and PointNet2SSG) and the grasp classifier
+    (grasp_classifier.py:13-143): the unmodified reference classes over the CPU backend (oracle/ops_np.py), checkpoint-like
+    state (trained_like_), seeded construction so that the product's mirrors reproduce the weights bit for bit."""
+    sys.modules.setdefault("trimesh", types.ModuleType("trimesh"))      # utils/gripper.py imports it at module level only
+    from grasp_ldm.models.modules.ext.pvcnn.modules.pointnet import PointNetFPModule, PointNetSAModule
+    from grasp_ldm.models.modules.ext.pvcnn.pointnet2 import PointNet2SSG
+    from grasp_ldm.models.modules.ext.pvcnn.pvcnn_base import PVCNN2
+    from grasp_ldm.models.grasp_classifier import PointsBasedGraspClassifier
+    np_ = lambda x: x.detach().cpu().numpy()
+    g = torch.Generator().manual_seed(31)
+    out, man = {}, {}
+    pcs = torch.cat([synthetic_clouds(1, seed=1234, dist="S"), synthetic_clouds(1, seed=99, dist="G") * 0.6]).transpose(1, 2).contiguous()
+    extra = torch.randn(2, 3, 1024, generator=g) * 0.5
+    with torch.no_grad():
+        # multi-radius set abstraction and feature propagation on their own
+        torch.manual_seed(3)
+        sa = _models.trained_like_(PointNetSAModule(num_centers=128, radius=[0.2, 0.4], num_neighbors=[16, 48], in_channels=5,
+                                                    out_channels=[(16, 32), (24, 40)]), 5).eval()
+        f5 = torch.randn(2, 5, 1024, generator=g)
+        sa_f, sa_c = sa((f5, pcs))
+        torch.manual_seed(4)
+        fp = _models.trained_like_(PointNetFPModule(in_channels=72 + 5, out_channels=(32, 16)), 6).eval()
+        fp_f, _ = fp((pcs, sa_c, sa_f, f5))
+        out.update(sa_in=np_(f5), sa_features=np_(sa_f), sa_centers=np_(sa_c), fp_features=np_(fp_f))
+        man["sa"], man["fp"] = manifest(sa.state_dict()), manifest(fp.state_dict())
+        torch.manual_seed(0)
+        ssg = _models.trained_like_(PointNet2SSG(width_multiplier=0.5), 7).eval()
+        out["ssg_in"] = np_(torch.cat([pcs, extra], 1))
+        out["ssg_out"] = np_(ssg(torch.cat([pcs, extra], 1)))
+        man["ssg"] = manifest(ssg.state_dict())
+        torch.manual_seed(0)
+        p2 = _models.trained_like_(PVCNN2(extra_feature_channels=0, width_multiplier=0.5, voxel_resolution_multiplier=0.5), 8).eval()
+        out["pvcnn2_out"] = np_(p2(pcs))
+        man["pvcnn2"] = manifest(p2.state_dict())
+        torch.manual_seed(0)
+        cls = PointsBasedGraspClassifier(
+            num_pc_points=1024 + 64,
+            points_backbone_config=dict(type="PVCNN", args=dict(in_channels=3, extra_feature_channels=1, scale_channels=0.25,
+                                                                scale_voxel_resolution=0.5, num_blocks=(1, 1, 1, 1))),
+            loss_config=types.SimpleNamespace(classification_loss=dict(type="BCEClassificationLoss", args={})))
+        cls = _models.trained_like_(cls, 9).eval()
+        grasp_pts = torch.randn(2, 64, 3, generator=g) * 0.3
+        _, preds = cls(pcs.transpose(1, 2).contiguous(), grasp_pts, compute_loss=False)
+        out.update(cls_grasp_points=np_(grasp_pts), cls_preds=np_(preds))
+        man["classifier"] = manifest(cls.state_dict())
+    np.savez_compressed(f"{HERE}/pointnet_family.npz", coords=np_(pcs), **out)
+    with open(f"{HERE}/pointnet_manifest.json", "w") as f:
+        json.dump(man, f, indent=0, sort_keys=True)
+
+
 def manifest(sd):
     out = {}
     for k, v in sd.items():
@@ -291,7 +343,8 @@ def main():
             man = trained_golden(man)
             with open(f"{HERE}/state_dict_manifest.json", "w") as f:
                 json.dump(man, f, indent=0, sort_keys=True)
-        for tag, fn in (("normalize", normalize_golden), ("edm", edm_golden), ("ppc_ldm", ppc_ldm_golden)):
+        for tag, fn in (("normalize", normalize_golden), ("edm", edm_golden), ("ppc_ldm", ppc_ldm_golden),
+                        ("pointnet", pointnet_golden)):
             if tag in only:
                 fn()
         return
@@ -356,6 +409,7 @@ def main():
     normalize_golden()
     edm_golden()
     ppc_ldm_golden()
+    pointnet_golden()
     print("golden fixtures written to", HERE)
 
 
