@@ -13,6 +13,13 @@ LIB_PATH = os.path.join(_HERE, "libgraspldm_b200.so")
 P = c_void_p  # device / host pointers travel as integers
 
 
+class GldmSamplerArgs(Structure):
+    _fields_ = [("x_init", c_void_p), ("z_obj", c_void_p), ("n", c_int), ("grasps_per_obj", c_int), ("sched_kind", c_int),
+                ("n_steps", c_int), ("coef", c_void_p), ("timesteps", c_void_p), ("times", c_void_p), ("te", c_void_p),
+                ("clip_sample", c_int), ("noise", c_void_p), ("seed", c_ulonglong), ("cls_emb", c_void_p),
+                ("x_out", c_void_p), ("x_all", c_void_p)]
+
+
 class GldmResNetCfg(Structure):
     _fields_ = [("L", c_int), ("n_stages", c_int), ("ch", c_int * 6), ("emb_dim", c_int), ("cond_ch", c_int),
                 ("cond_dim", c_int), ("groups", c_int), ("time_cond", c_int), ("fourier_half", c_int),
@@ -86,6 +93,12 @@ _SIGS = {
     "gldm_normalize_clouds": [P, P, P, P, c_int, c_int, P, P, P, P],
     "gldm_sa_mlp_max_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P],
     "gldm_se_gate_relu_f32": [P, P, P, c_int, c_int, c_int, P, P],
+    "gldm_sampler_run_ex_f32": [POINTER(GldmResNetCfg), P, POINTER(GldmSamplerArgs), P],
+    "gldm_sampler_run_ex_tc": [POINTER(GldmResNetCfg), P, P, POINTER(GldmSamplerArgs), P],
+    "gldm_denoiser_forward_ex_f32": [POINTER(GldmResNetCfg), P, P, P, P, P, P, c_int, P, P],
+    "gldm_denoiser_forward_ex_tc": [POINTER(GldmResNetCfg), P, P, P, P, P, P, P, c_int, P, P],
+    "gldm_time_embed_table_f": [POINTER(GldmResNetCfg), P, P, c_int, P, P],
+    "gldm_class_embed": [P, P, P, c_int, c_int, P, P],
 }
 _SIGS.update({"gldm_last_error": [], "gldm_version": [], "gldm_launch_count": []})
 _RESTYPES = {"gldm_last_error": c_char_p, "gldm_launch_count": c_ulonglong, "gldm_voxel_ws_bytes": c_longlong, "gldm_conv3d_tc16_weight_bytes": c_longlong,

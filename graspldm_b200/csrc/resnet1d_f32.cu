@@ -78,7 +78,9 @@ struct ResNetParams {
   const float* tf_sample;  // mode 1, continuous time (elucidated sampler: c_noise(sigma)); used when non-NULL
   int n_steps;
   const int* timesteps;    // device [n_steps]
-  const float* coef;       // device [n_steps][8]
+  const float* times_f;    // device [n_steps] continuous time (evaluation programs); used when non-NULL
+  const float* cls_emb;    // [n_obj][emb] added to the time embedding (class-conditioned denoiser) or NULL
+  const float* coef;       // device [n_steps][8] (DDPM / DDIM) or [n_steps][16] (GLDM_SCHED_EDM)
   int sched_kind, clip;
   const float* noise;      // [n_steps][n][L] or null
   unsigned long long seed;
@@ -384,6 +386,9 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
   float* s_four = s_h1 + S * 64;        // [S][36]
   float* s_x = s_four + S * 36;         // [32]   state, row m = l*S + s
   float* s_eps = s_x + 32;              // [32]
+  float* s_y = s_eps + 32;              // [32]   evaluation programs: second / third state vector, network input
+  float* s_z = s_y + 32;
+  float* s_xin = s_z + 32;
 
   const GldmResNetCfg& cfg = p.cfg;
   const ResNetLayout& lay = p.lay;
@@ -406,6 +411,8 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
       }
     }
     s_x[tid] = v;
+    s_y[tid] = 0.f;
+    s_z[tid] = 0.f;
     if (p.mode == 0 && p.x_all && s0 + s < p.n) p.x_all[(size_t)(s0 + s) * L + l] = v;
   }
   // ---- input (conditioning) embedding: SiLU(Linear(z_cond))  (resnets.py:531-533,596) - once per launch
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
       for (int idx = tid; idx < S * fd; idx += 256) {
         const int s = idx / fd, j = idx - s * fd;
         float tf = 0.f;
-        if (p.mode == 0) tf = (float)p.timesteps[step];
+        if (p.mode == 0) tf = p.times_f ? p.times_f[step] : (float)p.timesteps[step];
         else if (s0 + s < p.n) tf = p.tf_sample ? p.tf_sample[s0 + s] : (float)p.t_sample[s0 + s];
         float v = tf;
         if (j > 0) {
@@ -456,10 +463,29 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
         float a = __ldg(W + lay.tm_b2 + e);
         const float* w = W + lay.tm_w2 + e * emb;
         for (int j = 0; j < emb; ++j) a = fmaf(__ldg(w + j), s_h1[s * 64 + j], a);
+        if (p.cls_emb) a += __ldg(p.cls_emb + (size_t)(min(s0 + s, p.n - 1) / p.gpo) * emb + e);    // class_conditioned_resnet.py:96-98
         s_te[s * 64 + e] = a;
       }
       __syncthreads();
     }
+    // ---- network input: the state itself, or (evaluation programs) c_in * x_in with the stochastic churn added
+    const bool edm = p.mode == 0 && p.sched_kind == GLDM_SCHED_EDM;
+    if (tid < 32) {
+      float v = s_x[tid];
+      if (edm) {
+        const float* cf = p.coef + (size_t)step * kEvalRow;
+        const int l = tid / S, s = tid % S, slot = (int)cf[8];
+        float z = 0.f;
+        if (slot >= 0 && s0 + s < p.n)
+          z = p.noise ? __ldg(p.noise + ((size_t)slot * p.n + s0 + s) * L + l)
+                      : philox_normal(p.seed, (unsigned)(s0 + s), (unsigned)slot, (unsigned)l);
+        v = eval_input(cf, v, z);
+        s_xin[tid] = v;
+        v = __fmul_rn(cf[0], v);
+      }
+      s_eps[tid] = v;                       // init_conv reads the (scaled) input from here
+    }
+    __syncthreads();
     // ---- u[s][e] = sum_r silu(latent_emb[s][r][e])   (ResnetBlock.mlp's SiLU, hoisted; :183-197)
     for (int idx = tid; idx < S * emb; idx += 256) {
       const int s = idx / emb, e = idx - s * emb;
@@ -477,7 +503,7 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
           const int ll = l + j - 3;
-          if (ll >= 0 && ll < L) a = fmaf(__ldg(W + lay.init_w + co * 7 + j), s_x[ll * S + s], a);
+          if (ll >= 0 && ll < L) a = fmaf(__ldg(W + lay.init_w + co * 7 + j), s_eps[ll * S + s], a);
         }
         X[(size_t)co * CS + PAD + m] = a;
       }
@@ -512,7 +538,14 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
       for (int ch = 0; ch < cl; ++ch) a = fmaf(__ldg(W + lay.fc_w + ch), xp[(size_t)ch * CS], a);
       const int l = lane / S, s = lane % S;
       const bool valid = s0 + s < p.n;
-      if (p.mode == 0) {
+      if (edm) {
+        const float* cf = p.coef + (size_t)step * kEvalRow;
+        float x = s_x[lane], y = s_y[lane], z = s_z[lane];
+        eval_update(cf, s_xin[lane], a, p.clip, x, y, z);
+        s_x[lane] = x; s_y[lane] = y; s_z[lane] = z;
+        const int slot = (int)cf[9];
+        if (p.x_all && valid && slot >= 0) p.x_all[((size_t)slot * p.n + s0 + s) * L + l] = x;
+      } else if (p.mode == 0) {
         const float* cf = p.coef + (size_t)step * 8;
         const float x = s_x[lane];
         float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(cf[0], a)), cf[1]);
@@ -567,7 +600,7 @@ __global__ void __launch_bounds__(256, 1) resnet_kernel(const ResNetParams p) {
 template <int L>
 static size_t resnet_smem_bytes() {
   using T = Tile<L>;
-  return sizeof(float) * ((256 + 256 + 384) * T::CS + 2 * kWStage + T::S * (64 + 256 + 64 + 64 + 36) + 64);
+  return sizeof(float) * ((256 + 256 + 384) * T::CS + 2 * kWStage + T::S * (64 + 256 + 64 + 64 + 36) + 160);
 }
 
 static int launch_resnet(const ResNetParams& p, cudaStream_t s) {
@@ -679,6 +712,57 @@ extern "C" int gldm_sampler_run_f32(const GldmResNetCfg* cfg, const float* prepa
   rc = launch_resnet(p, s);
   cudaFreeAsync(scratch, s);
   return rc;
+}
+
+extern "C" int gldm_sampler_run_ex_f32(const GldmResNetCfg* cfg, const float* prepared, const GldmSamplerArgs* a, void* stream) {
+  ResNetParams p = {};
+  int rc = fill_common(p, cfg, prepared);
+  if (rc) return rc;
+  GLDM_REQUIRE(a, "sampler_run_ex: null arguments");
+  GLDM_REQUIRE(cfg->time_cond, "sampler_run_ex: the denoiser must be time conditioned");
+  GLDM_REQUIRE(a->n >= 0 && a->grasps_per_obj > 0 && a->n_steps > 0, "sampler_run_ex: bad sizes");
+  if (a->n == 0) return GLDM_OK;
+  GLDM_REQUIRE(a->x_init && a->z_obj && a->x_out && a->coef, "sampler_run_ex: null pointer");
+  const bool edm = a->sched_kind == GLDM_SCHED_EDM;
+  GLDM_REQUIRE(a->sched_kind == GLDM_SCHED_DDPM || a->sched_kind == GLDM_SCHED_DDIM || edm, "sampler_run_ex: bad scheduler");
+  GLDM_REQUIRE(edm ? a->times != nullptr : (a->timesteps != nullptr || a->times != nullptr),
+               "sampler_run_ex: the fp32 kernel needs the (device) time of every evaluation");
+  p.mode = 0; p.n = a->n; p.gpo = a->grasps_per_obj; p.x_in = a->x_init; p.z_cond = a->z_obj;
+  p.n_steps = a->n_steps; p.timesteps = a->timesteps; p.times_f = a->times; p.coef = a->coef; p.sched_kind = a->sched_kind;
+  p.clip = a->clip_sample; p.noise = a->noise; p.seed = a->seed; p.cls_emb = a->cls_emb; p.x_out = a->x_out; p.x_all = a->x_all;
+  return launch_resnet(p, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_denoiser_forward_ex_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x, const int* t,
+                                            const float* tf, const float* z_cond, const float* cls_emb, int n, float* eps,
+                                            void* stream) {
+  ResNetParams p = {};
+  int rc = fill_common(p, cfg, prepared);
+  if (rc) return rc;
+  GLDM_REQUIRE(n >= 0, "denoiser_forward_ex: bad n");
+  if (n == 0) return GLDM_OK;
+  GLDM_REQUIRE(x && z_cond && eps && (t || tf || !cfg->time_cond), "denoiser_forward_ex: null pointer");
+  p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.t_sample = t; p.tf_sample = tf; p.cls_emb = cls_emb;
+  p.x_out = eps;
+  return launch_resnet(p, (cudaStream_t)stream);
+}
+
+// cls_embed of the class-conditioned denoiser: SiLU(Linear(1 -> emb))   R/grasp_ldm/models/modules/class_conditioned_resnet.py:43-46
+__global__ void class_embed_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ cls,
+                                   int n, int emb, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * emb) return;
+  const int e = i % emb;
+  const float a = fmaf(__ldg(w + e), __ldg(cls + i / emb), __ldg(b + e));
+  out[i] = silu_acc(a);
+}
+
+extern "C" int gldm_class_embed(const float* w, const float* b, const float* cls, int n, int emb, float* out, void* stream) {
+  GLDM_REQUIRE(n <= 0 || (w && b && cls && out), "class_embed: null pointer");
+  GLDM_REQUIRE(n >= 0 && emb > 0, "class_embed: bad sizes");
+  if (n == 0) return GLDM_OK;
+  class_embed_kernel<<<ceil_div(n * emb, 256), 256, 0, (cudaStream_t)stream>>>(w, b, cls, n, emb, out);
+  return check_launch("class_embed_kernel");
 }
 
 extern "C" int gldm_denoiser_forward_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x,

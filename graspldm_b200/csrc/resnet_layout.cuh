@@ -105,4 +105,37 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
   return (l & 1) ? rad * sn : rad * cs;
 }
 
+// ---------------------------------------------------------------------------------------------
+// evaluation programs (GLDM_SCHED_EDM): the elucidated samplers as a list of network evaluations, one 16-float row each
+//   [0] c_in  [1] c_skip  [2] c_out  [3] kind  [4..7] k0..k3  [8] noise slot (-1: none)  [9] x_all slot (-1: none)
+// state per (sample, position): x (current), y, z.  D = c_skip * x_in + c_out * net(c_in * x_in)   (Karras et al. eq. 7,
+// R/grasp_ldm/models/diffusion/elucidated_diffusion.py:126-150), clamped to [-1, 1] when the caller asks for it.
+//   kind 0  stochastic Heun, first evaluation (:214-237):  x_in = x + k0 * (k3 * noise)   [k0 = sqrt(s_hat^2 - s^2), k3 = S_noise]
+//           d = (x_in - D) / k1 [s_hat];  x <- x_in + k2 * d [k2 = s_next - s_hat];  y <- x_in;  z <- d
+//   kind 1  second-order correction (:239-256):  x_in = x;  d' = (x_in - D) / k1 [s_next];  x <- y + k2 * (z + d') [k2 = (s_next - s_hat) / 2]
+//   kind 2  DPM-Solver++(2M) (:282-313):  x_in = x;  dd = k0 * D + k1 * y [1 - gamma, gamma];  x <- k2 * x - k3 * dd;  y <- D
+// ---------------------------------------------------------------------------------------------
+constexpr int kEvalRow = 16;
+__device__ __forceinline__ float eval_input(const float* cf, float x, float noise) {
+  return ((int)cf[3] == 0) ? __fadd_rn(x, __fmul_rn(cf[4], __fmul_rn(cf[7], noise))) : x;
+}
+__device__ __forceinline__ void eval_update(const float* cf, float xin, float net, int clip, float& x, float& y, float& z) {
+  float D = __fadd_rn(__fmul_rn(cf[1], xin), __fmul_rn(cf[2], net));
+  if (clip) D = fminf(fmaxf(D, -1.0f), 1.0f);
+  const int kind = (int)cf[3];
+  if (kind == 0) {
+    const float d = __fdiv_rn(__fsub_rn(xin, D), cf[5]);
+    x = __fadd_rn(xin, __fmul_rn(cf[6], d));
+    y = xin;
+    z = d;
+  } else if (kind == 1) {
+    const float d2 = __fdiv_rn(__fsub_rn(xin, D), cf[5]);
+    x = __fadd_rn(y, __fmul_rn(cf[6], __fadd_rn(z, d2)));
+  } else {
+    const float dd = __fadd_rn(__fmul_rn(cf[4], D), __fmul_rn(cf[5], y));
+    x = __fsub_rn(__fmul_rn(cf[6], xin), __fmul_rn(cf[7], dd));
+    y = D;
+  }
+}
+
 }  // namespace gldm

@@ -47,8 +47,8 @@ constexpr int SM_PTAB = SM_PAR + PAR_FLOATS * 4;          // [MAXRJ][5] int16: o
 constexpr int SM_JD = SM_PTAB + MAXRJ * 5 * 2 + 16;       // [MAXRJ] uint4 job descriptors read by the epilogue warps
 constexpr int SM_XG = SM_JD + MAXRJ * 16;                 // GroupNorm exchange [4 groups][4 positions][32] float2
 constexpr int SM_XL = SM_XG + 4 * 4 * 32 * 8;             // row exchange [128 rows][4 warp-groups] float2
-constexpr int SM_X = SM_XL + 128 * 4 * 8;                 // state [32][4]
-constexpr int SM_BAR = SM_X + 32 * 4 * 4;
+constexpr int SM_X = SM_XL + 128 * 4 * 8;                 // state x [32][4], then y, z (evaluation programs), x_in, scaled input
+constexpr int SM_BAR = SM_X + 5 * 32 * 4 * 4;
 constexpr int SM_CHUNKS = SM_BAR + 256;
 constexpr int SM_OPS = SM_CHUNKS + MAXCHUNKS * 8;
 constexpr int SM_OPBEG = SM_OPS + MAXOPS * 16;
@@ -651,6 +651,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     float v = 0.f;
     if (cta_s0 + s < p.n) v = __ldg(p.x_in + (size_t)(cta_s0 + s) * L + l);
     s_x[s * L + l] = v;
+    s_x[128 + s * L + l] = 0.f;
+    s_x[256 + s * L + l] = 0.f;
     if (p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
   }
   // ---- weight-chunk and UMMA op tables of one step (only the convolution / projection blocks of a job's image are
@@ -827,7 +829,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
       const float* film_step = p.film + (film_row0 + (size_t)step * p.film_stride);
-      // ---- init_conv: Conv1d(1 -> 4, k7, p3) on the state -> residual stream and operand (warp-group 0: 4 channels)
+      // ---- network input: the state, or (evaluation programs) c_in * x_in with the stochastic churn added
+      const bool edm = p.mode == 0 && p.sched_kind == GLDM_SCHED_EDM;
+      float* s_y = s_x + 128;
+      float* s_z = s_x + 256;
+      float* s_xin = s_x + 384;
+      float* s_sc = s_x + 512;
+      if (e.g == 0) {
+        float v = s_x[e.s * 4 + e.pos];
+        if (edm) {
+          const float* cf = p.coef + (size_t)step * kEvalRow;
+          const int slot = (int)__ldg(cf + 8);
+          float z = 0.f;
+          if (slot >= 0 && cta_s0 + e.s < p.n)
+            z = p.noise ? __ldg(p.noise + ((size_t)slot * p.n + cta_s0 + e.s) * L + e.pos)
+                        : philox_normal(p.seed, (unsigned)(cta_s0 + e.s), (unsigned)slot, (unsigned)e.pos);
+          float c4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) c4[i] = __ldg(cf + i);
+          v = eval_input(c4, v, z);
+          s_xin[e.s * 4 + e.pos] = v;
+          v = __fmul_rn(c4[0], v);
+        }
+        s_sc[e.s * 4 + e.pos] = v;
+        bar_wg(0);
+      }
+      // ---- init_conv: Conv1d(1 -> 4, k7, p3) on the input -> residual stream and operand (warp-group 0: 4 channels)
       if (e.g == 0) {
         float v[4];
 #pragma unroll
@@ -836,7 +863,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
 #pragma unroll
           for (int t = 0; t < 7; ++t) {
             const int ll = e.pos + t - 3;
-            if (ll >= 0 && ll < 4) a = fmaf(__ldg(W + lay.init_w + c * 7 + t), s_x[e.s * 4 + ll], a);
+            if (ll >= 0 && ll < 4) a = fmaf(__ldg(W + lay.init_w + c * 7 + t), s_sc[e.s * 4 + ll], a);
           }
           v[c] = a;
         }
@@ -895,7 +922,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
               for (int w = 0; w < 4; ++w) eps += e.xl()[e.row * 4 + w].x;
               const int l = e.pos, s = e.s;
               const bool ok = cta_s0 + s < p.n;
-              if (p.mode == 0) {
+              if (edm) {
+                float c16[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) c16[i] = __ldg(p.coef + (size_t)step * kEvalRow + i);
+                float x = s_x[s * 4 + l], y = s_y[s * 4 + l], z = s_z[s * 4 + l];
+                eval_update(c16, s_xin[s * 4 + l], eps, p.clip, x, y, z);
+                s_x[s * 4 + l] = x; s_y[s * 4 + l] = y; s_z[s * 4 + l] = z;
+                const int slot = (int)c16[9];
+                if (p.x_all && ok && slot >= 0) p.x_all[((size_t)slot * p.n + cta_s0 + s) * L + l] = x;
+              } else if (p.mode == 0) {
                 const float* cf = p.coef + (size_t)step * 8;
                 const float x = s_x[s * 4 + l];
                 float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));

@@ -121,6 +121,7 @@ struct TcParams {
   // multi-channel scale (+1 each) / shift of resnets.py:163-175: GroupNorm affine and FiLM as ONE multiply-add.
   const float* film;
   int film_stride;
+  const float* cls_emb;    // [n_obj][EMB] added to the time embedding (class-conditioned denoiser) or NULL
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -815,6 +816,7 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
           if (cfg.time_cond) {
             const int ti = (p.mode == 0) ? step : min(s0 + s, p.n - 1);
             te = __ldg(p.te + (size_t)ti * EMB + e);
+            if (p.cls_emb) te += __ldg(p.cls_emb + (size_t)(min(s0 + s, p.n - 1) / p.gpo) * EMB + e);
           }
           float a = 0.f;
           for (int r = 0; r < R; ++r) { const float z = te + s_inemb[(s * 3 + r) * EMB + e]; a += z / (1.0f + __expf(-z)); }
@@ -1220,7 +1222,8 @@ template <int EMB>
 __global__ void __launch_bounds__(256) film_table_kernel(const float* __restrict__ W, ResNetLayout lay, FilmJobs fj, int R,
                                                          int cond_dim, const float* __restrict__ z_cond, int z_div,
                                                          const float* __restrict__ te, int te_per_block, int n_steps,
-                                                         int stride, float* __restrict__ film) {
+                                                         int stride, const float* __restrict__ cls_emb,
+                                                         float* __restrict__ film) {
   constexpr int TS = 32;                        // steps per tile
   __shared__ float s_ie[4 * EMB];
   __shared__ float s_u[TS][EMB];
@@ -1240,7 +1243,8 @@ __global__ void __launch_bounds__(256) film_table_kernel(const float* __restrict
     __syncthreads();
     for (int idx = tid; idx < nt * EMB; idx += 256) {
       const int e = idx % EMB, t = idx / EMB;
-      const float tv = __ldg(te + (size_t)(te_per_block ? b : t0 + t) * EMB + e);
+      float tv = __ldg(te + (size_t)(te_per_block ? b : t0 + t) * EMB + e);
+      if (cls_emb) tv += __ldg(cls_emb + (size_t)(b / z_div) * EMB + e);      // class_conditioned_resnet.py:96-98
       float a = 0.f;
       for (int r = 0; r < R; ++r) { const float zz = tv + s_ie[r * EMB + e]; a += zz / (1.0f + __expf(-zz)); }
       s_u[t][e] = a;
@@ -1331,7 +1335,7 @@ static int launch_rows(TcParams& p, cudaStream_t s) {
     return GLDM_ECUDA;
   }
   film_table_kernel<16><<<blocks, 256, 0, s>>>(p.W, p.lay, fj, p.cfg.cond_ch, p.cfg.cond_dim, p.z_cond, p.mode == 0 ? 1 : p.gpo,
-                                               p.te, p.mode == 0 ? 0 : 1, steps, p.film_stride, film);
+                                               p.te, p.mode == 0 ? 0 : 1, steps, p.film_stride, p.cls_emb, film);
   int rc = check_launch("film_table_kernel");
   if (rc == GLDM_OK) {
     p.film = film;
@@ -1344,6 +1348,14 @@ static int launch_rows(TcParams& p, cudaStream_t s) {
 
 static int launch_tc(TcParams& p, cudaStream_t s) {
   p.prof = g_tc_prof;
+  if (p.mode == 0 && p.sched_kind == GLDM_SCHED_EDM) {
+    // evaluation programs (elucidated samplers) are implemented by the row-major kernel
+    if (!rows_supported(p.cfg)) {
+      set_error("sampler_tc: the elucidated samplers run on the row-major kernel (fpc latent denoiser); use precision fp32 for this model");
+      return GLDM_ENOSUP;
+    }
+    return launch_rows(p, s);
+  }
   const bool want_rows = g_tc_rows == 1 || (g_tc_rows < 0 && p.n > 16 * kNumSMs);
   if (want_rows && p.mode != 2 && rows_supported(p.cfg)) return launch_rows(p, s);
   if (p.cfg.L != 4) return launch_tc_l<16, 1>(p, s);
@@ -1517,6 +1529,59 @@ extern "C" int gldm_sampler_run_tc_dev(const GldmResNetCfg* cfg, const float* ra
   p.n_steps = n_steps; p.coef = coef_dev; p.sched_kind = sched_kind; p.clip = clip_sample;
   p.noise = noise; p.seed = seed; p.x_out = x_out; p.x_all = x_all;
   return launch_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_time_embed_table_f(const GldmResNetCfg* cfg, const float* raw, const float* times_dev, int count,
+                                       float* te_dev, void* stream) {
+  int rc = check_tc_cfg(cfg);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->time_cond && raw && times_dev && te_dev && count > 0, "time_embed_table_f: bad arguments");
+  TcParams p = {};
+  p.cfg = *cfg;
+  make_layout(*cfg, p.lay);
+  p.W = raw;
+  return run_time_embed(p, nullptr, count, te_dev, (cudaStream_t)stream, times_dev);
+}
+
+extern "C" int gldm_sampler_run_ex_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const GldmSamplerArgs* a,
+                                      void* stream) {
+  TcParams p = {};
+  int rc = fill_tc(p, cfg, raw, pack);
+  if (rc) return rc;
+  GLDM_REQUIRE(a, "sampler_run_ex_tc: null arguments");
+  GLDM_REQUIRE(cfg->time_cond, "sampler_run_ex_tc: the sampler needs a time-conditioned denoiser configuration");
+  GLDM_REQUIRE(a->n >= 0 && a->grasps_per_obj > 0 && a->n_steps > 0, "sampler_run_ex_tc: bad sizes");
+  if (a->n == 0) return GLDM_OK;
+  GLDM_REQUIRE(a->x_init && a->z_obj && a->x_out && a->coef && a->te, "sampler_run_ex_tc: null pointer");
+  GLDM_REQUIRE(a->sched_kind == GLDM_SCHED_DDPM || a->sched_kind == GLDM_SCHED_DDIM || a->sched_kind == GLDM_SCHED_EDM,
+               "sampler_run_ex_tc: bad scheduler");
+  p.mode = 0; p.n = a->n; p.gpo = a->grasps_per_obj; p.x_in = a->x_init; p.z_cond = a->z_obj; p.te = a->te;
+  p.n_steps = a->n_steps; p.coef = a->coef; p.sched_kind = a->sched_kind; p.clip = a->clip_sample;
+  p.noise = a->noise; p.seed = a->seed; p.cls_emb = a->cls_emb; p.x_out = a->x_out; p.x_all = a->x_all;
+  return launch_tc(p, (cudaStream_t)stream);
+}
+
+extern "C" int gldm_denoiser_forward_ex_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,
+                                           const int* t, const float* tf, const float* z_cond, const float* cls_emb, int n,
+                                           float* eps, void* stream) {
+  TcParams p = {};
+  int rc = fill_tc(p, cfg, raw, pack);
+  if (rc) return rc;
+  GLDM_REQUIRE(cfg->time_cond, "denoiser_forward_ex_tc: needs a time-conditioned denoiser configuration");
+  GLDM_REQUIRE(n >= 0, "denoiser_forward_ex_tc: bad n");
+  if (n == 0) return GLDM_OK;
+  GLDM_REQUIRE(x && (t || tf) && z_cond && eps, "denoiser_forward_ex_tc: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* d_te = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_te), sizeof(float) * p.cfg.emb_dim * (size_t)n, s) != cudaSuccess) {
+    set_error("denoiser_forward_ex_tc: cudaMallocAsync failed");
+    return GLDM_ECUDA;
+  }
+  p.mode = 1; p.n = n; p.gpo = 1; p.x_in = x; p.z_cond = z_cond; p.te = d_te; p.n_steps = 1; p.x_out = eps; p.cls_emb = cls_emb;
+  rc = run_time_embed(p, t, n, d_te, s, tf);
+  if (rc == GLDM_OK) rc = launch_tc(p, s);
+  cudaFreeAsync(d_te, s);
+  return rc;
 }
 
 extern "C" int gldm_denoiser_forward_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x,

@@ -1,18 +1,24 @@
 """ElucidatedDiffusion (R/grasp_ldm/models/diffusion/elucidated_diffusion.py) - sampling side.
 
-Same constructor arguments, `sample(use_dpmpp=..., batch_size=..., z_cond=..., num_sample_steps=..., clamp=...,
-return_all=...)`, `sample_normal` (stochastic Heun sampler of Karras et al. 2022, :179-258) and `sample_using_dpmpp`
-(DPM-Solver++ 2M, :260-315).  Every network evaluation is one launch of the denoiser kernel (tensor-core or strict fp32,
-continuous time c_noise(sigma) = log(sigma) / 4 through `gldm_denoiser_forward_*_ftime`); the update rule between two
-evaluations is O(16 bytes) per sample and stays in a handful of element-wise operations on the device.  Unlike the
-DDPM / DDIM path the loop is not fused into one persistent launch yet.
+Same constructor arguments and the same `sample(use_dpmpp=..., batch_size=..., z_cond=..., num_sample_steps=..., clamp=...,
+return_all=...)` / `sample_normal` / `sample_using_dpmpp` / `preconditioned_network_forward` surface.  A sampler is compiled
+on the host into an EVALUATION PROGRAM - one 16-float row per network evaluation holding the preconditioning constants
+(c_in, c_skip, c_out), the update rule (stochastic Heun first / second evaluation, DPM-Solver++(2M) step) and its scalar
+coefficients - and the persistent sampler kernel executes the whole program in ONE launch: network evaluations, churn noise,
+Heun / multistep updates (csrc/resnet_layout.cuh::eval_update; GLDM_SCHED_EDM in include/graspldm_b200.h).  No Python loop
+and no element-wise launches between evaluations.
 
-Keyword-only extensions for parity runs: `x_init` (the N(0,1) draw that is scaled by sigma_0) and `noise`
-([num_sample_steps, B, C, L] N(0,1) draws of the stochastic sampler), `precision`."""
-from math import sqrt
+Keyword-only extensions: `x_init` (the N(0,1) draw that is scaled by sigma_0), `noise` ([num_sample_steps, B, C, L] N(0,1)
+draws of the stochastic sampler) for parity runs, `seed` for the in-kernel Philox stream, `grasps_per_object` when z_cond
+holds one row per object, `precision`."""
+import math
 
 import torch
 from torch import nn
+
+from . import engine
+
+HEUN_FIRST, HEUN_SECOND, DPMPP_2M = 0.0, 1.0, 2.0
 
 
 class ElucidatedDiffusion(nn.Module):
@@ -33,95 +39,111 @@ class ElucidatedDiffusion(nn.Module):
     def device(self):
         return next(self.net.parameters()).device
 
-    # preconditioning (Table 1 of the paper; reference :111-124)
-    def c_skip(self, sigma):
-        return (self.sigma_data ** 2) / (sigma ** 2 + self.sigma_data ** 2)
+    def forward(self, *a, **k):
+        raise NotImplementedError("ElucidatedDiffusion.forward (training loss) is outside the generation path")
 
-    def c_out(self, sigma):
-        return sigma * self.sigma_data * (self.sigma_data ** 2 + sigma ** 2) ** -0.5
-
-    def c_in(self, sigma):
-        return 1 * (sigma ** 2 + self.sigma_data ** 2) ** -0.5
-
-    def c_noise(self, sigma):
-        return torch.log(sigma.clamp(min=1e-20)) * 0.25
-
-    def preconditioned_network_forward(self, noised_x, sigma, *, z_cond=None, self_cond=None, clamp=False, precision=None):
-        batch, device = noised_x.shape[0], noised_x.device
-        if isinstance(sigma, float):
-            sigma = torch.full((batch,), sigma, device=device)
-        padded = sigma.view(-1, 1, 1)
-        net_out = self.net(self.c_in(padded) * noised_x, time=self.c_noise(sigma), z_cond=z_cond,
-                           precision=precision or self.precision)
-        out = self.c_skip(padded) * noised_x + self.c_out(padded) * net_out
-        return out.clamp(-1.0, 1.0) if clamp else out
-
+    # ------------------------------------------------------------------ host-side scalar tables (fp32, as the reference)
     def sample_schedule(self, num_sample_steps=None):
-        n = num_sample_steps if num_sample_steps is not None else self.num_sample_steps
-        inv_rho = 1 / self.rho
-        steps = torch.arange(n, device=self.device, dtype=torch.float32)
-        sigmas = (self.sigma_max ** inv_rho + steps / (n - 1) * (self.sigma_min ** inv_rho - self.sigma_max ** inv_rho)) ** self.rho
-        return torch.nn.functional.pad(sigmas, (0, 1), value=0.0)
+        """sigma_i of Karras et al. eq. 5 with a trailing 0 (:152-168)"""
+        n = self.num_sample_steps if num_sample_steps is None else num_sample_steps
+        i = torch.arange(n, dtype=torch.float32)
+        lo, hi = self.sigma_max ** (1 / self.rho), self.sigma_min ** (1 / self.rho)
+        return torch.cat([(lo + i / (n - 1) * (hi - lo)) ** self.rho, torch.zeros(1)]).to(self.device)
+
+    def _precondition(self, sigma):
+        """(c_in, c_skip, c_out, c_noise) of Table 1 for a float sigma, rounded as fp32 tensor arithmetic would (:111-124)"""
+        s = torch.tensor(float(sigma), dtype=torch.float32)
+        sd = self.sigma_data
+        var = s ** 2 + sd ** 2
+        return (float(var ** -0.5), float(sd ** 2 / var), float(s * sd * var ** -0.5), float(torch.log(s.clamp(min=1e-20)) * 0.25))
+
+    def _row(self, sigma, kind, k, noise_slot=-1, out_slot=-1):
+        c_in, c_skip, c_out, c_noise = self._precondition(sigma)
+        return [c_in, c_skip, c_out, kind, *k, float(noise_slot), float(out_slot)] + [0.0] * 6, c_noise
+
+    def heun_program(self, n):
+        """stochastic sampler of Algorithm 2 (:179-258): per step one evaluation at sigma_hat, and - unless the step lands on
+        sigma = 0 - the second-order correction at sigma_next"""
+        sig = self.sample_schedule(n).cpu()
+        churn = min(self.S_churn / n, math.sqrt(2) - 1)
+        rows, times = [], []
+        for i in range(n):
+            s, s_next = float(sig[i]), float(sig[i + 1])
+            s_hat = s + (churn if self.S_tmin <= s <= self.S_tmax else 0.0) * s
+            last = s_next == 0
+            r, t = self._row(s_hat, HEUN_FIRST, [math.sqrt(s_hat ** 2 - s ** 2), s_hat, s_next - s_hat, self.S_noise],
+                             noise_slot=i, out_slot=i + 1 if last else -1)
+            rows.append(r), times.append(t)
+            if not last:
+                r, t = self._row(s_next, HEUN_SECOND, [0.0, s_next, 0.5 * (s_next - s_hat), 0.0], out_slot=i + 1)
+                rows.append(r), times.append(t)
+        return torch.tensor(times, dtype=torch.float32), torch.tensor(rows, dtype=torch.float32), float(sig[0])
+
+    def dpmpp_program(self, n):
+        """DPM-Solver++(2M) in the sigma parametrisation (:260-315): t = -log sigma, h = t_next - t, multistep weights from
+        the previous step size - all as 0-dim fp32 tensors, as there"""
+        sig = self.sample_schedule(n).cpu()
+        t_of = lambda s: s.log().neg()
+        rows, times = [], []
+        for i in range(n):
+            t, t_next = t_of(sig[i]), t_of(sig[i + 1])
+            h = t_next - t
+            if i == 0 or float(sig[i + 1]) == 0:
+                w_new, w_old = 1.0, 0.0
+            else:
+                gamma = -1 / (2 * ((t - t_of(sig[i - 1])) / h))
+                w_new, w_old = float(1 - gamma), float(gamma)
+            r, tm = self._row(float(sig[i]), DPMPP_2M, [w_new, w_old, float(t_next.neg().exp() / t.neg().exp()), float((-h).expm1())],
+                              out_slot=i + 1)
+            rows.append(r), times.append(tm)
+        return torch.tensor(times, dtype=torch.float32), torch.tensor(rows, dtype=torch.float32), float(sig[0])
+
+    # ------------------------------------------------------------------ sampling
+    def _run(self, program, batch_size, z_cond, clamp, return_all, x_init, noise, precision, seed, grasps_per_object, n_slots,
+             cls_cond=None):
+        times, rows, sigma0 = program
+        dev = self.device
+        shape = (batch_size, self.channels, self.seq_length)
+        x0 = x_init.to(dev).view(shape) if x_init is not None else torch.randn(shape, device=dev)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if noise is None else 0
+        if hasattr(self.net, "cls_embed") and cls_cond is None:
+            raise RuntimeError("the class-conditioned denoiser needs cls_cond=")
+        x, x_all = engine.sampler_program(self.net, sigma0 * x0, z_cond, grasps_per_object, times, rows, n_slots, clip_sample=clamp,
+                                          noise=noise, seed=seed, return_all=return_all, precision=precision or self.precision,
+                                          cls_cond=cls_cond)
+        return x, (list(x_all) if return_all else [])
 
     def sample(self, **kwargs):
         if kwargs.pop("use_dpmpp"):
             return self.sample_using_dpmpp(**kwargs)
         return self.sample_normal(**kwargs)
 
-    def _draw(self, given, shape):
-        return given.to(self.device).view(shape) if given is not None else torch.randn(shape, device=self.device)
-
     @torch.no_grad()
     def sample_normal(self, batch_size=16, z_cond=None, num_sample_steps=None, clamp=False, return_all=False, *, x_init=None,
-                      noise=None, precision=None):
-        n = num_sample_steps if num_sample_steps is not None else self.num_sample_steps
-        shape = (batch_size, self.channels, self.seq_length)
-        sigmas = self.sample_schedule(n)
-        gammas = torch.where((sigmas >= self.S_tmin) & (sigmas <= self.S_tmax), min(self.S_churn / n, sqrt(2) - 1), 0.0)
-        x = sigmas[0] * self._draw(x_init, shape)
-        all_x = [x]
-        for i, (sigma, sigma_next, gamma) in enumerate(zip(sigmas[:-1].tolist(), sigmas[1:].tolist(), gammas[:-1].tolist())):
-            eps = self.S_noise * self._draw(None if noise is None else noise[i], shape)
-            sigma_hat = sigma + gamma * sigma
-            x_hat = x + sqrt(sigma_hat ** 2 - sigma ** 2) * eps
-            out = self.preconditioned_network_forward(x_hat, sigma_hat, z_cond=z_cond, clamp=clamp, precision=precision)
-            d = (x_hat - out) / sigma_hat
-            x_next = x_hat + (sigma_next - sigma_hat) * d
-            if sigma_next != 0:           # second-order (Heun) correction
-                out_next = self.preconditioned_network_forward(x_next, sigma_next, z_cond=z_cond, clamp=clamp,
-                                                               precision=precision)
-                d_prime = (x_next - out_next) / sigma_next
-                x_next = x_hat + 0.5 * (sigma_next - sigma_hat) * (d + d_prime)
-            x = x_next
-            all_x += [x] if return_all else []
-        return x, all_x
+                      noise=None, precision=None, seed=None, grasps_per_object=1, cls_cond=None, **kwargs):
+        n = self.num_sample_steps if num_sample_steps is None else num_sample_steps
+        x, xs = self._run(self.heun_program(n), batch_size, z_cond, clamp, return_all, x_init, noise, precision, seed,
+                          grasps_per_object, n + 1, cls_cond)
+        return x, xs
 
     @torch.no_grad()
-    def sample_using_dpmpp(self, batch_size=16, z_cond=None, num_sample_steps=20, clamp=False, return_all=False, *,
-                           x_init=None, precision=None):
-        n = num_sample_steps if num_sample_steps is not None else self.num_sample_steps
-        sigmas = self.sample_schedule(n)
-        shape = (batch_size, self.channels, self.seq_length)
-        x = sigmas[0] * self._draw(x_init, shape)
-        all_x = [x]
-        sigma_fn = lambda t: t.neg().exp()
-        t_fn = lambda sigma: sigma.log().neg()
-        old_denoised = None
-        for i in range(len(sigmas) - 1):
-            denoised = self.preconditioned_network_forward(x, sigmas[i].item(), z_cond=z_cond, clamp=clamp, precision=precision)
-            t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
-            h = t_next - t
-            if old_denoised is None or sigmas[i + 1] == 0:
-                denoised_d = denoised
-            else:
-                h_last = t - t_fn(sigmas[i - 1])
-                r = h_last / h
-                gamma = -1 / (2 * r)
-                denoised_d = (1 - gamma) * denoised + gamma * old_denoised
-            x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_d
-            all_x += [x] if return_all else []
-            old_denoised = denoised
-        return x, all_x
+    def sample_using_dpmpp(self, batch_size=16, z_cond=None, num_sample_steps=20, clamp=False, return_all=False, *, x_init=None,
+                           precision=None, seed=None, grasps_per_object=1, cls_cond=None, **kwargs):
+        n = self.num_sample_steps if num_sample_steps is None else num_sample_steps
+        x, xs = self._run(self.dpmpp_program(n), batch_size, z_cond, clamp, return_all, x_init, None, precision, seed,
+                          grasps_per_object, n + 1, cls_cond)
+        return x, xs
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("ElucidatedDiffusion.forward (training loss) is outside the generation path")
+    @torch.no_grad()
+    def preconditioned_network_forward(self, noised_x, sigma, *, z_cond=None, self_cond=None, clamp=False, precision=None,
+                                       grasps_per_object=1, cls_cond=None):
+        """D(x; sigma) = c_skip x + c_out F(c_in x; c_noise(sigma))  (eq. 7, :126-150) as a one-evaluation program."""
+        if torch.is_tensor(sigma):
+            if sigma.numel() > 1 and not bool((sigma == sigma.reshape(-1)[0]).all()):
+                raise NotImplementedError("per-sample noise levels occur only in the training loss")
+            sigma = float(sigma.reshape(-1)[0])
+        row, t = self._row(sigma, DPMPP_2M, [1.0, 0.0, 0.0, -1.0])               # x <- 0 * x + 1 * D
+        x, _ = engine.sampler_program(self.net, noised_x, z_cond, grasps_per_object, torch.tensor([t]), torch.tensor([row]), 1,
+                                      clip_sample=clamp, precision=precision or self.precision, cls_cond=cls_cond)
+        return x

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GldmResNetCfg
+from ._lib import GldmResNetCfg, GldmSamplerArgs
 
 PRECISIONS = ("fp32", "bf16")   # "bf16": tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation)
 
@@ -188,7 +188,20 @@ def _cond3d(z):
     return z
 
 
-def resnet_forward(module, x, time, z_cond, precision="fp32"):
+def class_embedding(module, cls_cond, rows, dev):
+    """cls_embed of a class-conditioned denoiser (class_conditioned_resnet.py:43-46, 96-98): cls_cond [rows] / [rows,1] ->
+    f32 [rows, emb] = SiLU(Linear(1 -> emb)), added to the time embedding inside the kernels."""
+    lin = module.cls_embed[0]
+    c = cls_cond.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+    if c.numel() != rows:
+        raise RuntimeError(f"class conditioning has {c.numel()} entries for {rows} conditioning rows")
+    out = torch.empty((rows, lin.out_features), device=dev, dtype=torch.float32)
+    _lib.call("gldm_class_embed", lin.weight.detach().float().contiguous().data_ptr(), lin.bias.detach().float().contiguous().data_ptr(),
+              c.data_ptr(), rows, lin.out_features, out.data_ptr(), _stream(dev))
+    return out
+
+
+def resnet_forward(module, x, time, z_cond, precision="fp32", cls_cond=None):
     """One network evaluation: x [B,1,L], time int[B] or None, z_cond [B,C,Dc] -> [B,1,L]."""
     _check_precision(precision)
     _require_cuda(x, "x")
@@ -197,6 +210,22 @@ def resnet_forward(module, x, time, z_cond, precision="fp32"):
     B, _, L = x.shape
     pk = packed_resnet(module, L, z_cond.shape[1])
     dev = x.device
+    if cls_cond is not None:
+        with torch.cuda.device(dev):
+            xin = x.reshape(B, L).contiguous().float()
+            zc = z_cond.contiguous().float()
+            out = torch.empty((B, L), device=dev, dtype=torch.float32)
+            ftime = torch.is_floating_point(time)
+            t32 = time.to(device=dev, dtype=torch.float32 if ftime else torch.int32).contiguous()
+            ce = class_embedding(module, cls_cond, B, dev)
+            ti, tf = (None, t32.data_ptr()) if ftime else (t32.data_ptr(), None)
+            if precision == "bf16":
+                _lib.call("gldm_denoiser_forward_ex_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pk.tc_pack().data_ptr(),
+                          xin.data_ptr(), ti, tf, zc.data_ptr(), ce.data_ptr(), B, out.data_ptr(), _stream(dev))
+            else:
+                _lib.call("gldm_denoiser_forward_ex_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(), ti, tf,
+                          zc.data_ptr(), ce.data_ptr(), B, out.data_ptr(), _stream(dev))
+        return out.view(B, 1, L)
     with torch.cuda.device(dev):
         xin = x.reshape(B, L).contiguous().float()
         zc = z_cond.contiguous().float()
@@ -214,11 +243,78 @@ def resnet_forward(module, x, time, z_cond, precision="fp32"):
     return out.view(B, 1, L)
 
 
+SCHED_EDM = 2
+
+
+def _per_object_class(cls_cond, n, n_obj, gpo):
+    """class conditioning per conditioning row: [n_obj] as is; [n] (the reference's per-sample layout) must be constant
+    over the grasps of an object"""
+    c = cls_cond.reshape(-1)
+    if c.numel() == n_obj:
+        return c
+    if c.numel() == n:
+        c2 = c.reshape(n_obj, gpo)
+        if not bool((c2 == c2[:, :1]).all()):
+            raise NotImplementedError("class conditioning must be the same for all grasps of an object")
+        return c2[:, 0].contiguous()
+    raise RuntimeError(f"class conditioning has {c.numel()} entries for {n} samples of {n_obj} objects")
+
+
+def sampler_program(denoiser, x_init, z_obj, grasps_per_obj, times, rows, n_out_slots, clip_sample=False, noise=None, seed=0,
+                    return_all=False, precision="fp32", cls_cond=None, sched_kind=SCHED_EDM):
+    """Persistent sampler on an evaluation program (the elucidated samplers: one launch for all network evaluations and
+    updates).  times f32[n_evals] (c_noise of every evaluation), rows f32[n_evals,16] (include/graspldm_b200.h,
+    GldmSamplerArgs) - both host tensors.  Returns (x [n,1,D], x_all [n_out_slots,n,1,D] or None)."""
+    _check_precision(precision)
+    _require_cuda(x_init, "x_init")
+    _require_cuda(z_obj, "z_cond")
+    n, _, D = x_init.shape
+    z_obj = _cond3d(z_obj)
+    pk = packed_resnet(denoiser, D, z_obj.shape[1])
+    dev = x_init.device
+    n_evals = rows.shape[0]
+    with torch.cuda.device(dev):
+        xin = x_init.reshape(n, D).contiguous().float()
+        zc = z_obj.contiguous().float()
+        out = torch.empty((n, D), device=dev, dtype=torch.float32)
+        x_all = torch.empty((n_out_slots, n, D), device=dev, dtype=torch.float32) if return_all else None
+        nz = None
+        if noise is not None:
+            _require_cuda(noise, "noise")
+            nz = noise.reshape(-1, n, D).contiguous().float()
+        cf = rows.detach().to(device=dev, dtype=torch.float32).contiguous()
+        tm = times.detach().to(device=dev, dtype=torch.float32).contiguous()
+        a = GldmSamplerArgs()
+        a.x_init, a.z_obj, a.n, a.grasps_per_obj = xin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj)
+        a.sched_kind, a.n_steps, a.coef, a.times = int(sched_kind), n_evals, cf.data_ptr(), tm.data_ptr()
+        a.clip_sample, a.noise, a.seed = int(bool(clip_sample)), (nz.data_ptr() if nz is not None else None), int(seed) & (2 ** 64 - 1)
+        a.x_out, a.x_all = out.data_ptr(), (x_all.data_ptr() if x_all is not None else None)
+        ce = None
+        if cls_cond is not None:
+            ce = class_embedding(denoiser, _per_object_class(cls_cond, n, zc.shape[0], int(grasps_per_obj)), zc.shape[0], dev)
+            a.cls_emb = ce.data_ptr()
+        if precision == "bf16":
+            te = torch.empty((n_evals, pk.cfg.emb_dim), device=dev, dtype=torch.float32)
+            _lib.call("gldm_time_embed_table_f", ctypes.byref(pk.cfg), pk.raw.data_ptr(), tm.data_ptr(), n_evals, te.data_ptr(), _stream(dev))
+            a.te = te.data_ptr()
+            pack = pk.tc_pack()
+            tok = SECTIONS.start("sampler", dev)
+            _lib.call("gldm_sampler_run_ex_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pack.data_ptr(), ctypes.byref(a), _stream(dev))
+        else:
+            tok = SECTIONS.start("sampler", dev)
+            _lib.call("gldm_sampler_run_ex_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), ctypes.byref(a), _stream(dev))
+        SECTIONS.stop(tok)
+    return out.view(n, 1, D), (x_all.view(n_out_slots, n, 1, D) if x_all is not None else None)
+
+
 def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kind, clip_sample, noise=None,
-                seed=0, return_all=False, precision="fp32"):
+                seed=0, return_all=False, precision="fp32", cls_cond=None):
     """Whole reverse-diffusion loop in one launch.  x_T [n,1,D]; z_obj [n_obj,C,Dc]; timesteps list[int];
     coef float32 [n_steps,8] (host).  Returns (x_0 [n,1,D], x_all [n_steps+1,n,1,D] or None)."""
     _check_precision(precision)
+    if cls_cond is not None:
+        return _sampler_run_class_conditioned(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kind, clip_sample,
+                                              noise, seed, return_all, precision, cls_cond)
     _require_cuda(x_T, "x_T")
     _require_cuda(z_obj, "z_cond")
     n, _, D = x_T.shape
@@ -254,6 +350,40 @@ def sampler_run(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kin
             _lib.call("gldm_sampler_run_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), xin.data_ptr(),
                       zc.data_ptr(), *tail)
         SECTIONS.stop(tok)
+    return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
+
+
+def _sampler_run_class_conditioned(denoiser, x_T, z_obj, grasps_per_obj, timesteps, coef, sched_kind, clip_sample, noise, seed,
+                                   return_all, precision, cls_cond):
+    """DDPM / DDIM loop of a ClassTimeConditionedResNet1D: the class embedding of every object rides along
+    (GldmSamplerArgs.cls_emb) and is added to the time embedding of every step inside the kernel."""
+    _require_cuda(x_T, "x_T")
+    _require_cuda(z_obj, "z_cond")
+    n, _, D = x_T.shape
+    z_obj = _cond3d(z_obj)
+    pk = packed_resnet(denoiser, D, z_obj.shape[1])
+    dev = x_T.device
+    n_steps = len(timesteps)
+    with torch.cuda.device(dev):
+        xin = x_T.reshape(n, D).contiguous().float()
+        zc = z_obj.contiguous().float()
+        out = torch.empty((n, D), device=dev, dtype=torch.float32)
+        x_all = torch.empty((n_steps + 1, n, D), device=dev, dtype=torch.float32) if return_all else None
+        nz = noise.reshape(n_steps, n, D).contiguous().float() if noise is not None else None
+        ts = torch.tensor([int(t) for t in timesteps], dtype=torch.int32, device=dev)
+        cf = coef.detach().to(device=dev, dtype=torch.float32).contiguous()
+        ce = class_embedding(denoiser, _per_object_class(cls_cond, n, zc.shape[0], int(grasps_per_obj)), zc.shape[0], dev)
+        a = GldmSamplerArgs()
+        a.x_init, a.z_obj, a.n, a.grasps_per_obj = xin.data_ptr(), zc.data_ptr(), n, int(grasps_per_obj)
+        a.sched_kind, a.n_steps, a.coef, a.timesteps = int(sched_kind), n_steps, cf.data_ptr(), ts.data_ptr()
+        a.clip_sample, a.noise, a.seed = int(bool(clip_sample)), (nz.data_ptr() if nz is not None else None), int(seed) & (2 ** 64 - 1)
+        a.cls_emb, a.x_out, a.x_all = ce.data_ptr(), out.data_ptr(), (x_all.data_ptr() if x_all is not None else None)
+        if precision == "bf16":
+            _, te = pk.tc_tables(timesteps, coef)
+            a.te = te.data_ptr()
+            _lib.call("gldm_sampler_run_ex_tc", ctypes.byref(pk.cfg), pk.raw.data_ptr(), pk.tc_pack().data_ptr(), ctypes.byref(a), _stream(dev))
+        else:
+            _lib.call("gldm_sampler_run_ex_f32", ctypes.byref(pk.cfg), pk.prepared.data_ptr(), ctypes.byref(a), _stream(dev))
     return out.view(n, 1, D), (x_all.view(n_steps + 1, n, 1, D) if x_all is not None else None)
 
 

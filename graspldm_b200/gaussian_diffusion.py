@@ -56,7 +56,8 @@ class GaussianDiffusion1D(nn.Module):
         """Reverse diffusion.  Reference arguments: z_cond [B,C,Dc] (already repeated per grasp), batch_size,
         return_all, device.  Extensions (keyword-only): x_T and per-step `noise` [n_steps,B,1,D] for parity runs,
         `grasps_per_object` when z_cond holds one row per OBJECT (avoids materialising the repeat),
-        `seed` for the fused RNG.  Extra kwargs (e.g. metas=) are ignored, as the reference's denoiser does."""
+        `seed` for the fused RNG, `cls_cond` for a ClassTimeConditionedResNet1D (default: kwargs["metas"]["mode_cls"], as
+        the reference's denoiser reads it).  Other extra kwargs (e.g. metas=) are ignored, as the reference's denoiser does."""
         device = z_cond.device if z_cond is not None and z_cond.is_cuda else torch.device(device)
         if x_T is None:
             # gaussian_diffusion.py:253 - drawn on the CPU generator, then moved
@@ -74,7 +75,10 @@ class GaussianDiffusion1D(nn.Module):
                                      for t in ts])
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if noise is None else 0
+        cls_cond = None
+        if hasattr(self.model, "cls_embed"):
+            cls_cond = self.model.class_condition(kwargs.get("cls_cond"), kwargs)
         x0, x_all = engine.sampler_run(self.model, x_T, z_cond, grasps_per_object, ts, coef, kind, self.clip_sample,
                                        noise=noise, seed=seed, return_all=return_all,
-                                       precision=kwargs.get("precision", self.precision))
+                                       precision=kwargs.get("precision", self.precision), cls_cond=cls_cond)
         return x0, (list(x_all) if return_all else [])

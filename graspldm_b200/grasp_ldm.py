@@ -56,10 +56,12 @@ class GraspLatentDDM(nn.Module):
         z_pc = self.vae_model.encode_pc(xyz)
         n = z_pc.shape[0] * num_grasps
         if self.is_elucidated_diffusion:
-            # the reference forwards **kwargs (use_dpmpp, num_sample_steps, clamp) to ElucidatedDiffusion.sample (:214-219)
-            kw = {k: kwargs[k] for k in ("use_dpmpp", "num_sample_steps", "clamp", "x_init", "noise", "precision") if k in kwargs}
-            z_rep = z_pc.repeat_interleave(num_grasps, dim=0)
-            out, all_outs = self.diffusion_model.sample(z_cond=z_rep, batch_size=n, return_all=return_intermediate, **kw)
+            # the reference forwards **kwargs (use_dpmpp, num_sample_steps, clamp) to ElucidatedDiffusion.sample (:214-219);
+            # the object latent is indexed per grasp inside the kernel instead of being repeated in HBM
+            kw = {k: kwargs[k] for k in ("use_dpmpp", "num_sample_steps", "clamp", "x_init", "noise", "precision", "seed", "cls_cond")
+                  if k in kwargs}
+            out, all_outs = self.diffusion_model.sample(z_cond=z_pc, batch_size=n, return_all=return_intermediate,
+                                                        grasps_per_object=num_grasps, **kw)
             res = self.vae_model.decoder(out.squeeze(-2), z_pc, grasps_per_object=num_grasps)
             if not return_intermediate:
                 return (res, [])
@@ -68,7 +70,7 @@ class GraspLatentDDM(nn.Module):
                 _out = self.vae_model.decoder(all_outs[idx].squeeze(-2), z_pc, grasps_per_object=num_grasps)
                 step_outs.append([t.detach().cpu() for t in _out])
             return res, step_outs
-        sample_kw = {k: kwargs[k] for k in ("x_T", "noise", "seed", "device") if k in kwargs}
+        sample_kw = {k: kwargs[k] for k in ("x_T", "noise", "seed", "device", "cls_cond", "metas") if k in kwargs}
         out, all_outs = self.diffusion_model.sample(z_cond=z_pc, batch_size=n, return_all=return_intermediate,
                                                     grasps_per_object=num_grasps, **sample_kw)
         res = self.vae_model.decoder(out.squeeze(-2), z_pc, grasps_per_object=num_grasps)

@@ -176,3 +176,26 @@ class TimeConditionedResNet1D(_ResNetBase):
     def forward(self, x, *, time=None, z_cond=None, x_self_cond=None, **kwargs):
         assert time is not None
         return engine.resnet_forward(self, x, time, z_cond, precision=kwargs.get("precision", "fp32"))
+
+
+class ClassTimeConditionedResNet1D(TimeConditionedResNet1D):
+    """class_conditioned_resnet.py:9-122: the time-conditioned denoiser plus a class embedding
+    cls_embed = SiLU(Linear(1 -> emb)) that is added to the time embedding (:96-98).  forward(x, *, time, z_cond,
+    cls_cond [B,1]) - without cls_cond the class is read from kwargs["metas"]["mode_cls"], as the reference does."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.cls_embed = nn.Sequential(nn.Linear(1, self.emb_dim), nn.SiLU())
+
+    @staticmethod
+    def class_condition(cls_cond, kwargs, dtype=torch.float32):
+        if cls_cond is None:
+            assert "metas" in kwargs and "mode_cls" in kwargs["metas"], "Class conditioning tensor is required"
+            cls_cond = kwargs["metas"]["mode_cls"].unsqueeze(-1).reshape(-1, 1).to(dtype=dtype)
+        return cls_cond
+
+    @torch.no_grad()
+    def forward(self, x, *, time=None, z_cond=None, x_self_cond=None, cls_cond=None, **kwargs):
+        assert time is not None
+        cls_cond = self.class_condition(cls_cond, kwargs, x.dtype)
+        return engine.resnet_forward(self, x, time, z_cond, precision=kwargs.get("precision", "fp32"), cls_cond=cls_cond)

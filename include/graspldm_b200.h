@@ -151,6 +151,7 @@ int gldm_resnet_prepare(const GldmResNetCfg* cfg, const float* raw, float* prepa
  * restates them): coef[i] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt_or_eps, sigma, 0,0,0}. */
 #define GLDM_SCHED_DDPM 0
 #define GLDM_SCHED_DDIM 1
+#define GLDM_SCHED_EDM 2   /* evaluation program of the elucidated samplers, see GldmSamplerArgs */
 /* Whole T-step reverse diffusion in ONE launch  (GaussianDiffusion1D.sample,
  * R/models/diffusion/gaussian_diffusion.py:232-277 + TimeConditionedResNet1D.forward resnets.py:558-616):
  *   x_T f32[n,D] initial latents, z_obj f32[n_obj,cond_ch,cond_dim] per-object conditioning,
@@ -295,6 +296,46 @@ int gldm_pose_postprocess_rows(const float* tmrp, const float* logit, const floa
  * pc_out must not alias pc (the reference centres its argument in place; this entry leaves it untouched). */
 int gldm_normalize_clouds(const float* pc, const float* pc_shift, const float* pc_scale, const float* grasp_shift, int b,
                           int n, float* pc_out, float* pc_mean, float* grasp_mean, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Extended sampler / denoiser entry points: class conditioning and the elucidated samplers
+ * ------------------------------------------------------------------------------------------ */
+/* All pointers are DEVICE pointers.  sched_kind GLDM_SCHED_EDM runs an evaluation program: one 16-float row per network
+ * evaluation - [0] c_in [1] c_skip [2] c_out [3] kind [4..7] k0..k3 [8] noise slot (-1: none) [9] x_all slot (-1: none) -
+ *   kind 0  stochastic Heun, first evaluation   R/grasp_ldm/models/diffusion/elucidated_diffusion.py:214-237
+ *   kind 1  second-order correction             :239-256
+ *   kind 2  DPM-Solver++(2M) step               :282-313
+ * (formulas next to eval_update in csrc/resnet_layout.cuh).  x_all f32[slots][n][L]: slot 0 receives x_init. */
+typedef struct {
+  const float* x_init;       /* f32[n][L] */
+  const float* z_obj;        /* f32[n_obj][cond_ch][cond_dim], sample i uses row i / grasps_per_obj */
+  int n, grasps_per_obj;
+  int sched_kind;            /* GLDM_SCHED_DDPM / DDIM / EDM */
+  int n_steps;               /* network evaluations */
+  const float* coef;         /* f32[n_steps][8] (DDPM / DDIM, as gldm_sampler_run_*) or f32[n_steps][16] (EDM) */
+  const int* timesteps;      /* i32[n_steps]  (DDPM / DDIM; fp32 kernel only) */
+  const float* times;        /* f32[n_steps] continuous time c_noise(sigma) (EDM; fp32 kernel only) */
+  const float* te;           /* f32[n_steps][emb] time-embedding table (tensor-core kernels only, gldm_time_embed_table_f) */
+  int clip_sample;
+  const float* noise;        /* f32[noise slots][n][L] pre-drawn N(0,1) or NULL (in-kernel Philox keyed by seed) */
+  unsigned long long seed;
+  const float* cls_emb;      /* f32[n_obj][emb] added to the time embedding (class_conditioned_resnet.py:96-98) or NULL */
+  float* x_out;              /* f32[n][L] */
+  float* x_all;              /* NULL or f32[slots][n][L] */
+} GldmSamplerArgs;
+int gldm_sampler_run_ex_f32(const GldmResNetCfg* cfg, const float* prepared, const GldmSamplerArgs* args, void* stream);
+int gldm_sampler_run_ex_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const GldmSamplerArgs* args,
+                           void* stream);
+/* single evaluation with integer (t) or continuous (tf) time and an optional class embedding f32[n][emb] */
+int gldm_denoiser_forward_ex_f32(const GldmResNetCfg* cfg, const float* prepared, const float* x, const int* t,
+                                 const float* tf, const float* z_cond, const float* cls_emb, int n, float* eps, void* stream);
+int gldm_denoiser_forward_ex_tc(const GldmResNetCfg* cfg, const float* raw, const void* pack, const float* x, const int* t,
+                                const float* tf, const float* z_cond, const float* cls_emb, int n, float* eps, void* stream);
+/* time-embedding table from continuous times f32[count] -> f32[count][emb] */
+int gldm_time_embed_table_f(const GldmResNetCfg* cfg, const float* raw, const float* times_dev, int count, float* te_dev,
+                            void* stream);
+/* cls_embed: out f32[n][emb] = SiLU(w * cls + b)   (class_conditioned_resnet.py:43-46) */
+int gldm_class_embed(const float* w, const float* b, const float* cls, int n, int emb, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Set abstraction (PointNet++ / PVCNN2 side of the operator family), fused

@@ -112,9 +112,12 @@ def time_embedding(sd, p, time):
     return F.linear(F.gelu(h), sd[p + "time_mlp.3.weight"], sd[p + "time_mlp.3.bias"])
 
 
-def denoiser_forward(sd, p, x, time, z_cond, groups=4):
-    """TimeConditionedResNet1D.forward, resnets.py:558-616: eps prediction [B,1,D]."""
+def denoiser_forward(sd, p, x, time, z_cond, groups=4, cls_cond=None):
+    """TimeConditionedResNet1D.forward, resnets.py:558-616: eps prediction [B,1,D].  With cls_cond [B,1] the class-conditioned
+    variant (class_conditioned_resnet.py:48-122): SiLU(Linear(1 -> emb)) of the class is added to the time embedding."""
     emb = time_embedding(sd, p, time)
+    if cls_cond is not None:
+        emb = emb + F.silu(F.linear(cls_cond.reshape(-1, 1).to(x.dtype), sd[p + "cls_embed.0.weight"], sd[p + "cls_embed.0.bias"]))
     inp = F.silu(F.linear(z_cond, sd[p + "input_emb_layers.0.weight"], sd[p + "input_emb_layers.0.bias"]))
     if inp.ndim == 3:
         emb = emb.unsqueeze(-2).repeat(1, inp.shape[1], 1)
@@ -235,7 +238,7 @@ def pvcnn_encoder_forward(sd, p, xyz, resolutions=(24, 12)):
 
 # ----------------------------------------------------------------------------- sampling loop
 def ldm_sample(sd_ddm, z_cond, x_T, *, noise=None, num_inference_steps=None, kind="ddpm",
-               scheduler_kwargs=None, groups=4, return_all=False, prefix="diffusion_model.model."):
+               scheduler_kwargs=None, groups=4, return_all=False, prefix="diffusion_model.model.", cls_cond=None):
     """GaussianDiffusion1D.sample, R/models/diffusion/gaussian_diffusion.py:232-277.
     x_T [B,1,D]; noise: optional [n_steps,B,1,D] consumed in loop order (entry i for the i-th
     executed step; the t == 0 entry is ignored as in DDPMScheduler.step)."""
@@ -249,7 +252,7 @@ def ldm_sample(sd_ddm, z_cond, x_T, *, noise=None, num_inference_steps=None, kin
     allx = [x_T] if return_all else []
     for i, t in enumerate(timestep_list(sch.T, sch.num_inference_steps)):
         tb = torch.full((x.shape[0],), t, dtype=torch.long)
-        eps = denoiser_forward(sd_ddm, prefix, x, tb, z_cond, groups)
+        eps = denoiser_forward(sd_ddm, prefix, x, tb, z_cond, groups, cls_cond=cls_cond)
         x = sch.step(eps, t, x, None if noise is None else noise[i])
         if return_all:
             allx.append(x)

@@ -273,6 +273,36 @@ def trained_golden(man):
     return man
 
 
+def class_conditioned_golden():
+    """ClassTimeConditionedResNet1D (class_conditioned_resnet.py:9-122) with the fpc denoiser arguments: single evaluations
+    and a 10-step DDPM run of the reference GaussianDiffusion1D whose kwargs carry metas["mode_cls"] (gaussian_diffusion.py:271)."""
+    from grasp_ldm.models.diffusion.gaussian_diffusion import GaussianDiffusion1D
+    from grasp_ldm.models.modules.class_conditioned_resnet import ClassTimeConditionedResNet1D
+    cfg = Config.fromfile(CONFIGS["fpc"])
+    torch.manual_seed(0)
+    den = _models.trained_like_(ClassTimeConditionedResNet1D(**dict(cfg.model.ddm.model.args)["model"]["args"]), 4).eval()
+    g = torch.Generator().manual_seed(17)
+    B = 6
+    x, zc = torch.randn(B, 1, 4, generator=g), torch.randn(B, 3, 64, generator=g)
+    t = torch.tensor([0, 3, 250, 500, 990, 999])
+    cls = torch.tensor([0.0, 1.0, 1.0, 0.0, 2.0, -1.0]).view(B, 1)
+    with torch.no_grad():
+        eps = den(x, time=t, z_cond=zc, cls_cond=cls)
+        ddm_args = dict(cfg.model.ddm.model.args)
+        gd = GaussianDiffusion1D(model=den, n_dims=4, num_steps=1000, loss_type="l2", beta_schedule="linear", beta_start=5e-5,
+                                 beta_end=1e-3, noise_scheduler_type="ddpm", variance_type="fixed_large").eval()
+        gd.set_inference_timesteps(10)
+        noise = torch.randn(10, B, 1, 4, generator=g)
+        gd.noise_scheduler.injected_noise = list(noise)
+        torch.manual_seed(8)
+        x_T = torch.randn((B, 1, 4))
+        torch.manual_seed(8)
+        x0, _ = gd.sample(z_cond=zc, batch_size=B, device="cpu", metas=dict(mode_cls=cls.view(B)))
+    np.savez_compressed(f"{HERE}/cls_fpc.npz", x=x.numpy(), t=t.numpy(), z_cond=zc.numpy(), cls=cls.numpy(), eps=eps.numpy(),
+                        x_T=x_T.numpy(), noise=noise.numpy(), x0=x0.numpy(),
+                        cls_w=den.cls_embed[0].weight.detach().numpy(), cls_b=den.cls_embed[0].bias.detach().numpy())
+
+
 def pointnet_golden():
     """Set-abstraction family (SURVEY.md finding 1: the FPS / ball-query / grouping / 3-NN side of the operator extension is
     reached through PointNetSAModule / PointNetFPModule, i.e. PVCNN2 and PointNet2SSG) and the grasp classifier
@@ -344,7 +374,7 @@ def main():
             with open(f"{HERE}/state_dict_manifest.json", "w") as f:
                 json.dump(man, f, indent=0, sort_keys=True)
         for tag, fn in (("normalize", normalize_golden), ("edm", edm_golden), ("ppc_ldm", ppc_ldm_golden),
-                        ("pointnet", pointnet_golden)):
+                        ("pointnet", pointnet_golden), ("cls", class_conditioned_golden)):
             if tag in only:
                 fn()
         return
@@ -410,6 +440,7 @@ def main():
     edm_golden()
     ppc_ldm_golden()
     pointnet_golden()
+    class_conditioned_golden()
     print("golden fixtures written to", HERE)
 
 

@@ -252,3 +252,20 @@ def test_oracle_vs_reference_on_trained_like_state(name):
                                            num_inference_steps=steps, kind=kind)
         np.testing.assert_allclose(tm.numpy(), f["tmrp"], rtol=1e-4, atol=5e-5)
         np.testing.assert_allclose(lg.numpy(), f["logit"], rtol=1e-4, atol=5e-5)
+
+
+def test_oracle_class_conditioned_denoiser_vs_reference():
+    from graspldm_b200 import configs
+    from graspldm_b200.resnets import ClassTimeConditionedResNet1D
+    g = np.load(os.path.join(G, "cls_fpc.npz"))
+    torch.manual_seed(0)
+    den = _models.trained_like_(ClassTimeConditionedResNet1D(**configs.model_config("fpc")["denoiser"]), 4).eval()
+    np.testing.assert_array_equal(den.cls_embed[0].weight.detach().numpy(), g["cls_w"])
+    np.testing.assert_array_equal(den.cls_embed[0].bias.detach().numpy(), g["cls_b"])
+    sd = {"diffusion_model.model." + k: v.detach() for k, v in den.state_dict().items()}
+    t = lambda k: torch.from_numpy(g[k])
+    with torch.no_grad():
+        eps = M.denoiser_forward(sd, "diffusion_model.model.", t("x"), t("t"), t("z_cond"), cls_cond=t("cls"))
+        x0, _ = M.ldm_sample(sd, t("z_cond"), t("x_T"), noise=t("noise"), num_inference_steps=10, cls_cond=t("cls"))
+    np.testing.assert_allclose(eps.numpy(), g["eps"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(x0.numpy(), g["x0"], rtol=1e-4, atol=2e-5)
