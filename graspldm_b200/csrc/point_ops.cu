@@ -23,10 +23,15 @@ namespace gldm {
 // smallest k.  Encoded as a 32-bit key whose minimum wins.
 __device__ __forceinline__ unsigned fps_key(int k) { return ((unsigned)(k & 511) << 22) | (unsigned)k; }
 
-template <int PPT>
+// One CTA per cloud with FOUR points per thread where the cloud allows it (256 threads for 1024 points): a round is
+// distance update -> warp arg-max (two REDUX) -> one block barrier -> second-level arg-max over <= 32 warp results.
+// The winner's coordinates come from a shared-memory copy of the cloud (broadcast LDS, ~30 cycles) instead of a
+// global load (~an L2 round trip per round), and the small CTAs let 8 clouds share an SM at large batch.
+template <int PPT, bool SMEM>
 __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coords, int n, int m,
                                                    int* __restrict__ indices) {
   if (m <= 0) return;
+  extern __shared__ float s_pts[];           // SMEM: [3][n]
   const int b = blockIdx.x;
   const float* cx = coords + (size_t)b * 3 * n;
   const float* cy = cx + n;
@@ -38,6 +43,7 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
   __shared__ unsigned s_key[2][32];
 
   float px[PPT], py[PPT], pz[PPT], dist[PPT];
+  unsigned kk[PPT];                            // tie-break keys of this thread's points (0xffffffff: no point)
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     int k = tid + j * blockDim.x;
@@ -45,40 +51,43 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
     px[j] = v ? cx[k] : 0.f;
     py[j] = v ? cy[k] : 0.f;
     pz[j] = v ? cz[k] : 0.f;
-    dist[j] = 1e38f;   // sampling.cpp:53-54
+    dist[j] = v ? 1e38f : 0.f;   // sampling.cpp:53-54; a missing point can never exceed a real distance (>= 0) on bits
+    kk[j] = v ? fps_key(k) : 0xffffffffu;
+    if (SMEM && v) { s_pts[k] = px[j]; s_pts[n + k] = py[j]; s_pts[2 * n + k] = pz[j]; }
   }
+  if (SMEM) __syncthreads();
   int old = 0;
   if (tid == 0) out[0] = 0;
   for (int r = 1; r < m; ++r) {
-    const float x1 = __ldg(cx + old), y1 = __ldg(cy + old), z1 = __ldg(cz + old);
-    unsigned bits = 0u, key = 0xffffffffu;
+    const float x1 = SMEM ? s_pts[old] : __ldg(cx + old), y1 = SMEM ? s_pts[n + old] : __ldg(cy + old),
+                z1 = SMEM ? s_pts[2 * n + old] : __ldg(cz + old);
+    // running min-distances (d2 >= +0: bit order == value order), the thread's maximum first, then the smallest key
+    // among the points that reach it (ties inside a thread follow the same key order as across threads)
+    unsigned bits = 0u;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      int k = tid + j * blockDim.x;
-      if (k < n) {
-        float d = sqdist_ref(px[j] - x1, py[j] - y1, pz[j] - z1);
-        float d2 = fminf(d, dist[j]);
-        dist[j] = d2;
-        unsigned db = __float_as_uint(d2);        // d2 >= +0: bit order == value order
-        if (key == 0xffffffffu || db > bits) {    // first strictly greater within the thread
-          bits = db;
-          key = fps_key(k);
-        }
-      }
+      const float d = sqdist_ref(px[j] - x1, py[j] - y1, pz[j] - z1);
+      dist[j] = fminf(d, dist[j]);
+      bits = max(bits, __float_as_uint(dist[j]));
     }
+    unsigned key = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) key = min(key, __float_as_uint(dist[j]) == bits ? kk[j] : 0xffffffffu);
     // warp level: max distance, then min key among the maxima
-    unsigned wb = __reduce_max_sync(0xffffffffu, bits);
-    unsigned wk = __reduce_min_sync(0xffffffffu, bits == wb ? key : 0xffffffffu);
-    const int buf = r & 1;
-    if (lane == 0) {
-      s_bits[buf][wid] = wb;
-      s_key[buf][wid] = wk;
+    unsigned gb = __reduce_max_sync(0xffffffffu, bits);
+    unsigned gk = __reduce_min_sync(0xffffffffu, bits == gb ? key : 0xffffffffu);
+    if (nwarps > 1) {
+      const int buf = r & 1;
+      if (lane == 0) {
+        s_bits[buf][wid] = gb;
+        s_key[buf][wid] = gk;
+      }
+      __syncthreads();
+      unsigned b2 = lane < nwarps ? s_bits[buf][lane] : 0u;
+      unsigned k2 = lane < nwarps ? s_key[buf][lane] : 0xffffffffu;
+      gb = __reduce_max_sync(0xffffffffu, b2);
+      gk = __reduce_min_sync(0xffffffffu, (b2 == gb) ? k2 : 0xffffffffu);
     }
-    __syncthreads();
-    unsigned b2 = lane < nwarps ? s_bits[buf][lane] : 0u;
-    unsigned k2 = lane < nwarps ? s_key[buf][lane] : 0xffffffffu;
-    unsigned gb = __reduce_max_sync(0xffffffffu, b2);
-    unsigned gk = __reduce_min_sync(0xffffffffu, (b2 == gb) ? k2 : 0xffffffffu);
     old = (gk == 0xffffffffu) ? 0 : (int)(gk & 0x3fffffu);
     if (tid == 0) out[r] = old;
   }
@@ -87,40 +96,154 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
 // ------------------------------------------------------------------------------------------------
 // ball query                                     R/ball_query/ball_query.cu:19-50
 // ------------------------------------------------------------------------------------------------
+// Thread = centre: a CTA stages the cloud once in shared memory (12 n bytes) and every thread scans it in ascending
+// index for its own centre, two points per step as packed f32x2 operations (FADD2 / FMUL2 / FFMA2 round per element
+// like the scalar chain, so the indices stay bit-exact).  A point is one broadcast LDS for the whole warp, a hit is an
+// append to the thread's own list - no ballot / compaction - and the tail of every list (slots the reference pre-fills
+// with the first hit) is written by the whole CTA, coalesced.  ~6 thread instructions per (centre, point) pair.
+constexpr int kBqThreads = 128;
+constexpr int kBqMaxSmemPoints = 16384;
+template <bool SMEM>
+__global__ void __launch_bounds__(kBqThreads) ball_query_kernel(const float* __restrict__ centers,
+                                                                const float* __restrict__ points, int n, int m,
+                                                                float r2, int u, int* __restrict__ out) {
+  extern __shared__ float s_pts[];           // SMEM: [3][np], np = n rounded up to 2, the padding at +inf (never a hit)
+  __shared__ int s_cnt[kBqThreads], s_first[kBqThreads];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int np = (n + 1) & ~1;
+  const float* gx = points + (size_t)b * 3 * n;
+  if (SMEM) {
+    for (int k = tid; k < np; k += kBqThreads) {
+      const bool v = k < n;
+      s_pts[k] = v ? gx[k] : INFINITY;
+      s_pts[np + k] = v ? gx[n + k] : INFINITY;
+      s_pts[2 * np + k] = v ? gx[2 * n + k] : INFINITY;
+    }
+    __syncthreads();
+  }
+  const int j = blockIdx.x * kBqThreads + tid;
+  const bool valid = j < m;
+  const float* cc = centers + (size_t)b * 3 * m;
+  const float c0 = valid ? __ldg(cc + j) : 0.f, c1 = valid ? __ldg(cc + m + j) : 0.f, c2 = valid ? __ldg(cc + 2 * m + j) : 0.f;
+  const float2 cx = make_float2(c0, c0), cy = make_float2(c1, c1), cz = make_float2(c2, c2);
+  int* o = out + ((size_t)b * m + (valid ? j : 0)) * u;
+  int cnt = valid ? 0 : u, first = 0;
+  for (int k = 0; k < np; k += 2) {
+    float2 x, y, z;
+    if (SMEM) {
+      x = *reinterpret_cast<const float2*>(s_pts + k);
+      y = *reinterpret_cast<const float2*>(s_pts + np + k);
+      z = *reinterpret_cast<const float2*>(s_pts + 2 * np + k);
+    } else {
+      const bool v1 = k + 1 < n;
+      x = make_float2(__ldg(gx + k), v1 ? __ldg(gx + k + 1) : INFINITY);
+      y = make_float2(__ldg(gx + n + k), v1 ? __ldg(gx + n + k + 1) : INFINITY);
+      z = make_float2(__ldg(gx + 2 * n + k), v1 ? __ldg(gx + 2 * n + k + 1) : INFINITY);
+    }
+    // d = fma(dz, dz, fma(dx, dx, dy * dy)) with d* = centre - point (ball_query.cu:36-40, FMA chain of the reference build)
+    const float2 dx = __fadd2_rn(cx, make_float2(-x.x, -x.y)), dy = __fadd2_rn(cy, make_float2(-y.x, -y.y)),
+                 dz = __fadd2_rn(cz, make_float2(-z.x, -z.y));
+    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+    if (d.x < r2 && cnt < u) {
+      if (cnt == 0) first = k;
+      o[cnt++] = k;
+    }
+    if (d.y < r2 && cnt < u) {
+      if (cnt == 0) first = k + 1;
+      o[cnt++] = k + 1;
+    }
+    if ((k & 62) == 62 && __all_sync(0xffffffffu, cnt >= u)) break;
+  }
+  // the first hit pre-fills every slot; no hit leaves zeros (ball_query.cu:39-44): tails written by the whole CTA
+  s_cnt[tid] = cnt;
+  s_first[tid] = first;
+  __syncthreads();
+  const int nc = min(kBqThreads, m - (int)blockIdx.x * kBqThreads);
+  int* ob = out + ((size_t)b * m + (size_t)blockIdx.x * kBqThreads) * u;
+  for (int idx = tid; idx < nc * u; idx += kBqThreads) {
+    const int c = idx / u, slot = idx - c * u;
+    if (slot >= s_cnt[c]) ob[idx] = s_first[c];
+  }
+}
+
+// Small batches (latency): the warps of a CTA take the centres FOUR at a time; a 32-point chunk is read once (three LDS)
+// and tested against four centres held in registers (two packed pairs), ballot / popc compaction of the hits in ascending
+// point index, early exit when all four lists are full.  More parallelism per cloud than thread = centre, more
+// instructions per test.
 constexpr int kBqCentersPerBlock = 32;
-__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ centers,
-                                                         const float* __restrict__ points, int n, int m,
-                                                         float r2, int u, int* __restrict__ out) {
+template <bool SMEM>
+__global__ void __launch_bounds__(256) ball_query_warp_kernel(const float* __restrict__ centers,
+                                                              const float* __restrict__ points, int n, int m,
+                                                              float r2, int u, int* __restrict__ out) {
+  extern __shared__ float s_pts[];           // SMEM: [3][np], np = n rounded up to 32, the padding at +inf (never a hit)
   const int b = blockIdx.y;
-  const float* px = points + (size_t)b * 3 * n;
-  const float* py = px + n;
-  const float* pz = py + n;
+  const int np = (n + 31) & ~31;
+  const float* gx = points + (size_t)b * 3 * n;
+  if (SMEM) {
+    for (int k = threadIdx.x; k < np; k += blockDim.x) {
+      const bool v = k < n;
+      s_pts[k] = v ? gx[k] : INFINITY;
+      s_pts[np + k] = v ? gx[n + k] : INFINITY;
+      s_pts[2 * np + k] = v ? gx[2 * n + k] : INFINITY;
+    }
+    __syncthreads();
+  }
   const float* cc = centers + (size_t)b * 3 * m;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int j = blockIdx.x * kBqCentersPerBlock + wid; j < min(m, (blockIdx.x + 1) * kBqCentersPerBlock);
-       j += nw) {
-    const float cx = __ldg(cc + j), cy = __ldg(cc + m + j), cz = __ldg(cc + 2 * m + j);
-    int* o = out + ((size_t)b * m + j) * u;
-    int cnt = 0, first = 0;
-    for (int base = 0; base < n && cnt < u; base += 32) {
-      int k = base + lane;
-      bool hit = false;
-      if (k < n) {
-        float d2 = sqdist_ref(cx - __ldg(px + k), cy - __ldg(py + k), cz - __ldg(pz + k));
-        hit = d2 < r2;
+  const int j_end = min(m, (int)(blockIdx.x + 1) * kBqCentersPerBlock);
+  for (int j0 = blockIdx.x * kBqCentersPerBlock + 4 * wid; j0 < j_end; j0 += 4 * nw) {
+    float2 cxa, cya, cza, cxb, cyb, czb;     // centres (j0, j0+1) and (j0+2, j0+3); a missing centre repeats the last one
+    int jj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) jj[q] = min(j0 + q, j_end - 1);
+    cxa = make_float2(__ldg(cc + jj[0]), __ldg(cc + jj[1]));
+    cya = make_float2(__ldg(cc + m + jj[0]), __ldg(cc + m + jj[1]));
+    cza = make_float2(__ldg(cc + 2 * m + jj[0]), __ldg(cc + 2 * m + jj[1]));
+    cxb = make_float2(__ldg(cc + jj[2]), __ldg(cc + jj[3]));
+    cyb = make_float2(__ldg(cc + m + jj[2]), __ldg(cc + m + jj[3]));
+    czb = make_float2(__ldg(cc + 2 * m + jj[2]), __ldg(cc + 2 * m + jj[3]));
+    int cnt[4] = {0, 0, 0, 0}, first[4] = {0, 0, 0, 0};
+    for (int base = 0; base < np; base += 32) {
+      const int k = base + lane;
+      float x, y, z;
+      if (SMEM) {
+        x = s_pts[k]; y = s_pts[np + k]; z = s_pts[2 * np + k];
+      } else {
+        const bool valid = k < n;
+        x = valid ? __ldg(gx + k) : INFINITY;
+        y = valid ? __ldg(gx + n + k) : INFINITY;
+        z = valid ? __ldg(gx + 2 * n + k) : INFINITY;
       }
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      if (mask) {
-        if (cnt == 0) first = base + __ffs(mask) - 1;
-        int pos = cnt + __popc(mask & lt);
-        if (hit && pos < u) o[pos] = k;
-        cnt += __popc(mask);
+      const float2 nx = make_float2(-x, -x), ny = make_float2(-y, -y), nz = make_float2(-z, -z);
+      const float2 dxa = __fadd2_rn(cxa, nx), dya = __fadd2_rn(cya, ny), dza = __fadd2_rn(cza, nz);
+      const float2 dxb = __fadd2_rn(cxb, nx), dyb = __fadd2_rn(cyb, ny), dzb = __fadd2_rn(czb, nz);
+      const float2 da = __ffma2_rn(dza, dza, __ffma2_rn(dxa, dxa, __fmul2_rn(dya, dya)));
+      const float2 db = __ffma2_rn(dzb, dzb, __ffma2_rn(dxb, dxb, __fmul2_rn(dyb, dyb)));
+      unsigned mk[4];
+      mk[0] = __ballot_sync(0xffffffffu, da.x < r2);
+      mk[1] = __ballot_sync(0xffffffffu, da.y < r2);
+      mk[2] = __ballot_sync(0xffffffffu, db.x < r2);
+      mk[3] = __ballot_sync(0xffffffffu, db.y < r2);
+      if ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned mask = mk[q];
+        if (mask && cnt[q] < u && j0 + q < j_end) {
+          if (cnt[q] == 0) first[q] = base + __ffs(mask) - 1;
+          const int pos = cnt[q] + __popc(mask & lt);
+          if (((mask >> lane) & 1u) && pos < u) out[((size_t)b * m + j0 + q) * u + pos] = k;
+          cnt[q] += __popc(mask);
+        }
       }
+      if (cnt[0] >= u && cnt[1] >= u && cnt[2] >= u && cnt[3] >= u) break;
     }
-    // the first hit pre-fills every slot; no hit leaves zeros (ball_query.cu:39-44)
-    cnt = min(cnt, u);
-    for (int v = cnt + lane; v < u; v += 32) o[v] = first;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (j0 + q < j_end) {
+        int* o = out + ((size_t)b * m + j0 + q) * u;
+        for (int v = min(cnt[q], u) + lane; v < u; v += 32) o[v] = first[q];
+      }
   }
 }
 
@@ -237,13 +360,14 @@ __global__ void __launch_bounds__(256) three_nn_grad_kernel(const float* __restr
 // One block per cloud; per-voxel state (count, list tail) lives in shared memory as 16-bit values.
 // Phase B threads the points of each voxel into a linked list in ascending point index: 32-point chunks
 // are processed in order (one warp per chunk), match.any finds the in-chunk predecessor and s_tail
-// carries the link across chunks.  Phase C gives every (list head, channel) pair to one thread, which
-// walks the list and sums in index order - the order the oracle uses - so the averages are
-// bit-reproducible (the reference's float atomics are not) and no global atomics are issued.
+// carries the link across chunks.  Phase C is VOXEL-centric: a thread owns a voxel, walks its list once and sums up
+// to 8 channels in index order - the order the oracle uses - so the averages are bit-reproducible (the reference's
+// float atomics are not), no global atomics are issued, and the grid is written exactly once, coalesced over the
+// voxels (empty voxels included: no separate zero pass, no scattered 4-byte stores).
 // ------------------------------------------------------------------------------------------------
 constexpr int kVoxMaxPPT = 16;      // 512 threads x 16 -> n <= 8192 points per cloud
 constexpr int kVoxMaxPoints = 8192;
-template <bool FUSED>
+template <bool FUSED, int CH>
 __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__ feat,
                                                         const void* __restrict__ coords_in, int c, int n, int r,
                                                         float* __restrict__ out, int* __restrict__ ind_out,
@@ -255,7 +379,7 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int r2 = r * r, r3 = r2 * r;
-  // carve: cnt u16[r3] | tail i16[r3] | next i16[n] | vox i32[n]
+  // carve: cnt u16[r3] | tail i16[r3] (list tails while the lists are built, list heads afterwards) | next i16[n] | vox i32[n]
   unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_raw);
   short* s_tail = reinterpret_cast<short*>(s_cnt + ((r3 + 1) & ~1));
   short* s_next = s_tail + ((r3 + 1) & ~1);
@@ -269,16 +393,6 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
 
   for (int i = tid; i < r3; i += nthreads) { s_cnt[i] = 0; s_tail[i] = -1; }
   for (int i = tid; i < n; i += nthreads) s_next[i] = -1;
-  // zero the output grid (the reference relies on torch::zeros); 128-bit stores when aligned
-  {
-    size_t tot = (size_t)ch_n * r3;
-    if ((tot & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
-      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (size_t i = tid; i < tot / 4; i += nthreads) reinterpret_cast<float4*>(ob)[i] = z;
-    } else {
-      for (size_t i = tid; i < tot; i += nthreads) ob[i] = 0.f;
-    }
-  }
   const int ppt = (n + nthreads - 1) / nthreads;
   if (FUSED) {
     const float* cf = reinterpret_cast<const float*>(coords_in) + (size_t)b * 3 * n;
@@ -342,6 +456,7 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
           __syncwarp(act);
           const int pred = below ? i - (lane - (31 - __clz(below))) : tail;
           if (pred >= 0) s_next[pred] = (short)i;
+          else s_vox[i] = v | 0x40000000;                       // first point of its voxel (own entry; unmarked below)
           if (below == 0) s_cnt[v] = (unsigned short)(base + __popc(same));
           if ((same >> lane) == 1u) s_tail[v] = (short)i;       // highest lane of the group
         }
@@ -349,28 +464,49 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
       __syncthreads();
     }
   }
+  // the tails are no longer needed: the same table now records the list heads
+  for (int i = tid; i < n; i += nthreads) {
+    const int vv = s_vox[i];
+    if (vv & 0x40000000) {
+      s_vox[i] = vv & 0x3fffffff;
+      s_tail[vv & 0x3fffffff] = (short)i;
+    }
+  }
+  __syncthreads();
+  short* s_head = s_tail;
   if (ind_out && side)
     for (int i = tid; i < n; i += nthreads) ind_out[(size_t)b * n + i] = s_vox[i];
   if (cnt_out && side)
     for (int i = tid; i < r3; i += nthreads) cnt_out[(size_t)b * r3 + i] = s_cnt[i];
   __syncthreads();
-  // Phase C: item (ch, i) with i a list head (the first point of its voxel, i.e. no point links to it).
-  // Successors are marked by setting bit 30 of their s_vox entry.
-  for (int i = tid; i < n; i += nthreads) {
-    int nx = s_next[i];
-    if (nx >= 0) atomicOr(&s_vox[nx], 0x40000000);               // successor is not a head
-  }
-  __syncthreads();
-  const int items = ch_n * n;
-  for (int it = tid; it < items; it += nthreads) {
-    const int ch = it / n, i = it - ch * n;
-    const int vv = s_vox[i];
-    if (vv & 0x40000000) continue;
-    const float div = (float)(1.0 / (double)(float)s_cnt[vv]);    // vox.cu:65
-    const float* f = fb + (size_t)ch * n;
-    float acc = 0.f;
-    for (int p = i; p >= 0; p = s_next[p]) acc = __fadd_rn(acc, __fmul_rn(__ldg(f + p), div));
-    ob[(size_t)ch * r3 + vv] = acc;
+  // Phase C: a thread owns four consecutive voxels; an all-empty quad (most of a 24^3 grid) is ch_n 16-byte zero stores,
+  // otherwise every non-empty voxel's point list is walked once for all (<= CH) channels of this slice
+  const bool quads = (r3 & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0;
+  for (int v0 = tid * 4; v0 < r3; v0 += nthreads * 4) {
+    const int nv = min(4, r3 - v0);
+    if (quads && *reinterpret_cast<const unsigned long long*>(s_cnt + v0) == 0ull) {
+      const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < ch_n; ++k) *reinterpret_cast<float4*>(ob + (size_t)k * r3 + v0) = zz;
+      continue;
+    }
+    for (int dv = 0; dv < nv; ++dv) {
+      const int v = v0 + dv;
+      float acc[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+      const int cv = s_cnt[v];
+      if (cv) {
+        const float div = (float)(1.0 / (double)(float)cv);       // vox.cu:65
+        for (int p = s_head[v]; p >= 0; p = s_next[p]) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (k < ch_n) acc[k] = __fadd_rn(acc[k], __fmul_rn(__ldg(fb + (size_t)k * n + p), div));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        if (k < ch_n) ob[(size_t)k * r3 + v] = acc[k];
+    }
   }
 }
 
@@ -487,9 +623,21 @@ extern "C" int gldm_furthest_point_sampling(const float* coords, int b, int n, i
   GLDM_REQUIRE(n < (1 << 22), "furthest_point_sampling: n=%d exceeds 2^22", n);
   if (b == 0 || m == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  int threads = min(1024, ceil_div(n, 32) * 32);
+  // four points per thread up to 4096 points (256 threads for the 1024-point clouds of the model), more beyond
+  int threads = min(1024, max(32, ceil_div(ceil_div(n, 4), 32) * 32));
   int ppt = ceil_div(n, threads);
-#define FPS_LAUNCH(P) fps_kernel<P><<<b, threads, 0, s>>>(coords, n, m, indices)
+  const bool use_smem = n <= 8192;                         // 12 n bytes: the winner's coordinates by broadcast LDS
+  const size_t smem = use_smem ? sizeof(float) * 3 * (size_t)n : 0;
+  if (smem > 48 * 1024) {
+    static SmemOptIn a4, a8;
+    if (int rc = opt_in_smem(a4, fps_kernel<4, true>, 96 * 1024, "fps_kernel")) return rc;
+    if (int rc = opt_in_smem(a8, fps_kernel<8, true>, 96 * 1024, "fps_kernel")) return rc;
+  }
+#define FPS_LAUNCH(P)                                                                   \
+  do {                                                                                  \
+    if (use_smem) fps_kernel<P, true><<<b, threads, smem, s>>>(coords, n, m, indices);  \
+    else fps_kernel<P, false><<<b, threads, 0, s>>>(coords, n, m, indices);             \
+  } while (0)
   if (ppt <= 1) FPS_LAUNCH(1);
   else if (ppt <= 2) FPS_LAUNCH(2);
   else if (ppt <= 4) FPS_LAUNCH(4);
@@ -510,8 +658,26 @@ extern "C" int gldm_ball_query(const float* centers, const float* points, int b,
   GLDM_REQUIRE(b >= 0 && n > 0 && m > 0 && u > 0, "ball_query: bad sizes");
   if (b == 0) return GLDM_OK;
   float r2 = radius * radius;   // ball_query.cpp:24 (float multiply)
-  dim3 grid(ceil_div(m, kBqCentersPerBlock), b);
-  ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(centers, points, n, m, r2, u, neighbors);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool smem_ok = n <= kBqMaxSmemPoints;
+  static SmemOptIn attr_t, attr_w;
+  if ((long long)b * m >= 131072) {
+    // throughput: thread = centre (fewest instructions per distance test)
+    dim3 grid(ceil_div(m, kBqThreads), b);
+    const int smem = 3 * ((n + 1) & ~1) * (int)sizeof(float);
+    if (smem_ok && smem > 48 * 1024)
+      if (int rc = opt_in_smem(attr_t, ball_query_kernel<true>, 3 * kBqMaxSmemPoints * (int)sizeof(float), "ball_query_kernel")) return rc;
+    if (smem_ok) ball_query_kernel<true><<<grid, kBqThreads, smem, s>>>(centers, points, n, m, r2, u, neighbors);
+    else ball_query_kernel<false><<<grid, kBqThreads, 0, s>>>(centers, points, n, m, r2, u, neighbors);
+  } else {
+    // latency: warp-cooperative scan, 32 centres per CTA
+    dim3 grid(ceil_div(m, kBqCentersPerBlock), b);
+    const int smem = 3 * ((n + 31) & ~31) * (int)sizeof(float);
+    if (smem_ok && smem > 48 * 1024)
+      if (int rc = opt_in_smem(attr_w, ball_query_warp_kernel<true>, 3 * kBqMaxSmemPoints * (int)sizeof(float), "ball_query_warp_kernel")) return rc;
+    if (smem_ok) ball_query_warp_kernel<true><<<grid, 256, smem, s>>>(centers, points, n, m, r2, u, neighbors);
+    else ball_query_warp_kernel<false><<<grid, 256, 0, s>>>(centers, points, n, m, r2, u, neighbors);
+  }
   return check_launch("ball_query_kernel");
 }
 
@@ -601,16 +767,22 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   const size_t r3 = (size_t)r * r * r;
   size_t smem = 2 * ((r3 + 1) & ~(size_t)1) * 2 + (((size_t)n + 1) & ~(size_t)1) * 2 + (size_t)n * 4;
   int threads = min(512, ceil_div(n, 32) * 32);
-  const int slices = min(8, ceil_div(c, 8));      // channel slices per cloud: more CTAs than clouds for wide features
+  // channels per CTA (phase C keeps them in registers): 4 for the coordinate-only first block, 16 for wide features
+  // (fewer CTAs repeat the point binning), 8 otherwise
+  const int ch = c <= 4 ? 4 : (c >= 32 && (long long)b * ceil_div(c, 16) >= 2 * kNumSMs) ? 16 : 8;
+  const int slices = ceil_div(c, ch);
+#define VOX_LAUNCH(F, C_)                                                                                          \
+  do {                                                                                                             \
+    static SmemOptIn attr;                                                                                         \
+    if (int rc = opt_in_smem(attr, voxelize_kernel<F, C_>, 200 * 1024, "voxelize_kernel")) return rc;              \
+    voxelize_kernel<F, C_><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox); \
+  } while (0)
   if (fused) {
-    static SmemOptIn attr;
-    if (int rc = opt_in_smem(attr, voxelize_kernel<true>, 200 * 1024, "voxelize_kernel<fused>")) return rc;
-    voxelize_kernel<true><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
+    if (ch == 4) VOX_LAUNCH(true, 4); else if (ch == 16) VOX_LAUNCH(true, 16); else VOX_LAUNCH(true, 8);
   } else {
-    static SmemOptIn attr;
-    if (int rc = opt_in_smem(attr, voxelize_kernel<false>, 200 * 1024, "voxelize_kernel")) return rc;
-    voxelize_kernel<false><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox);
+    if (ch == 4) VOX_LAUNCH(false, 4); else if (ch == 16) VOX_LAUNCH(false, 16); else VOX_LAUNCH(false, 8);
   }
+#undef VOX_LAUNCH
   return check_launch("voxelize_kernel");
 }
 

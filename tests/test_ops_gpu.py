@@ -192,3 +192,21 @@ def test_backward_ops_match_autograd_of_oracle_math(be, cuda):
     for k in range(3):
         want.scatter_add_(2, i3[:, k].long().view(B, 1, N).expand(B, 4, N), w3[:, k].view(B, 1, N) * gy)
     torch.testing.assert_close(gx, want, rtol=1e-4, atol=1e-5)
+
+
+def test_ball_query_large_batch_kernel(be, cuda, ref_backend):
+    """Above 131072 centres per call gldm_ball_query switches from the warp-cooperative kernel to the thread = centre kernel
+    (csrc/point_ops.cu): same bit-exact contract - checked against the numpy oracle on distinct clouds (odd point count,
+    ties lattice included) tiled up to that size, and against the reference's own kernel when it is available."""
+    base = torch.cat([_data.synthetic_clouds(2, 777, 3, "S"), _data.quantised_clouds(2, 777, 8, 0.25)]).transpose(1, 2).contiguous()
+    m, reps = 129, 260                                       # 4 * 260 * 129 = 134160 centres
+    centers_b = be.gather_features_forward(base.to(cuda), be.furthest_point_sampling(base.to(cuda), m))
+    pts = base.repeat(reps, 1, 1).to(cuda)
+    ctr = centers_b.repeat(reps, 1, 1).contiguous()
+    for r, u in ((0.2, 32), (0.45, 7), (2.5, 64)):
+        want = ops_np.ball_query(centers_b.cpu().numpy(), base.numpy(), r, u)
+        got = be.ball_query(ctr, pts, r, u)
+        assert np.array_equal(got[:4].cpu().numpy(), want) and np.array_equal(got[-4:].cpu().numpy(), want), (r, u)
+        assert torch.equal(got, got[:4].repeat(reps, 1, 1))
+        if ref_backend is not None:
+            assert torch.equal(got, ref_backend.ball_query(ctr, pts, r, u))

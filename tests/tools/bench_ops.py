@@ -56,6 +56,17 @@ def main():
             vc12 = vc12.to(dev)
             r["avg_voxelize_c48_r12_ms"] = timeit(lambda: be.avg_voxelize_forward(f48, vc12, 12))
             row[name] = r
+        # algorithmic bytes per cloud -> achieved GB/s of our kernels
+        N, M, U = 1024, 256, 32
+        byt = {"avg_voxelize_c3_r24_ms": 4 * (3 * N + 3 * N + 3 * 24 ** 3), "avg_voxelize_c48_r12_ms": 4 * (48 * N + 3 * N + 48 * 12 ** 3),
+               "devoxelize_c48_r24_ms": 4 * (48 * 24 ** 3 + 3 * N + 48 * N), "grouping_c32_ms": 4 * (32 * N + M * U + 32 * M * U),
+               "fps_1024to256_ms": 12 * N + 4 * M, "ball_query_r0.2_u32_ms": 12 * (N + M) + 4 * M * U}
+        row["ours_gbs"] = {k: round(B * v / (row["ours"][k] * 1e-3) / 1e9, 1) for k, v in byt.items()}
+        row["ours_rates"] = {"fps_rounds_per_s": B * 256 / (row["ours"]["fps_1024to256_ms"] * 1e-3),
+                             "fps_ns_per_round_per_cloud_stream": row["ours"]["fps_1024to256_ms"] * 1e6 / 256,
+                             "ball_query_distance_tests_per_s": B * M * N / (row["ours"]["ball_query_r0.2_u32_ms"] * 1e-3)}
+        if "ref" in row:
+            row["speedup_vs_reference_kernels"] = {k: round(row["ref"][k] / row["ours"][k], 2) for k in row["ours"]}
         res[f"B{B}"] = row
         print(B, json.dumps(row))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
