@@ -52,7 +52,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 
 // epilogue warps (2..5) of both kernel variants: thread <-> padded voxel row; halo voxels and rows past the end are dropped
 __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t* smem, uint32_t tmem, uint64_t* acc_full,
-                                                long long row0, int tid, int lane, int wid) {
+                                                long long row0, int tid, int lane, int wid, const float* s_bias,
+                                                uint32_t parity = 0, long long tile = -1) {
+  // s_bias: the layer's bias staged in shared memory by the CTA (zeros when the layer has none): a global load per
+  // element here cost ~1 us per 16-channel batch behind the TMA traffic - 60 % of the epilogue, which bounds the kernel
+  if (tile < 0) tile = blockIdx.x;
   const int rp = p.r + 2, rp2 = rp * rp;
   {
     const int q = wid & 3;
@@ -65,7 +69,7 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
     const int r3 = p.r * p.r * p.r;
     const int v = ((x - 1) * p.r + (yy - 1)) * p.r + (z - 1);
     float* yb = p.y + ((size_t)b * p.co) * r3 + v;
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full, parity);
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
     if (p.out_mode == 0) {
@@ -77,7 +81,7 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
         if (interior) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + s_bias[c0 + j];
         }
       }
     } else {
@@ -97,7 +101,7 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) : 0.f;
+            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + s_bias[c0 + j] : 0.f;
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -142,7 +146,7 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) t += (double)wtot[(w * 2 + slot) * 16 + idx];
-        p.stats[((size_t)blockIdx.x * 2 + slot) * 16 + idx] = t;          // p.stats = per-CTA partials here
+        p.stats[((size_t)tile * 2 + slot) * 16 + idx] = t;                // p.stats = per-tile partials here
       }
     }
     tc_fence_before();
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const long long row0 = (long long)blockIdx.x * 128;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, (WSLOT <= 12288) ? 2 : 1) conv3d
     }
     umma_commit_elect(acc_full);
   } else {
-    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid, s_bias);
   }
   __syncthreads();
   if (wid == 1) tmem_dealloc<128>(tmem);
@@ -246,6 +252,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc3_kernel(const __gri
   uint64_t* empty = bars + STAGES3;
   uint64_t* acc_full = bars + 2 * STAGES3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES3 + 1);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const long long row0 = (long long)blockIdx.x * 128;
@@ -308,10 +316,140 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc3_kernel(const __gri
     }
     umma_commit_elect(acc_full);
   } else {
-    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid, s_bias);
   }
   __syncthreads();
   if (wid == 1) tmem_dealloc<128>(tmem);
+}
+
+// Persistent, weight-stationary variant of conv3d_tc3_kernel for layers whose whole filter bank fits beside the pipeline
+// (48 -> 48: 27 x 6 KB = 162 KB): one CTA per SM loads the 27 weight blocks ONCE and walks the 128-voxel tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The one-tile-per-CTA kernel re-streams the bank for every tile (162 KB of
+// weights against 153 KB of activations per tile, both L2 -> shared memory) and pays TMEM allocation, barrier set-up and
+// pipeline fill / drain per tile; here a tile costs only its nine activation boxes, and two TMEM accumulators let the
+// epilogue of tile t run under the UMMAs of tile t + 1.
+namespace c3 {
+constexpr int P_SCRATCH = 10240;            // epilogue partial sums [128][17] + [4][2][16] floats
+}
+// Activation rows are fetched once per dx PLANE: the three dy columns of a plane are the same rows shifted by r + 2, so
+// one box of 130 + 2 (r + 2) rows serves nine UMMA groups whose A descriptors start (dy (r + 2) + dz) rows into it
+// (SWIZZLE_128B is a function of the absolute shared-memory address: any row offset works with base-offset 0).  Three
+// 23 KB loads per tile instead of nine 17 KB ones: the one-tile kernels were bound by the latency of those round trips.
+__global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                      const __grid_constant__ Conv3dTcParams p, int n_tiles,
+                                                                      int stages, int a_rows, int a_slot) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int n_blocks = 27 * p.k_blocks;
+  uint8_t* s_w = smem;                                        // [27 * k_blocks][w_rows_bytes]
+  uint8_t* s_a = s_w + (size_t)n_blocks * p.w_rows_bytes;     // [stages][a_slot]
+  uint8_t* s_scr = s_a + stages * a_slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scr + P_SCRATCH);
+  uint64_t* full = bars;             // [4]
+  uint64_t* empty = bars + 4;        // [4]
+  uint64_t* acc_full = bars + 8;     // [2]
+  uint64_t* acc_empty = bars + 10;   // [2]
+  uint64_t* w_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int rp = p.r + 2, rp2 = rp * rp;
+  const int n_it = 3 * p.k_blocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer: the filter bank once, then the activation boxes of every tile through the ring
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)(n_blocks * p.w_rows_bytes));
+      for (int k = 0; k < n_blocks; ++k)
+        bulk_g2s(s_w + (size_t)k * p.w_rows_bytes, p.w_img + (size_t)k * W_BYTES, p.w_rows_bytes, w_full);
+    }
+    __syncwarp();
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * 128;
+#pragma unroll 1
+      for (int i = 0; i < n_it; ++i, ++it) {
+        const int s = it % stages, round = it / stages;
+        const int dx = i / p.k_blocks, kb = i - dx * p.k_blocks;
+        const int shift = (dx - 1) * rp2 - rp - 1;                          // row of the (dy, dz) = (-1, -1) tap
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], (uint32_t)a_rows * 128u);
+          tma_load_2d(s_a + s * a_slot, &xmap, kb * 64, (int)(row0 + shift), &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int it = 0, tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      if (tl >= 2) { mbar_wait(&acc_empty[buf], ((tl >> 1) - 1) & 1); tc_fence_after(); }
+      const uint32_t d = tmem + buf * 128;
+#pragma unroll 1
+      for (int i = 0; i < n_it; ++i, ++it) {
+        const int s = it % stages;
+        const int dx = i / p.k_blocks, kb = i - dx * p.k_blocks;
+        mbar_wait(&full[s], (it / stages) & 1);
+        tc_fence_after();
+        const int ks = (kb == p.k_blocks - 1) ? p.ksteps_last : 4;
+#pragma unroll 1
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int dy = t9 / 3, dz = t9 - dy * 3;
+          const uint32_t a_addr = a_base + s * a_slot + (uint32_t)(dy * rp + dz) * 128u;
+          const uint32_t b_addr = w_base + (uint32_t)((((dx * 3 + dy) * 3 + dz) * p.k_blocks + kb) * p.w_rows_bytes);
+          const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | (a_addr >> 4));
+          const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | (b_addr >> 4));
+          const uint32_t acc = (i != 0 || t9 != 0) ? 1u : 0u;
+          if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
+          else if (ks == 3) { umma_bf16_block_elect<2>(d, ad, bd, idesc, acc); umma_bf16_block_elect<1>(d, ad + 4, bd + 4, idesc, 1u); }
+          else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
+          else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
+        }
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ---- epilogue warps: tile t while the issuer works on tile t + 1
+    int tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      conv3d_epilogue(p, s_scr, tmem + buf * 128, &acc_full[buf], (long long)tile * 128, tid, lane, wid, s_bias,
+                      (uint32_t)((tl >> 1) & 1), tile);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the scratch sums of this tile have been consumed
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<256>(tmem);
 }
 
 // Narrow-input variant (ci <= 16: the 3 -> 48 first layer): the padded grid has 16 channels (32-byte rows, SWIZZLE_32B),
@@ -333,6 +471,8 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc16_kernel(const __gr
   uint64_t* empty = bars + STAGES16;
   uint64_t* acc_full = bars + 2 * STAGES16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES16 + 1);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const long long row0 = (long long)blockIdx.x * 128;
@@ -386,7 +526,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc16_kernel(const __gr
     }
     umma_commit_elect(acc_full);
   } else {
-    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid);
+    conv3d_epilogue(p, smem, tmem, acc_full, row0, tid, lane, wid, s_bias);
   }
   __syncthreads();
   if (wid == 1) tmem_dealloc<128>(tmem);
@@ -456,25 +596,21 @@ __global__ void __launch_bounds__(256) cl_pad_kernel(const float* __restrict__ x
       make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-// stats[b][g][moment] = sum over the CTAs covering cloud b of their slot partials, in CTA order (deterministic)
-__global__ void conv_stats_finalize_kernel(const double* __restrict__ part, int P, long long rows, double* __restrict__ stats) {
-  const int b = blockIdx.x, idx = threadIdx.x;       // 16 threads: 0..7 sums, 8..15 sums of squares
+// stats[b][g][moment] = sum over the CTAs covering cloud b of their slot partials.  One warp per statistic: lane l adds
+// the CTAs l, l + 32, ... in order, then a fixed xor tree - the same summation order on every run (bit-reproducible), and
+// 32 loads in flight per statistic instead of a serial walk over the ~140 CTAs of a 24^3 cloud.
+__global__ void __launch_bounds__(512) conv_stats_finalize_kernel(const double* __restrict__ part, int P, long long rows,
+                                                                  double* __restrict__ stats) {
+  const int b = blockIdx.x, idx = threadIdx.x >> 5, lane = threadIdx.x & 31;       // idx 0..7 sums, 8..15 sums of squares
   const long long r_lo = (long long)b * P, r_hi = r_lo + P - 1;
   const long long c_lo = r_lo / 128, c_hi = r_hi / 128;
-  // same order as a plain loop, but eight independent loads in flight at a time
   double t = 0.0;
-  for (long long c = c_lo; c <= c_hi; c += 8) {
-    double v[8];
+  for (long long cc = c_lo + lane; cc <= c_hi; cc += 32)
+    t += part[((size_t)cc * 2 + (b - (int)((cc * 128) / P))) * 16 + idx];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const long long cc = c + u;
-      v[u] = cc <= c_hi ? part[((size_t)cc * 2 + (b - (int)((cc * 128) / P))) * 16 + idx] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) t += v[u];
-  }
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   (void)rows;
-  stats[((size_t)b * 8 + (idx & 7)) * 2 + (idx >> 3)] = t;
+  if (lane == 0) stats[((size_t)b * 8 + (idx & 7)) * 2 + (idx >> 3)] = t;
 }
 // the same for per-block partials laid out [b][nblk][16] (SIMT first conv) and [b][nblk][c] (SE squeeze sums)
 __global__ void block_partials_finalize_kernel(const double* __restrict__ part, int nblk, int width, int remap,
@@ -534,7 +670,7 @@ __global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(v[j], A[j], B[j]);
-        v[j] = t * (1.0f / (1.0f + expf(-t)));
+        v[j] = __fdividef(t, 1.0f + __expf(-t));          // fast-math exp / divide: ~1e-6 relative, far below the bf16 operands
         acc[j] += v[j];
       }
       ptr[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -551,8 +687,10 @@ __global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(v[j], A[j], B[j]);
-        v[j] = t * (1.0f / (1.0f + expf(-t)));
+        const float t = fmaf(v[j], A[j], B[j]), h = 0.5f * t;
+        float th;                                          // x * sigmoid(x) = h (1 + tanh h): one MUFU op, bf16 output
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+        v[j] = fmaf(h, th, h);
         acc[j] += v[j];
       }
       *ptr = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -742,8 +880,8 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
   p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b;
   static SmemOptIn attr_s, attr_b;
-  const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 256;
-  const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 256;
+  const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 768;
+  const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 768;
   if (int rc = opt_in_smem(attr_s, conv3d_tc_kernel<c3::W_SLOT>, smem_small, "conv3d_tc_kernel")) return rc;
   if (int rc = opt_in_smem(attr_b, conv3d_tc_kernel<c3::W_BYTES>, smem_big, "conv3d_tc_kernel (wide)")) return rc;
   const unsigned grid = (unsigned)((rows + 127) / 128);
@@ -760,7 +898,32 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
       set_error("conv3d_k3_tc: cuTensorMapEncodeTiled (136-row box) failed (%d)", (int)cr3);
       return GLDM_ECUDA;
     }
-    const int smem3 = c3::STAGES3 * (c3::A3_BYTES + 3 * c3::W_SLOT) + 1024 + 256;
+    // the whole filter bank resident beside a 2- or 3-deep activation ring: persistent, weight-stationary kernel
+    static int persist = -1;
+    if (persist < 0) { const char* ev = getenv("GLDM_CONV3D_PERSISTENT"); persist = ev ? atoi(ev) : 1; }
+    const int bank = 27 * kb * p.w_rows_bytes;
+    const int fixed = c3::P_SCRATCH + 768 + 1024;
+    const int a_rows = 130 + 2 * (r + 2);                               // one dx plane: dy in {-1,0,1} x dz in {-1,0,1}
+    const int a_slot = ((a_rows * 128 + 1023) / 1024) * 1024;
+    const int stages_p = (bank + 3 * a_slot + fixed <= 232448) ? 3 : 2;
+    if (persist && out_mode != 0 && a_rows <= 256 && bank + stages_p * a_slot + fixed <= 232448) {
+      CUtensorMap mapp;
+      const cuuint32_t boxp[2] = {64, (cuuint32_t)a_rows};
+      const CUresult crp = enc(&mapp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_cl), gdim, gstride, boxp, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (crp != CUDA_SUCCESS) {
+        set_error("conv3d_k3_tc: cuTensorMapEncodeTiled (%d-row box) failed (%d)", a_rows, (int)crp);
+        return GLDM_ECUDA;
+      }
+      const int smem_p = bank + stages_p * a_slot + fixed;
+      static SmemOptIn attr_p;
+      if (int rc = opt_in_smem(attr_p, conv3d_tc3p_kernel, 232448, "conv3d_tc3p_kernel")) return rc;
+      const int n_tiles = (int)grid;
+      conv3d_tc3p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot);
+      return check_launch("conv3d_tc3p_kernel");
+    }
+    const int smem3 = c3::STAGES3 * (c3::A3_BYTES + 3 * c3::W_SLOT) + 1024 + 768;
     static SmemOptIn attr3;
     if (int rc = opt_in_smem(attr3, conv3d_tc3_kernel<c3::W_SLOT>, smem3, "conv3d_tc3_kernel")) return rc;
     conv3d_tc3_kernel<c3::W_SLOT><<<grid, c3::NTHREADS, smem3, s>>>(map3, p, taps3);
@@ -828,7 +991,7 @@ extern "C" int gldm_conv3d_tc_cl(const void* x_cl, const void* w_img, const floa
                          reinterpret_cast<double*>(ws), (cudaStream_t)stream);
   if (rc) return rc;
   const int P = (r + 2) * (r + 2) * (r + 2);
-  conv_stats_finalize_kernel<<<b, 16, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(ws), P, (long long)b * P, stats);
+  conv_stats_finalize_kernel<<<b, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(ws), P, (long long)b * P, stats);
   return check_launch("conv_stats_finalize_kernel");
 }
 
@@ -895,13 +1058,13 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 256;
   p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b;
-  const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 256;
+  const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 768;
   static SmemOptIn attr16;
   if (int rc2 = opt_in_smem(attr16, conv3d_tc16_kernel, smem16, "conv3d_tc16_kernel")) return rc2;
   conv3d_tc16_kernel<<<(unsigned)((rows + 127) / 128), c3::NTHREADS, smem16, s>>>(map, p);
   rc = check_launch("conv3d_tc16_kernel");
   if (rc) return rc;
-  conv_stats_finalize_kernel<<<b, 16, 0, s>>>(reinterpret_cast<const double*>(ws), (int)P, rows, stats);
+  conv_stats_finalize_kernel<<<b, 512, 0, s>>>(reinterpret_cast<const double*>(ws), (int)P, rows, stats);
   return check_launch("conv_stats_finalize_kernel");
 }
 
