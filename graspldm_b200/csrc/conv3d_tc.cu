@@ -50,6 +50,59 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// One output row (CO channels of one padded voxel) of the channels-last epilogue: accumulator + bias -> bf16 / fp32 row
+// (padding channels up to out_stride written as zero) and the row's GroupNorm(8) partial sums into part[0..7] (sums) and
+// part[8..15] (sums of squares).  Everything indexed at compile time.
+template <int CO>
+__device__ __forceinline__ void conv3d_row_epilogue(const Conv3dTcParams& p, uint32_t taddr, const float* s_bias, bool interior,
+                                                    uint8_t* yrow, float* part) {
+  constexpr int CPG = CO / 8;
+  float gs[8], gq[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+#pragma unroll
+  for (int c0 = 0; c0 < CO; c0 += 16) {
+    uint32_t u[16];
+    tmem_ld16(taddr + c0, u);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      uint32_t t = u[j];
+      asm volatile("" : "+r"(t));
+      v[j] = interior ? __uint_as_float(t) + s_bias[c0 + j] : 0.f;
+      gs[(c0 + j) / CPG] += v[j];
+      gq[(c0 + j) / CPG] = fmaf(v[j], v[j], gq[(c0 + j) / CPG]);
+    }
+    if (interior) {
+      if (p.out_mode == 1) {
+        uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
+        dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+      } else {
+        float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+    }
+  }
+  if (interior) {           // padding channels of the row (a bf16 row is padded to a multiple of 64 channels)
+    for (int c0 = CO; c0 < p.out_stride; c0 += 16) {
+      if (p.out_mode == 1) {
+        uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
+        dst[0] = make_uint4(0, 0, 0, 0);
+        dst[1] = make_uint4(0, 0, 0, 0);
+      } else {
+        float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { part[g] = gs[g]; part[8 + g] = gq[g]; }
+}
+
 // epilogue warps (2..5) of both kernel variants: thread <-> padded voxel row; halo voxels and rows past the end are dropped
 __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t* smem, uint32_t tmem, uint64_t* acc_full,
                                                 long long row0, int tid, int lane, int wid, const float* s_bias,
@@ -88,10 +141,16 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
       // channels-last row of this voxel + GroupNorm partial sums.  The pipeline stages are idle once acc_full fired:
       // their memory holds the per-thread group partials [128][17].
       float* part = reinterpret_cast<float*>(smem) + (tid - 64) * 17;
+      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
+      if (p.co == 48 || p.co == 96) {
+        // the two widths of the model: channel loop fully unrolled, the GroupNorm group of every channel is a compile-time
+        // constant, eight (sum, sum of squares) pairs in registers - no running counter, no branches
+        if (p.co == 48) conv3d_row_epilogue<48>(p, taddr, s_bias, interior, yrow, part);
+        else conv3d_row_epilogue<96>(p, taddr, s_bias, interior, yrow, part);
+      } else {
       const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
       float gs = 0.f, gq = 0.f;
       int g = 0, in_g = 0;
-      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
 #pragma unroll 1
       for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
         float v[16];
@@ -125,6 +184,7 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
             for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           }
         }
+      }
       }
       __syncwarp();
       // warp totals of the 16 partials (32 voxels) per cloud slot (the 128 rows of a CTA touch at most two clouds:

@@ -20,7 +20,7 @@ namespace gtc {
 constexpr int BLOCK = 16384;                 // one operand block: 128 rows x 64 bf16
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
-constexpr int SMEM = STAGES * 2 * BLOCK + 1024 + 256;
+constexpr int SMEM = STAGES * 2 * BLOCK + 1024 + 256 + 1024;    // + scale / shift of the CTA's 128 columns
 }  // namespace gtc
 
 struct GemmTcParams {
@@ -46,6 +46,14 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nt = blockIdx.x, mt = blockIdx.y;
   const int kb_n = p.k_blocks;
+  // per-column scale / shift of this CTA's tile, staged once: a global load per element in the epilogue sits behind the
+  // bulk-copy traffic (the same finding as in the Conv3d epilogue)
+  float* s_sc = reinterpret_cast<float*>(smem + STAGES * 2 * BLOCK + 256);
+  float* s_sh = s_sc + 128;
+  for (int i = tid; i < 128; i += NTHREADS) {
+    s_sc[i] = p.scale ? __ldg(p.scale + nt * 128 + i) : 1.f;
+    s_sh[i] = p.shift ? __ldg(p.shift + nt * 128 + i) : 0.f;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -106,12 +114,11 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
         uint32_t pk[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const int n = nt * 128 + c0 + j8 * 8 + 2 * h;
+          const int n = c0 + j8 * 8 + 2 * h;
           float y0 = __uint_as_float(v[j8 * 8 + 2 * h]), y1 = __uint_as_float(v[j8 * 8 + 2 * h + 1]);
-          const float s0 = p.scale ? __ldg(p.scale + n) : 1.f, s1 = p.scale ? __ldg(p.scale + n + 1) : 1.f;
-          const float h0 = p.shift ? __ldg(p.shift + n) : 0.f, h1 = p.shift ? __ldg(p.shift + n + 1) : 0.f;
-          y0 = fmaf(y0, s0, h0);
-          y1 = fmaf(y1, s1, h1);
+          const float2 sc = *reinterpret_cast<const float2*>(s_sc + n), sh = *reinterpret_cast<const float2*>(s_sh + n);
+          y0 = fmaf(y0, sc.x, sh.x);
+          y1 = fmaf(y1, sc.y, sh.y);
           if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
           pk[h] = pack_bf16(y0, y1);
         }
