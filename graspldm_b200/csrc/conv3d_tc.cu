@@ -25,7 +25,7 @@ constexpr int A_BYTES = 16384;              // 128 voxels x 64 channels bf16
 constexpr int W_BYTES = 16384;              // one weight block in the pack
 constexpr int W_SLOT = 12288;               // shared-memory slot of a weight block: rows 0..95 (co <= 96), 16384 otherwise
 constexpr int STAGES = 3;                   // 3 x 28 KB: two CTAs per SM overlap each other's load latency and epilogue
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;               // producer, UMMA issuer, 8 epilogue warps
 }  // namespace c3
 
 struct Conv3dTcParams {
@@ -40,8 +40,13 @@ struct Conv3dTcParams {
   void* y_cl;                 // [rows][out_stride]; halo rows are never written (they must be zero on entry)
   double* stats;              // [b][8][2]: sum, sum of squares per GroupNorm group (8 groups), accumulated
   int batch;
+  int n_acc;                  // accumulators per tile, 64 TMEM columns apart, summed by the epilogue (1, or 3: one per dz tap)
 };
 
+// L2 prefetch of a 2-D box (no shared memory involved): hides the HBM leg of a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -50,69 +55,72 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// One output row (CO channels of one padded voxel) of the channels-last epilogue: accumulator + bias -> bf16 / fp32 row
-// (padding channels up to out_stride written as zero) and the row's GroupNorm(8) partial sums into part[0..7] (sums) and
-// part[8..15] (sums of squares).  Everything indexed at compile time.
-template <int CO>
+// Half an output row (channels [H * CO / 2, (H + 1) * CO / 2) of one padded voxel) of the channels-last epilogue:
+// accumulator + bias -> bf16 / fp32 row piece (the upper half also writes the padding channels up to out_stride as zero)
+// and the GroupNorm(8) partial sums of those channels into st[0..7] (sums) / st[8..15] (sums of squares).  Everything is
+// indexed at compile time: no running counters, no branches, the statistics never leave the registers.
+template <int CO, int H>
 __device__ __forceinline__ void conv3d_row_epilogue(const Conv3dTcParams& p, uint32_t taddr, const float* s_bias, bool interior,
-                                                    uint8_t* yrow, float* part) {
-  constexpr int CPG = CO / 8;
-  float gs[8], gq[8];
+                                                    uint8_t* yrow, float (&st)[16]) {
+  constexpr int CPG = CO / 8, C_LO = H * (CO / 2);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
-#pragma unroll
-  for (int c0 = 0; c0 < CO; c0 += 16) {
-    uint32_t u[16];
-    tmem_ld16(taddr + c0, u);
+  for (int cc = 0; cc < CO / 2; cc += 8) {
+    const int c0 = C_LO + cc;
+    uint32_t u[8], u1[8], u2[8];
+    tmem_ld8(taddr + c0, u);
+    if (p.n_acc == 3) { tmem_ld8(taddr + 64 + c0, u1); tmem_ld8(taddr + 128 + c0, u2); }
     tmem_ld_wait();
-    float v[16];
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
       uint32_t t = u[j];
       asm volatile("" : "+r"(t));
-      v[j] = interior ? __uint_as_float(t) + s_bias[c0 + j] : 0.f;
-      gs[(c0 + j) / CPG] += v[j];
-      gq[(c0 + j) / CPG] = fmaf(v[j], v[j], gq[(c0 + j) / CPG]);
+      float a = __uint_as_float(t);
+      if (p.n_acc == 3) {
+        uint32_t t1 = u1[j], t2 = u2[j];
+        asm volatile("" : "+r"(t1), "+r"(t2));
+        a += __uint_as_float(t1) + __uint_as_float(t2);
+      }
+      v[j] = interior ? a + s_bias[c0 + j] : 0.f;
+      st[(C_LO + cc + j) / CPG] += v[j];
+      st[8 + (C_LO + cc + j) / CPG] = fmaf(v[j], v[j], st[8 + (C_LO + cc + j) / CPG]);
     }
     if (interior) {
       if (p.out_mode == 1) {
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
-        dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        *reinterpret_cast<uint4*>(yrow + c0 * 2) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                                              pack_bf16(v[6], v[7]));
       } else {
         float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
   }
-  if (interior) {           // padding channels of the row (a bf16 row is padded to a multiple of 64 channels)
-    for (int c0 = CO; c0 < p.out_stride; c0 += 16) {
+  if (H == 1 && interior) {           // padding channels of the row (a bf16 row is padded to a multiple of 64 channels)
+    for (int c0 = CO; c0 < p.out_stride; c0 += 8) {
       if (p.out_mode == 1) {
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
-        dst[0] = make_uint4(0, 0, 0, 0);
-        dst[1] = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(yrow + c0 * 2) = make_uint4(0, 0, 0, 0);
       } else {
         float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
-#pragma unroll
-  for (int g = 0; g < 8; ++g) { part[g] = gs[g]; part[8 + g] = gq[g]; }
 }
 
-// epilogue warps (2..5) of both kernel variants: thread <-> padded voxel row; halo voxels and rows past the end are dropped
+// epilogue warps (2..9) of every kernel variant: thread <-> padded voxel row; two warps share a TMEM lane quarter and take
+// half of the channels each (the epilogue, not the tensor pipe, bounds these layers: N = 48 / 96 columns per 128 rows);
+// halo voxels and rows past the end are dropped
 __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t* smem, uint32_t tmem, uint64_t* acc_full,
                                                 long long row0, int tid, int lane, int wid, const float* s_bias,
                                                 uint32_t parity = 0, long long tile = -1) {
   // s_bias: the layer's bias staged in shared memory by the CTA (zeros when the layer has none): a global load per
-  // element here cost ~1 us per 16-channel batch behind the TMA traffic - 60 % of the epilogue, which bounds the kernel
+  // element here cost ~1 us per 16-channel batch behind the TMA traffic - 60 % of the epilogue, which bounded the kernel
   if (tile < 0) tile = blockIdx.x;
   const int rp = p.r + 2, rp2 = rp * rp;
   {
-    const int q = wid & 3;
+    const int ew = wid - 2, q = wid & 3, half = ew >> 2;      // warps 2..5: lower channel half, 6..9: upper (wid & 3 = TMEM quarter)
     const long long m = row0 + q * 32 + lane;
     const int P = rp2 * rp;
     const long long b = m / P;
@@ -126,86 +134,94 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
     if (p.out_mode == 0) {
+      if (half == 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.co; c0 += 16) {
-        uint32_t u[16];
-        tmem_ld16(taddr + c0, u);
-        tmem_ld_wait();
-        if (interior) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + s_bias[c0 + j];
-        }
-      }
-    } else {
-      // channels-last row of this voxel + GroupNorm partial sums.  The pipeline stages are idle once acc_full fired:
-      // their memory holds the per-thread group partials [128][17].
-      float* part = reinterpret_cast<float*>(smem) + (tid - 64) * 17;
-      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
-      if (p.co == 48 || p.co == 96) {
-        // the two widths of the model: channel loop fully unrolled, the GroupNorm group of every channel is a compile-time
-        // constant, eight (sum, sum of squares) pairs in registers - no running counter, no branches
-        if (p.co == 48) conv3d_row_epilogue<48>(p, taddr, s_bias, interior, yrow, part);
-        else conv3d_row_epilogue<96>(p, taddr, s_bias, interior, yrow, part);
-      } else {
-      const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
-      float gs = 0.f, gq = 0.f;
-      int g = 0, in_g = 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
-        float v[16];
-        if (c0 < n_umma) {
+        for (int c0 = 0; c0 < p.co; c0 += 16) {
           uint32_t u[16];
           tmem_ld16(taddr + c0, u);
           tmem_ld_wait();
+          if (interior) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + s_bias[c0 + j] : 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < p.co) {
-            gs += v[j];
-            gq = fmaf(v[j], v[j], gq);
-            if (++in_g == cpg) { part[g] = gs; part[8 + g] = gq; ++g; in_g = 0; gs = 0.f; gq = 0.f; }
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.co) yb[(size_t)(c0 + j) * r3] = __uint_as_float(u[j]) + s_bias[c0 + j];
           }
         }
-        if (interior) {
-          if (p.out_mode == 1) {
-            uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
-            dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+      }
+    } else {
+      // channels-last row of this voxel + GroupNorm partial sums
+      float st[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) st[i] = 0.f;
+      uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
+      if (p.co == 48) {
+        if (half == 0) conv3d_row_epilogue<48, 0>(p, taddr, s_bias, interior, yrow, st);
+        else conv3d_row_epilogue<48, 1>(p, taddr, s_bias, interior, yrow, st);
+      } else if (p.co == 96) {
+        if (half == 0) conv3d_row_epilogue<96, 0>(p, taddr, s_bias, interior, yrow, st);
+        else conv3d_row_epilogue<96, 1>(p, taddr, s_bias, interior, yrow, st);
+      } else if (half == 0) {
+        // other widths: one warp per quarter walks the whole row with a running group counter
+        float* part = reinterpret_cast<float*>(smem) + 256 + (ew * 32 + lane) * 17;
+        const int cpg = p.co >> 3, n_umma = (p.co + 15) & ~15;
+        float gs = 0.f, gq = 0.f;
+        int g = 0, in_g = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.out_stride; c0 += 16) {
+          float vv[16];
+          if (c0 < n_umma) {
+            uint32_t u[16];
+            tmem_ld16(taddr + c0, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              vv[j] = (interior && c0 + j < p.co) ? __uint_as_float(u[j]) + s_bias[c0 + j] : 0.f;
           } else {
-            float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            for (int j = 0; j < 16; ++j) vv[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < p.co) {
+              gs += vv[j];
+              gq = fmaf(vv[j], vv[j], gq);
+              if (++in_g == cpg) { part[g] = gs; part[8 + g] = gq; ++g; in_g = 0; gs = 0.f; gq = 0.f; }
+            }
+          }
+          if (interior) {
+            if (p.out_mode == 1) {
+              uint4* dst = reinterpret_cast<uint4*>(yrow + c0 * 2);
+              dst[0] = make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]), pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
+              dst[1] = make_uint4(pack_bf16(vv[8], vv[9]), pack_bf16(vv[10], vv[11]), pack_bf16(vv[12], vv[13]), pack_bf16(vv[14], vv[15]));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(yrow + c0 * 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) dst[k] = make_float4(vv[4 * k], vv[4 * k + 1], vv[4 * k + 2], vv[4 * k + 3]);
+            }
           }
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st[i] = part[i];
       }
-      }
-      __syncwarp();
-      // warp totals of the 16 partials (32 voxels) per cloud slot (the 128 rows of a CTA touch at most two clouds:
-      // slot 0 = the cloud of its first row, slot 1 = the next one), then a fixed-order sum over the 4 epilogue warps:
-      // the statistics are bit-reproducible (no atomics); conv_stats_finalize_kernel adds the CTAs of a cloud in order
-      float* wtot = reinterpret_cast<float*>(smem) + 128 * 17;          // [4 warps][2 slots][16]
+      // warp totals of the 16 statistics (32 voxels) per cloud slot (the 128 rows of a CTA touch at most two clouds:
+      // slot 0 = the cloud of its first row, slot 1 = the next one), then a fixed-order sum over the 8 epilogue warps:
+      // the statistics are bit-reproducible (no atomics); conv_stats_finalize_kernel adds the tiles of a cloud in a fixed order
+      float* wtot = reinterpret_cast<float*>(smem);                     // [8 warps][2 slots][16]
       const int b0 = (int)(row0 / P);
       for (int slot = 0; slot < 2; ++slot) {
         float a[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = (interior && b == b0 + slot) ? part[i] : 0.f;
+        for (int i = 0; i < 16; ++i) a[i] = (interior && b == b0 + slot) ? st[i] : 0.f;
         rs_step<16, 8>(a, lane); rs_step<8, 4>(a, lane); rs_step<4, 2>(a, lane); rs_step<2, 1>(a, lane);
         a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-        if ((lane & 1) == 0) wtot[(q * 2 + slot) * 16 + (lane >> 1)] = a[0];   // index 0..7 sums, 8..15 sums of squares
+        if ((lane & 1) == 0) wtot[(ew * 2 + slot) * 16 + (lane >> 1)] = a[0];   // index 0..7 sums, 8..15 sums of squares
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (q == 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0) {
         const int slot = lane >> 4, idx = lane & 15;
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) t += (double)wtot[(w * 2 + slot) * 16 + idx];
+        for (int w = 0; w < 8; ++w) t += (double)wtot[(w * 2 + slot) * 16 + idx];
         p.stats[((size_t)tile * 2 + slot) * 16 + idx] = t;                // p.stats = per-tile partials here
       }
     }
@@ -421,12 +437,12 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     mbar_init(w_full, 1);
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
   }
-  if (wid == 1) tmem_alloc<256>(tmem_slot);
+  if (wid == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -444,6 +460,16 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * 128;
+      // the boxes of this CTA's NEXT tile on their way into L2 while this one is computed: the ring (two 23 KB stages
+      // beside the resident filter bank) is too shallow to cover an HBM round trip per box
+      if (tile + (int)gridDim.x < n_tiles && elect_one_sync()) {
+        const long long rown = (long long)(tile + gridDim.x) * 128;
+        for (int i = 0; i < n_it; ++i) {
+          const int dx = i / p.k_blocks, kb = i - dx * p.k_blocks;
+          tma_prefetch_2d(&xmap, kb * 64, (int)(rown + (dx - 1) * rp2 - rp - 1));
+        }
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int i = 0; i < n_it; ++i, ++it) {
         const int s = it % stages, round = it / stages;
@@ -469,7 +495,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       const int buf = tl & 1;
       if (tl >= 2) { mbar_wait(&acc_empty[buf], ((tl >> 1) - 1) & 1); tc_fence_after(); }
-      const uint32_t d = tmem + buf * 128;
+      const uint32_t d = tmem + buf * 256;
 #pragma unroll 1
       for (int i = 0; i < n_it; ++i, ++it) {
         const int s = it % stages;
@@ -477,18 +503,20 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
         mbar_wait(&full[s], (it / stages) & 1);
         tc_fence_after();
         const int ks = (kb == p.k_blocks - 1) ? p.ksteps_last : 4;
-#pragma unroll 1
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int dy = t9 / 3, dz = t9 - dy * 3;
-          const uint32_t a_addr = a_base + s * a_slot + (uint32_t)(dy * rp + dz) * 128u;
-          const uint32_t b_addr = w_base + (uint32_t)((((dx * 3 + dy) * 3 + dz) * p.k_blocks + kb) * p.w_rows_bytes);
-          const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | (a_addr >> 4));
-          const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | (b_addr >> 4));
-          const uint32_t acc = (i != 0 || t9 != 0) ? 1u : 0u;
-          if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
-          else if (ks == 3) { umma_bf16_block_elect<2>(d, ad, bd, idesc, acc); umma_bf16_block_elect<1>(d, ad + 4, bd + 4, idesc, 1u); }
-          else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
-          else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
+        // three accumulators, one per dz tap, 64 TMEM columns apart (the epilogue adds them): consecutive UMMAs never
+        // accumulate into the same tile, and the three dz taps of a (dy, k) step go out behind one elect with their
+        // descriptors formed by constant adds - the issuing warp, not the tensor pipe, bounded this loop
+        const uint64_t a0 = ((uint64_t)hi << 32) | (0x10000u | ((a_base + s * a_slot) >> 4));
+        const uint64_t b0 = ((uint64_t)hi << 32) | (0x10000u | ((w_base + (uint32_t)((dx * 9 * p.k_blocks + kb) * p.w_rows_bytes)) >> 4));
+        const uint64_t b_tap = (uint64_t)((p.k_blocks * p.w_rows_bytes) >> 4), rp8 = (uint64_t)(rp * 8);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ks)
+              umma_bf16_x3_elect(d, a0 + dy * rp8 + 2 * k, b0 + 3 * dy * b_tap + 2 * k, b_tap, idesc,
+                                 (dy != 0 || k != 0) ? 1u : (i != 0 ? 1u : 0u));
+          }
         }
         umma_commit_elect(&empty[s]);
       }
@@ -500,16 +528,16 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       const int buf = tl & 1;
-      conv3d_epilogue(p, s_scr, tmem + buf * 128, &acc_full[buf], (long long)tile * 128, tid, lane, wid, s_bias,
+      conv3d_epilogue(p, s_scr, tmem + buf * 256, &acc_full[buf], (long long)tile * 128, tid, lane, wid, s_bias,
                       (uint32_t)((tl >> 1) & 1), tile);
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // the scratch sums of this tile have been consumed
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the scratch sums of this tile have been consumed
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (wid == 1) tmem_dealloc<256>(tmem);
+  if (wid == 1) tmem_dealloc<512>(tmem);
 }
 
 // Narrow-input variant (ci <= 16: the 3 -> 48 first layer): the padded grid has 16 channels (32-byte rows, SWIZZLE_32B),
@@ -938,7 +966,7 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
   p.ksteps_last = (last_valid + 15) / 16;
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
-  p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b;
+  p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b; p.n_acc = 1;
   static SmemOptIn attr_s, attr_b;
   const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 768;
   const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 768;
@@ -966,7 +994,7 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
     const int a_rows = 130 + 2 * (r + 2);                               // one dx plane: dy in {-1,0,1} x dz in {-1,0,1}
     const int a_slot = ((a_rows * 128 + 1023) / 1024) * 1024;
     const int stages_p = (bank + 3 * a_slot + fixed <= 232448) ? 3 : 2;
-    if (persist && out_mode != 0 && a_rows <= 256 && bank + stages_p * a_slot + fixed <= 232448) {
+    if (persist && out_mode != 0 && a_rows <= 256 && ((co + 15) & ~15) <= 64 && bank + stages_p * a_slot + fixed <= 232448) {
       CUtensorMap mapp;
       const cuuint32_t boxp[2] = {64, (cuuint32_t)a_rows};
       const CUresult crp = enc(&mapp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_cl), gdim, gstride, boxp, estr,
@@ -980,6 +1008,7 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
       static SmemOptIn attr_p;
       if (int rc = opt_in_smem(attr_p, conv3d_tc3p_kernel, 232448, "conv3d_tc3p_kernel")) return rc;
       const int n_tiles = (int)grid;
+      p.n_acc = 3;
       conv3d_tc3p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot);
       return check_launch("conv3d_tc3p_kernel");
     }
@@ -1117,7 +1146,7 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
   p.bias = bias; p.y = nullptr; p.r = r; p.co = co; p.k_blocks = 1; p.ksteps_last = 1;
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 256;
-  p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b;
+  p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b; p.n_acc = 1;
   const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 768;
   static SmemOptIn attr16;
   if (int rc2 = opt_in_smem(attr16, conv3d_tc16_kernel, smem16, "conv3d_tc16_kernel")) return rc2;

@@ -159,6 +159,25 @@ __device__ __forceinline__ void umma_bf16_block_elect(uint32_t tmem_d, uint64_t 
         : "memory");
   }
 }
+// Three UMMAs behind one elect: accumulators d, d + 64, d + 128 columns; A descriptors 8 units (one 128-byte row) apart,
+// B descriptors b_step units apart.  The issuing warp is instruction bound when every UMMA carries its own address
+// arithmetic and elect (measured: ~86 cycles per 128 x 48 x 16 UMMA in the Conv3d issue loop), so the per-UMMA work
+// is kept to the adds below.
+__device__ __forceinline__ void umma_bf16_x3_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t b_step,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred q, p;\n\t.reg .b64 a1, a2, b1, b2;\n\t.reg .b32 d1, d2;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "add.u64 a1, %1, 8;\n\tadd.u64 a2, %1, 16;\n\t"
+      "add.u64 b1, %2, %4;\n\tadd.u64 b2, b1, %4;\n\t"
+      "add.u32 d1, %0, 64;\n\tadd.u32 d2, %0, 128;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [d1], a1, b1, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [d2], a2, b2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "l"(b_step), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
