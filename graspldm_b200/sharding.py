@@ -90,6 +90,9 @@ def gather_results(local, counts, group=None, num_grasps=None, n_objects=None):
             allb = _all_gather_packed(pad, world, group)                              # [world, 1, g_max, F]
             full = torch.cat([torch.cat([allb[r, :, :p[3] - p[2]] for r, p in enumerate(plans) if p[0] == o], dim=1)
                               for o in range(n_objects)], dim=0)
+        elif len(set(counts)) == 1:
+            # even shards (the usual case): no padding, and the gathered buffer already is the result
+            full = _all_gather_packed(buf.contiguous(), world, group).view((world * counts[0],) + tuple(buf.shape[1:]))
         else:
             pad = torch.zeros((max(counts),) + tuple(buf.shape[1:]), dtype=dtype, device=buf.device)
             pad[:buf.shape[0]] = buf

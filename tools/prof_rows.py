@@ -40,3 +40,4 @@ for j, nm in enumerate(names):
     print(f"{nm:14s} " + " ".join(f"{x:9d}" for x in row))
     prev = t[6]
 print("total          " + " ".join(f"{x:9d}" for x in tot), "  first..last", b[64 + 8 * (len(names) - 1) + 6] - b[64])
+
