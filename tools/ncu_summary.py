@@ -51,18 +51,79 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
-    hdr, units = rows[0], rows[1]
+    # src: a .ncu-rep, or the `ncu -i x.ncu-rep --page raw --csv` export of one (made on the GPU box when the report
+    # itself is too large to bring back)
+    if src.endswith(".csv"):
+        out = open(src, errors="replace").read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(io.StringIO(out)) if r]
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units = rows[hi], rows[hi + 1]
+    stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     with open(dst, "w") as f:
-        f.write(f"# ncu --set full summary ({src})\n\n")
-        for r in rows[2:]:
+        f.write(f"# ncu --set full summary ({src})\n\n`ncu --set full --clock-control none`: one replayed launch per kernel, "
+                "cold caches; durations are not bench values.\n\n")
+        for r in rows[hi + 2:]:
             f.write(f"## `{r[hdr.index('Kernel Name')]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
             for m in FULL_METRICS:
                 if m in hdr:
                     f.write(f"| {m} | {r[hdr.index(m)]} | {units[hdr.index(m)]} |\n")
+            top = []
+            for h in stall:
+                try:
+                    top.append((float(r[hdr.index(h)].replace(",", "")), h))
+                except ValueError:
+                    pass
+            top.sort(reverse=True)
+            if top:
+                f.write("\nwarp stall reasons (warps stalled per issue-active cycle, top 6): "
+                        + ", ".join(f"{h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {v:.2f}" for v, h in top[:6]) + "\n")
             f.write("\n")
 
 
+TABLE = [("time us", "gpu__time_duration.sum"), ("grid", "launch__grid_size"), ("block", "launch__block_size"),
+         ("regs", "launch__registers_per_thread"), ("DRAM rd", "dram__bytes_read.sum"), ("DRAM wr", "dram__bytes_write.sum"),
+         ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), ("L2 %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+         ("tensor %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+         ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("warps %", "sm__warps_active.avg.pct_of_peak_sustained_active")]
+
+
+def table(src, dst):
+    """One row per captured launch (raw-page CSV export): the compact form for multi-kernel passes."""
+    rows = [r for r in csv.reader(open(src, errors="replace")) if r]
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units = rows[hi], rows[hi + 1]
+    stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full, one row per launch ({src})\n\n`ncu --set full --clock-control none`; cold caches, replayed launches: "
+                "durations are not bench values.  Units as ncu printed them.\n\n| # | kernel | " + " | ".join(t for t, _ in TABLE)
+                + " | top stalls |\n|---:|---|" + "---:|" * len(TABLE) + "---|\n")
+        for n, r in enumerate(rows[hi + 2:]):
+            cells = []
+            for t, m in TABLE:
+                if m not in hdr:
+                    cells.append("")
+                    continue
+                v, u = r[hdr.index(m)], units[hdr.index(m)]
+                try:
+                    x = float(v.replace(",", ""))
+                    if t == "time us":
+                        x = x * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u.replace("second", "s").replace("nsecond", "ns"), 1.0) if u in ("ns", "us", "ms", "s") else x
+                        v = f"{x:.1f}"
+                    elif "bytes" in m:
+                        v = f"{x:.2f} {u.replace('byte', 'B')}"
+                    elif t in ("grid", "block", "regs"):
+                        v = f"{int(x)}"
+                    else:
+                        v = f"{x:.1f}"
+                except ValueError:
+                    pass
+                cells.append(v)
+            top = sorted(((float(r[hdr.index(h)].replace(",", "")), h) for h in stall), reverse=True)[:3]
+            st = ", ".join(f"{h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {v:.1f}" for v, h in top)
+            f.write(f"| {n} | `{r[hdr.index('Kernel Name')].split('(')[0]}` | " + " | ".join(cells) + f" | {st} |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "table": table}[sys.argv[1]](sys.argv[2], sys.argv[3])
