@@ -642,57 +642,76 @@ __global__ void __launch_bounds__(stc::NTHREADS, 1) resnet_tc_kernel(const __gri
   // op.w bits: [0,9) TMEM column, [9,12) UMMAs in the block (1/2/4), 12 accumulate-first, 13 first block of a chunk,
   //            14 FiLM tile (N = 16, operand u), 15 first block of the job, [16,19) ring stage, 19 ring padding (no UMMA),
   //            20 owner (which of the two issuer warps executes it; both walk every op for the ring bookkeeping)
-  if (tid == 0) {
-    const uint32_t ring_a = smem_u32(smem + T::SM_RING);
+  // Built by the whole CTA: thread 0 only lays out the prefix sums (first op / first chunk of every (job, set) entry), then
+  // every op and chunk is written from a closed form of its index.  (A serial build by one thread cost more than the
+  // network evaluation itself in the single-evaluation launches - the decoder runs 4 samples per CTA.)
+  uint32_t* ent_chunk0 = reinterpret_cast<uint32_t*>(smem + T::SM_SCR);                 // [n_jobs * NSETS + 1] first chunk of an entry
+  {
     const uint32_t f_swb = swb_for(pad16(EMB)), f_bytes = 128u * f_swb;
-    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
-    uint32_t nops = 0, chunk_base = 0, ncp = 0;
-    for (int j = 0; j < n_jobs; ++j)
-      for (int set = 0; set < NSETS; ++set) {
+    if (tid == 0) {
+      uint32_t nops = 0, ncp = 0;
+      for (int j = 0; j < n_jobs; ++j) {
         const TcJob& job = p.jobs[j];
-        const uint32_t b_base = smem_u32(smem + T::SM_B + set * T::B_BYTES), u_base = smem_u32(smem + T::SM_U + set * 2048);
-        for (uint32_t off = 0; off < job.bytes; off += CHUNK)
-          chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, job.bytes - off));
-        op_begin[j * NSETS + set] = (uint16_t)nops;
-        const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
-        const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
-                              ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
-        uint32_t off = 0;
-        auto emit = [&](uint32_t hi, uint32_t b_addr, uint32_t col, uint32_t ks, uint32_t acc, uint32_t film, uint32_t bytes) {
-          const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
-          const uint32_t a_addr = ring_a + stage * CHUNK + (off % CHUNK);
-          const uint32_t w = (col + set * T_SET) | (ks << 9) | (acc << 12) | ((off % CHUNK == 0 ? 1u : 0u) << 13) |
-                             (film << 14) | ((off == 0 ? 1u : 0u) << 15) | (stage << 16);
-          ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
-          off += bytes;
-        };
-        const bool ffirst = job.film_tiles && f_bytes > blk;      // blocks in descending size (see film_first)
-        auto emit_film = [&]() {
-          for (uint32_t f = 0; f < job.film_tiles; ++f) emit(f_hi, u_base, T_FILM + f * 16, f_swb >> 5, 0u, 1u, f_bytes);
-        };
-        if (ffirst) emit_film();
-        const uint32_t nblk = job.mtiles * job.taps * nkb;
-        for (uint32_t bi = 0; bi < nblk; ++bi) {
+        const uint32_t nkb = job.a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+        const uint32_t n_e = job.film_tiles + job.mtiles * job.taps * nkb, c_e = (job.bytes + CHUNK - 1) / CHUNK;
+        for (int set = 0; set < NSETS; ++set) {
+          op_begin[j * NSETS + set] = (uint16_t)nops;
+          ent_chunk0[j * NSETS + set] = ncp;
+          nops += n_e;
+          ncp += c_e;
+        }
+      }
+      ent_chunk0[n_jobs * NSETS] = ncp;
+      // a step must span a whole number of ring revolutions: pad with 16-byte dummy chunks consumed by no-op entries
+      // of the last (job, set)
+      while (ncp % STAGES) {
+        ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
+        chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
+      }
+      op_begin[n_jobs * NSETS] = (uint16_t)nops;
+      op_begin[n_jobs * NSETS + 1] = (uint16_t)ncp;      // chunks per step
+    }
+    __syncthreads();
+    const uint32_t ring_a = smem_u32(smem + T::SM_RING);
+    const uint32_t f_hi = ((8u * f_swb) >> 4) | (1u << 14) | ((f_swb == 128 ? (uint32_t)SW_128 : (uint32_t)SW_32) << 29);
+    for (int e = 0; e < n_jobs * NSETS; ++e) {
+      const int j = e / NSETS, set = e % NSETS;
+      const TcJob& job = p.jobs[j];
+      const uint32_t op0 = op_begin[e], chunk_base = ent_chunk0[e];
+      const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+      const uint32_t nfilm = job.film_tiles, nblk = job.mtiles * job.taps * nkb;
+      for (uint32_t c = tid; c * CHUNK < job.bytes; c += NTHREADS)
+        chunk_tab[chunk_base + c] = make_uint2(job.a_off + c * CHUNK, min((uint32_t)CHUNK, job.bytes - c * CHUNK));
+      if ((uint32_t)tid >= nfilm + nblk) continue;
+      const uint32_t b_base = smem_u32(smem + T::SM_B + set * T::B_BYTES), u_base = smem_u32(smem + T::SM_U + set * 2048);
+      const uint32_t a_hi = ((8u * a_swb) >> 4) | (1u << 14) |
+                            ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
+      const bool ffirst = nfilm && f_bytes > blk;           // blocks in descending size (see film_first)
+      for (uint32_t i = tid; i < nfilm + nblk; i += NTHREADS) {
+        const bool is_film = ffirst ? i < nfilm : i >= nblk;
+        uint32_t off, hi, b_addr, col, ks, acc, owner = 0;
+        if (is_film) {
+          const uint32_t f = ffirst ? i : i - nblk;
+          off = (ffirst ? 0u : nblk * blk) + f * f_bytes;
+          hi = f_hi; b_addr = u_base; col = T_FILM + f * 16; ks = f_swb >> 5; acc = 0;
+        } else {
+          const uint32_t bi = ffirst ? i - nfilm : i;
+          off = (ffirst ? nfilm * f_bytes : 0u) + bi * blk;
           uint32_t t, tap, kb;
           if (job.mtiles >= 2) { t = bi % job.mtiles; kb = (bi / job.mtiles) % nkb; tap = bi / (job.mtiles * nkb); }
           else { t = 0; kb = bi % nkb; tap = bi / nkb; }
           const uint32_t tsel = job.taps == 3 ? tap : 1u;
-          const uint32_t b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB
-                                           : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
-          emit(a_hi, b_addr, T_ACC + t * NCOL, a_swb >> 5, (tap | kb) != 0 ? 1u : 0u, 0u, blk);
-          if (job.mtiles >= 2 && (t & 1u)) ops[nops - 1].w |= 1u << 20;      // issued by the second issuer warp
+          b_addr = (L == 4) ? b_base + tsel * (T::HALO * 128) + kb * T::SLAB : b_base + tsel * (BSLABS * T::SLAB) + kb * T::SLAB;
+          hi = a_hi; col = T_ACC + t * NCOL; ks = a_swb >> 5; acc = (tap | kb) != 0 ? 1u : 0u;
+          owner = (job.mtiles >= 2 && (t & 1u)) ? 1u : 0u;      // issued by the second issuer warp
         }
-        if (!ffirst) emit_film();
-        chunk_base += (job.bytes + CHUNK - 1) / CHUNK;
+        const uint32_t stage = (chunk_base + off / CHUNK) % STAGES;
+        const uint32_t a_addr = ring_a + stage * CHUNK + (off % CHUNK);
+        const uint32_t w = (col + set * T_SET) | (ks << 9) | (acc << 12) | ((off % CHUNK == 0 ? 1u : 0u) << 13) |
+                           ((is_film ? 1u : 0u) << 14) | ((off == 0 ? 1u : 0u) << 15) | (stage << 16) | (owner << 20);
+        ops[op0 + i] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), hi, w);
       }
-    // a step must span a whole number of ring revolutions: pad with 16-byte dummy chunks consumed by no-op entries
-    // of the last (job, set)
-    while (ncp % STAGES) {
-      ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
-      chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
     }
-    op_begin[n_jobs * NSETS] = (uint16_t)nops;
-    op_begin[n_jobs * NSETS + 1] = (uint16_t)ncp;      // chunks per step
   }
   fence_async_smem();
   tc_fence_before();
