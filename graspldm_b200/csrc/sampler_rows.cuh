@@ -31,7 +31,7 @@
 #pragma once
 
 namespace rows {
-constexpr int NS = 32;                          // samples per CTA
+template <int L> struct Geo { static constexpr int NS = 128 / L; };   // samples per CTA: 32 (L = 4) or 8 (L = 16)
 constexpr int NEPI = 512;                       // 16 epilogue warps
 constexpr int NTHREADS = 640;                   // + producer, issuer, two idle register donors (warps are allocated in fours)
 constexpr int SLAB = 192 * 128;                 // 64 channels x (32 halo + 128 + 32 halo) rows
@@ -76,12 +76,30 @@ __device__ __forceinline__ void bar_job_arrive() { asm volatile("bar.arrive 6, 5
 // per-thread epilogue state, kept small: the epilogue warps run at the register limit
 struct Ep {
   uint32_t tmem;        // TMEM base + this warp's lane quarter
-  int g, pos, s, row;   // warp-group, position, sample (lane), row = pos * 32 + s
+  int g, q, lane;       // warp-group, TMEM lane quarter (warp & 3), lane: row = q * 32 + lane
+  int pos, s, row;      // position and sample of the row: row = pos * NS + s (L = 4: pos = q, s = lane)
   uint8_t* smem;
   uint32_t po[3];       // this job's channel parameters (float offsets into SM_PAR): bias | gamma << 16, beta | g1 << 16, g2
   __device__ __forceinline__ float2* xg() const { return reinterpret_cast<float2*>(smem + SM_XG); }
   __device__ __forceinline__ float2* xl() const { return reinterpret_cast<float2*>(smem + SM_XL); }
 };
+
+// GroupNorm statistics of a sample's group: this thread's partial (sum, sum of squares) over its channels, summed over all
+// L positions of the sample.  A warp holds 32 / NS positions of a sample (lanes s, s + NS, ...): butterfly over those,
+// then the four lane quarters through shared memory.
+template <int L>
+__device__ __forceinline__ float2 gn_total(const Ep& e, float2 part) {
+  if (L == 16) {
+    part.x += __shfl_xor_sync(0xffffffffu, part.x, 8);  part.y += __shfl_xor_sync(0xffffffffu, part.y, 8);
+    part.x += __shfl_xor_sync(0xffffffffu, part.x, 16); part.y += __shfl_xor_sync(0xffffffffu, part.y, 16);
+  }
+  e.xg()[(e.g * 4 + e.q) * 32 + e.lane] = part;
+  bar_wg(e.g);
+  float2 t = e.xg()[(e.g * 4) * 32 + e.lane];
+#pragma unroll
+  for (int pp = 1; pp < 4; ++pp) { const float2 u = e.xg()[(e.g * 4 + pp) * 32 + e.lane]; t.x += u.x; t.y += u.y; }
+  return t;
+}
 
 template <int NV>
 __device__ __forceinline__ void ld_cols(const Ep& e, uint32_t col, float (&v)[NV]) {
@@ -224,6 +242,81 @@ __device__ __forceinline__ void narrow_epilogue(const Ep& e, int flags, const fl
   st_operand<4>(e, 0, x);
 }
 
+// 16-channel first stage of the L = 16 networks (grasp decoder, ppc latent denoiser): 4 channels per thread = GroupNorm
+// group g; same recipe flags as reg_epilogue.
+template <int L>
+__device__ __forceinline__ void quad_epilogue(const Ep& e, int flags, const float* film) {
+  constexpr int CH = 16, CW = 4;
+  const int c = e.g * CW;
+  float x[4], a[4], b[4];
+  ld_cols<4>(e, T_ACC + c, x);
+  ld_par<4>(e, 0, c, b);
+  float sm = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { x[i] += b[i]; sm += x[i]; sq = fmaf(x[i], x[i], sq); }
+  float mean = 0.f, rstd = 1.f;
+  if (flags & (E_GN | E_LN)) {
+    float ts, tq, inv;
+    if (flags & E_GN) {
+      const float2 t = gn_total<L>(e, make_float2(sm, sq));
+      ts = t.x; tq = t.y; inv = 1.0f / (float)(CW * L);
+    } else {
+      e.xl()[e.row * 4 + e.g] = make_float2(sm, sq);
+      bar_all();
+      ts = 0.f; tq = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { const float2 t = e.xl()[e.row * 4 + w]; ts += t.x; tq += t.y; }
+      inv = 1.0f / (float)CH;
+    }
+    mean = ts * inv;
+    rstd = rsqrtf(fmaxf(tq * inv - mean * mean, 0.f) + 1e-5f);
+  }
+  if (flags & E_GN) {
+    if (flags & E_FILM) {
+      ld_film<4>(film + c, a);
+      ld_film<4>(film + CH + c, b);
+    } else {
+      ld_par<4>(e, 1, c, a);
+      ld_par<4>(e, 2, c, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = fmaf(x[i] - mean, rstd * a[i], b[i]);
+  }
+  if (flags & E_SILU) {
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      const float2 t = silu_fast2(make_float2(x[i], x[i + 1]));
+      x[i] = t.x; x[i + 1] = t.y;
+    }
+  }
+  if (flags & E_LN) {
+    ld_par<4>(e, 3, c, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (x[i] - mean) * rstd * a[i];
+  }
+  if (flags & E_ADDRES) {
+    ld_cols<4>(e, T_RES + c, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] += b[i];
+  }
+  if (flags & E_STORERES) {
+    st_cols<4>(e, T_RES + c, x);
+    tmem_st_wait();
+  }
+  if (flags & E_LNNEXT) {       // PreNorm of the attention: operand = LayerNorm(result) * g2 over the 16 channels of the row
+    e.xl()[e.row * 4 + e.g] = make_float2((x[0] + x[1]) + (x[2] + x[3]), fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
+    bar_all();
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { const float2 t = e.xl()[e.row * 4 + w]; ts += t.x; tq += t.y; }
+    const float m = ts * (1.0f / CH), r = rsqrtf(fmaxf(tq * (1.0f / CH) - m * m, 0.f) + 1e-5f);
+    ld_par<4>(e, 4, c, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (x[i] - m) * r * a[i];
+  }
+  st_operand<4>(e, c, x);
+}
+
 // packed fp32 pairs: FADD2 / FMUL2 / FFMA2 do two values per issue slot, and the epilogue is issue bound
 struct F8 { float2 p[4]; };
 __device__ __forceinline__ F8 ld_par8(const Ep& e, int k, int c) {
@@ -269,6 +362,7 @@ __device__ __forceinline__ void silu8(float2 (&v)[4]) {
 
 // register-resident layer epilogue: ch = 32 / 64 / 128, this thread's cw = ch / 4 channels ([g * cw, (g+1) * cw) = one
 // GroupNorm group) stay in x[] from the single TMEM read to the operand store; chunks of 8 channels, k < cw / 8.
+template <int L>
 __device__ __forceinline__ void reg_epilogue(const Ep& e, int flags, int ch, const float* film, long long* rec) {
   const int cw = ch >> 2, nk = cw >> 3, c_lo = e.g * cw;
   float2 x[4][4];
@@ -296,12 +390,10 @@ __device__ __forceinline__ void reg_epilogue(const Ep& e, int flags, int ch, con
   float mean = 0.f, rstd = 1.f;           // GroupNorm of this thread's group, or channel LayerNorm of its row
   if (flags & (E_GN | E_LN)) {
     float ts = 0.f, tq = 0.f, inv;
-    if (flags & E_GN) {                   // sums over the 4 positions of a sample: the 4 warps of this warp-group
-      e.xg()[(e.g * 4 + e.pos) * 32 + e.s] = make_float2(s2.x + s2.y, q2.x + q2.y);
-      bar_wg(e.g);
-#pragma unroll
-      for (int pp = 0; pp < 4; ++pp) { const float2 t = e.xg()[(e.g * 4 + pp) * 32 + e.s]; ts += t.x; tq += t.y; }
-      inv = 1.0f / (float)(cw * 4);
+    if (flags & E_GN) {                   // sums over the L positions of a sample
+      const float2 t = gn_total<L>(e, make_float2(s2.x + s2.y, q2.x + q2.y));
+      ts = t.x; tq = t.y;
+      inv = 1.0f / (float)(cw * L);
     } else {                              // sums over the 4 warp-groups of a row
       e.xl()[e.row * 4 + e.g] = make_float2(s2.x + s2.y, q2.x + q2.y);
       bar_all();
@@ -380,6 +472,7 @@ __device__ __forceinline__ void reg_epilogue(const Ep& e, int flags, int ch, con
 // 256-wide layers (final block, last stage conv): 64 channels per thread do not fit the register file, so the
 // accumulator is read twice (statistics, apply) - 32 / 16 columns per tcgen05.wait::ld.  Residual stream: packed bf16 pairs.
 // Returns the final-conv partial dot product (E_FINAL) of this thread's channels.
+template <int L>
 __device__ __forceinline__ float wide_epilogue(const Ep& e, int flags, const float* film) {
   constexpr int CH = 256, CW = 64;
   const int c_lo = e.g * CW;
@@ -405,14 +498,10 @@ __device__ __forceinline__ float wide_epilogue(const Ep& e, int flags, const flo
         }
       }
     }
-    e.xg()[(e.g * 4 + e.pos) * 32 + e.s] = make_float2(s2.x + s2.y, q2.x + q2.y);
-    bar_wg(e.g);
-    float ts = 0.f, tq = 0.f;
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp) { const float2 t = e.xg()[(e.g * 4 + pp) * 32 + e.s]; ts += t.x; tq += t.y; }
-    const float inv = 1.0f / (float)(CW * 4);
-    mean = ts * inv;
-    rstd = rsqrtf(fmaxf(tq * inv - mean * mean, 0.f) + 1e-5f);
+    const float2 t = gn_total<L>(e, make_float2(s2.x + s2.y, q2.x + q2.y));
+    const float inv = 1.0f / (float)(CW * L);
+    mean = t.x * inv;
+    rstd = rsqrtf(fmaxf(t.y * inv - mean * mean, 0.f) + 1e-5f);
   }
   const float2 nmean = make_float2(-mean, -mean), rstd2 = make_float2(rstd, rstd);
   float2 dot2 = make_float2(0.f, 0.f);
@@ -613,7 +702,165 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
   }
 }
 
+// ---- linear attention for L = 16 (8 samples per CTA, row = position * 8 + sample) -----------------------------------
+// Per (sample, head): out[n][e] = sum_n' S[n][n'] v[n'][e],  S = Q^ K^T,  Q^[n][d] = softmax_d(q[n][d]) * 32^-0.5,
+// K^[n'][d] = softmax over the 16 positions n' of k[n'][d]   (resnets.py:211-235).  16 x 16 x 32 per pair is too much to
+// pass around thread by thread (every thread would read every k / v row), so the rows go to shared memory once as bf16
+// [sample][position][32] matrices and the two small products run on mma.sync (m16n8k16, fp32 accumulate): warp q of
+// head h takes samples 2q and 2q + 1.  Matrices live in rows 32..159 of the head's idle operand slab: K^ (8 KB), then
+// Q^ and later V (8 KB).  16-byte chunk c of row (s, n) sits at chunk c ^ (n >> 1) ^ s: conflict-free for the row
+// writers (lanes = 4 positions x 8 samples) and for ldmatrix (8 consecutive positions of one sample).
+__device__ __forceinline__ uint8_t* arow(uint8_t* base, int s, int n, int c) {
+  return base + (s * 16 + n) * 64 + (((c ^ (n >> 1) ^ s) & 3) << 4);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void attention16_epilogue(const Ep& e) {
+  uint8_t* Kb = e.smem + SM_A + e.g * SLAB + 32 * 128;      // K^ [8][16][32] bf16
+  uint8_t* Qb = Kb + 8192;                                   // Q^, later V
+  const int h = e.g, n = e.pos, s = e.s;
+  {  // raw k row of this (position, sample)
+    uint32_t rk[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_issue<8>(e, T_ACC + 128 + h * 32 + i * 8, rk[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[8];
+      ld_use<8>(rk[i], t);
+      *reinterpret_cast<uint4*>(arow(Kb, s, n, i)) = pack8(t);
+    }
+  }
+  {  // Q^ row: softmax over the 32 head channels, in-thread
+    float qs[32];
+    uint32_t rq[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_issue<8>(e, T_ACC + h * 32 + i * 8, rq[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[8];
+      ld_use<8>(rq[i], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qs[i * 8 + j] = t[j];
+    }
+    float m = qs[0];
+#pragma unroll
+    for (int d = 1; d < 32; ++d) m = fmaxf(m, qs[d]);
+    float sum = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { qs[d] = __expf(qs[d] - m); sum += qs[d]; }
+    const float sc = __fdividef(0.17677669529663687f, sum);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) qs[d] *= sc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(arow(Qb, s, n, i)) = pack8(&qs[8 * i]);
+  }
+  bar_wg(h);
+  {  // K^: soft-max over the 16 positions, in place.  Thread (of the 128 of the head) = (sample, channel pair).
+    const int tl = e.q * 32 + e.lane, ks = tl >> 4, j = tl & 15;
+    float2 v[16];
+    float2 mx = make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn) {
+      const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(arow(Kb, ks, nn, j >> 2) + (j & 3) * 4);
+      v[nn] = make_float2(__low2float(hh), __high2float(hh));
+      mx.x = fmaxf(mx.x, v[nn].x); mx.y = fmaxf(mx.y, v[nn].y);
+    }
+    float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn) {
+      v[nn].x = __expf(v[nn].x - mx.x); v[nn].y = __expf(v[nn].y - mx.y);
+      z.x += v[nn].x; z.y += v[nn].y;
+    }
+    z.x = __fdividef(1.0f, z.x); z.y = __fdividef(1.0f, z.y);
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn)
+      *reinterpret_cast<uint32_t*>(arow(Kb, ks, nn, j >> 2) + (j & 3) * 4) = pack_bf16(v[nn].x * z.x, v[nn].y * z.y);
+  }
+  bar_wg(h);
+  // S = Q^ K^T for the two samples of this warp (fp32 accumulators), as bf16 A fragments of the second product
+  const int l = e.lane;
+  uint32_t pa[2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int ss = 2 * e.q + u;
+    float sacc[2][4] = {};
+    uint32_t a0[4], a1[4], b[4];
+    ldsm_x4(a0, arow(Qb, ss, l & 15, l >> 4));            // d 0..15: (rows 0-7, lo), (rows 8-15, lo), (rows 0-7, hi), (rows 8-15, hi)
+    ldsm_x4(a1, arow(Qb, ss, l & 15, 2 + (l >> 4)));      // d 16..31
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {                         // n' tile: positions 8t .. 8t+7, the four 8-channel chunks
+      ldsm_x4(b, arow(Kb, ss, 8 * t + (l & 7), l >> 3));
+      mma_bf16_16816(sacc[t], a0, b[0], b[1]);
+      mma_bf16_16816(sacc[t], a1, b[2], b[3]);
+    }
+    pa[u][0] = pack_bf16(sacc[0][0], sacc[0][1]); pa[u][1] = pack_bf16(sacc[0][2], sacc[0][3]);
+    pa[u][2] = pack_bf16(sacc[1][0], sacc[1][1]); pa[u][3] = pack_bf16(sacc[1][2], sacc[1][3]);
+  }
+  bar_wg(h);                                              // every Q^ fragment has been read: V takes its place
+  {
+    uint32_t rv[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_issue<8>(e, T_ACC + 256 + h * 32 + i * 8, rv[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[8];
+      ld_use<8>(rv[i], t);
+      *reinterpret_cast<uint4*>(arow(Qb, s, n, i)) = pack8(t);
+    }
+  }
+  bar_wg(h);
+  float o[2][4][4];                                       // out[n][e]: [sample][e tile][fragment]
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int ss = 2 * e.q + u;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {                      // e tiles 2 t2, 2 t2 + 1: V^T fragments (k = n', n = e)
+      uint32_t b[4];
+      ldsm_x4_t(b, arow(Qb, ss, l & 15, 2 * t2 + (l >> 4)));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[u][2 * t2][i] = 0.f; o[u][2 * t2 + 1][i] = 0.f; }
+      mma_bf16_16816(o[u][2 * t2], pa[u], b[0], b[1]);
+      mma_bf16_16816(o[u][2 * t2 + 1], pa[u], b[2], b[3]);
+    }
+  }
+  bar_all();                                              // the exchange rows become operand rows again
+  {
+    const int gid = l >> 2, tig = l & 3;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ss = 2 * e.q + u;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int chan = h * 32 + 8 * t + 2 * tig;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int R = 32 + (gid + 8 * hf) * 8 + ss;
+          *reinterpret_cast<uint32_t*>(e.smem + SM_A + (chan >> 6) * SLAB + R * 128 + ((((chan & 63) >> 3) ^ (R & 7)) << 4) +
+                                       (chan & 7) * 2) = pack_bf16(o[u][t][2 * hf], o[u][t][2 * hf + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int L>
 __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_constant__ TcParams p) {
+  constexpr int NS = Geo<L>::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -633,11 +880,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   const int cta_s0 = blockIdx.x * NS;
   const ResNetLayout& lay = p.lay;
   const float* W = p.W;
-  constexpr int L = 4;
   const int n_steps = (p.mode == 0) ? p.n_steps : 1;
   const int n_rj = p.n_jobs;
 
   // ---- one-time setup
+  if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[0] = clock64();
   for (int i = tid; i < SM_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -649,7 +896,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   if (tid < NS * L) {
     const int s = tid / L, l = tid % L;
     float v = 0.f;
-    if (cta_s0 + s < p.n) v = __ldg(p.x_in + (size_t)(cta_s0 + s) * L + l);
+    if (cta_s0 + s < p.n) {
+      if (p.mode != 2) {   // denoiser: the latent itself
+        v = __ldg(p.x_in + (size_t)(cta_s0 + s) * L + l);
+      } else {             // decoder in_layer: Linear(D -> L)   (grasp_vae.py:419)
+        v = __ldg(p.head + L * p.D + l);
+        for (int d = 0; d < p.D; ++d) v = fmaf(__ldg(p.head + l * p.D + d), __ldg(p.x_in + (size_t)(cta_s0 + s) * p.D + d), v);
+      }
+    }
     s_x[s * L + l] = v;
     s_x[128 + s * L + l] = 0.f;
     s_x[256 + s * L + l] = 0.f;
@@ -660,60 +914,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   // op.x / op.y: low words of the A (activation) / B (weight) descriptors; op.z: high word of the B descriptor;
   // op.w: [0,9) TMEM column, [9,12) K steps, 12 accumulate, 13 first use of a ring chunk, 15 first op of the job,
   //       [16,19) ring stage, 19 ring padding, [20,25) N / 16
+  // Thread 0 lays out the prefix sums only (parameter offsets, first op / first chunk of every job); the tables themselves
+  // are written by one thread per job.  (A fully serial build cost 80 k cycles: nothing next to a 100-step sampler launch,
+  // 40 % on top of the single evaluation of the decoder.)
+  uint32_t* chunk_begin = reinterpret_cast<uint32_t*>(smem + SM_XL);       // [n_rj + 1], scratch until the step loop starts
   if (tid == 0) {
-    const uint32_t ring_a = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A);
-    uint32_t nops = 0, chunk_base = 0, ncp = 0;
+    uint32_t nops = 0, ncp = 0;
     int npar = 0;
     for (int j = 0; j < n_rj; ++j) {
       const TcJob& job = p.jobs[j];
-      {
-        // FiLM layers take their GroupNorm affine from the FiLM table (folded), so gamma / beta are not staged for them
-        const bool film = (job.flags & E_FILM) != 0;
-        const int src[5] = {job.o_bias, film ? -1 : job.o_gamma, film ? -1 : job.o_beta, job.o_g, job.o_g2};
-        for (int k = 0; k < 5; ++k) {
-          const bool use = src[k] >= 0 && !(job.flags & E_ATTN) && npar + job.ch <= PAR_FLOATS;
-          s_ptab[j * 5 + k] = (int16_t)(use ? npar : -1);
-          if (use) npar += (job.ch + 3) & ~3;
-        }
-        // x: flags | ch << 16; y: FiLM offset | g2 << 16; z: bias | gamma << 16; w: beta | g1 << 16 (float offsets in SM_PAR)
-        uint32_t o[5];
-        for (int k = 0; k < 5; ++k) o[k] = (uint32_t)max((int)s_ptab[j * 5 + k], 0);
-        reinterpret_cast<uint4*>(smem + SM_JD)[j] = make_uint4((uint32_t)job.flags | ((uint32_t)job.ch << 16),
-                                                              (uint32_t)max(job.o_film, 0) | (o[4] << 16), o[0] | (o[1] << 16),
-                                                              o[2] | (o[3] << 16));
+      // FiLM layers take their GroupNorm affine from the FiLM table (folded), so gamma / beta are not staged for them
+      const bool film = (job.flags & E_FILM) != 0;
+      const int src[5] = {job.o_bias, film ? -1 : job.o_gamma, film ? -1 : job.o_beta, job.o_g, job.o_g2};
+      for (int k = 0; k < 5; ++k) {
+        const bool use = src[k] >= 0 && !(job.flags & E_ATTN) && npar + job.ch <= PAR_FLOATS;
+        s_ptab[j * 5 + k] = (int16_t)(use ? npar : -1);
+        if (use) npar += (job.ch + 3) & ~3;
       }
-      const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
-      const uint32_t mb = job.mtiles * job.taps * nkb * blk;            // bytes of the main blocks
-      const uint32_t w_hi = ((8u * a_swb) >> 4) | (1u << 14) |
-                            ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
-      for (uint32_t off = 0; off < mb; off += CHUNK) chunk_tab[ncp++] = make_uint2(job.a_off + off, min((uint32_t)CHUNK, mb - off));
+      const uint32_t a_swb = job.a_swb, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+      const uint32_t mb = job.mtiles * job.taps * nkb * (a_swb << 7);            // bytes of the main blocks
       op_begin[j] = (uint16_t)nops;
-      const uint32_t n_main = (job.flags & E_ATTN) ? 128u : (uint32_t)((job.ch + 15) & ~15);
-      uint32_t last_chunk = 0xffffffffu;
-      bool first = true;
-      auto emit = [&](uint32_t a_addr, uint32_t off, uint32_t col, uint32_t ks, uint32_t acc, uint32_t nn) {
-        const uint32_t ci = chunk_base + off / CHUNK, stage = ci % STAGES;
-        const uint32_t b_addr = ring_a + stage * CHUNK + (off % CHUNK);
-        const uint32_t w = col | (ks << 9) | (acc << 12) | ((ci != last_chunk ? 1u : 0u) << 13) | ((first ? 1u : 0u) << 15) |
-                           (stage << 16) | ((nn >> 4) << 20);
-        ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), w_hi, w);
-        last_chunk = ci;
-        first = false;
-      };
-      for (uint32_t tap = 0; tap < job.taps; ++tap)
-        for (uint32_t kb = 0; kb < nkb; ++kb) {
-          const uint32_t tsel = job.taps == 3 ? tap : 1u;
-          const uint32_t a_addr = a_base + kb * SLAB + tsel * 32 * 128;
-          const uint32_t boff = (tap * nkb + kb) * job.mtiles * blk;
-          const uint32_t acc = (tap | kb) != 0 ? 1u : 0u;
-          if (job.flags & E_ATTN) {
-            for (uint32_t t = 0; t < 3; ++t) emit(a_addr, boff + t * blk, T_ACC + t * 128, a_swb >> 5, acc, 128u);
-          } else {
-            emit(a_addr, boff, T_ACC, a_swb >> 5, acc, job.mtiles == 2 ? 256u : n_main);
-          }
-        }
-      chunk_base += (mb + CHUNK - 1) / CHUNK;
+      chunk_begin[j] = ncp;
+      nops += job.taps * nkb * ((job.flags & E_ATTN) ? 3u : 1u);
+      ncp += (mb + CHUNK - 1) / CHUNK;
     }
+    chunk_begin[n_rj] = ncp;
     while (ncp % STAGES) {
       ops[nops++] = make_uint4(0, 0, 0, (1u << 13) | (1u << 19) | ((ncp % STAGES) << 16));
       chunk_tab[ncp++] = make_uint2(p.jobs[0].a_off, 16u);
@@ -722,22 +947,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     op_begin[MAXRJ] = (uint16_t)ncp;
   }
   __syncthreads();
-  // every per-channel parameter of the network, once (step-invariant)
-  for (int j = 0; j < n_rj; ++j) {
+  if (tid < n_rj) {
+    const int j = tid;
     const TcJob& job = p.jobs[j];
-    const int src[5] = {job.o_bias, job.o_gamma, job.o_beta, job.o_g, job.o_g2};
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int o = s_ptab[j * 5 + k];
-      if (o >= 0)
-        for (int i = tid; i < job.ch; i += NTHREADS) s_par[o + i] = __ldg(W + src[k] + i);
+    const uint32_t ring_a = smem_u32(smem + SM_RING), a_base = smem_u32(smem + SM_A);
+    {
+      // x: flags | ch << 16; y: FiLM offset | g2 << 16; z: bias | gamma << 16; w: beta | g1 << 16 (float offsets in SM_PAR)
+      uint32_t o[5];
+      for (int k = 0; k < 5; ++k) o[k] = (uint32_t)max((int)s_ptab[j * 5 + k], 0);
+      reinterpret_cast<uint4*>(smem + SM_JD)[j] = make_uint4((uint32_t)job.flags | ((uint32_t)job.ch << 16),
+                                                            (uint32_t)max(job.o_film, 0) | (o[4] << 16), o[0] | (o[1] << 16),
+                                                            o[2] | (o[3] << 16));
     }
+    const uint32_t a_swb = job.a_swb, blk = a_swb << 7, nkb = a_swb == 128 ? (uint32_t)job.kpt >> 6 : 1u;
+    const uint32_t mb = job.mtiles * job.taps * nkb * blk;            // bytes of the main blocks
+    const uint32_t w_hi = ((8u * a_swb) >> 4) | (1u << 14) |
+                          ((a_swb == 128 ? (uint32_t)SW_128 : a_swb == 64 ? (uint32_t)SW_64 : (uint32_t)SW_32) << 29);
+    // the image stores a job's blocks in descending size: FiLM tiles (emb 64: 16 KB) come first when they are larger
+    // than the main blocks (see film_first in sampler_tc.cu)
+    const uint32_t f_bytes = 128u * swb_for(pad16(L == 4 ? 16 : 64));
+    const uint32_t main_off = (job.film_tiles && f_bytes > blk) ? job.film_tiles * f_bytes : 0u;
+    const uint32_t chunk_base = chunk_begin[j];
+    for (uint32_t off = 0, c = chunk_base; off < mb; off += CHUNK, ++c)
+      chunk_tab[c] = make_uint2(job.a_off + main_off + off, min((uint32_t)CHUNK, mb - off));
+    uint32_t nops = op_begin[j];
+    const uint32_t n_main = (job.flags & E_ATTN) ? 128u : (uint32_t)((job.ch + 15) & ~15);
+    uint32_t last_chunk = 0xffffffffu;
+    bool first = true;
+    auto emit = [&](uint32_t a_addr, uint32_t off, uint32_t col, uint32_t ks, uint32_t acc, uint32_t nn) {
+      const uint32_t ci = chunk_base + off / CHUNK, stage = ci % STAGES;
+      const uint32_t b_addr = ring_a + stage * CHUNK + (off % CHUNK);
+      const uint32_t w = col | (ks << 9) | (acc << 12) | ((ci != last_chunk ? 1u : 0u) << 13) | ((first ? 1u : 0u) << 15) |
+                         (stage << 16) | ((nn >> 4) << 20);
+      ops[nops++] = make_uint4(0x10000u | (a_addr >> 4), 0x10000u | (b_addr >> 4), w_hi, w);
+      last_chunk = ci;
+      first = false;
+    };
+    for (uint32_t tap = 0; tap < job.taps; ++tap)
+      for (uint32_t kb = 0; kb < nkb; ++kb) {
+        const uint32_t tsel = job.taps == 3 ? tap : 1u;
+        const uint32_t a_addr = a_base + kb * SLAB + (32 + ((int)tsel - 1) * NS) * 128;      // a tap = a shift by one position = NS rows
+        const uint32_t boff = (tap * nkb + kb) * job.mtiles * blk;
+        const uint32_t acc = (tap | kb) != 0 ? 1u : 0u;
+        if (job.flags & E_ATTN) {
+          for (uint32_t t = 0; t < 3; ++t) emit(a_addr, boff + t * blk, T_ACC + t * 128, a_swb >> 5, acc, 128u);
+        } else {
+          emit(a_addr, boff, T_ACC, a_swb >> 5, acc, job.mtiles == 2 ? 256u : n_main);
+        }
+      }
+  }
+  // every per-channel parameter of the network, once (step-invariant): one (job, parameter) pair per warp at a time
+  for (int jk = wid; jk < n_rj * 5; jk += NTHREADS / 32) {
+    const int j = jk / 5, k = jk - 5 * j;
+    const TcJob& job = p.jobs[j];
+    const int o = s_ptab[jk];
+    if (o < 0) continue;
+    const int src = k == 0 ? job.o_bias : k == 1 ? job.o_gamma : k == 2 ? job.o_beta : k == 3 ? job.o_g : job.o_g2;
+    for (int i = lane; i < job.ch; i += 32) s_par[o + i] = __ldg(W + src + i);
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[1] = clock64();
   const uint32_t cps = op_begin[MAXRJ];
   const int wid_u = __shfl_sync(0xffffffffu, wid, 0);
   if (wid_u >= 16) {
@@ -813,8 +1086,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     // =========================== epilogue warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     Ep e;
-    e.g = wid >> 2; e.pos = wid & 3; e.s = lane; e.row = e.pos * 32 + lane;
-    e.tmem = tmem_base + ((uint32_t)(e.pos * 32) << 16);
+    e.g = wid >> 2; e.q = wid & 3; e.lane = lane; e.row = e.q * 32 + lane;
+    e.pos = e.row / NS; e.s = e.row % NS;
+    e.tmem = tmem_base + ((uint32_t)(e.q * 32) << 16);
     e.smem = smem;
     const bool dbg = p.prof != nullptr && blockIdx.x == 0;
     auto handoff = [&]() {
@@ -825,7 +1099,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     };
     // FiLM table row of this thread's sample: (object, step) in the sampler, the sample itself in a single evaluation
     const int smp = min(cta_s0 + e.s, p.n - 1);
-    const size_t film_row0 = ((p.mode == 0) ? (size_t)(smp / p.gpo) * n_steps : (size_t)smp) * p.film_stride;
+    const size_t film_row0 = ((p.mode == 0) ? (size_t)(smp / p.gpo) * n_steps : (p.mode == 2) ? (size_t)(smp / p.gpo) : (size_t)smp) *
+                             p.film_stride;
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
       const float* film_step = p.film + (film_row0 + (size_t)step * p.film_stride);
@@ -836,7 +1111,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
       float* s_xin = s_x + 384;
       float* s_sc = s_x + 512;
       if (e.g == 0) {
-        float v = s_x[e.s * 4 + e.pos];
+        float v = s_x[e.s * L + e.pos];
         if (edm) {
           const float* cf = p.coef + (size_t)step * kEvalRow;
           const int slot = (int)__ldg(cf + 8);
@@ -848,28 +1123,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 8; ++i) c4[i] = __ldg(cf + i);
           v = eval_input(c4, v, z);
-          s_xin[e.s * 4 + e.pos] = v;
+          s_xin[e.s * L + e.pos] = v;
           v = __fmul_rn(c4[0], v);
         }
-        s_sc[e.s * 4 + e.pos] = v;
+        s_sc[e.s * L + e.pos] = v;
         bar_wg(0);
       }
-      // ---- init_conv: Conv1d(1 -> 4, k7, p3) on the input -> residual stream and operand (warp-group 0: 4 channels)
-      if (e.g == 0) {
+      // ---- init_conv: Conv1d(1 -> dim, k7, p3) on the input -> residual stream and operand.  dim = 4 (L = 4): warp-group
+      //      0 alone; dim = 16 (L = 16): four channels per warp-group
+      if (L == 16) bar_all();          // every warp-group reads s_sc
+      if (L == 16 || e.g == 0) {
+        const int c0 = (L == 16) ? 4 * e.g : 0;
         float v[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float a = __ldg(W + lay.init_b + c);
+          float a = __ldg(W + lay.init_b + c0 + c);
 #pragma unroll
           for (int t = 0; t < 7; ++t) {
             const int ll = e.pos + t - 3;
-            if (ll >= 0 && ll < 4) a = fmaf(__ldg(W + lay.init_w + c * 7 + t), s_sc[e.s * 4 + ll], a);
+            if (ll >= 0 && ll < L) a = fmaf(__ldg(W + lay.init_w + (c0 + c) * 7 + t), s_sc[e.s * L + ll], a);
           }
           v[c] = a;
         }
-        st_res<4>(e, false, 0, v);
+        st_res<4>(e, false, c0, v);
         tmem_st_wait();
-        st_operand<4>(e, 0, v);
+        st_operand<4>(e, c0, v);
       }
       handoff();
 #pragma unroll 1
@@ -881,14 +1159,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
         if (!(flags & E_ATTN)) {
           e.po[0] = jd.z; e.po[1] = jd.w; e.po[2] = jd.y >> 16;
           if (flags & E_FILM) {
-            const int cw = ch >= 32 ? ch >> 2 : 4, c_lo = ch >= 32 ? e.g * cw : 0;
+            const int cw = ch >= 32 ? ch >> 2 : 4, c_lo = ch >= 32 ? e.g * cw : ch == 16 ? 4 * e.g : 0;
             prefetch_l1(film + c_lo);
             prefetch_l1(film + c_lo + cw - 1);
             prefetch_l1(film + ch + c_lo);
             prefetch_l1(film + ch + c_lo + cw - 1);
           }
         }
-        const bool rec = dbg && tid == 0 && step == 1;
+        const bool rec = dbg && tid == 0 && step == (n_steps > 1 ? 1 : 0);
         if (rec) p.prof[64 + 8 * j] = clock64();
         bar_job_sync();
         tc_fence_after();
@@ -905,13 +1183,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
           }
         }
         if (flags & E_ATTN) {
-          attention_epilogue(e);
+          if (L == 4) attention_epilogue(e);
+          else attention16_epilogue(e);
         } else if (ch >= 32 && ch <= 128) {
-          reg_epilogue(e, flags, ch, film, rec ? p.prof + 64 + 8 * j : nullptr);
-        } else if (ch == 4) {
-          narrow_epilogue(e, flags, film);
+          reg_epilogue<L>(e, flags, ch, film, rec ? p.prof + 64 + 8 * j : nullptr);
+        } else if (ch < 32) {
+          if (L == 4) narrow_epilogue(e, flags, film);
+          else quad_epilogue<L>(e, flags, film);
         } else {
-          const float dot = wide_epilogue(e, flags, film);
+          const float dot = wide_epilogue<L>(e, flags, film);
           if (flags & E_FINAL) {
             // ======== final_conv (1x1 -> 1 channel) + scheduler update of x[sample][position]
             e.xl()[e.row * 4 + e.g] = make_float2(dot, 0.f);
@@ -926,14 +1206,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
                 float c16[10];
 #pragma unroll
                 for (int i = 0; i < 10; ++i) c16[i] = __ldg(p.coef + (size_t)step * kEvalRow + i);
-                float x = s_x[s * 4 + l], y = s_y[s * 4 + l], z = s_z[s * 4 + l];
-                eval_update(c16, s_xin[s * 4 + l], eps, p.clip, x, y, z);
-                s_x[s * 4 + l] = x; s_y[s * 4 + l] = y; s_z[s * 4 + l] = z;
+                float x = s_x[s * L + l], y = s_y[s * L + l], z = s_z[s * L + l];
+                eval_update(c16, s_xin[s * L + l], eps, p.clip, x, y, z);
+                s_x[s * L + l] = x; s_y[s * L + l] = y; s_z[s * L + l] = z;
                 const int slot = (int)c16[9];
                 if (p.x_all && ok && slot >= 0) p.x_all[((size_t)slot * p.n + cta_s0 + s) * L + l] = x;
               } else if (p.mode == 0) {
                 const float* cf = p.coef + (size_t)step * 8;
-                const float x = s_x[s * 4 + l];
+                const float x = s_x[s * L + l];
                 float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(__ldg(cf + 0), eps)), __ldg(cf + 1));
                 if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
                 float prev;
@@ -948,10 +1228,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
                 } else {
                   prev = __fadd_rn(__fmul_rn(__ldg(cf + 2), x0), __fmul_rn(__ldg(cf + 3), eps));
                 }
-                s_x[s * 4 + l] = prev;
+                s_x[s * L + l] = prev;
                 if (p.x_all && ok) p.x_all[((size_t)(step + 1) * p.n + cta_s0 + s) * L + l] = prev;
               } else {
-                s_x[s * 4 + l] = eps;
+                s_x[s * L + l] = eps;
               }
             }
             bar_all();
@@ -961,10 +1241,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
         if (j + 1 < n_rj) handoff();
       }
     }
-    if (e.g == 0 && cta_s0 + e.s < p.n) p.x_out[(size_t)(cta_s0 + e.s) * L + e.pos] = s_x[e.s * 4 + e.pos];
+    if (p.mode != 2) {
+      if (e.g == 0 && cta_s0 + e.s < p.n) p.x_out[(size_t)(cta_s0 + e.s) * L + e.pos] = s_x[e.s * L + e.pos];
+    } else if (tid < NS * 7) {
+      // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430); s_x was written by
+      // warp-group 0 behind the bar_all of the final job
+      const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
+      const int s = tid / 7, o = tid - s * 7;
+      if (cta_s0 + s < p.n) {
+        const float* x = s_x + s * L;
+        if (o < 6) {
+          float a = __ldg(hw + 6 * L + o);
+          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
+          p.tmrp[(size_t)(cta_s0 + s) * 6 + o] = a;
+        } else {
+          float a = __ldg(hw + 6 * L + 6 + L);
+          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
+          p.logit[cta_s0 + s] = a;
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[2] = clock64();
   if (wid == 0) tmem_dealloc<512>(tmem_base);
 }
 

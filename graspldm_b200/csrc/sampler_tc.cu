@@ -1262,7 +1262,7 @@ __global__ void __launch_bounds__(256) film_table_kernel(const float* __restrict
     __syncthreads();
     for (int idx = tid; idx < nt * EMB; idx += 256) {
       const int e = idx % EMB, t = idx / EMB;
-      float tv = __ldg(te + (size_t)(te_per_block ? b : t0 + t) * EMB + e);
+      float tv = te ? __ldg(te + (size_t)(te_per_block ? b : t0 + t) * EMB + e) : 0.f;      // no time embedding: ResNet1D
       if (cls_emb) tv += __ldg(cls_emb + (size_t)(b / z_div) * EMB + e);      // class_conditioned_resnet.py:96-98
       float a = 0.f;
       for (int r = 0; r < R; ++r) { const float zz = tv + s_ie[r * EMB + e]; a += zz / (1.0f + __expf(-zz)); }
@@ -1328,16 +1328,21 @@ static int g_tc_sets = 0;
 // spreads a small batch over twice as many SMs (16 samples per CTA) and finishes it sooner
 static int g_tc_rows = -1;
 
+// fpc latent denoiser (L = 4, dim 4, emb 16) or the L = 16 family (ppc latent denoiser, grasp decoder trunk: dim 16, emb 64)
 static bool rows_supported(const GldmResNetCfg& c) {
-  return c.L == 4 && c.emb_dim == 16 && c.time_cond && c.n_stages == 4 && c.groups == 4 && c.ch[0] == 4 && c.ch[1] == 32 &&
-         c.ch[2] == 64 && c.ch[3] == 128 && c.ch[4] == 256;
+  const bool l4 = c.L == 4 && c.emb_dim == 16 && c.time_cond && c.ch[0] == 4;
+  const bool l16 = c.L == 16 && c.emb_dim == 64 && c.ch[0] == 16;
+  return (l4 || l16) && c.n_stages == 4 && c.groups == 4 && c.ch[1] == 32 && c.ch[2] == 64 && c.ch[3] == 128 && c.ch[4] == 256;
 }
 
-static int launch_rows(TcParams& p, cudaStream_t s) {
+template <int L>
+static int launch_rows_l(TcParams& p, cudaStream_t s) {
   static SmemOptIn attr;
+  constexpr int EMB = (L == 4) ? 16 : 64;
   const int smem = rows::SM_TOTAL + 1024;
-  if (int rc = opt_in_smem(attr, rows::resnet_rows_kernel, smem, "resnet_rows_kernel")) return rc;
-  // FiLM table: one row per (object, step) in the sampler, one per sample in a single evaluation; stream-ordered scratch
+  if (int rc = opt_in_smem(attr, rows::resnet_rows_kernel<L>, smem, "resnet_rows_kernel")) return rc;
+  // FiLM table: one row per (object, step) in the sampler, per sample in a single evaluation with its own time, per object
+  // in the decoder (no time embedding); stream-ordered scratch
   FilmJobs fj = {};
   for (int j = 0; j < p.n_jobs; ++j)
     if (p.jobs[j].o_film >= 0) {
@@ -1346,38 +1351,54 @@ static int launch_rows(TcParams& p, cudaStream_t s) {
       fj.o_gamma[fj.n] = p.jobs[j].o_gamma; fj.o_beta[fj.n] = p.jobs[j].o_beta; fj.o_film[fj.n] = p.jobs[j].o_film;
       ++fj.n;
     }
-  const int blocks = p.mode == 0 ? ceil_div(p.n, p.gpo) : p.n, steps = p.mode == 0 ? p.n_steps : 1;
+  const int blocks = p.mode == 1 ? p.n : ceil_div(p.n, p.gpo), steps = p.mode == 0 ? p.n_steps : 1;
   float* film = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&film), sizeof(float) * (size_t)blocks * steps * p.film_stride, s) != cudaSuccess) {
     set_error("resnet_rows: cudaMallocAsync of the FiLM table (%lld bytes) failed",
               (long long)(sizeof(float) * (size_t)blocks * steps * p.film_stride));
     return GLDM_ECUDA;
   }
-  film_table_kernel<16><<<blocks, 256, 0, s>>>(p.W, p.lay, fj, p.cfg.cond_ch, p.cfg.cond_dim, p.z_cond, p.mode == 0 ? 1 : p.gpo,
-                                               p.te, p.mode == 0 ? 0 : 1, steps, p.film_stride, p.cls_emb, film);
+  film_table_kernel<EMB><<<blocks, 256, 0, s>>>(p.W, p.lay, fj, p.cfg.cond_ch, p.cfg.cond_dim, p.z_cond, p.mode == 1 ? p.gpo : 1,
+                                                p.cfg.time_cond ? p.te : nullptr, p.mode == 1 ? 1 : 0, steps, p.film_stride,
+                                                p.cls_emb, film);
   int rc = check_launch("film_table_kernel");
   if (rc == GLDM_OK) {
     p.film = film;
-    rows::resnet_rows_kernel<<<ceil_div(p.n, rows::NS), rows::NTHREADS, smem, s>>>(p);
+    rows::resnet_rows_kernel<L><<<ceil_div(p.n, rows::Geo<L>::NS), rows::NTHREADS, smem, s>>>(p);
     rc = check_launch("resnet_rows_kernel");
   }
   cudaFreeAsync(film, s);
   return rc;
 }
 
+static int launch_rows(TcParams& p, cudaStream_t s) {
+  return p.cfg.L == 4 ? launch_rows_l<4>(p, s) : launch_rows_l<16>(p, s);
+}
+
+// L = 16 networks (grasp decoder trunk, ppc latent denoiser) on the row-major kernel: 8 samples per CTA instead of the
+// channel-major kernel's 4, at any batch size.  GLDM_TC_ROWS16=0 selects the channel-major kernel.
+static bool rows16_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* ev = getenv("GLDM_TC_ROWS16"); on = ev ? atoi(ev) : 1; }
+  return on != 0;
+}
+
 static int launch_tc(TcParams& p, cudaStream_t s) {
   p.prof = g_tc_prof;
   if (p.mode == 0 && p.sched_kind == GLDM_SCHED_EDM) {
     // evaluation programs (elucidated samplers) are implemented by the row-major kernel
-    if (!rows_supported(p.cfg)) {
+    if (!(rows_supported(p.cfg) && p.cfg.L == 4)) {
       set_error("sampler_tc: the elucidated samplers run on the row-major kernel (fpc latent denoiser); use precision fp32 for this model");
       return GLDM_ENOSUP;
     }
     return launch_rows(p, s);
   }
+  if (p.cfg.L != 4) {
+    if (g_tc_rows != 0 && rows16_enabled() && rows_supported(p.cfg)) return launch_rows(p, s);
+    return launch_tc_l<16, 1>(p, s);
+  }
   const bool want_rows = g_tc_rows == 1 || (g_tc_rows < 0 && p.n > 16 * kNumSMs);
-  if (want_rows && p.mode != 2 && rows_supported(p.cfg)) return launch_rows(p, s);
-  if (p.cfg.L != 4) return launch_tc_l<16, 1>(p, s);
+  if (want_rows && rows_supported(p.cfg)) return launch_rows(p, s);
   const bool two = g_tc_sets == 2 || (g_tc_sets == 0 && p.n > 16 * kNumSMs);
   return two ? launch_tc_l<4, 2>(p, s) : launch_tc_l<4, 1>(p, s);
 }

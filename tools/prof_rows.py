@@ -8,19 +8,27 @@ import _models
 from graspldm_b200 import _lib
 dev = torch.device("cuda:0")
 n = 1280
+what = sys.argv[1] if len(sys.argv) > 1 else "sampler"      # sampler (fpc, 10 steps) | decoder (one evaluation, L = 16)
 m = _models.build("fpc").to(dev)
 m.set_inference_timesteps(10)
 m.diffusion_model.rng_mode = "fused"
 m.diffusion_model.precision = "bf16"
+m.vae_model.decoder.precision = "bf16"
 z = torch.randn(n // 20, 3, 64, device=dev)
 x_T = torch.randn(n, 1, 4, device=dev)
-m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, grasps_per_object=20, seed=0)
+def run(seed):
+    if what == "sampler":
+        m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, grasps_per_object=20, seed=seed)
+    else:
+        m.vae_model.decoder(x_T[:, 0], z, grasps_per_object=20)
+run(0)
 buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 _lib.call("gldm_sampler_tc_set_profile", buf.data_ptr())
-m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, grasps_per_object=20, seed=1)
+run(1)
 torch.cuda.synchronize()
 _lib.call("gldm_sampler_tc_set_profile", None)
 b = buf.cpu().tolist()
+print(f"CTA 0: setup {b[1] - b[0]} cycles, whole kernel {b[2] - b[0]} cycles, first job starts {b[64] - b[0]} after entry")
 names = []
 for st in range(4):
     names += [f"s{st}.rb0.c1", f"s{st}.rb0.c2", f"s{st}.rb1.c1", f"s{st}.rb1.c2", f"s{st}.qkv", f"s{st}.out", f"s{st}.down"]
