@@ -466,7 +466,7 @@ def main():
                          if tc else "PVCNN encoder pass (fp32 SIMT)"),
              "sampler": (("rows::resnet_rows_kernel" if rows_kernel else "resnet_tc_kernel<L,NSETS>") +
                          " (tcgen05 persistent T-step sampler, one launch per call)") if tc else "resnet_kernel<L> (fp32 SIMT persistent sampler)",
-             "decoder": "resnet_tc_kernel<16,1> (tcgen05 grasp decoder)" if tc else "resnet_kernel<16> (fp32 SIMT decoder)"}
+             "decoder": "rows::resnet_rows_kernel<16> (tcgen05 grasp decoder, row-major, 8 grasps per CTA)" if tc else "resnet_kernel<16> (fp32 SIMT decoder)"}
     kernels = []
     for sec, fl in (("encoder", f_enc), ("sampler", f_samp), ("decoder", f_dec)):
         ms = mean(sections.get(sec, []))

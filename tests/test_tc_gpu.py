@@ -93,8 +93,18 @@ def _set_precision(model, prec):
     model.vae_model.decoder.precision = prec
 
 
-@pytest.mark.parametrize("B,gpo", [(1, 1), (4, 1), (37, 1), (40, 20)])
-def test_decoder_forward_bf16(fpc, cuda, B, gpo):
+@pytest.fixture(params=["row_major", "channel_major"])
+def l16_kernel(request, cuda):
+    """The L = 16 networks (decoder trunk, ppc denoiser) run on the row-major kernel by default (8 samples per CTA);
+    gldm_sampler_tc_set_rows(0) forces the channel-major one (4 samples per CTA).  Both stay covered."""
+    from graspldm_b200 import _lib
+    _lib.call("gldm_sampler_tc_set_rows", 0 if request.param == "channel_major" else -1)
+    yield request.param
+    _lib.call("gldm_sampler_tc_set_rows", -1)
+
+
+@pytest.mark.parametrize("B,gpo", [(1, 1), (4, 1), (37, 1), (40, 20), (300, 20)])
+def test_decoder_forward_bf16(fpc, cuda, B, gpo, l16_kernel):
     """Grasp decoder (in_layer -> ResNet1D trunk L = 16 -> heads) on the tensor cores vs the oracle."""
     m, vae, _ = fpc
     gen = torch.Generator().manual_seed(21 + B)
@@ -307,8 +317,41 @@ def test_first_conv3d_channels_last(cuda):
     torch.testing.assert_close(stats[..., 1], (g * g).sum(-1), rtol=1e-4, atol=0.05)
 
 
-def test_ppc_denoiser_forward_bf16_vs_reference_fixture(cuda):
-    """ppc latent denoiser (16 positions, time conditioned, embedding width 64) on the tensor-core kernel, against the
+def test_l16_row_major_matches_channel_major(cuda):
+    """The two tcgen05 kernels of the L = 16 networks compute the same function with different operand roles (different
+    summation orders, the attention on mma.sync instead of SIMT): 10 DDPM steps of the ppc sampler and the decoder must
+    agree within the bf16 noise floor, ragged sizes included (sample counts that are not multiples of 8 or 4)."""
+    from graspldm_b200 import _lib
+    m = _models.build("ppc").to(cuda)
+    m.set_inference_timesteps(10)
+    gen = torch.Generator().manual_seed(77)
+    for n_obj, G_ in ((3, 7), (1, 1), (5, 16)):
+        n = n_obj * G_
+        z = torch.randn(n_obj, 3, 256, generator=gen).to(cuda)
+        x_T = torch.randn(n, 1, 16, generator=gen).to(cuda)
+        noise = torch.randn(10, n, 1, 16, generator=gen).to(cuda)
+        zh = torch.randn(n, 16, generator=gen).to(cuda)
+        out = {}
+        for kern, flag in (("rows", -1), ("chan", 0)):
+            _lib.call("gldm_sampler_tc_set_rows", flag)
+            try:
+                x, _ = m.diffusion_model.sample(z_cond=z, batch_size=n, x_T=x_T, noise=noise, grasps_per_object=G_, precision="bf16")
+                dec = m.vae_model.decoder
+                dec.precision = "bf16"
+                t, l = dec(zh, z, grasps_per_object=G_)
+                dec.precision = "fp32"
+            finally:
+                _lib.call("gldm_sampler_tc_set_rows", -1)
+            out[kern] = (x, t, l)
+        for a, b, what in zip(out["rows"], out["chan"], ("latents", "tmrp", "logits")):
+            err = (a - b).abs().max().item()
+            print(f"[{n_obj}x{G_}] row-major vs channel-major {what}: max|diff| {err:.3e}")
+            assert torch.isfinite(a).all()
+            assert err < 3e-2, (what, err)
+
+
+def test_ppc_denoiser_forward_bf16_vs_reference_fixture(cuda, l16_kernel):
+    """ppc latent denoiser (16 positions, time conditioned, embedding width 64) on the tensor-core kernels, against the
     fixture of the reference module (resnets.py:558-616)."""
     g = np.load(os.path.join(G, "dense_ppc.npz"))
     m = _models.build("ppc").to(cuda)
