@@ -481,6 +481,14 @@ def main():
     if dom["section"] == "sampler" and tc and os.path.exists(tp):
         t = json.load(open(tp))["resnet_rows_kernel"]          # dram__bytes_read + write of one ncu --set full capture
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    # the persistent sampler holds ONE CTA per SM for its whole launch and fills only ceil(samples / samples-per-CTA) SMs:
+    # its rate against the peak of the SMs it actually holds (the rest of the GPU runs the other batches' kernels meanwhile)
+    for k in kernels:
+        if k["section"] == "sampler" and tc and w["model"] == "fpc":
+            per_cta = 32 if rows_kernel else 16
+            ctas = min(148, -(-(min(chunk, n_loc) * G) // per_cta))
+            k["ctas"] = ctas
+            k["frac_of_held_sms"] = k["achieved_tflops"] / (pk["tflops_sustained"] * ctas / 148.0)
     total_flops = f_enc + f_samp + f_dec
     roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["achieved_tflops"], "peak": pk["tflops_sustained"],
                 "unit": "TFLOP/s", "frac": dom["frac"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",

@@ -34,13 +34,14 @@ namespace rows {
 template <int L> struct Geo { static constexpr int NS = 128 / L; };   // samples per CTA: 32 (L = 4) or 8 (L = 16)
 constexpr int NEPI = 512;                       // 16 epilogue warps
 constexpr int NTHREADS = 640;                   // + producer, issuer, two idle register donors (warps are allocated in fours)
-constexpr int SLAB = 192 * 128;                 // 64 channels x (32 halo + 128 + 32 halo) rows
-constexpr int CHUNK = stc::CHUNK, STAGES = 2;
+constexpr int SLAB = 160 * 128;                 // slab stride: 64 channels x (32 halo + 128) rows; the upper 32-row halo of a slab
+                                                // IS the lower halo of the next one (both stay zero), one extra halo after the last
+constexpr int CHUNK = stc::CHUNK, STAGES = 3;      // 96 KB in flight: the 256-wide jobs were bound by ring depth x L2 latency
 constexpr int MAXRJ = 40, MAXOPS = 400, MAXCHUNKS = 256;
 constexpr uint32_t T_ACC = 0, T_RES = 384;
 // shared memory map (from a 1024-aligned base)
 constexpr int SM_A = 0;
-constexpr int SM_RING = SM_A + 4 * SLAB;
+constexpr int SM_RING = SM_A + 4 * SLAB + 32 * 128;
 constexpr int PAR_FLOATS = 5120;                          // every per-channel parameter of the network, resident for all steps
 constexpr int SM_PAR = SM_RING + STAGES * CHUNK;
 constexpr int SM_PTAB = SM_PAR + PAR_FLOATS * 4;          // [MAXRJ][5] int16: offsets of a job's bias, gamma, beta, g1, g2 (-1: none)
