@@ -583,11 +583,41 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // e in [8t, 8t+8) for all positions.  Rows travel through the idle operand slab of the head as bf16 (q^, k, v: every
 // thread of a sample sees the same rounded values, so the soft-max over positions stays consistent); the partial A's
 // as fp32.
-__device__ __forceinline__ void attention_epilogue(const Ep& e) {
+// packed-pair helpers of the attention epilogues: the epilogue is issue bound, so its arithmetic runs on float2 (FFMA2 /
+// FADD2 / FMUL2), the exponentials as ex2(x * log2e - m * log2e) with the scale folded into one FFMA2 per pair
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 ex2_pair(float2 x) { return make_float2(ex2f(x.x), ex2f(x.y)); }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ void unpack8p(const uint4 u, float2 (&f)[4]) {
+  f[0] = bf2_to_f2(u.x); f[1] = bf2_to_f2(u.y); f[2] = bf2_to_f2(u.z); f[3] = bf2_to_f2(u.w);
+}
+__device__ __forceinline__ uint4 pack8p(const float2* f) {
+  return make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y), pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// q^ = softmax over the 32 head channels of this thread's row, times 32^-0.5: 16 accumulator pairs in, 16 pairs out
+__device__ __forceinline__ void softmax32_scaled(float2 (&q)[16]) {
+  float m = fmaxf(q[0].x, q[0].y);
+#pragma unroll
+  for (int i = 1; i < 16; ++i) m = fmaxf(fmaxf(m, q[i].x), q[i].y);
+  const float2 l2 = make_float2(kLog2e, kLog2e), nm = make_float2(-m * kLog2e, -m * kLog2e);
+  float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { q[i] = ex2_pair(__ffma2_rn(q[i], l2, nm)); sum = __fadd2_rn(sum, q[i]); }
+  const float sc = __fdividef(0.17677669529663687f, sum.x + sum.y);
+  const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) q[i] = __fmul2_rn(q[i], sc2);
+}
+
+__device__ __forceinline__ void attention_epilogue(const Ep& e, long long* rec) {
   uint8_t* X = e.smem + SM_A + e.g * SLAB;        // rows 32..159 of this head's slab (the halo rows are not touched)
   const int h = e.g, t = e.pos, s = e.s;
   {
-    float qs[32], kv[32];
     uint32_t rq[4][8], rk[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -595,59 +625,52 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
       ld_issue<8>(e, T_ACC + 128 + h * 32 + i * 8, rk[i]);
     }
     tmem_ld_wait();
+    float2 qs[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float tmp[8];
-      ld_use<8>(rq[i], tmp);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qs[i * 8 + j] = tmp[j];
-      ld_use<8>(rk[i], tmp);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) kv[i * 8 + j] = tmp[j];
+      float2 kk[4];
+      use8(rk[i], kk);
+      *xslot(X, 1, t, s, i) = pack8p(kk);               // raw k of this position
+      use8(rq[i], *reinterpret_cast<float2(*)[4]>(&qs[4 * i]));
     }
-    float m = qs[0];
+    softmax32_scaled(qs);
 #pragma unroll
-    for (int d = 1; d < 32; ++d) m = fmaxf(m, qs[d]);
-    float sum = 0.f;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) { qs[d] = __expf(qs[d] - m); sum += qs[d]; }
-    const float sc = __fdividef(0.17677669529663687f, sum);
-#pragma unroll
-    for (int d = 0; d < 32; ++d) qs[d] *= sc;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      *xslot(X, 0, t, s, j) = pack8(&qs[8 * j]);      // q^ of this position
-      *xslot(X, 1, t, s, j) = pack8(&kv[8 * j]);      // raw k of this position
-    }
+    for (int j = 0; j < 4; ++j) *xslot(X, 0, t, s, j) = pack8p(&qs[4 * j]);      // q^ of this position
   }
+  if (rec) rec[3] = clock64();
   bar_wg(h);
   float Ap[16];                                       // partial A[n][n'] over this thread's quarter of d
   {
-    float q[4][8], k[4][8];
+    float2 q[4][4], k[4][4];
 #pragma unroll
     for (int pp = 0; pp < 4; ++pp) {
-      unpack8(*xslot(X, 0, pp, s, t), q[pp]);
-      unpack8(*xslot(X, 1, pp, s, t), k[pp]);
+      unpack8p(*xslot(X, 0, pp, s, t), q[pp]);
+      unpack8p(*xslot(X, 1, pp, s, t), k[pp]);
     }
+    const float2 l2 = make_float2(kLog2e, kLog2e);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float m = fmaxf(fmaxf(k[0][i], k[1][i]), fmaxf(k[2][i], k[3][i]));
+    for (int i = 0; i < 4; ++i) {                     // soft-max over the 4 positions, two channels at a time
+      const float mx = fmaxf(fmaxf(k[0][i].x, k[1][i].x), fmaxf(k[2][i].x, k[3][i].x));
+      const float my = fmaxf(fmaxf(k[0][i].y, k[1][i].y), fmaxf(k[2][i].y, k[3][i].y));
+      const float2 nm = make_float2(-mx * kLog2e, -my * kLog2e);
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) k[pp][i] = __expf(k[pp][i] - m);
-      const float zi = __fdividef(1.0f, (k[0][i] + k[1][i]) + (k[2][i] + k[3][i]));
+      for (int pp = 0; pp < 4; ++pp) k[pp][i] = ex2_pair(__ffma2_rn(k[pp][i], l2, nm));
+      const float2 z = __fadd2_rn(__fadd2_rn(k[0][i], k[1][i]), __fadd2_rn(k[2][i], k[3][i]));
+      const float2 zi = make_float2(__fdividef(1.0f, z.x), __fdividef(1.0f, z.y));
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) k[pp][i] *= zi;
+      for (int pp = 0; pp < 4; ++pp) k[pp][i] = __fmul2_rn(k[pp][i], zi);
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n)
 #pragma unroll
       for (int n1 = 0; n1 < 4; ++n1) {
-        float a = 0.f;
+        float2 a = __fmul2_rn(q[n][0], k[n1][0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a = fmaf(q[n][i], k[n1][i], a);
-        Ap[n * 4 + n1] = a;
+        for (int i = 1; i < 4; ++i) a = __ffma2_rn(q[n][i], k[n1][i], a);
+        Ap[n * 4 + n1] = a.x + a.y;
       }
   }
+  if (rec) rec[4] = clock64();
   bar_wg(h);                                          // every q^ / k row has been read
   {
     uint32_t rv[4][8];
@@ -659,35 +682,36 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float tmp[8];
-      ld_use<8>(rv[i], tmp);
-      *xslot(X, 1, t, s, i) = pack8(tmp);             // v of this position
+      float2 vv[4];
+      use8(rv[i], vv);
+      *xslot(X, 1, t, s, i) = pack8p(vv);             // v of this position
     }
   }
   bar_wg(h);
-  float o[4][8];                                      // out[e in quarter t][position n]
+  if (rec) rec[5] = clock64();
+  float2 o[4][4];                                     // out[position n][e in quarter t], channel pairs
   {
     float A[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float4 acc = *reinterpret_cast<const float4*>(xslot(X, 0, 0, s, j));
-#pragma unroll
-      for (int pp = 1; pp < 4; ++pp) {
-        const float4 x = *reinterpret_cast<const float4*>(xslot(X, 0, pp, s, j));
-        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-      }
-      A[4 * j] = acc.x; A[4 * j + 1] = acc.y; A[4 * j + 2] = acc.z; A[4 * j + 3] = acc.w;
+      const float4 x0 = *reinterpret_cast<const float4*>(xslot(X, 0, 0, s, j)), x1 = *reinterpret_cast<const float4*>(xslot(X, 0, 1, s, j));
+      const float4 x2 = *reinterpret_cast<const float4*>(xslot(X, 0, 2, s, j)), x3 = *reinterpret_cast<const float4*>(xslot(X, 0, 3, s, j));
+      const float2 lo = __fadd2_rn(__fadd2_rn(make_float2(x0.x, x0.y), make_float2(x1.x, x1.y)),
+                                   __fadd2_rn(make_float2(x2.x, x2.y), make_float2(x3.x, x3.y)));
+      const float2 hi = __fadd2_rn(__fadd2_rn(make_float2(x0.z, x0.w), make_float2(x1.z, x1.w)),
+                                   __fadd2_rn(make_float2(x2.z, x2.w), make_float2(x3.z, x3.w)));
+      A[4 * j] = lo.x; A[4 * j + 1] = lo.y; A[4 * j + 2] = hi.x; A[4 * j + 3] = hi.y;
     }
-    float v[4][8];
+    float2 v[4][4];
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) unpack8(*xslot(X, 1, pp, s, t), v[pp]);
+    for (int pp = 0; pp < 4; ++pp) unpack8p(*xslot(X, 1, pp, s, t), v[pp]);
 #pragma unroll
     for (int n = 0; n < 4; ++n)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = A[n * 4] * v[0][i];
+      for (int i = 0; i < 4; ++i) {
+        float2 a = __fmul2_rn(v[0][i], make_float2(A[n * 4], A[n * 4]));
 #pragma unroll
-        for (int n1 = 1; n1 < 4; ++n1) a = fmaf(A[n * 4 + n1], v[n1][i], a);
+        for (int n1 = 1; n1 < 4; ++n1) a = __ffma2_rn(v[n1][i], make_float2(A[n * 4 + n1], A[n * 4 + n1]), a);
         o[n][i] = a;
       }
   }
@@ -698,7 +722,7 @@ __device__ __forceinline__ void attention_epilogue(const Ep& e) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const int R = 32 + n * 32 + s;
-      *reinterpret_cast<uint4*>(e.smem + SM_A + (chan >> 6) * SLAB + R * 128 + ((((chan & 63) >> 3) ^ (R & 7)) << 4)) = pack8(o[n]);
+      *reinterpret_cast<uint4*>(e.smem + SM_A + (chan >> 6) * SLAB + R * 128 + ((((chan & 63) >> 3) ^ (R & 7)) << 4)) = pack8p(o[n]);
     }
   }
 }
@@ -745,29 +769,16 @@ __device__ __forceinline__ void attention16_epilogue(const Ep& e) {
     }
   }
   {  // Q^ row: softmax over the 32 head channels, in-thread
-    float qs[32];
+    float2 qs[16];
     uint32_t rq[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) ld_issue<8>(e, T_ACC + h * 32 + i * 8, rq[i]);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float t[8];
-      ld_use<8>(rq[i], t);
+    for (int i = 0; i < 4; ++i) use8(rq[i], *reinterpret_cast<float2(*)[4]>(&qs[4 * i]));
+    softmax32_scaled(qs);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) qs[i * 8 + j] = t[j];
-    }
-    float m = qs[0];
-#pragma unroll
-    for (int d = 1; d < 32; ++d) m = fmaxf(m, qs[d]);
-    float sum = 0.f;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) { qs[d] = __expf(qs[d] - m); sum += qs[d]; }
-    const float sc = __fdividef(0.17677669529663687f, sum);
-#pragma unroll
-    for (int d = 0; d < 32; ++d) qs[d] *= sc;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(arow(Qb, s, n, i)) = pack8(&qs[8 * i]);
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(arow(Qb, s, n, i)) = pack8p(&qs[4 * i]);
   }
   bar_wg(h);
   {  // K^: soft-max over the 16 positions, in place.  Thread (of the 128 of the head) = (sample, channel pair).
@@ -1184,7 +1195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
           }
         }
         if (flags & E_ATTN) {
-          if (L == 4) attention_epilogue(e);
+          if (L == 4) attention_epilogue(e, rec ? p.prof + 64 + 8 * j : nullptr);
           else attention16_epilogue(e);
         } else if (ch >= 32 && ch <= 128) {
           reg_epilogue<L>(e, flags, ch, film, rec ? p.prof + 64 + 8 * j : nullptr);
