@@ -727,9 +727,11 @@ __global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, 
                                                           int rpb) {
   __shared__ float s_red[2048];
   const int b = blockIdx.y, tid = threadIdx.x;
-  const int nchunk = stride >> 3, rl = 256 / nchunk;
+  // only the 8-channel chunks that hold channels get a thread (the bf16 row stride is padded to 64 / 128 channels)
+  const int nchunk = (c + 7) >> 3, rl = 256 / nchunk, cw = nchunk * 8;
   const int chunk = tid % nchunk, rsub = tid / nchunk;
   const int rp = r + 2, rp2 = rp * rp, P = rp2 * rp, cpg = c >> 3;
+  const float inv_rp2 = 1.0f / (float)rp2, inv_rp = 1.0f / (float)rp;
   const double cnt = (double)cpg * r * r * r;
   float A[8], B[8], acc[8];
 #pragma unroll
@@ -747,52 +749,73 @@ __global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, 
   }
   const bool active = rsub < rl;        // 256 is not a multiple of every chunk count (6, 12 chunks for fp32 rows)
   const int p_end = active ? min(P, (int)(blockIdx.x + 1) * rpb) : 0;
-  for (int pp = blockIdx.x * rpb + rsub; pp < p_end; pp += rl) {
-    const int x = pp / rp2, yy = (pp / rp) % rp, z = pp % rp;
-    if (x < 1 || x > r || yy < 1 || yy > r || z < 1 || z > r) continue;
-    float v[8];
-    if (F32) {
-      float4* ptr = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ((size_t)b * P + pp) * stride + chunk * 8);
-      const float4 lo = ptr[0], hi = ptr[1];
-      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  // four rows per thread and iteration: all loads are issued before the first value is used (one 16-byte load in flight per
+  // thread left the pass latency bound at 40 % of the HBM rate); the rows are finished in ascending order, so the SE sums
+  // accumulate exactly as before
+  constexpr int U = 4;
+  for (int pp0 = blockIdx.x * rpb + rsub; pp0 < p_end; pp0 += U * rl) {
+    bool ok[U];
+    uint4 raw[U][F32 ? 2 : 1];
+    uint4* ptr[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(v[j], A[j], B[j]);
-        v[j] = __fdividef(t, 1.0f + __expf(-t));          // fast-math exp / divide: ~1e-6 relative, far below the bf16 operands
-        acc[j] += v[j];
+    for (int u = 0; u < U; ++u) {
+      const int pp = pp0 + u * rl;
+      // exact for these sizes: (pp + 0.5) / rp2 is at least 0.5 / rp2 away from an integer, far more than the fp32 rounding
+      const int x = (int)(((float)pp + 0.5f) * inv_rp2), rem = pp - x * rp2;
+      const int yy = (int)(((float)rem + 0.5f) * inv_rp), z = rem - yy * rp;
+      ok[u] = pp < p_end && !(x < 1 || x > r || yy < 1 || yy > r || z < 1 || z > r);
+      ptr[u] = F32 ? reinterpret_cast<uint4*>(reinterpret_cast<float*>(y) + ((size_t)b * P + pp) * stride + chunk * 8)
+                   : reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + ((size_t)b * P + pp) * stride + chunk * 8);
+      if (ok[u]) {
+        raw[u][0] = ptr[u][0];
+        if (F32) raw[u][F32 ? 1 : 0] = ptr[u][1];
       }
-      ptr[0] = make_float4(v[0], v[1], v[2], v[3]);
-      ptr[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      uint4* ptr = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + ((size_t)b * P + pp) * stride + chunk * 8);
-      const uint4 raw = *ptr;
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-        v[2 * k] = __low2float(h);
-        v[2 * k + 1] = __high2float(h);
-      }
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float v[8];
+      if (F32) {
+        const uint4 lo = raw[u][0], hi = raw[u][F32 ? 1 : 0];
+        v[0] = __uint_as_float(lo.x); v[1] = __uint_as_float(lo.y); v[2] = __uint_as_float(lo.z); v[3] = __uint_as_float(lo.w);
+        v[4] = __uint_as_float(hi.x); v[5] = __uint_as_float(hi.y); v[6] = __uint_as_float(hi.z); v[7] = __uint_as_float(hi.w);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(v[j], A[j], B[j]), h = 0.5f * t;
-        float th;                                          // x * sigmoid(x) = h (1 + tanh h): one MUFU op, bf16 output
-        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-        v[j] = fmaf(h, th, h);
-        acc[j] += v[j];
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(v[j], A[j], B[j]);
+          v[j] = __fdividef(t, 1.0f + __expf(-t));          // fast-math exp / divide: ~1e-6 relative, far below the bf16 operands
+          acc[j] += v[j];
+        }
+        ptr[u][0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+        ptr[u][1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+      } else {
+        const uint32_t w[4] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+          v[2 * k] = __low2float(h);
+          v[2 * k + 1] = __high2float(h);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(v[j], A[j], B[j]), h = 0.5f * t;
+          float th;                                          // x * sigmoid(x) = h (1 + tanh h): one MUFU op, bf16 output
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+          v[j] = fmaf(h, th, h);
+          acc[j] += v[j];
+        }
+        *ptr[u] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       }
-      *ptr = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
   }
   if (se_sum) {
     if (active) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_red[rsub * stride + chunk * 8 + j] = acc[j];
+      for (int j = 0; j < 8; ++j) s_red[rsub * cw + chunk * 8 + j] = acc[j];
     }
     __syncthreads();
     if (tid < c) {
       float t = 0.f;
-      for (int k = 0; k < rl; ++k) t += s_red[k * stride + tid];
+      for (int k = 0; k < rl; ++k) t += s_red[k * cw + tid];
       se_sum[((size_t)b * gridDim.x + blockIdx.x) * c + tid] = (double)t;     // per-block partial (summed in order later)
     }
   }
