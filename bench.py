@@ -478,7 +478,7 @@ def main():
     dom = max(kernels, key=lambda k: k["ms_in_timed_region"] * k["launches_per_step"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r02_tc_sampler_traffic.json")
-    if dom["section"] == "sampler" and tc and os.path.exists(tp):
+    if dom["section"] == "sampler" and tc and w["id"] == 2 and os.path.exists(tp):      # the capture is config 2's launch
         t = json.load(open(tp))["resnet_rows_kernel"]          # dram__bytes_read + write of one ncu --set full capture
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     # the persistent sampler holds ONE CTA per SM for its whole launch and fills only ceil(samples / samples-per-CTA) SMs:
