@@ -819,17 +819,22 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
                   blk["groups"], blk["eps1"], None, st)
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
         _lib.call("gldm_cl_pad", t.data_ptr(), B, co, r, y1.data_ptr(), st)
-    y2 = _cl_grid(pk, dev, ("y2", bi), rows, co, torch.float32)
-    _lib.call("gldm_conv3d_tc_cl", y1.data_ptr(), w2_img.data_ptr(), blk["b2"].data_ptr(), B, co, co, r, y2.data_ptr(), 1, co,
-              stats[1].data_ptr(), ws.data_ptr(), st)
-    _lib.call("gldm_gn_swish_cl", y2.data_ptr(), 1, co, stats[1].data_ptr(), blk["g2w"].data_ptr(), blk["g2b"].data_ptr(),
-              B, co, r, blk["eps2"], se_sum.data_ptr(), ws.data_ptr(), st)
+    # grid the devoxelisation reads: bf16 rows like every other activation of this path (half the traffic of the second
+    # GroupNorm pass and of the corner gathers; encoder latent 3.5e-4 from the fp32 path instead of 3.1e-4), or fp32 rows
+    # with GLDM_DEVOX_BF16=0
+    y2_f32 = 1 if os.environ.get("GLDM_DEVOX_BF16") == "0" else 0
+    y2_stride = co if y2_f32 else cpad_o
+    y2 = _cl_grid(pk, dev, ("y2", bi, y2_f32), rows, y2_stride, torch.float32 if y2_f32 else torch.bfloat16)
+    _lib.call("gldm_conv3d_tc_cl", y1.data_ptr(), w2_img.data_ptr(), blk["b2"].data_ptr(), B, co, co, r, y2.data_ptr(), y2_f32,
+              y2_stride, stats[1].data_ptr(), ws.data_ptr(), st)
+    _lib.call("gldm_gn_swish_cl", y2.data_ptr(), y2_f32, y2_stride, stats[1].data_ptr(), blk["g2w"].data_ptr(),
+              blk["g2b"].data_ptr(), B, co, r, blk["eps2"], se_sum.data_ptr(), ws.data_ptr(), st)
     gate = torch.empty((B, co), device=dev, dtype=torch.float32)
     _lib.call("gldm_se_gate_sum", se_sum.data_ptr(), r3, blk["se1"].data_ptr(), blk["se2"].data_ptr(), B, co,
               blk["se1"].shape[0], gate.data_ptr(), st)
     pt = _pw(feats, blk["pw"], blk["pscale"], blk["pshift"], None, 1)
     fused = torch.empty((B, co, N), device=dev, dtype=torch.float32)
-    _lib.call("gldm_devox_cl", norm.data_ptr(), y2.data_ptr(), 1, co, gate.data_ptr(), pt.data_ptr(), B, co, N, r,
+    _lib.call("gldm_devox_cl", norm.data_ptr(), y2.data_ptr(), y2_f32, y2_stride, gate.data_ptr(), pt.data_ptr(), B, co, N, r,
               fused.data_ptr(), st)
     return fused
 
