@@ -41,6 +41,7 @@ _SIGS = {
     "gldm_three_nn_interpolate_forward": [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "gldm_three_nn_interpolate_backward": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "gldm_voxelize_fused": [P, P, c_int, c_int, c_int, c_int, P, P, P, P],
+    "gldm_voxelize_fused_cl": [P, P, c_int, c_int, c_int, c_int, P, c_int, P, P],
     "gldm_pointwise_conv_f32": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P],
     "gldm_conv3d_k3_f32": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "gldm_groupnorm_swish_f32": [P, P, P, c_int, c_int, c_int, c_int, c_float, P, P],

@@ -1138,15 +1138,19 @@ extern "C" int gldm_conv3d_tc16_pack_weight(const float* w, int co, int ci, void
 }
 extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const float* bias, int b, int ci, int co, int r,
                                    void* scratch, void* y_cl, int out_stride, double* stats, void* ws, void* stream) {
-  GLDM_REQUIRE(b <= 0 || (x && w_img && scratch && y_cl && stats && ws), "conv3d_tc16_cl: null pointer");
+  // x == NULL: `scratch` already holds the zero-padded 16-channel bf16 grid (gldm_voxelize_fused_cl wrote it)
+  GLDM_REQUIRE(b <= 0 || (w_img && scratch && y_cl && stats && ws), "conv3d_tc16_cl: null pointer");
   GLDM_REQUIRE(b >= 0 && ci > 0 && ci <= 16 && co > 0 && co <= 128 && co % 8 == 0 && r > 0, "conv3d_tc16_cl: bad sizes");
   GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc16_cl: bad out_stride");
   if (b == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const long long P = (long long)(r + 2) * (r + 2) * (r + 2), rows = (long long)b * P;
-  cl_pad16_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(scratch), ci, r, rows);
-  int rc = check_launch("cl_pad16_kernel");
-  if (rc) return rc;
+  int rc = GLDM_OK;
+  if (x) {
+    cl_pad16_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(scratch), ci, r, rows);
+    rc = check_launch("cl_pad16_kernel");
+    if (rc) return rc;
+  }
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("conv3d_tc16_cl: cuTensorMapEncodeTiled is not available from the driver");

@@ -11,6 +11,8 @@
 //   * grouping / gather are 128-bit vectorised, write-coalesced gathers;
 //   * voxelisation ranks the points of a voxel in index order (match.any + ordered warp rounds) and
 //     accumulates in that order, so results are deterministic.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gldm {
@@ -365,6 +367,10 @@ __global__ void __launch_bounds__(256) three_nn_grad_kernel(const float* __restr
 // float atomics are not), no global atomics are issued, and the grid is written exactly once, coalesced over the
 // voxels (empty voxels included: no separate zero pass, no scattered 4-byte stores).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gldm_pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&t);
+}
 constexpr int kVoxMaxPPT = 16;      // 512 threads x 16 -> n <= 8192 points per cloud
 constexpr int kVoxMaxPoints = 8192;
 template <bool FUSED, int CH>
@@ -372,7 +378,8 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
                                                         const void* __restrict__ coords_in, int c, int n, int r,
                                                         float* __restrict__ out, int* __restrict__ ind_out,
                                                         int* __restrict__ cnt_out, float* __restrict__ norm_out,
-                                                        int* __restrict__ vox_out) {
+                                                        int* __restrict__ vox_out, __nv_bfloat16* __restrict__ cl_out,
+                                                        int cl_stride) {
   extern __shared__ unsigned char s_raw[];
   __shared__ double s_red[3][16];
   __shared__ float s_mean[3];
@@ -481,6 +488,36 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
   __syncthreads();
   // Phase C: a thread owns four consecutive voxels; an all-empty quad (most of a 24^3 grid) is ch_n 16-byte zero stores,
   // otherwise every non-empty voxel's point list is walked once for all (<= CH) channels of this slice
+  // channels-last output (the Conv3d kernels' operand form, written directly: no fp32 grid, no separate padding pass):
+  // row (x+1, y+1, z+1) of the zero-padded grid of this cloud, this slice's channels as one or two 16-byte chunks
+  if (cl_out) {
+    const int rp = r + 2;
+    __nv_bfloat16* cb = cl_out + (size_t)b * rp * rp * rp * cl_stride + ch_lo;
+    for (int v = tid; v < r3; v += nthreads) {
+      float acc[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+      const int cv = s_cnt[v];
+      if (cv) {
+        const float div = (float)(1.0 / (double)(float)cv);       // vox.cu:65
+        for (int p = s_head[v]; p >= 0; p = s_next[p]) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (k < ch_n) acc[k] = __fadd_rn(acc[k], __fmul_rn(__ldg(fb + (size_t)k * n + p), div));
+        }
+      }
+      const int x = v / r2, y = (v / r) % r, z = v % r;
+      uint4* dst = reinterpret_cast<uint4*>(cb + (size_t)(((x + 1) * rp + (y + 1)) * rp + (z + 1)) * cl_stride);
+      auto pk = [&](int k) { return gldm_pack_bf16(acc[k < CH ? k : 0], acc[k + 1 < CH ? k + 1 : 0]); };
+      if (CH == 4) {
+        dst[0] = make_uint4(pk(0), pk(2), 0u, 0u);
+      } else {
+        dst[0] = make_uint4(pk(0), pk(2), pk(4), pk(6));
+        if (CH == 16) dst[1] = make_uint4(pk(8), pk(10), pk(12), pk(14));
+      }
+    }
+    return;
+  }
   const bool quads = (r3 & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0;
   for (int v0 = tid * 4; v0 < r3; v0 += nthreads * 4) {
     const int nv = min(4, r3 - v0);
@@ -758,8 +795,9 @@ extern "C" int gldm_three_nn_interpolate_backward(const float* grad_y, const int
 }
 
 static int launch_voxelize(bool fused, const float* feat, const void* coords, int b, int c, int n, int r,
-                           float* out, int* ind, int* cnt, float* norm, int* vox, cudaStream_t s) {
-  GLDM_REQUIRE(b <= 0 || (feat && coords && out), "voxelize: null pointer");
+                           float* out, int* ind, int* cnt, float* norm, int* vox, cudaStream_t s,
+                           __nv_bfloat16* cl_out = nullptr, int cl_stride = 0) {
+  GLDM_REQUIRE(b <= 0 || (feat && coords && (out || cl_out)), "voxelize: null pointer");
   GLDM_REQUIRE(b >= 0 && c > 0 && n > 0 && r > 0, "voxelize: bad sizes b=%d c=%d n=%d r=%d", b, c, n, r);
   GLDM_REQUIRE(n <= kVoxMaxPoints, "voxelize: n=%d > %d points per cloud not supported", n, kVoxMaxPoints);
   GLDM_REQUIRE(r <= 36, "voxelize: resolution %d > 36 not supported (shared-memory voxel table)", r);
@@ -771,11 +809,17 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   // (fewer CTAs repeat the point binning), 8 otherwise
   const int ch = c <= 4 ? 4 : (c >= 32 && (long long)b * ceil_div(c, 16) >= 2 * kNumSMs) ? 16 : 8;
   const int slices = ceil_div(c, ch);
+  if (cl_out) {
+    // a slice must be whole 16-byte chunks of the rows (or the single narrow slice of a <= 4-channel input)
+    GLDM_REQUIRE((slices == 1 && c <= 4) || (c % ch == 0), "voxelize (channels-last): %d channels are not a multiple of %d", c, ch);
+    GLDM_REQUIRE(cl_stride % 8 == 0 && cl_stride >= (slices == 1 && c <= 4 ? 8 : c), "voxelize (channels-last): bad row stride %d", cl_stride);
+  }
 #define VOX_LAUNCH(F, C_)                                                                                          \
   do {                                                                                                             \
     static SmemOptIn attr;                                                                                         \
     if (int rc = opt_in_smem(attr, voxelize_kernel<F, C_>, 200 * 1024, "voxelize_kernel")) return rc;              \
-    voxelize_kernel<F, C_><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox); \
+    voxelize_kernel<F, C_><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox, \
+                                                                  cl_out, cl_stride);                              \
   } while (0)
   if (fused) {
     if (ch == 4) VOX_LAUNCH(true, 4); else if (ch == 16) VOX_LAUNCH(true, 16); else VOX_LAUNCH(true, 8);
@@ -790,6 +834,13 @@ extern "C" int gldm_avg_voxelize_forward(const float* features, const int* coord
                                          float* out, int* ind, int* cnt, void* stream) {
   return launch_voxelize(false, features, coords, b, c, n, r, out, ind, cnt, nullptr, nullptr,
                          (cudaStream_t)stream);
+}
+
+extern "C" int gldm_voxelize_fused_cl(const float* features, const float* coords, int b, int c, int n, int r, void* x_cl,
+                                      int stride, float* norm_coords, void* stream) {
+  GLDM_REQUIRE(norm_coords && x_cl, "voxelize_fused_cl: null pointer");
+  return launch_voxelize(true, features, coords, b, c, n, r, nullptr, nullptr, nullptr, norm_coords, nullptr,
+                         (cudaStream_t)stream, reinterpret_cast<__nv_bfloat16*>(x_cl), stride);
 }
 
 extern "C" int gldm_voxelize_fused(const float* features, const float* coords, int b, int c, int n, int r,

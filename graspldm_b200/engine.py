@@ -781,10 +781,15 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
     w1_img, w2_img = pk.tc_conv_weights()[bi]
     r3, P = r ** 3, (r + 2) ** 3
     rows = B * P
-    grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
     norm = torch.empty((B, 3, N), device=dev, dtype=torch.float32)
-    _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(), norm.data_ptr(),
-              None, st)
+    # tensor-core first conv: the voxelisation writes the Conv3d operand (zero-padded channels-last bf16 rows) directly;
+    # otherwise the reference's fp32 [B, C, r^3] grid
+    direct = w1_img is not None and (ci <= 4 or ci % 8 == 0) and os.environ.get("GLDM_VOX_CL") != "0"
+    grid = None
+    if not direct:
+        grid = torch.empty((B, ci, r3), device=dev, dtype=torch.float32)
+        _lib.call("gldm_voxelize_fused", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, grid.data_ptr(), norm.data_ptr(),
+                  None, st)
     stats = torch.empty((2, B, 8, 2), device=dev, dtype=torch.float64)
     se_sum = torch.empty((B, co), device=dev, dtype=torch.float64)
     # workspace of the bit-reproducible (atomic-free) statistics: per-block partials, added in a fixed order
@@ -793,13 +798,20 @@ def _pvconv_voxel_branch_tc(pk, bi, blk, feats, coords, B, N, st, dev):
     if w1_img is not None and getattr(w1_img, "narrow_k", False):
         x16 = _cl_grid(pk, dev, ("x16", bi), rows, 16, torch.bfloat16)
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
-        _lib.call("gldm_conv3d_tc16_cl", grid.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r,
+        if direct:
+            _lib.call("gldm_voxelize_fused_cl", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, x16.data_ptr(), 16,
+                      norm.data_ptr(), st)
+        _lib.call("gldm_conv3d_tc16_cl", None if direct else grid.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r,
                   x16.data_ptr(), y1.data_ptr(), cpad_o, stats[0].data_ptr(), ws.data_ptr(), st)
         _lib.call("gldm_gn_swish_cl", y1.data_ptr(), 0, cpad_o, stats[0].data_ptr(), blk["g1w"].data_ptr(),
                   blk["g1b"].data_ptr(), B, co, r, blk["eps1"], None, None, st)
     elif w1_img is not None:
         x_cl = _cl_grid(pk, dev, ("x", bi), rows, -(-ci // 64) * 64, torch.bfloat16)
-        _lib.call("gldm_cl_pad", grid.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
+        if direct:
+            _lib.call("gldm_voxelize_fused_cl", feats.data_ptr(), coords.data_ptr(), B, ci, N, r, x_cl.data_ptr(),
+                      -(-ci // 64) * 64, norm.data_ptr(), st)
+        else:
+            _lib.call("gldm_cl_pad", grid.data_ptr(), B, ci, r, x_cl.data_ptr(), st)
         y1 = _cl_grid(pk, dev, ("y1", bi), rows, cpad_o, torch.bfloat16)
         _lib.call("gldm_conv3d_tc_cl", x_cl.data_ptr(), w1_img.data_ptr(), blk["b1"].data_ptr(), B, ci, co, r, y1.data_ptr(),
                   0, cpad_o, stats[0].data_ptr(), ws.data_ptr(), st)

@@ -98,6 +98,11 @@ int gldm_three_nn_interpolate_backward(const float* grad_y, const int* idx, cons
  * (the clamped float coordinates devoxelize consumes), vox i32[b,3,n] (optional, may be NULL). */
 int gldm_voxelize_fused(const float* features, const float* coords, int b, int c, int n, int r, float* grid,
                         float* norm_coords, int* vox, void* stream);
+/* The same, writing the averaged features straight into the zero-padded channels-last bf16 grid the Conv3d kernels read
+ * (x_cl [b * (r+2)^3][stride] bf16, halo rows and padding channels are left untouched: allocate the grid zeroed).
+ * Requires c <= 4 or c a multiple of 8.  Replaces gldm_voxelize_fused + gldm_cl_pad of the tensor-core path. */
+int gldm_voxelize_fused_cl(const float* features, const float* coords, int b, int c, int n, int r, void* x_cl, int stride,
+                           float* norm_coords, void* stream);
 
 /* ---- dense fp32 building blocks of the encoder (SIMT, strict-fp32 parity mode) ---- */
 /* y[b,co,n] = act(scale[co] * (sum_ci W[co,ci] x[b,ci,n]) + shift[co]) (+ add[b,co,n] when add != NULL)
