@@ -73,6 +73,7 @@ _SIGS = {
     "gldm_gemm_tc_to_image": [P, c_int, c_int, c_int, P, P],
     "gldm_gemm_tc_run": [P, P, P, P, c_longlong, c_int, c_int, c_int, P, P],
     "gldm_gemm_tc_image_small_co": [P, P, P, c_longlong, c_int, c_int, c_int, P, P],
+    "gldm_gemm_tc_run_proj": [P, P, P, P, c_longlong, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P],
     "gldm_conv3d_tc_weight_bytes": [c_int],
     "gldm_conv3d_tc_grid_bytes": [c_int, c_int, c_int],
     "gldm_conv3d_tc_pack_weight": [P, c_int, c_int, P, P],

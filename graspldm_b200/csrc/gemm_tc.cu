@@ -21,6 +21,7 @@ constexpr int BLOCK = 16384;                 // one operand block: 128 rows x 64
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
 constexpr int SMEM = STAGES * 2 * BLOCK + 1024 + 256 + 1024;    // + scale / shift of the CTA's 128 columns
+constexpr int SMEM_PROJ = SMEM + 2048;                          // + the [128][4] projection weights of the tile
 }  // namespace gtc
 
 struct GemmTcParams {
@@ -30,8 +31,14 @@ struct GemmTcParams {
   const float* scale;       // [n] or NULL (1)
   const float* shift;       // [n] or NULL (0)
   int k_blocks, n_tiles, relu;
+  // fused projection (PROJ): instead of writing the activation image, the epilogue multiplies the tile's fp32
+  // activations by proj_w [128 columns][4] and writes the partial sums proj_out [n_tiles][rows][4]
+  const float* proj_w;      // [n_tiles * 128][4] fp32 (output channel fastest, unused channels zero)
+  float* proj_out;          // [n_tiles][rows][4] fp32
+  long long rows;
 };
 
+template <bool PROJ>
 __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   using namespace gtc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -54,6 +61,9 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
     s_sc[i] = p.scale ? __ldg(p.scale + nt * 128 + i) : 1.f;
     s_sh[i] = p.shift ? __ldg(p.shift + nt * 128 + i) : 0.f;
   }
+  float4* s_pw = reinterpret_cast<float4*>(s_sh + 128);
+  if (PROJ)
+    for (int i = tid; i < 128; i += NTHREADS) s_pw[i] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + nt * 128 + i);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -102,29 +112,51 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
     const int q = wid & 3, r = q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 2) * BLOCK;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    if (PROJ) {
+      // y = act(scale * acc + shift) stays fp32 in registers; four running dot products per row, columns in order
+      float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c0, v);
-      tmem_ld_wait();
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int n = c0 + j8 * 8 + 2 * h;
-          float y0 = __uint_as_float(v[j8 * 8 + 2 * h]), y1 = __uint_as_float(v[j8 * 8 + 2 * h + 1]);
-          const float2 sc = *reinterpret_cast<const float2*>(s_sc + n), sh = *reinterpret_cast<const float2*>(s_sh + n);
-          y0 = fmaf(y0, sc.x, sh.x);
-          y1 = fmaf(y1, sc.y, sh.y);
-          if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-          pk[h] = pack_bf16(y0, y1);
+        for (int j = 0; j < 32; ++j) {
+          float y = fmaf(__uint_as_float(v[j]), s_sc[c0 + j], s_sh[c0 + j]);
+          if (p.relu) y = fmaxf(y, 0.f);
+          const float4 w = s_pw[c0 + j];
+          dot.x = fmaf(y, w.x, dot.x);
+          dot.y = fmaf(y, w.y, dot.y);
+          dot.z = fmaf(y, w.z, dot.z);
+          dot.w = fmaf(y, w.w, dot.w);
         }
-        const int c = c0 + j8 * 8;                         // column inside the 128-wide tile
-        uint8_t* dst = out_tile + (size_t)(c >> 6) * BLOCK + swz_off<128>(r, (c & 63) >> 3);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      reinterpret_cast<float4*>(p.proj_out)[(size_t)nt * p.rows + (size_t)mt * 128 + r] = dot;
+    } else {
+      uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 2) * BLOCK;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int n = c0 + j8 * 8 + 2 * h;
+            float y0 = __uint_as_float(v[j8 * 8 + 2 * h]), y1 = __uint_as_float(v[j8 * 8 + 2 * h + 1]);
+            const float2 sc = *reinterpret_cast<const float2*>(s_sc + n), sh = *reinterpret_cast<const float2*>(s_sh + n);
+            y0 = fmaf(y0, sc.x, sh.x);
+            y1 = fmaf(y1, sc.y, sh.y);
+            if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            pk[h] = pack_bf16(y0, y1);
+          }
+          const int c = c0 + j8 * 8;                         // column inside the 128-wide tile
+          uint8_t* dst = out_tile + (size_t)(c >> 6) * BLOCK + swz_off<128>(r, (c & 63) >> 3);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
     tc_fence_before();
@@ -191,6 +223,22 @@ __global__ void __launch_bounds__(128) image_small_co_kernel(const uint8_t* __re
   for (int o = 0; o < CO; ++o) y[((size_t)b * CO + o) * n + pt] = acc[o] + (bias ? bias[o] : 0.f);
 }
 
+// sum of the per-tile partial projections (fixed order: deterministic) + bias, to the reference's [b, co, n] layout
+__global__ void __launch_bounds__(256) proj_sum_kernel(const float4* __restrict__ part, const float* __restrict__ bias,
+                                                       int n_tiles, long long rows, int co, int n, float* __restrict__ y) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  float4 a = part[m];
+  for (int t = 1; t < n_tiles; ++t) {
+    const float4 v = part[(size_t)t * rows + m];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const long long b = m / n;
+  const int pt = (int)(m - b * n);
+  const float o[4] = {a.x, a.y, a.z, a.w};
+  for (int c = 0; c < co; ++c) y[((size_t)b * co + c) * n + pt] = o[c] + (bias ? bias[c] : 0.f);
+}
+
 // weight matrix fp32 [n_out][k] -> B image [n_tiles][k_blocks][BLOCK]
 __global__ void __launch_bounds__(256) weight_image_kernel(const float* __restrict__ w, uint8_t* __restrict__ img, int n_out,
                                                            int k, int k_blocks) {
@@ -246,16 +294,43 @@ extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const floa
   GLDM_REQUIRE(k > 0 && n_out > 0 && n_out % 128 == 0, "gemm_tc_run: n_out = %d must be a multiple of 128", n_out);
   if (rows == 0) return GLDM_OK;
   static SmemOptIn attr;
-  if (int rc = opt_in_smem(attr, gemm_tc_kernel, gtc::SMEM, "gemm_tc_kernel")) return rc;
-  GemmTcParams p;
+  if (int rc = opt_in_smem(attr, gemm_tc_kernel<false>, gtc::SMEM, "gemm_tc_kernel")) return rc;
+  GemmTcParams p = {};
   p.a_img = reinterpret_cast<const uint8_t*>(a_img);
   p.b_img = reinterpret_cast<const uint8_t*>(w_img);
   p.out_img = reinterpret_cast<uint8_t*>(out_img);
   p.scale = scale; p.shift = shift;
   p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
   dim3 grid(p.n_tiles, (unsigned)(rows / 128));
-  gemm_tc_kernel<<<grid, gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
+  gemm_tc_kernel<false><<<grid, gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
   return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int gldm_gemm_tc_run_proj(const void* a_img, const void* w_img, const float* scale, const float* shift,
+                                     long long rows, int k, int n_out, int relu, const float* proj_w, const float* proj_bias,
+                                     int co, int n, void* partials, float* y, void* stream) {
+  GLDM_REQUIRE(a_img && w_img && proj_w && partials && y, "gemm_tc_run_proj: null pointer");
+  GLDM_REQUIRE(rows >= 0 && rows % 128 == 0, "gemm_tc_run_proj: rows = %lld must be a multiple of 128", rows);
+  GLDM_REQUIRE(k > 0 && n_out > 0 && n_out % 128 == 0, "gemm_tc_run_proj: n_out = %d must be a multiple of 128", n_out);
+  GLDM_REQUIRE(co >= 1 && co <= 4 && n > 0 && rows % n == 0, "gemm_tc_run_proj: bad projection sizes co=%d n=%d", co, n);
+  GLDM_REQUIRE((reinterpret_cast<uintptr_t>(proj_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(partials) & 15) == 0,
+               "gemm_tc_run_proj: proj_w / partials must be 16-byte aligned");
+  if (rows == 0) return GLDM_OK;
+  static SmemOptIn attr;
+  if (int rc = opt_in_smem(attr, gemm_tc_kernel<true>, gtc::SMEM_PROJ, "gemm_tc_kernel<proj>")) return rc;
+  GemmTcParams p = {};
+  p.a_img = reinterpret_cast<const uint8_t*>(a_img);
+  p.b_img = reinterpret_cast<const uint8_t*>(w_img);
+  p.scale = scale; p.shift = shift;
+  p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
+  p.proj_w = proj_w; p.proj_out = reinterpret_cast<float*>(partials); p.rows = rows;
+  dim3 grid(p.n_tiles, (unsigned)(rows / 128));
+  cudaStream_t s = (cudaStream_t)stream;
+  gemm_tc_kernel<true><<<grid, gtc::NTHREADS, gtc::SMEM_PROJ, s>>>(p);
+  if (int rc = check_launch("gemm_tc_kernel<proj>")) return rc;
+  proj_sum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(partials), proj_bias, p.n_tiles,
+                                                                  rows, co, n, y);
+  return check_launch("proj_sum_kernel");
 }
 
 extern "C" int gldm_gemm_tc_image_small_co(const void* img, const float* w, const float* bias, long long rows, int k,

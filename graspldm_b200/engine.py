@@ -487,7 +487,24 @@ def _pointwise_tail_tc(pk, feats, st):
     L = _lib.lib()
     img = _aligned_bytes(L.gldm_gemm_tc_image_bytes(rows, C), dev)
     _lib.call("gldm_gemm_tc_to_image", feats.data_ptr(), B, C, N, img.data_ptr(), st)
-    for layer in pk.tc_weights():
+    layers = pk.tc_weights()
+    proj = pk.tc_projection()
+    if proj is not None:
+        # conv_downscale and out_layer.0 are composed into one [C_out, width] projection that the epilogue of the last
+        # SharedMLP applies to its fp32 activations: neither the widest activation nor conv_downscale's output exists
+        for layer in layers[:-2]:
+            out = _aligned_bytes(L.gldm_gemm_tc_image_bytes(rows, layer["n"]), dev)
+            _lib.call("gldm_gemm_tc_run", img.data_ptr(), layer["img"].data_ptr(), layer["scale"].data_ptr(),
+                      layer["shift"].data_ptr(), rows, layer["k"], layer["n"], layer["relu"], out.data_ptr(), st)
+            img = out
+        layer = layers[-2]
+        part = torch.empty((layer["n"] // 128, rows, 4), device=dev, dtype=torch.float32)
+        h = torch.empty((B, pk.out_channels, N), device=dev, dtype=torch.float32)
+        _lib.call("gldm_gemm_tc_run_proj", img.data_ptr(), layer["img"].data_ptr(), layer["scale"].data_ptr(),
+                  layer["shift"].data_ptr(), rows, layer["k"], layer["n"], layer["relu"], proj[0].data_ptr(),
+                  proj[1].data_ptr(), pk.out_channels, N, part.data_ptr(), h.data_ptr(), st)
+        return h
+    for layer in layers:
         out = _aligned_bytes(L.gldm_gemm_tc_image_bytes(rows, layer["n"]), dev)
         _lib.call("gldm_gemm_tc_run", img.data_ptr(), layer["img"].data_ptr(),
                   layer["scale"].data_ptr() if layer["scale"] is not None else None,
@@ -652,6 +669,7 @@ class PackedEncoder:
         self.out_features = enc.out_layer[1].out_features
         self._tc = None
         self._tc_conv = None
+        self._proj = None
 
     def tc_conv_weights(self):
         """bf16 UMMA images of the Conv3d weights that qualify for the tensor-core kernel (16 <= ci, co <= 128);
@@ -681,6 +699,22 @@ class PackedEncoder:
                     out.append(pair)
             self._tc_conv = out
         return self._tc_conv
+
+    def tc_projection(self):
+        """(proj_w [width, 4], proj_bias [C_out]) of conv_downscale followed by out_layer.0, composed in fp64 (two affine
+        maps in a row, pc_encoders.py:104-112 without global attention), or None when there is no SharedMLP tail to
+        fuse it into, C_out > 4, or GLDM_FOLD_DOWNSCALE=0 (the layer-by-layer tensor-core chain)."""
+        if os.environ.get("GLDM_FOLD_DOWNSCALE", "1") == "0" or self.out_channels > 4:
+            return None
+        if not self.blocks or self.blocks[-1]["kind"] != "mlp" or self.blocks[-1]["pscale"] is None:
+            return None
+        if self._proj is None:
+            w = self.wo.double() @ self.wd.double()                       # [C_out, width]
+            b = self.wo.double() @ self.bd.double() + self.bo.double()
+            pw = torch.zeros((w.shape[1], 4), device=self.device, dtype=torch.float32)
+            pw[:, :w.shape[0]] = w.t().float()
+            self._proj = (pw.contiguous(), b.float().contiguous())
+        return self._proj
 
     def tc_weights(self):
         """bf16 UMMA images of the point-wise layers that run on the tensor cores (built on first use):

@@ -237,6 +237,16 @@ int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, c
                      int k, int n_out, int relu, void* out_img, void* stream);
 int gldm_gemm_tc_image_small_co(const void* img, const float* w, const float* bias, long long rows, int k, int co,
                                 int n, float* y, void* stream);
+/* gldm_gemm_tc_run with a fused projection instead of an output image:
+ *   y f32[b, co, n] = sum_j proj_w[j][c] * act(scale[j] * sum_k A[m,k] W[j,k] + shift[j]) + proj_bias[c],   co <= 4.
+ * proj_w f32[n_out][4] (output channel fastest, unused entries zero, 16-byte aligned); partials: 16 * rows * n_out / 128
+ * bytes of scratch (per-tile partial sums, added in tile order: deterministic).  Used for the last SharedMLP of the
+ * encoder followed by conv_downscale and out_layer.0, which are two affine maps in a row without a non-linearity
+ * (R/models/modules/pc_encoders.py:60-75, 104-112 with use_global_attention=False) and are composed once into
+ * proj_w = (W_out W_down)^T, proj_bias = W_out b_down + b_out: the [rows, 1536] and [rows, 768] activations never exist. */
+int gldm_gemm_tc_run_proj(const void* a_img, const void* w_img, const float* scale, const float* shift, long long rows,
+                          int k, int n_out, int relu, const float* proj_w, const float* proj_bias, int co, int n,
+                          void* partials, float* y, void* stream);
 
 /* ---- tensor-core Conv3d k3 p1 (bf16 operands, fp32 accumulation), implicit GEMM over a zero-padded channels-last
  * grid loaded with TMA tensor copies (R/../pvcnn/modules/pvconv.py:48-67).  16 <= ci, co <= 128.

@@ -60,9 +60,13 @@ def test_sampler_bf16_tracks_fp32(cuda, name, kind, steps):
     np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=3e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize("fold", ["1", "0"])
 @pytest.mark.parametrize("name", ["fpc", "ppc"])
-def test_encoder_bf16_pointwise_layers(cuda, name):
-    """Conv3d stacks and the point-wise tail (96->768->1536->768) on the tensor cores vs the committed reference fixture."""
+def test_encoder_bf16_pointwise_layers(cuda, name, fold, monkeypatch):
+    """Conv3d stacks and the point-wise tail (96->768->1536->768->3) on the tensor cores vs the committed reference
+    fixture: with conv_downscale and out_layer.0 composed into the epilogue of the 768->1536 GEMM (default) and layer by
+    layer (GLDM_FOLD_DOWNSCALE=0)."""
+    monkeypatch.setenv("GLDM_FOLD_DOWNSCALE", fold)
     m = _models.build(name).to(cuda)
     enc = m.vae_model.encoder.pc_encoder
     xyz = torch.cat([_data.synthetic_clouds(2, seed=1234, dist="S"), _data.synthetic_clouds(1, seed=99, dist="G")]).to(cuda)
