@@ -9,8 +9,8 @@
 //     block barrier per round;
 //   * ball query is a warp-per-centre ballot/popc compaction with early exit;
 //   * grouping / gather are 128-bit vectorised, write-coalesced gathers;
-//   * voxelisation ranks the points of a voxel in index order (match.any + ordered warp rounds) and
-//     accumulates in that order, so results are deterministic.
+//   * voxelisation buckets the points by voxel with a shared-memory counting sort, orders every bucket by point index
+//     and accumulates in that order, so results are deterministic.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -359,48 +359,65 @@ __global__ void __launch_bounds__(256) three_nn_grad_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------
 // voxelisation                                   R/voxelization/vox.cu:18-72 (+ voxelization.py:16-35 when FUSED)
-// One block per cloud; per-voxel state (count, list tail) lives in shared memory as 16-bit values.
-// Phase B threads the points of each voxel into a linked list in ascending point index: 32-point chunks
-// are processed in order (one warp per chunk), match.any finds the in-chunk predecessor and s_tail
-// carries the link across chunks.  Phase C is VOXEL-centric: a thread owns a voxel, walks its list once and sums up
-// to 8 channels in index order - the order the oracle uses - so the averages are bit-reproducible (the reference's
-// float atomics are not), no global atomics are issued, and the grid is written exactly once, coalesced over the
-// voxels (empty voxels included: no separate zero pass, no scattered 4-byte stores).
+// One block per (cloud, channel slice, cell range); per-voxel state lives in shared memory as 16-bit values.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned gldm_pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&t);
 }
-constexpr int kVoxMaxPPT = 16;      // 512 threads x 16 -> n <= 8192 points per cloud
-constexpr int kVoxMaxPoints = 8192;
+constexpr int kVoxMaxPoints = 8192;  // point indices, bucket offsets and voxel ids (r <= 36) are 16-bit values in shared memory
+// Bucket version (round 2).  The first version threaded the points of a voxel into a linked list, 32-point chunk after
+// chunk (one block barrier per chunk: the order is what makes the sums reproducible), and its averaging phase gave a
+// thread four voxels and all channels of the slice - ncu: 55 % of the executed instructions in divergent list walks whose
+// length is set by the fullest voxels, 20 % of the stall samples in the serial chunk loop.  Now
+//   B  counting sort: per-voxel counts by shared-memory atomics (the arrival slot is arbitrary), exclusive scan over the
+//      voxels in place, scatter into buckets, then every point ranks itself inside its bucket by counting the smaller
+//      indices - the bucket is in ascending index whatever order the atomics ran in: six barriers instead of n / 32;
+//   C  empty cells are zero-filled coalesced; the non-empty ones are compacted and averaged as (cell, channel group) items
+//      spread evenly over the threads: a planar item is four consecutive voxels of one channel (one 16-byte store), a
+//      channels-last item is eight channels of one voxel (one 16-byte bf16 chunk).  Sums run in ascending point index, the
+//      order the oracle uses, so results stay bit-reproducible (the reference's float atomics are not).
 template <bool FUSED, int CH>
 __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__ feat,
                                                         const void* __restrict__ coords_in, int c, int n, int r,
                                                         float* __restrict__ out, int* __restrict__ ind_out,
                                                         int* __restrict__ cnt_out, float* __restrict__ norm_out,
                                                         int* __restrict__ vox_out, __nv_bfloat16* __restrict__ cl_out,
-                                                        int cl_stride) {
-  extern __shared__ unsigned char s_raw[];
+                                                        int cl_stride, int stage_feat) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ double s_red[3][16];
   __shared__ float s_mean[3];
+  __shared__ unsigned s_wsum[16];
+  __shared__ int s_ncells;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int r2 = r * r, r3 = r2 * r;
-  // carve: cnt u16[r3] | tail i16[r3] (list tails while the lists are built, list heads afterwards) | next i16[n] | vox i32[n]
-  unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_raw);
-  short* s_tail = reinterpret_cast<short*>(s_cnt + ((r3 + 1) & ~1));
-  short* s_next = s_tail + ((r3 + 1) & ~1);
-  int* s_vox = reinterpret_cast<int*>(s_next + ((n + 1) & ~1));
+  // carve (16-bit entries): off[r3 + 1] counts, then exclusive bucket offsets (off[r3] = n) | vox[n] | perm[n] buckets in
+  // arrival order | sorted[n] arrival slot, then the buckets in ascending index | cells[n] non-empty cells
+  const int offw = (r3 + 2 + 1) & ~1, ne = (n + 1) & ~1;
+  unsigned short* s_off = reinterpret_cast<unsigned short*>(s_raw);
+  unsigned short* s_vox = s_off + offw;
+  unsigned short* s_perm = s_vox + ne;
+  unsigned short* s_sorted = s_perm + ne;
+  unsigned short* s_cells = s_sorted + ne;
+  float* s_feat = reinterpret_cast<float*>(s_raw + (((size_t)(offw + 4 * ne) * 2 + 15) & ~(size_t)15));   // [ch_n][n] when staged
   // blockIdx.y owns a slice of the channels (the point binning is cheap and repeated per slice); slice 0 also writes
   // the per-point / per-voxel side outputs
   const int cs = (c + gridDim.y - 1) / gridDim.y, ch_lo = blockIdx.y * cs, ch_n = max(0, min(c, ch_lo + cs) - ch_lo);
-  const bool side = blockIdx.y == 0;
+  const bool side = blockIdx.y == 0 && blockIdx.z == 0;
   const float* fb = feat + ((size_t)b * c + ch_lo) * n;
-  float* ob = out + ((size_t)b * c + ch_lo) * r3;
 
-  for (int i = tid; i < r3; i += nthreads) { s_cnt[i] = 0; s_tail[i] = -1; }
-  for (int i = tid; i < n; i += nthreads) s_next[i] = -1;
-  const int ppt = (n + nthreads - 1) / nthreads;
+  // the slice's features on their way into shared memory (asynchronous copies, consumed in phase C): the bucket sums
+  // are chains of dependent loads - from global memory they were 44 % of the stall samples
+  if (stage_feat) {
+    const int nvec = ch_n * n / 4;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_feat);
+    for (int i = tid; i < nvec; i += nthreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(fb + (size_t)i * 4));
+    asm volatile("cp.async.commit_group;" ::);
+  }
+  for (int i = tid; i < offw / 2; i += nthreads) reinterpret_cast<unsigned*>(s_off)[i] = 0u;
+  if (tid == 0) s_ncells = 0;
   if (FUSED) {
     const float* cf = reinterpret_cast<const float*>(coords_in) + (size_t)b * 3 * n;
     // mean over the point axis, accumulated in double (voxelization.py:18)
@@ -438,111 +455,136 @@ __global__ void __launch_bounds__(512) voxelize_kernel(const float* __restrict__
         v3[a] = (int)rintf(x);                                   // torch.round: half to even
         if (vox_out && side) vox_out[((size_t)b * 3 + a) * n + i] = v3[a];
       }
-      s_vox[i] = v3[0] * r2 + v3[1] * r + v3[2];
+      s_vox[i] = (unsigned short)(v3[0] * r2 + v3[1] * r + v3[2]);
     }
   } else {
     const int* ci = reinterpret_cast<const int*>(coords_in) + (size_t)b * 3 * n;
-    for (int i = tid; i < n; i += nthreads) s_vox[i] = ci[i] * r2 + ci[i + n] * r + ci[i + 2 * n];
+    for (int i = tid; i < n; i += nthreads) s_vox[i] = (unsigned short)(ci[i] * r2 + ci[i + n] * r + ci[i + 2 * n]);
   }
   __syncthreads();
-  // Phase B: ordered chunks.  Chunk q covers points [32q, 32q+32); warp (q mod nwarps) owns it and the
-  // block barrier between consecutive groups of nwarps chunks keeps the order.
-  const int nchunks = (n + 31) >> 5;
-  for (int q0 = 0; q0 < nchunks; q0 += nwarps) {
-    for (int w = 0; w < nwarps; ++w) {
-      if (wid == w && q0 + w < nchunks) {
-        const int i = ((q0 + w) << 5) + lane;
-        const bool valid = i < n;
-        const int v = valid ? s_vox[i] : -1;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-          const unsigned same = __match_any_sync(act, v);
-          const unsigned below = same & ((1u << lane) - 1u);
-          const int base = s_cnt[v];
-          const int tail = s_tail[v];
-          __syncwarp(act);
-          const int pred = below ? i - (lane - (31 - __clz(below))) : tail;
-          if (pred >= 0) s_next[pred] = (short)i;
-          else s_vox[i] = v | 0x40000000;                       // first point of its voxel (own entry; unmarked below)
-          if (below == 0) s_cnt[v] = (unsigned short)(base + __popc(same));
-          if ((same >> lane) == 1u) s_tail[v] = (short)i;       // highest lane of the group
-        }
-      }
-      __syncthreads();
-    }
-  }
-  // the tails are no longer needed: the same table now records the list heads
+  // ---- B1: counts (two 16-bit counters per 32-bit word; n <= 8192 cannot carry into the upper half)
   for (int i = tid; i < n; i += nthreads) {
-    const int vv = s_vox[i];
-    if (vv & 0x40000000) {
-      s_vox[i] = vv & 0x3fffffff;
-      s_tail[vv & 0x3fffffff] = (short)i;
-    }
+    const int v = s_vox[i], sh = (v & 1) << 4;
+    const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(s_off) + (v >> 1), 1u << sh);
+    s_sorted[i] = (unsigned short)((old >> sh) & 0xffffu);
   }
   __syncthreads();
-  short* s_head = s_tail;
+  // ---- B2: exclusive scan over the voxels, in place (a thread owns a contiguous segment)
+  {
+    const int seg = (r3 + nthreads - 1) / nthreads, lo = min(r3, tid * seg), hi = min(r3, lo + seg);
+    unsigned sum = 0;
+    for (int v = lo; v < hi; ++v) sum += s_off[v];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    unsigned run = incl - sum;
+    for (int w = 0; w < wid; ++w) run += s_wsum[w];
+    for (int v = lo; v < hi; ++v) {
+      const unsigned cv = s_off[v];
+      s_off[v] = (unsigned short)run;
+      run += cv;
+    }
+    if (tid == 0) s_off[r3] = (unsigned short)n;
+  }
+  __syncthreads();
+  // ---- B3: buckets in arrival order;  B4: rank inside the bucket = number of smaller indices
+  for (int i = tid; i < n; i += nthreads) s_perm[s_off[s_vox[i]] + s_sorted[i]] = (unsigned short)i;
+  __syncthreads();
+  for (int i = tid; i < n; i += nthreads) {
+    const int v = s_vox[i], o = s_off[v], cv = s_off[v + 1] - o;
+    int rank = 0;
+    for (int j = 0; j < cv; ++j) rank += (int)(s_perm[o + j] < (unsigned short)i);
+    s_sorted[o + rank] = (unsigned short)i;
+  }
   if (ind_out && side)
     for (int i = tid; i < n; i += nthreads) ind_out[(size_t)b * n + i] = s_vox[i];
-  if (cnt_out && side)
-    for (int i = tid; i < r3; i += nthreads) cnt_out[(size_t)b * r3 + i] = s_cnt[i];
   __syncthreads();
-  // Phase C: a thread owns four consecutive voxels; an all-empty quad (most of a 24^3 grid) is ch_n 16-byte zero stores,
-  // otherwise every non-empty voxel's point list is walked once for all (<= CH) channels of this slice
-  // channels-last output (the Conv3d kernels' operand form, written directly: no fp32 grid, no separate padding pass):
-  // row (x+1, y+1, z+1) of the zero-padded grid of this cloud, this slice's channels as one or two 16-byte chunks
-  if (cl_out) {
-    const int rp = r + 2;
-    __nv_bfloat16* cb = cl_out + (size_t)b * rp * rp * rp * cl_stride + ch_lo;
-    for (int v = tid; v < r3; v += nthreads) {
-      float acc[CH];
-#pragma unroll
-      for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-      const int cv = s_cnt[v];
-      if (cv) {
-        const float div = (float)(1.0 / (double)(float)cv);       // vox.cu:65
-        for (int p = s_head[v]; p >= 0; p = s_next[p]) {
-#pragma unroll
-          for (int k = 0; k < CH; ++k)
-            if (k < ch_n) acc[k] = __fadd_rn(acc[k], __fmul_rn(__ldg(fb + (size_t)k * n + p), div));
-        }
-      }
-      const int x = v / r2, y = (v / r) % r, z = v % r;
-      uint4* dst = reinterpret_cast<uint4*>(cb + (size_t)(((x + 1) * rp + (y + 1)) * rp + (z + 1)) * cl_stride);
-      auto pk = [&](int k) { return gldm_pack_bf16(acc[k < CH ? k : 0], acc[k + 1 < CH ? k + 1 : 0]); };
-      if (CH == 4) {
-        dst[0] = make_uint4(pk(0), pk(2), 0u, 0u);
+  if (cnt_out && side)
+    for (int i = tid; i < r3; i += nthreads) cnt_out[(size_t)b * r3 + i] = (int)s_off[i + 1] - (int)s_off[i];
+
+  // ---- C: cells.  planar: four consecutive voxels (one voxel when the grid cannot be written in 16-byte pieces);
+  //      channels-last: one voxel = one row of the zero-padded grid of this cloud
+  float* ob = out ? out + ((size_t)b * c + ch_lo) * r3 : nullptr;
+  const bool quads = !cl_out && (r3 & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0;
+  const int cw = quads ? 4 : 1, ncell = r3 / cw;
+  const int rp = r + 2;
+  __nv_bfloat16* cb = cl_out ? cl_out + (size_t)b * rp * rp * rp * cl_stride + ch_lo : nullptr;
+  auto cl_row = [&](int v) {
+    const int x = v / r2, y = (v / r) % r, z = v % r;
+    return reinterpret_cast<uint4*>(cb + (size_t)(((x + 1) * rp + (y + 1)) * rp + (z + 1)) * cl_stride);
+  };
+  const int groups = cl_out ? (CH == 4 ? 1 : (ch_n + 7) >> 3) : ch_n;
+  // blockIdx.z owns a contiguous range of the cells (small batches: more CTAs than clouds x channel slices)
+  const int cell_per = (ncell + gridDim.z - 1) / gridDim.z, cell_lo = blockIdx.z * cell_per, cell_hi = min(ncell, cell_lo + cell_per);
+  for (int base = cell_lo + wid * 32; base < cell_hi; base += nthreads) {
+    const int cell = base + lane;
+    const bool valid = cell < cell_hi;
+    const bool empty = valid && s_off[cell * cw + cw] == s_off[cell * cw];
+    if (empty) {
+      if (cl_out) {
+        uint4* dst = cl_row(cell);
+        for (int g = 0; g < groups; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
+      } else if (quads) {
+        const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < ch_n; ++k) *reinterpret_cast<float4*>(ob + (size_t)k * r3 + 4 * cell) = zz;
       } else {
-        dst[0] = make_uint4(pk(0), pk(2), pk(4), pk(6));
-        if (CH == 16) dst[1] = make_uint4(pk(8), pk(10), pk(12), pk(14));
+        for (int k = 0; k < ch_n; ++k) ob[(size_t)k * r3 + cell] = 0.f;
       }
     }
-    return;
+    const unsigned m = __ballot_sync(0xffffffffu, valid && !empty);
+    int pos = 0;
+    if (lane == 0 && m) pos = atomicAdd(&s_ncells, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (valid && !empty) s_cells[pos + __popc(m & ((1u << lane) - 1u))] = (unsigned short)cell;
   }
-  const bool quads = (r3 & 3) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0;
-  for (int v0 = tid * 4; v0 < r3; v0 += nthreads * 4) {
-    const int nv = min(4, r3 - v0);
-    if (quads && *reinterpret_cast<const unsigned long long*>(s_cnt + v0) == 0ull) {
-      const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < ch_n; ++k) *reinterpret_cast<float4*>(ob + (size_t)k * r3 + v0) = zz;
-      continue;
+  if (stage_feat) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int ncells = s_ncells, items = ncells * groups;
+  const float* fsrc = stage_feat ? s_feat : fb;       // (generic loads: shared when staged)
+  // divisor (float)(1.0 / (double)(float)cnt) of vox.cu:65 == the correctly rounded fp32 reciprocal for every count up to
+  // 8192 (checked exhaustively), so no double-precision division here
+  auto bucket_sum = [&](const float* f, int v) {      // one channel of voxel v: ascending point index
+    const int o = s_off[v], cv = s_off[v + 1] - o;
+    float acc = 0.f;
+    if (cv) {
+      const float div = __frcp_rn((float)cv);
+      for (int j = 0; j < cv; ++j) acc = __fadd_rn(acc, __fmul_rn(f[s_sorted[o + j]], div));
     }
-    for (int dv = 0; dv < nv; ++dv) {
-      const int v = v0 + dv;
-      float acc[CH];
+    return acc;
+  };
+  for (int it = tid; it < items; it += nthreads) {
+    const int g = it / ncells, cell = s_cells[it - g * ncells];
+    if (cl_out) {
+      const int o = s_off[cell], cv = s_off[cell + 1] - o;
+      const float div = __frcp_rn((float)cv);
+      constexpr int CK = CH == 4 ? 4 : 8;
+      float acc[CK];
 #pragma unroll
-      for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-      const int cv = s_cnt[v];
-      if (cv) {
-        const float div = (float)(1.0 / (double)(float)cv);       // vox.cu:65
-        for (int p = s_head[v]; p >= 0; p = s_next[p]) {
+      for (int k = 0; k < CK; ++k) acc[k] = 0.f;
+      const float* f = fsrc + (size_t)(g * 8) * n;
+      const int kn = min(CK, ch_n - g * 8);
+      for (int j = 0; j < cv; ++j) {
+        const int p = s_sorted[o + j];
 #pragma unroll
-          for (int k = 0; k < CH; ++k)
-            if (k < ch_n) acc[k] = __fadd_rn(acc[k], __fmul_rn(__ldg(fb + (size_t)k * n + p), div));
-        }
+        for (int k = 0; k < CK; ++k)
+          if (k < kn) acc[k] = __fadd_rn(acc[k], __fmul_rn(f[(size_t)k * n + p], div));
       }
-#pragma unroll
-      for (int k = 0; k < CH; ++k)
-        if (k < ch_n) ob[(size_t)k * r3 + v] = acc[k];
+      uint4* dst = cl_row(cell) + g;
+      if (CK == 4) *dst = make_uint4(gldm_pack_bf16(acc[0], acc[1]), gldm_pack_bf16(acc[2], acc[3]), 0u, 0u);
+      else *dst = make_uint4(gldm_pack_bf16(acc[0], acc[1]), gldm_pack_bf16(acc[2], acc[3]),
+                             gldm_pack_bf16(acc[4 % CK], acc[5 % CK]), gldm_pack_bf16(acc[6 % CK], acc[7 % CK]));
+    } else if (quads) {
+      const float* f = fsrc + (size_t)g * n;
+      const float4 val = make_float4(bucket_sum(f, 4 * cell), bucket_sum(f, 4 * cell + 1), bucket_sum(f, 4 * cell + 2),
+                                     bucket_sum(f, 4 * cell + 3));
+      *reinterpret_cast<float4*>(ob + (size_t)g * r3 + 4 * cell) = val;
+    } else {
+      ob[(size_t)g * r3 + cell] = bucket_sum(fsrc + (size_t)g * n, cell);
     }
   }
 }
@@ -803,12 +845,20 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   GLDM_REQUIRE(r <= 36, "voxelize: resolution %d > 36 not supported (shared-memory voxel table)", r);
   if (b == 0) return GLDM_OK;
   const size_t r3 = (size_t)r * r * r;
-  size_t smem = 2 * ((r3 + 1) & ~(size_t)1) * 2 + (((size_t)n + 1) & ~(size_t)1) * 2 + (size_t)n * 4;
+  size_t smem = ((2 * (((r3 + 3) & ~(size_t)1) + 4 * (((size_t)n + 1) & ~(size_t)1)) + 15) & ~(size_t)15) + 16;
+  GLDM_REQUIRE(smem <= 200 * 1024, "voxelize: r=%d with n=%d points needs %zu bytes of shared memory (> 200 KB)", r, n, smem);
   int threads = min(512, ceil_div(n, 32) * 32);
-  // channels per CTA (phase C keeps them in registers): 4 for the coordinate-only first block, 16 for wide features
-  // (fewer CTAs repeat the point binning), 8 otherwise
-  const int ch = c <= 4 ? 4 : (c >= 32 && (long long)b * ceil_div(c, 16) >= 2 * kNumSMs) ? 16 : 8;
+  // channels per CTA: 4 for the coordinate-only first block, 16 for wide features in large batches, 8 otherwise
+  static const int ch_env = getenv("GLDM_VOX_CH") ? atoi(getenv("GLDM_VOX_CH")) : 0;
+  const int ch = c <= 4 ? 4 : ch_env ? ch_env : (c >= 32 && (long long)b * ceil_div(c, 16) >= 2 * kNumSMs) ? 16 : 8;
   const int slices = ceil_div(c, ch);
+  // the slice's features are staged in shared memory when that keeps >= 3 CTAs per SM (16-byte copies: n % 4, alignment)
+  const size_t feat_bytes = (size_t)min(c, ch) * n * 4;
+  static const bool no_stage = getenv("GLDM_VOX_NOSTAGE") != nullptr;      // development knobs: GLDM_VOX_NOSTAGE, GLDM_VOX_CH
+  const int stage = (n % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 && smem + feat_bytes <= 80 * 1024 && !no_stage) ? 1 : 0;
+  if (stage) smem += feat_bytes;
+  // small batches of large grids: split the cells of a cloud over up to 8 CTAs (each repeats the binning)
+  const int vsl = (r3 >= 4096) ? max(1, min(8, (2 * kNumSMs) / max(1, b * slices))) : 1;
   if (cl_out) {
     // a slice must be whole 16-byte chunks of the rows (or the single narrow slice of a <= 4-channel input)
     GLDM_REQUIRE((slices == 1 && c <= 4) || (c % ch == 0), "voxelize (channels-last): %d channels are not a multiple of %d", c, ch);
@@ -818,8 +868,8 @@ static int launch_voxelize(bool fused, const float* feat, const void* coords, in
   do {                                                                                                             \
     static SmemOptIn attr;                                                                                         \
     if (int rc = opt_in_smem(attr, voxelize_kernel<F, C_>, 200 * 1024, "voxelize_kernel")) return rc;              \
-    voxelize_kernel<F, C_><<<dim3(b, slices), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox, \
-                                                                  cl_out, cl_stride);                              \
+    voxelize_kernel<F, C_><<<dim3(b, slices, vsl), threads, smem, s>>>(feat, coords, c, n, r, out, ind, cnt, norm, vox, \
+                                                                  cl_out, cl_stride, stage);                       \
   } while (0)
   if (fused) {
     if (ch == 4) VOX_LAUNCH(true, 4); else if (ch == 16) VOX_LAUNCH(true, 16); else VOX_LAUNCH(true, 8);
