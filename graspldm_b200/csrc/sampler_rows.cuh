@@ -889,10 +889,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
   float* s_x = reinterpret_cast<float*>(smem + SM_X);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int cta_s0 = blockIdx.x * NS;
+  int cta_s0 = blockIdx.x * NS;
   const ResNetLayout& lay = p.lay;
   const float* W = p.W;
-  const int n_steps = (p.mode == 0) ? p.n_steps : 1;
+  // sampler: the denoising steps of this CTA's samples.  Decoder (mode 2): the CTA is persistent over sample groups
+  // blockIdx.x, blockIdx.x + gridDim.x, ... - one "step" per group, so the table set-up below (40 k cycles, a fifth of a
+  // single evaluation) is paid once per CTA instead of once per 8 grasps
+  const int n_groups = (p.n + NS - 1) / NS;
+  const int n_steps = (p.mode == 0) ? p.n_steps : (p.mode == 2) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 1;
   const int n_rj = p.n_jobs;
 
   // ---- one-time setup
@@ -905,7 +909,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     fence_barrier_init();
   }
   if (wid == 0) tmem_alloc<512>(tmem_slot);
-  if (tid < NS * L) {
+  auto load_input = [&]() {          // threads 0 .. NS * L - 1 (= warp-group 0): the state / network input of this group
     const int s = tid / L, l = tid % L;
     float v = 0.f;
     if (cta_s0 + s < p.n) {
@@ -920,7 +924,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
     s_x[128 + s * L + l] = 0.f;
     s_x[256 + s * L + l] = 0.f;
     if (p.mode == 0 && p.x_all && cta_s0 + s < p.n) p.x_all[(size_t)(cta_s0 + s) * L + l] = v;
-  }
+  };
+  if (tid < NS * L) load_input();
   // ---- weight-chunk and UMMA op tables of one step (only the convolution / projection blocks of a job's image are
   // streamed: the FiLM projection tiles behind them belong to the channel-major kernel)
   // op.x / op.y: low words of the A (activation) / B (weight) descriptors; op.z: high word of the B descriptor;
@@ -1109,13 +1114,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(b_ready);
     };
-    // FiLM table row of this thread's sample: (object, step) in the sampler, the sample itself in a single evaluation
+    // FiLM table row of this thread's sample: (object, step) in the sampler, the sample itself in a single evaluation,
+    // the object in the decoder
     const int smp = min(cta_s0 + e.s, p.n - 1);
     const size_t film_row0 = ((p.mode == 0) ? (size_t)(smp / p.gpo) * n_steps : (p.mode == 2) ? (size_t)(smp / p.gpo) : (size_t)smp) *
                              p.film_stride;
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
       const float* film_step = p.film + (film_row0 + (size_t)step * p.film_stride);
+      if (p.mode == 2) {
+        if (step > 0) {            // next sample group of this persistent decoder CTA (warp-group 0 = threads 0 .. 127)
+          cta_s0 = ((int)blockIdx.x + step * (int)gridDim.x) * NS;
+          bar_all();               // the heads of the previous group have read s_x
+          if (e.g == 0) {
+            load_input();
+            bar_wg(0);             // (sample, position) readers below are other threads than the writers
+          }
+        }
+        film_step = p.film + (size_t)(min(cta_s0 + e.s, p.n - 1) / p.gpo) * p.film_stride;
+      }
       // ---- network input: the state, or (evaluation programs) c_in * x_in with the stochastic churn added
       const bool edm = p.mode == 0 && p.sched_kind == GLDM_SCHED_EDM;
       float* s_y = s_x + 128;
@@ -1252,27 +1269,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) resnet_rows_kernel(const __grid_c
         if (rec) p.prof[64 + 8 * j + 6] = clock64();
         if (j + 1 < n_rj) handoff();
       }
-    }
-    if (p.mode != 2) {
-      if (e.g == 0 && cta_s0 + e.s < p.n) p.x_out[(size_t)(cta_s0 + e.s) * L + e.pos] = s_x[e.s * L + e.pos];
-    } else if (tid < NS * 7) {
-      // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430); s_x was written by
-      // warp-group 0 behind the bar_all of the final job
-      const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
-      const int s = tid / 7, o = tid - s * 7;
-      if (cta_s0 + s < p.n) {
-        const float* x = s_x + s * L;
-        if (o < 6) {
-          float a = __ldg(hw + 6 * L + o);
-          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
-          p.tmrp[(size_t)(cta_s0 + s) * 6 + o] = a;
-        } else {
-          float a = __ldg(hw + 6 * L + 6 + L);
-          for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
-          p.logit[cta_s0 + s] = a;
+      if (p.mode == 2 && tid < NS * 7) {
+        // decoder heads: tmrp = Linear(L -> 6), class_logits = Linear(L -> 1)   (grasp_vae.py:428-430); s_x was written by
+        // warp-group 0 behind the bar_all of the final job
+        const float* hw = p.head + L * p.D + L;   // tmrp_w [6][L], tmrp_b [6], cls_w [L], cls_b [1]
+        const int s = tid / 7, o = tid - s * 7;
+        if (cta_s0 + s < p.n) {
+          const float* x = s_x + s * L;
+          if (o < 6) {
+            float a = __ldg(hw + 6 * L + o);
+            for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + o * L + l), x[l], a);
+            p.tmrp[(size_t)(cta_s0 + s) * 6 + o] = a;
+          } else {
+            float a = __ldg(hw + 6 * L + 6 + L);
+            for (int l = 0; l < L; ++l) a = fmaf(__ldg(hw + 6 * L + 6 + l), x[l], a);
+            p.logit[cta_s0 + s] = a;
+          }
         }
       }
     }
+    if (p.mode != 2 && e.g == 0 && cta_s0 + e.s < p.n) p.x_out[(size_t)(cta_s0 + e.s) * L + e.pos] = s_x[e.s * L + e.pos];
   }
   tc_fence_before();
   __syncthreads();

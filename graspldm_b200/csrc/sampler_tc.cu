@@ -1335,6 +1335,7 @@ static bool rows_supported(const GldmResNetCfg& c) {
   return (l4 || l16) && c.n_stages == 4 && c.groups == 4 && c.ch[1] == 32 && c.ch[2] == 64 && c.ch[3] == 128 && c.ch[4] == 256;
 }
 
+static const bool g_rows_persistent_decoder = !(getenv("GLDM_DECODER_PERSISTENT") && atoi(getenv("GLDM_DECODER_PERSISTENT")) == 0);
 template <int L>
 static int launch_rows_l(TcParams& p, cudaStream_t s) {
   static SmemOptIn attr;
@@ -1364,7 +1365,10 @@ static int launch_rows_l(TcParams& p, cudaStream_t s) {
   int rc = check_launch("film_table_kernel");
   if (rc == GLDM_OK) {
     p.film = film;
-    rows::resnet_rows_kernel<L><<<ceil_div(p.n, rows::Geo<L>::NS), rows::NTHREADS, smem, s>>>(p);
+    // decoder: persistent CTAs, every one the same number of sample groups (+- 1); sampler / single evaluation: one group
+    int grid = ceil_div(p.n, rows::Geo<L>::NS);
+    if (p.mode == 2 && g_rows_persistent_decoder) grid = ceil_div(grid, ceil_div(grid, kNumSMs));
+    rows::resnet_rows_kernel<L><<<grid, rows::NTHREADS, smem, s>>>(p);
     rc = check_launch("resnet_rows_kernel");
   }
   cudaFreeAsync(film, s);

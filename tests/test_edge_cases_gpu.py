@@ -61,6 +61,31 @@ def test_maximum_sizes(be, cuda):
         be.avg_voxelize_forward(feats.to(cuda), coords.to(cuda), 37)
 
 
+@pytest.mark.parametrize("b,c,n,r,mode", [
+    (2, 3, 1024, 24, "one_voxel"),      # every point in the same voxel: one bucket of 1024 (the rank-by-counting worst case)
+    (3, 5, 1001, 5, "random"),          # n % 4 != 0 (no 16-byte feature staging), r^3 % 4 != 0 (scalar cells), odd channel count
+    (100, 48, 64, 12, "random"),        # 16-channel slices (wide features, large batch)
+    (2, 48, 4096, 12, "clustered"),     # ppc-sized clouds, features too large to stage, heavy buckets
+    (1, 9, 31, 24, "random"),           # fewer points than a warp; cells split over several CTAs (blockIdx.z)
+])
+def test_voxelize_bucket_paths(be, cuda, b, c, n, r, mode):
+    """avg_voxelize_forward (vox.cu:18-72) on the shapes that take the kernel's other branches; ind / cnt and the grid are
+    bit-exact against the oracle (both sum in ascending point index)."""
+    g = torch.Generator().manual_seed(b * 1000 + n)
+    if mode == "one_voxel":
+        coords = torch.full((b, 3, n), r // 2, dtype=torch.int32)
+    elif mode == "clustered":
+        coords = (torch.randn(b, 3, n, generator=g) * 1.2 + r / 2).round().clamp(0, r - 1).to(torch.int32)
+    else:
+        coords = torch.randint(0, r, (b, 3, n), generator=g, dtype=torch.int32)
+    feats = torch.randn(b, c, n, generator=g)
+    out, ind, cnt = be.avg_voxelize_forward(feats.to(cuda), coords.to(cuda), r)
+    wo, wi, wc = ops_np.avg_voxelize_forward(feats.numpy(), coords.numpy(), r)
+    np.testing.assert_array_equal(ind.cpu().numpy(), wi)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), wc)
+    np.testing.assert_array_equal(out.cpu().numpy(), wo)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_ragged_batches_and_batch_independence(cuda, precision):
     """1 sample, 33 samples (a partially filled second / third CTA), uneven grasps per object: a sample's latent does
