@@ -10,6 +10,11 @@
 // blocks through a 3-stage mbarrier ring, warp 1 issues the UMMAs (M = 128, N = 128, K = 16, fp32 accumulator in
 // TMEM), warps 2-5 run the epilogue (TMEM -> registers -> scale/shift/ReLU -> bf16 -> image).  Two CTAs fit per SM
 // (96 KB of shared memory, 128 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
+// NT = 2 (layers whose width is a multiple of 256): a CTA computes 128 x 256 - one N = 256 UMMA per K step on two adjacent
+// weight blocks, two 48 KB stages - so every A block fetched from L2 serves twice the output: the 128 x 128 form moved
+// 2.4 GB from L2 to shared memory for the 768 -> 1536 layer of 64 clouds (13.5 TB/s, the L2's limit, not the tensor pipe's).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -18,10 +23,10 @@ using namespace tc;
 
 namespace gtc {
 constexpr int BLOCK = 16384;                 // one operand block: 128 rows x 64 bf16
-constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
-constexpr int SMEM = STAGES * 2 * BLOCK + 1024 + 256 + 1024;    // + scale / shift of the CTA's 128 columns
-constexpr int SMEM_PROJ = SMEM + 2048;                          // + the [128][4] projection weights of the tile
+constexpr int RING = 96 * 1024;              // NT = 1: three 32 KB stages; NT = 2: two 48 KB stages
+constexpr int SMEM = RING + 1024 + 256 + 2048;                  // + scale / shift of the CTA's (up to 256) columns
+constexpr int SMEM_PROJ = SMEM + 4096;                          // + the [256][4] projection weights of the tile
 }  // namespace gtc
 
 struct GemmTcParams {
@@ -38,13 +43,14 @@ struct GemmTcParams {
   long long rows;
 };
 
-template <bool PROJ>
+template <bool PROJ, int NT>
 __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   using namespace gtc;
+  constexpr int STAGES = NT == 1 ? 3 : 2, STAGE = (1 + NT) * BLOCK, NCOL = 128 * NT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer arithmetic (no integer round trip) keeps the shared address space visible to the compiler: LDS / STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * BLOCK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;
@@ -55,22 +61,22 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
   const int kb_n = p.k_blocks;
   // per-column scale / shift of this CTA's tile, staged once: a global load per element in the epilogue sits behind the
   // bulk-copy traffic (the same finding as in the Conv3d epilogue)
-  float* s_sc = reinterpret_cast<float*>(smem + STAGES * 2 * BLOCK + 256);
-  float* s_sh = s_sc + 128;
-  for (int i = tid; i < 128; i += NTHREADS) {
-    s_sc[i] = p.scale ? __ldg(p.scale + nt * 128 + i) : 1.f;
-    s_sh[i] = p.shift ? __ldg(p.shift + nt * 128 + i) : 0.f;
+  float* s_sc = reinterpret_cast<float*>(smem + RING + 256);
+  float* s_sh = s_sc + 256;
+  for (int i = tid; i < NCOL; i += NTHREADS) {
+    s_sc[i] = p.scale ? __ldg(p.scale + nt * NCOL + i) : 1.f;
+    s_sh[i] = p.shift ? __ldg(p.shift + nt * NCOL + i) : 0.f;
   }
-  float4* s_pw = reinterpret_cast<float4*>(s_sh + 128);
+  float4* s_pw = reinterpret_cast<float4*>(s_sh + 256);
   if (PROJ)
-    for (int i = tid; i < 128; i += NTHREADS) s_pw[i] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + nt * 128 + i);
+    for (int i = tid; i < NCOL; i += NTHREADS) s_pw[i] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + nt * NCOL + i);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (wid == 1) tmem_alloc<128>(tmem_slot);
+  if (wid == 1) tmem_alloc<NCOL>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -79,21 +85,23 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
   if (wid == 0) {
     // ---- producer
     const uint8_t* a = p.a_img + (size_t)mt * kb_n * BLOCK;
-    const uint8_t* b = p.b_img + (size_t)nt * kb_n * BLOCK;
+    const uint8_t* b = p.b_img + (size_t)(nt * NT) * kb_n * BLOCK;      // NT adjacent 128-row weight tiles
 #pragma unroll 1
     for (int kb = 0; kb < kb_n; ++kb) {
       const int s = kb % STAGES, round = kb / STAGES;
       if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&full[s], 2 * BLOCK);
-        bulk_g2s(smem + (2 * s) * BLOCK, a + (size_t)kb * BLOCK, BLOCK, &full[s]);
-        bulk_g2s(smem + (2 * s + 1) * BLOCK, b + (size_t)kb * BLOCK, BLOCK, &full[s]);
+        mbar_arrive_expect_tx(&full[s], STAGE);
+        bulk_g2s(smem + s * STAGE, a + (size_t)kb * BLOCK, BLOCK, &full[s]);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)      // rows 128 t .. of the N = 128 NT operand: the same 1024-byte 8-row groups, contiguous
+          bulk_g2s(smem + s * STAGE + (1 + t) * BLOCK, b + ((size_t)t * kb_n + kb) * BLOCK, BLOCK, &full[s]);
       }
       __syncwarp();
     }
   } else if (wid == 1) {
     // ---- UMMA issuer
-    const uint32_t idesc = idesc_bf16(128, 128);
+    const uint32_t idesc = idesc_bf16(128, NCOL);
     const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
     const uint32_t base = smem_u32(smem);
 #pragma unroll 1
@@ -101,8 +109,8 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
       const int s = kb % STAGES;
       mbar_wait(&full[s], (kb / STAGES) & 1);
       tc_fence_after();
-      const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s) * BLOCK) >> 4));
-      const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + (2 * s + 1) * BLOCK) >> 4));
+      const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE) >> 4));
+      const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGE + BLOCK) >> 4));
       umma_bf16_block_elect<4>(tmem, ad, bd, idesc, kb != 0);
       umma_commit_elect(&empty[s]);
     }
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
       // y = act(scale * acc + shift) stays fp32 in registers; four running dot products per row, columns in order
       float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < NCOL; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -134,9 +142,9 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
       }
       reinterpret_cast<float4*>(p.proj_out)[(size_t)nt * p.rows + (size_t)mt * 128 + r] = dot;
     } else {
-      uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 2) * BLOCK;
+      uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 2 * NT) * BLOCK;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < NCOL; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
             if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
             pk[h] = pack_bf16(y0, y1);
           }
-          const int c = c0 + j8 * 8;                         // column inside the 128-wide tile
+          const int c = c0 + j8 * 8;                         // column inside the CTA's tile
           uint8_t* dst = out_tile + (size_t)(c >> 6) * BLOCK + swz_off<128>(r, (c & 63) >> 3);
           *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
     tc_fence_before();
   }
   __syncthreads();
-  if (wid == 1) tmem_dealloc<128>(tmem);
+  if (wid == 1) tmem_dealloc<NCOL>(tmem);
 }
 
 // fp32 channel-major activations [b, c, n] -> A image (rows m = b * n + point, K = c padded to a multiple of 64)
@@ -287,22 +295,33 @@ extern "C" int gldm_gemm_tc_to_image(const float* x, int b, int c, int n, void* 
   return check_launch("to_image_kernel");
 }
 
+// N tiles per CTA: 2 when the layer width allows it (GLDM_GEMM_NT=1 keeps the 128 x 128 form)
+static int gemm_nt(int n_out) {
+  static const int env = getenv("GLDM_GEMM_NT") ? atoi(getenv("GLDM_GEMM_NT")) : 2;
+  return (env == 2 && n_out % 256 == 0) ? 2 : 1;
+}
+
 extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, const float* shift,
                                 long long rows, int k, int n_out, int relu, void* out_img, void* stream) {
   GLDM_REQUIRE(a_img && w_img && out_img, "gemm_tc_run: null pointer");
   GLDM_REQUIRE(rows >= 0 && rows % 128 == 0, "gemm_tc_run: rows = %lld must be a multiple of 128", rows);
   GLDM_REQUIRE(k > 0 && n_out > 0 && n_out % 128 == 0, "gemm_tc_run: n_out = %d must be a multiple of 128", n_out);
   if (rows == 0) return GLDM_OK;
-  static SmemOptIn attr;
-  if (int rc = opt_in_smem(attr, gemm_tc_kernel<false>, gtc::SMEM, "gemm_tc_kernel")) return rc;
   GemmTcParams p = {};
   p.a_img = reinterpret_cast<const uint8_t*>(a_img);
   p.b_img = reinterpret_cast<const uint8_t*>(w_img);
   p.out_img = reinterpret_cast<uint8_t*>(out_img);
   p.scale = scale; p.shift = shift;
   p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
-  dim3 grid(p.n_tiles, (unsigned)(rows / 128));
-  gemm_tc_kernel<false><<<grid, gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
+  if (gemm_nt(n_out) == 2) {
+    static SmemOptIn attr2;
+    if (int rc = opt_in_smem(attr2, gemm_tc_kernel<false, 2>, gtc::SMEM, "gemm_tc_kernel")) return rc;
+    gemm_tc_kernel<false, 2><<<dim3(p.n_tiles / 2, (unsigned)(rows / 128)), gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
+  } else {
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, gemm_tc_kernel<false, 1>, gtc::SMEM, "gemm_tc_kernel")) return rc;
+    gemm_tc_kernel<false, 1><<<dim3(p.n_tiles, (unsigned)(rows / 128)), gtc::NTHREADS, gtc::SMEM, (cudaStream_t)stream>>>(p);
+  }
   return check_launch("gemm_tc_kernel");
 }
 
@@ -316,19 +335,25 @@ extern "C" int gldm_gemm_tc_run_proj(const void* a_img, const void* w_img, const
   GLDM_REQUIRE((reinterpret_cast<uintptr_t>(proj_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(partials) & 15) == 0,
                "gemm_tc_run_proj: proj_w / partials must be 16-byte aligned");
   if (rows == 0) return GLDM_OK;
-  static SmemOptIn attr;
-  if (int rc = opt_in_smem(attr, gemm_tc_kernel<true>, gtc::SMEM_PROJ, "gemm_tc_kernel<proj>")) return rc;
   GemmTcParams p = {};
   p.a_img = reinterpret_cast<const uint8_t*>(a_img);
   p.b_img = reinterpret_cast<const uint8_t*>(w_img);
   p.scale = scale; p.shift = shift;
   p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
   p.proj_w = proj_w; p.proj_out = reinterpret_cast<float*>(partials); p.rows = rows;
-  dim3 grid(p.n_tiles, (unsigned)(rows / 128));
   cudaStream_t s = (cudaStream_t)stream;
-  gemm_tc_kernel<true><<<grid, gtc::NTHREADS, gtc::SMEM_PROJ, s>>>(p);
+  const int nt = gemm_nt(n_out);
+  if (nt == 2) {
+    static SmemOptIn attr2;
+    if (int rc = opt_in_smem(attr2, gemm_tc_kernel<true, 2>, gtc::SMEM_PROJ, "gemm_tc_kernel<proj>")) return rc;
+    gemm_tc_kernel<true, 2><<<dim3(p.n_tiles / 2, (unsigned)(rows / 128)), gtc::NTHREADS, gtc::SMEM_PROJ, s>>>(p);
+  } else {
+    static SmemOptIn attr;
+    if (int rc = opt_in_smem(attr, gemm_tc_kernel<true, 1>, gtc::SMEM_PROJ, "gemm_tc_kernel<proj>")) return rc;
+    gemm_tc_kernel<true, 1><<<dim3(p.n_tiles, (unsigned)(rows / 128)), gtc::NTHREADS, gtc::SMEM_PROJ, s>>>(p);
+  }
   if (int rc = check_launch("gemm_tc_kernel<proj>")) return rc;
-  proj_sum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(partials), proj_bias, p.n_tiles,
+  proj_sum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(partials), proj_bias, p.n_tiles / nt,
                                                                   rows, co, n, y);
   return check_launch("proj_sum_kernel");
 }
