@@ -14,7 +14,7 @@ from graspldm_b200 import _pvcnn_backend as ours  # noqa: E402
 from oracle import build_ref  # noqa: E402
 
 
-def timeit(fn, iters=20, warm=3):
+def timeit(fn, iters=50, warm=10):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -31,6 +31,11 @@ def main():
     ref = build_ref.load()
     dev = torch.device("cuda:0")
     res = {}
+    # (clocks and caches warm before the first timed size: B = 1 is a handful of microseconds per call)
+    warm = _data.synthetic_clouds(64, 1024, 1, "S").transpose(1, 2).contiguous().to(dev)
+    for _ in range(20):
+        ours.furthest_point_sampling(warm, 256)
+    torch.cuda.synchronize()
     for B in (1, 64, 1024):
         coords = _data.synthetic_clouds(B, 1024, 1, "S").transpose(1, 2).contiguous().to(dev)
         row = {}

@@ -36,4 +36,9 @@ GLDM_PROFILE_RANGE=1 timeout 900 ncu --set full --clock-control none --profile-f
 ncu -i /tmp/${tag}_enc.ncu-rep --page raw --csv > $out/${tag}_enc_raw.csv 2>/dev/null
 
 
+# operator FFI against the reference's own kernels (oracle/_ref), per-row-job stamps of the sampler and of the decoder
+timeout 600 python tests/tools/bench_ops.py > $out/${tag}_ops_bench.log 2>&1 && cp $out/ops_bench.json $out/${tag}_ops_bench.json
+timeout 200 python tools/prof_rows.py sampler > $out/${tag}_prof_rows.log 2>&1
+timeout 200 python tools/prof_rows.py decoder > $out/${tag}_prof_rows_decoder.log 2>&1
+
 ls -la $out | tail -30
