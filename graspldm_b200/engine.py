@@ -709,11 +709,10 @@ class PackedEncoder:
         if not self.blocks or self.blocks[-1]["kind"] != "mlp" or self.blocks[-1]["pscale"] is None:
             return None
         if self._proj is None:
-            w = self.wo.double() @ self.wd.double()                       # [C_out, width]
-            b = self.wo.double() @ self.bd.double() + self.bo.double()
+            w, b = compose_affine(self.wo, self.bo, self.wd, self.bd)     # [C_out, width], [C_out]
             pw = torch.zeros((w.shape[1], 4), device=self.device, dtype=torch.float32)
-            pw[:, :w.shape[0]] = w.t().float()
-            self._proj = (pw.contiguous(), b.float().contiguous())
+            pw[:, :w.shape[0]] = w.t()
+            self._proj = (pw.contiguous(), b.contiguous())
         return self._proj
 
     def tc_weights(self):
@@ -735,6 +734,14 @@ class PackedEncoder:
                     layers.append(dict(img=img, scale=sc, shift=sh, relu=relu, k=k, n=n_out))
             self._tc = layers
         return self._tc
+
+
+def compose_affine(w2, b2, w1, b1):
+    """y = W2 (W1 x + b1) + b2 as one affine map (W, b), composed in fp64 and rounded to fp32 once: conv_downscale followed
+    by out_layer.0 (pc_encoders.py:104-112 with use_global_attention=False: no non-linearity in between)."""
+    w = w2.double() @ w1.double()
+    b = w2.double() @ b1.double() + b2.double()
+    return w.float(), b.float()
 
 
 def _aligned_bytes(nbytes, dev, align=1024):

@@ -53,3 +53,19 @@ def test_load_checkpoint_is_strict(tmp_path):
         assert "Missing key" in str(e)
     else:
         raise AssertionError("a checkpoint with a missing tensor must not load")
+
+
+def test_composed_encoder_projection_equals_the_two_layers():
+    """conv_downscale (Conv1d 1536 -> 768) followed by out_layer.0 (Conv1d 768 -> 3), pc_encoders.py:60-75: the tensor-core
+    path applies them as ONE [3, 1536] projection (engine.compose_affine); same result as the two layers in fp64."""
+    import torch
+    from graspldm_b200.engine import compose_affine
+    g = torch.Generator().manual_seed(5)
+    wd, bd = torch.randn(768, 1536, generator=g) * 0.03, torch.randn(768, generator=g) * 0.1
+    wo, bo = torch.randn(3, 768, generator=g) * 0.05, torch.randn(3, generator=g) * 0.1
+    x = torch.randn(1536, 257, generator=g).double()
+    want = wo.double() @ (wd.double() @ x + bd.double()[:, None]) + bo.double()[:, None]
+    w, b = compose_affine(wo, bo, wd, bd)
+    assert w.shape == (3, 1536) and b.shape == (3,) and w.dtype == torch.float32
+    got = w.double() @ x + b.double()[:, None]
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
