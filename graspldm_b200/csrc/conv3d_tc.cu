@@ -540,6 +540,134 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3p_kernel(const __gr
   if (wid == 1) tmem_dealloc<512>(tmem);
 }
 
+// Persistent variant for the layers whose filter bank does NOT fit beside the pipeline (48 -> 96 and 96 -> 96 at 12^3: 324 /
+// 648 KB of weight images): the one-tile-per-CTA kernel streams 36 KB of weights against 17 KB of activations per column
+// step - 1.33 GB through the L2 for the 96 -> 96 layer of 64 clouds, 13.7 TB/s: the L2's limit (~12 TB/s on this part),
+// not the tensor pipe's (46 % active).  Here a CTA works on TWO adjacent 128-voxel tiles per weight stage (every weight
+// block fetched from L2 feeds two UMMA groups), one CTA per SM walks tile pairs blockIdx.x, blockIdx.x + gridDim.x, ...,
+// and two TMEM accumulator sets let the epilogue of a pair run under the UMMAs of the next one.
+namespace c3 {
+constexpr int AM_BYTES = 17408;              // 136 x 128 B exactly (a multiple of 1024: SWIZZLE_128B tile base)
+constexpr int STAGESM = 3;
+constexpr int STAGEM_BYTES = 2 * AM_BYTES + 3 * W_SLOT;     // 71680
+}
+__global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc3m_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                      const __grid_constant__ Conv3dTcParams p, int n_tiles) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_scr = smem + STAGESM * STAGEM_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scr + P_SCRATCH);
+  uint64_t* full = bars;             // [4]
+  uint64_t* empty = bars + 4;        // [4]
+  uint64_t* acc_full = bars + 8;     // [2]
+  uint64_t* acc_empty = bars + 10;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int rp = p.r + 2, rp2 = rp * rp;
+  const int n_it = 9 * p.k_blocks;
+  const int n_groups = (n_tiles + 1) >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGESM; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer: per column step the activation boxes of both tiles and the three dz weight blocks
+    int it = 0;
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+      const long long row0 = (long long)grp * 256;
+#pragma unroll 1
+      for (int i = 0; i < n_it; ++i, ++it) {
+        const int s = it % STAGESM, round = it / STAGESM;
+        const int col = i / p.k_blocks, kb = i - col * p.k_blocks;          // col = dx*3 + dy
+        const int shift = (col / 3 - 1) * rp2 + (col % 3 - 1) * rp - 1;     // row of the dz = -1 tap
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], 2 * A3_ROWS * 128 + 3 * p.w_rows_bytes);
+          // (rows past the end of the grid - the second tile of an odd last pair - are filled with zeros by the TMA unit)
+          tma_load_2d(smem + s * STAGEM_BYTES, &xmap, kb * 64, (int)(row0 + shift), &full[s]);
+          tma_load_2d(smem + s * STAGEM_BYTES + AM_BYTES, &xmap, kb * 64, (int)(row0 + 128 + shift), &full[s]);
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+            bulk_g2s(smem + s * STAGEM_BYTES + 2 * AM_BYTES + dz * W_SLOT,
+                     p.w_img + ((size_t)(col * 3 + dz) * p.k_blocks + kb) * W_BYTES, p.w_rows_bytes, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const uint32_t base = smem_u32(smem);
+    int it = 0, gl = 0;
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++gl) {
+      const int buf = gl & 1;
+      if (gl >= 2) { mbar_wait(&acc_empty[buf], ((gl >> 1) - 1) & 1); tc_fence_after(); }
+#pragma unroll 1
+      for (int i = 0; i < n_it; ++i, ++it) {
+        const int s = it % STAGESM;
+        const int kb = i % p.k_blocks;
+        mbar_wait(&full[s], (it / STAGESM) & 1);
+        tc_fence_after();
+        const int ks = (kb == p.k_blocks - 1) ? p.ksteps_last : 4;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d = tmem + buf * 256 + t * 128;
+#pragma unroll 1
+          for (int dz = 0; dz < 3; ++dz) {
+            const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGEM_BYTES + t * AM_BYTES + dz * 128) >> 4));
+            const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * STAGEM_BYTES + 2 * AM_BYTES + dz * W_SLOT) >> 4));
+            const uint32_t acc = (i != 0 || dz != 0) ? 1u : 0u;
+            if (ks == 4) umma_bf16_block_elect<4>(d, ad, bd, idesc, acc);
+            else if (ks == 3) { umma_bf16_block_elect<2>(d, ad, bd, idesc, acc); umma_bf16_block_elect<1>(d, ad + 4, bd + 4, idesc, 1u); }
+            else if (ks == 2) umma_bf16_block_elect<2>(d, ad, bd, idesc, acc);
+            else umma_bf16_block_elect<1>(d, ad, bd, idesc, acc);
+          }
+        }
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ---- epilogue warps: the pair g while the issuer works on pair g + 1
+    int gl = 0;
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++gl) {
+      const int buf = gl & 1;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int tile = 2 * grp + t;
+        if (tile < n_tiles) {
+          conv3d_epilogue(p, s_scr, tmem + buf * 256 + t * 128, &acc_full[buf], (long long)tile * 128, tid, lane, wid, s_bias,
+                          (uint32_t)((gl >> 1) & 1), tile);
+          asm volatile("bar.sync 1, 256;" ::: "memory");       // the scratch sums of this tile have been consumed
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<512>(tmem);
+}
+
 // Narrow-input variant (ci <= 16: the 3 -> 48 first layer): the padded grid has 16 channels (32-byte rows, SWIZZLE_32B),
 // one K = 16 UMMA per tap, A rows again fetched once per filter column.  Weight image: [27 taps][128 rows x 32 B].
 namespace c3 {
@@ -1043,6 +1171,20 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
       p.n_acc = 3;
       conv3d_tc3p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot);
       return check_launch("conv3d_tc3p_kernel");
+    }
+    // filter bank too large to stay resident: two tiles per weight stage, persistent (the L2 -> shared-memory weight stream
+    // is what bounds these layers)
+    // GLDM_CONV3D_MULTI: 0 = never, 1 (default) = from two tiles per SM on, 2 = always (tests); read per call
+    const char* evm = getenv("GLDM_CONV3D_MULTI");
+    const int multi = evm ? atoi(evm) : 1;
+    if (multi && out_mode != 0 && (multi == 2 || grid >= 2 * (unsigned)kNumSMs)) {
+      const int smem_m = c3::STAGESM * c3::STAGEM_BYTES + c3::P_SCRATCH + 768 + 1024;
+      static SmemOptIn attr_m;
+      if (int rc = opt_in_smem(attr_m, conv3d_tc3m_kernel, smem_m, "conv3d_tc3m_kernel")) return rc;
+      const int n_tiles = (int)grid, n_groups = (n_tiles + 1) / 2;
+      p.n_acc = 1;
+      conv3d_tc3m_kernel<<<min(n_groups, kNumSMs), c3::NTHREADS, smem_m, s>>>(map3, p, n_tiles);
+      return check_launch("conv3d_tc3m_kernel");
     }
     const int smem3 = c3::STAGES3 * (c3::A3_BYTES + 3 * c3::W_SLOT) + 1024 + 768;
     static SmemOptIn attr3;

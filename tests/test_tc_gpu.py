@@ -224,10 +224,13 @@ def test_sampler_two_sets_per_cta_matches_one_set(cuda):
     np.testing.assert_allclose(r0.cpu().numpy(), outs[0][0].cpu().numpy(), rtol=3e-2, atol=3e-2)
 
 
-@pytest.mark.parametrize("B,ci,co,r", [(3, 48, 48, 24), (2, 48, 96, 12), (5, 96, 96, 12)])
-def test_fused_voxel_branch_ops(cuda, B, ci, co, r):
+@pytest.mark.parametrize("B,ci,co,r,multi", [(3, 48, 48, 24, "1"), (2, 48, 96, 12, "0"), (5, 96, 96, 12, "0"),
+                                             (2, 48, 96, 12, "2"), (5, 96, 96, 12, "2"), (3, 96, 96, 12, "2")])
+def test_fused_voxel_branch_ops(cuda, B, ci, co, r, multi, monkeypatch):
     """Channels-last Conv3d (+ GroupNorm statistics) -> GroupNorm + Swish in place (+ SE squeeze) -> SE gate ->
-    devoxelize, op by op against torch on the same bf16-rounded operands (pvconv.py:48-67, se.py:10-21)."""
+    devoxelize, op by op against torch on the same bf16-rounded operands (pvconv.py:48-67, se.py:10-21).  multi = "2"
+    forces the persistent two-tiles-per-weight-stage Conv3d kernel the large batches use (odd and even tile counts)."""
+    monkeypatch.setenv("GLDM_CONV3D_MULTI", multi)
     import torch.nn.functional as F
     from graspldm_b200 import _lib
     from graspldm_b200.engine import _aligned_bytes, _stream
