@@ -173,6 +173,165 @@ __global__ void __launch_bounds__(gtc::NTHREADS, 2) gemm_tc_kernel(const __grid_
   if (wid == 1) tmem_dealloc<NCOL>(tmem);
 }
 
+// Persistent form for large row counts: one CTA per SM walks 128 x 256 output tiles (the N tiles of a row tile are
+// consecutive, so its A blocks stay in L2), four 48 KB stages, TWO 256-column TMEM accumulators - the eight epilogue warps
+// (two per TMEM lane quarter, 128 columns each) finish tile i while the tensor pipe works on tile i + 1.  The one-tile
+// CTAs above (two per SM) left the tensor pipe idle whenever both were outside their main loop (TMEM allocation, first
+// loads, epilogue): 52 % active on the 768 -> 1536 layer.
+namespace gtc {
+constexpr int P_STAGES = 4, P_STAGE = 3 * BLOCK, P_THREADS = 320;
+constexpr int P_PARAMS = 2 * (2 * 256 * 4 + 256 * 16);          // two buffers of scale | shift | projection weights
+constexpr int P_SMEM = P_STAGES * P_STAGE + P_PARAMS + 256 + 1024;
+}  // namespace gtc
+
+template <bool PROJ>
+__global__ void __launch_bounds__(gtc::P_THREADS, 1) gemm_tc_persistent_kernel(const __grid_constant__ GemmTcParams p, int n_work) {
+  using namespace gtc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_par = smem + P_STAGES * P_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + P_PARAMS);
+  uint64_t* full = bars;             // [4]
+  uint64_t* empty = bars + 4;        // [4]
+  uint64_t* acc_full = bars + 8;     // [2]
+  uint64_t* acc_empty = bars + 10;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int kb_n = p.k_blocks, n2 = p.n_tiles >> 1;       // 256-column tiles per row tile
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    fence_barrier_init();
+  }
+  if (wid == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer
+    int it = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int mt = w / n2, nt = w - mt * n2;
+      const uint8_t* a = p.a_img + (size_t)mt * kb_n * BLOCK;
+      const uint8_t* b = p.b_img + (size_t)(nt * 2) * kb_n * BLOCK;
+#pragma unroll 1
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        const int s = it % P_STAGES, round = it / P_STAGES;
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], P_STAGE);
+          bulk_g2s(smem + s * P_STAGE, a + (size_t)kb * BLOCK, BLOCK, &full[s]);
+          bulk_g2s(smem + s * P_STAGE + BLOCK, b + (size_t)kb * BLOCK, BLOCK, &full[s]);
+          bulk_g2s(smem + s * P_STAGE + 2 * BLOCK, b + ((size_t)kb_n + kb) * BLOCK, BLOCK, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer
+    const uint32_t idesc = idesc_bf16(128, 256);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | ((uint32_t)SW_128 << 29);
+    const uint32_t base = smem_u32(smem);
+    int it = 0, wl = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wl) {
+      const int buf = wl & 1;
+      if (wl >= 2) { mbar_wait(&acc_empty[buf], ((wl >> 1) - 1) & 1); tc_fence_after(); }
+#pragma unroll 1
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        const int s = it % P_STAGES;
+        mbar_wait(&full[s], (it / P_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t ad = ((uint64_t)hi << 32) | (0x10000u | ((base + s * P_STAGE) >> 4));
+        const uint64_t bd = ((uint64_t)hi << 32) | (0x10000u | ((base + s * P_STAGE + BLOCK) >> 4));
+        umma_bf16_block_elect<4>(tmem + buf * 256, ad, bd, idesc, kb != 0);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ---- epilogue: warps 2..9; warp w reads TMEM lanes 32 * (w % 4), columns 128 * half; thread <-> output row
+    const int ew = wid - 2, q = wid & 3, half = ew >> 2, r = q * 32 + lane, et = tid - 64;
+    int wl = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wl) {
+      const int buf = wl & 1;
+      const int mt = w / n2, nt = w - mt * n2;
+      // this tile's per-column constants (the buffer was last read two tiles ago; the barrier below orders those reads)
+      float* s_sc = reinterpret_cast<float*>(s_par + buf * (P_PARAMS / 2));
+      float* s_sh = s_sc + 256;
+      float4* s_pw = reinterpret_cast<float4*>(s_sh + 256);
+      s_sc[et] = p.scale ? __ldg(p.scale + nt * 256 + et) : 1.f;
+      s_sh[et] = p.shift ? __ldg(p.shift + nt * 256 + et) : 0.f;
+      if (PROJ) s_pw[et] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + nt * 256 + et);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&acc_full[buf], (wl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + buf * 256 + half * 128 + ((uint32_t)(q * 32) << 16);
+      const float* sc = s_sc + half * 128;
+      const float* sh = s_sh + half * 128;
+      if (PROJ) {
+        const float4* pw = s_pw + half * 128;
+        float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = fmaf(__uint_as_float(v[j]), sc[c0 + j], sh[c0 + j]);
+            if (p.relu) y = fmaxf(y, 0.f);
+            const float4 wv = pw[c0 + j];
+            dot.x = fmaf(y, wv.x, dot.x);
+            dot.y = fmaf(y, wv.y, dot.y);
+            dot.z = fmaf(y, wv.z, dot.z);
+            dot.w = fmaf(y, wv.w, dot.w);
+          }
+        }
+        // partial-sum planes of 128 columns, as the one-tile kernel with NT = 1 writes them
+        reinterpret_cast<float4*>(p.proj_out)[(size_t)(nt * 2 + half) * p.rows + (size_t)mt * 128 + r] = dot;
+      } else {
+        uint8_t* out_tile = p.out_img + ((size_t)mt * (p.n_tiles * 2) + (size_t)nt * 4 + half * 2) * BLOCK;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int n = c0 + j8 * 8 + 2 * h;
+              float y0 = __uint_as_float(v[j8 * 8 + 2 * h]), y1 = __uint_as_float(v[j8 * 8 + 2 * h + 1]);
+              const float2 s2 = *reinterpret_cast<const float2*>(sc + n), h2 = *reinterpret_cast<const float2*>(sh + n);
+              y0 = fmaf(y0, s2.x, h2.x);
+              y1 = fmaf(y1, s2.y, h2.y);
+              if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+              pk[h] = pack_bf16(y0, y1);
+            }
+            const int c = c0 + j8 * 8;                         // column inside this warp's 128
+            uint8_t* dst = out_tile + (size_t)(c >> 6) * BLOCK + swz_off<128>(r, (c & 63) >> 3);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<512>(tmem);
+}
+
 // fp32 channel-major activations [b, c, n] -> A image (rows m = b * n + point, K = c padded to a multiple of 64)
 __global__ void __launch_bounds__(256) to_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int c, int n,
                                                        long long rows, int k_blocks) {
@@ -297,8 +456,17 @@ extern "C" int gldm_gemm_tc_to_image(const float* x, int b, int c, int n, void* 
 
 // N tiles per CTA: 2 when the layer width allows it (GLDM_GEMM_NT=1 keeps the 128 x 128 form)
 static int gemm_nt(int n_out) {
-  static const int env = getenv("GLDM_GEMM_NT") ? atoi(getenv("GLDM_GEMM_NT")) : 2;
-  return (env == 2 && n_out % 256 == 0) ? 2 : 1;
+  const char* ev = getenv("GLDM_GEMM_NT");                 // read per call (tests switch it)
+  return ((ev ? atoi(ev) : 2) == 2 && n_out % 256 == 0) ? 2 : 1;
+}
+
+// persistent kernel: widths that are multiples of 256 and at least two 128 x 256 tiles per SM (GLDM_GEMM_PERSISTENT: 0 =
+// never, 2 = whenever the width allows, for tests; read per call)
+static bool gemm_persistent(int n_out, long long rows) {
+  const char* ev = getenv("GLDM_GEMM_PERSISTENT");
+  const int mode = ev ? atoi(ev) : 1;
+  if (mode == 0 || n_out % 256 != 0 || rows / 128 * (n_out / 256) > 0x7fffffffLL) return false;
+  return mode == 2 || rows / 128 * (n_out / 256) >= 2 * kNumSMs;
 }
 
 extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const float* scale, const float* shift,
@@ -313,6 +481,13 @@ extern "C" int gldm_gemm_tc_run(const void* a_img, const void* w_img, const floa
   p.out_img = reinterpret_cast<uint8_t*>(out_img);
   p.scale = scale; p.shift = shift;
   p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
+  if (gemm_persistent(n_out, rows)) {
+    static SmemOptIn attrp;
+    if (int rc = opt_in_smem(attrp, gemm_tc_persistent_kernel<false>, gtc::P_SMEM, "gemm_tc_persistent_kernel")) return rc;
+    const int n_work = (int)(rows / 128) * (n_out / 256);
+    gemm_tc_persistent_kernel<false><<<min(n_work, kNumSMs), gtc::P_THREADS, gtc::P_SMEM, (cudaStream_t)stream>>>(p, n_work);
+    return check_launch("gemm_tc_persistent_kernel");
+  }
   if (gemm_nt(n_out) == 2) {
     static SmemOptIn attr2;
     if (int rc = opt_in_smem(attr2, gemm_tc_kernel<false, 2>, gtc::SMEM, "gemm_tc_kernel")) return rc;
@@ -342,8 +517,14 @@ extern "C" int gldm_gemm_tc_run_proj(const void* a_img, const void* w_img, const
   p.k_blocks = (k + 63) / 64; p.n_tiles = n_out / 128; p.relu = relu;
   p.proj_w = proj_w; p.proj_out = reinterpret_cast<float*>(partials); p.rows = rows;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nt = gemm_nt(n_out);
-  if (nt == 2) {
+  int nt = gemm_nt(n_out);
+  if (gemm_persistent(n_out, rows)) {
+    static SmemOptIn attrp;
+    if (int rc = opt_in_smem(attrp, gemm_tc_persistent_kernel<true>, gtc::P_SMEM, "gemm_tc_persistent_kernel<proj>")) return rc;
+    const int n_work = (int)(rows / 128) * (n_out / 256);
+    gemm_tc_persistent_kernel<true><<<min(n_work, kNumSMs), gtc::P_THREADS, gtc::P_SMEM, s>>>(p, n_work);
+    nt = 1;                              // (partial-sum planes of 128 columns)
+  } else if (nt == 2) {
     static SmemOptIn attr2;
     if (int rc = opt_in_smem(attr2, gemm_tc_kernel<true, 2>, gtc::SMEM_PROJ, "gemm_tc_kernel<proj>")) return rc;
     gemm_tc_kernel<true, 2><<<dim3(p.n_tiles / 2, (unsigned)(rows / 128)), gtc::NTHREADS, gtc::SMEM_PROJ, s>>>(p);

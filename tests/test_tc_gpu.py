@@ -84,6 +84,30 @@ def test_encoder_bf16_pointwise_layers(cuda, name, fold, monkeypatch):
     np.testing.assert_allclose(z16.cpu().numpy(), want, rtol=1e-2, atol=2e-3)
 
 
+@pytest.mark.parametrize("fold", ["1", "0"])
+def test_encoder_gemm_variants_agree(cuda, fold, monkeypatch):
+    """The point-wise GEMM kernels - one 128 x 128 tile per CTA, one 128 x 256 tile per CTA, persistent 128 x 256 tiles
+    with double-buffered accumulators (several tiles per CTA at this size) - on the same encoder pass."""
+    monkeypatch.setenv("GLDM_FOLD_DOWNSCALE", fold)
+    m = _models.build("fpc").to(cuda)
+    enc = m.vae_model.encoder.pc_encoder
+    enc.precision = "bf16"
+    xyz = _data.synthetic_clouds(9, seed=77, dist="S").to(cuda)
+    outs = {}
+    for name, env in (("tile128", {"GLDM_GEMM_PERSISTENT": "0", "GLDM_GEMM_NT": "1"}),
+                      ("tile256", {"GLDM_GEMM_PERSISTENT": "0", "GLDM_GEMM_NT": "2"}),
+                      ("persistent", {"GLDM_GEMM_PERSISTENT": "2", "GLDM_GEMM_NT": "2"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs[name] = m.vae_model.encode_pc(xyz).cpu().numpy()
+    enc.precision = "fp32"
+    z32 = m.vae_model.encode_pc(xyz).cpu().numpy()
+    # same bf16 operands and K order everywhere; only the order of the fp32 partial sums of the fused projection differs
+    np.testing.assert_allclose(outs["tile256"], outs["tile128"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(outs["persistent"], outs["tile128"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(outs["persistent"], z32, rtol=1e-2, atol=2e-3)
+
+
 def _rot_angle_deg(Ra, Rb):
     """geodesic angle between rotation matrices [..., 3, 3]"""
     R = Ra.transpose(-1, -2) @ Rb
