@@ -41,7 +41,14 @@ struct Conv3dTcParams {
   double* stats;              // [b][8][2]: sum, sum of squares per GroupNorm group (8 groups), accumulated
   int batch;
   int n_acc;                  // accumulators per tile, 64 TMEM columns apart, summed by the epilogue (1, or 3: one per dz tap)
+  // ceil(2^32 / (r+2)^2), ceil(2^32 / (r+2)): __umulhi(n, magic) == n / d exactly while n * d < 2^32 (n < (r+2)^3 <= 2^18)
+  unsigned magic_rp2, magic_rp;
 };
+static void conv3d_set_magic(Conv3dTcParams& p) {
+  const unsigned long long rp = (unsigned long long)p.r + 2;
+  p.magic_rp2 = (unsigned)(((1ull << 32) + rp * rp - 1) / (rp * rp));
+  p.magic_rp = (unsigned)(((1ull << 32) + rp - 1) / rp);
+}
 
 // L2 prefetch of a 2-D box (no shared memory involved): hides the HBM leg of a later tma_load_2d
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
@@ -123,9 +130,16 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
     const int ew = wid - 2, q = wid & 3, half = ew >> 2;      // warps 2..5: lower channel half, 6..9: upper (wid & 3 = TMEM quarter)
     const long long m = row0 + q * 32 + lane;
     const int P = rp2 * rp;
-    const long long b = m / P;
-    const int pp = (int)(m - b * P);
-    const int x = pp / rp2, yy = (pp / rp) % rp, z = pp % rp;
+    // One division per tile (32-bit whenever the grid has fewer than 2^31 rows), voxel coordinates by multiplication with
+    // the precomputed reciprocals: the 128 rows of a tile touch at most two clouds (P >= 216).  The per-thread 64-bit
+    // division and three 32-bit ones this replaces were a fifth of the stall samples of the first layer's epilogue, which
+    // is what bounds that layer.
+    const long long b0 = (p.rows < 0x7fffffffLL) ? (long long)((unsigned)row0 / (unsigned)P) : row0 / P;
+    int pp = (int)(row0 - b0 * P) + q * 32 + lane;
+    const long long b = b0 + (pp >= P ? 1 : 0);
+    pp -= pp >= P ? P : 0;
+    const int x = (int)__umulhi((unsigned)pp, p.magic_rp2), rem = pp - x * rp2;
+    const int yy = (int)__umulhi((unsigned)rem, p.magic_rp), z = rem - yy * rp;
     const bool interior = m < p.rows && x >= 1 && x <= p.r && yy >= 1 && yy <= p.r && z >= 1 && z <= p.r;
     const int r3 = p.r * p.r * p.r;
     const int v = ((x - 1) * p.r + (yy - 1)) * p.r + (z - 1);
@@ -207,8 +221,12 @@ __device__ __forceinline__ void conv3d_epilogue(const Conv3dTcParams& p, uint8_t
       // slot 0 = the cloud of its first row, slot 1 = the next one), then a fixed-order sum over the 8 epilogue warps:
       // the statistics are bit-reproducible (no atomics); conv_stats_finalize_kernel adds the tiles of a cloud in a fixed order
       float* wtot = reinterpret_cast<float*>(smem);                     // [8 warps][2 slots][16]
-      const int b0 = (int)(row0 / P);
       for (int slot = 0; slot < 2; ++slot) {
+        // (all but one tile in ~137 lie inside one cloud: the second reduce-scatter is skipped for them, warp-uniformly)
+        if (slot == 1 && !__any_sync(0xffffffffu, interior && b != b0)) {
+          if ((lane & 1) == 0) wtot[(ew * 2 + 1) * 16 + (lane >> 1)] = 0.f;
+          break;
+        }
         float a[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = (interior && b == b0 + slot) ? st[i] : 0.f;
@@ -748,6 +766,119 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc16_kernel(const __gr
   if (wid == 1) tmem_dealloc<128>(tmem);
 }
 
+// Persistent form of the narrow first layer for large grids, built like conv3d_tc3p_kernel: the 27 K = 16 taps (27 x co x
+// 32 B) stay resident, one CTA per SM walks the tiles, one activation box per dx plane (130 + 2 (r + 2) rows of 32 bytes
+// serve the nine (dy, dz) taps), three accumulators per tile (one per dz) in two TMEM buffers so the epilogue of tile t runs
+// under the UMMAs of tile t + 1.  The one-tile CTAs spent most of their life outside the main loop (TMEM allocation, first
+// loads, epilogue): 17 % tensor pipe, 4.4 us per tile and CTA.
+__global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc16p_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                       const __grid_constant__ Conv3dTcParams p, int n_tiles,
+                                                                       int stages, int a_rows, int a_slot, int w_slot) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                                        // [27][w_slot]
+  uint8_t* s_a = s_w + 27 * w_slot;                           // [stages][a_slot]
+  uint8_t* s_scr = s_a + stages * a_slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scr + P_SCRATCH);
+  uint64_t* full = bars;             // [4]
+  uint64_t* empty = bars + 4;        // [4]
+  uint64_t* acc_full = bars + 8;     // [2]
+  uint64_t* acc_empty = bars + 10;   // [2]
+  uint64_t* w_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_bias = reinterpret_cast<float*>(bars) + 32;        // [128], 128 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int rp = p.r + 2, rp2 = rp * rp;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer: the filter bank once, then three plane boxes per tile
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)(27 * p.w_rows_bytes));
+      for (int k = 0; k < 27; ++k) bulk_g2s(s_w + (size_t)k * w_slot, p.w_img + (size_t)k * W16_BYTES, p.w_rows_bytes, w_full);
+    }
+    __syncwarp();
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * 128;
+      if (tile + (int)gridDim.x < n_tiles && elect_one_sync()) {       // the next tile's boxes on their way into L2
+        const long long rown = (long long)(tile + gridDim.x) * 128;
+        for (int dx = 0; dx < 3; ++dx) tma_prefetch_2d(&xmap, 0, (int)(rown + (dx - 1) * rp2 - rp - 1));
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % stages, round = it / stages;
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], (uint32_t)a_rows * 32u);
+          tma_load_2d(s_a + s * a_slot, &xmap, 0, (int)(row0 + (dx - 1) * rp2 - rp - 1), &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer: nine K = 16 taps per plane, three per elect (the dz taps: operand row + 1, accumulator + 64 columns)
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (256u >> 4) | (1u << 14) | ((uint32_t)SW_32 << 29);      // 8-row groups of 32-byte rows
+    const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+    const uint64_t b_tap = (uint64_t)(w_slot >> 4), rp2u = (uint64_t)(rp * 2);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int it = 0, tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      if (tl >= 2) { mbar_wait(&acc_empty[buf], ((tl >> 1) - 1) & 1); tc_fence_after(); }
+      const uint32_t d = tmem + buf * 256;
+#pragma unroll 1
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full[s], (it / stages) & 1);
+        tc_fence_after();
+        const uint64_t a0 = ((uint64_t)hi << 32) | (0x10000u | ((a_base + s * a_slot) >> 4));
+        const uint64_t b0 = ((uint64_t)hi << 32) | (0x10000u | ((w_base + (uint32_t)(dx * 9 * w_slot)) >> 4));
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+          umma_bf16_x3_elect_a<2>(d, a0 + dy * rp2u, b0 + 3 * dy * b_tap, b_tap, idesc, (dx != 0 || dy != 0) ? 1u : 0u);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ---- epilogue warps: tile t while the issuer works on tile t + 1
+    int tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      conv3d_epilogue(p, s_scr, tmem + buf * 256, &acc_full[buf], (long long)tile * 128, tid, lane, wid, s_bias,
+                      (uint32_t)((tl >> 1) & 1), tile);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the scratch sums of this tile have been consumed
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<512>(tmem);
+}
+
 // fp32 [b, c <= 16, r^3] -> bf16 zero-padded grid with 16 channels per row; one thread per padded voxel
 __global__ void __launch_bounds__(256) cl_pad16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int r,
                                                        long long rows) {
@@ -1102,6 +1233,8 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
                          int out_mode, int out_stride, void* y_cl, double* stats, cudaStream_t s) {
   const int cpad = ((ci + 63) / 64) * 64, kb = cpad / 64;
   const long long P = (long long)(r + 2) * (r + 2) * (r + 2), rows = (long long)b * P;
+  // the epilogue's voxel indexing: a 128-row tile touches at most two clouds, coordinates by 32-bit reciprocal multiplication
+  GLDM_REQUIRE(r >= 4 && r <= 62, "conv3d (tensor cores): resolution %d outside [4, 62]", r);
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("conv3d_k3_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -1127,6 +1260,7 @@ static int launch_conv3d(const void* x_cl, const void* w_img, const float* bias,
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 1024;
   p.out_mode = out_mode; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = stats; p.batch = b; p.n_acc = 1;
+  conv3d_set_magic(p);
   static SmemOptIn attr_s, attr_b;
   const int smem_small = c3::STAGES * (c3::A_BYTES + c3::W_SLOT) + 1024 + 768;
   const int smem_big = c3::STAGES * (c3::A_BYTES + c3::W_BYTES) + 1024 + 768;
@@ -1291,7 +1425,7 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
                                    void* scratch, void* y_cl, int out_stride, double* stats, void* ws, void* stream) {
   // x == NULL: `scratch` already holds the zero-padded 16-channel bf16 grid (gldm_voxelize_fused_cl wrote it)
   GLDM_REQUIRE(b <= 0 || (w_img && scratch && y_cl && stats && ws), "conv3d_tc16_cl: null pointer");
-  GLDM_REQUIRE(b >= 0 && ci > 0 && ci <= 16 && co > 0 && co <= 128 && co % 8 == 0 && r > 0, "conv3d_tc16_cl: bad sizes");
+  GLDM_REQUIRE(b >= 0 && ci > 0 && ci <= 16 && co > 0 && co <= 128 && co % 8 == 0 && r >= 4 && r <= 62, "conv3d_tc16_cl: bad sizes");
   GLDM_REQUIRE(out_stride >= co && out_stride % 16 == 0 && out_stride <= 128, "conv3d_tc16_cl: bad out_stride");
   if (b == 0) return GLDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1325,6 +1459,36 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
   p.rows = rows;
   p.w_rows_bytes = ((co + 7) / 8) * 256;
   p.out_mode = 1; p.out_stride = out_stride; p.y_cl = y_cl; p.stats = reinterpret_cast<double*>(ws); p.batch = b; p.n_acc = 1;
+  conv3d_set_magic(p);
+  // large grids: persistent, weight-stationary kernel (GLDM_CONV3D_PERSISTENT16: 0 = never, 1 (default) = from two tiles per
+  // SM on, 2 = always, for tests; read per call)
+  {
+    const char* ev = getenv("GLDM_CONV3D_PERSISTENT16");
+    const int mode = ev ? atoi(ev) : 1;
+    const int n_tiles = (int)((rows + 127) / 128), a_rows = 130 + 2 * (r + 2);
+    if (mode && a_rows <= 256 && ((co + 15) & ~15) <= 64 && (mode == 2 || n_tiles >= 2 * kNumSMs)) {
+      CUtensorMap mapp;
+      const cuuint32_t boxp[2] = {16, (cuuint32_t)a_rows};
+      const CUresult crp = enc(&mapp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, scratch, gdim, gstride, boxp, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (crp != CUDA_SUCCESS) {
+        set_error("conv3d_tc16_cl: cuTensorMapEncodeTiled (%d-row box) failed (%d)", a_rows, (int)crp);
+        return GLDM_ECUDA;
+      }
+      const int w_slot = (p.w_rows_bytes + 1023) & ~1023, a_slot = (a_rows * 32 + 1023) & ~1023, stages_p = 4;
+      const int smem_p = 27 * w_slot + stages_p * a_slot + c3::P_SCRATCH + 768 + 1024;
+      static SmemOptIn attr_p;
+      if (int rc2 = opt_in_smem(attr_p, conv3d_tc16p_kernel, 27 * 4096 + 4 * 8192 + c3::P_SCRATCH + 768 + 1024, "conv3d_tc16p_kernel"))
+        return rc2;
+      p.n_acc = 3;
+      conv3d_tc16p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot, w_slot);
+      rc = check_launch("conv3d_tc16p_kernel");
+      if (rc) return rc;
+      conv_stats_finalize_kernel<<<b, 512, 0, s>>>(reinterpret_cast<const double*>(ws), (int)P, rows, stats);
+      return check_launch("conv_stats_finalize_kernel");
+    }
+  }
   const int smem16 = c3::STAGES16 * (c3::A16_BYTES + 3 * c3::W16_SLOT) + 1024 + 768;
   static SmemOptIn attr16;
   if (int rc2 = opt_in_smem(attr16, conv3d_tc16_kernel, smem16, "conv3d_tc16_kernel")) return rc2;

@@ -178,6 +178,23 @@ __device__ __forceinline__ void umma_bf16_x3_elect(uint32_t tmem_d, uint64_t ade
       "l"(adesc), "l"(bdesc), "r"(idesc), "l"(b_step), "r"(accumulate)
       : "memory");
 }
+// the same for operand rows of ASTEP 16-byte units (32-byte rows of the narrow first layer: ASTEP = 2)
+template <int ASTEP>
+__device__ __forceinline__ void umma_bf16_x3_elect_a(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t b_step,
+                                                     uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred q, p;\n\t.reg .b64 a1, a2, b1, b2;\n\t.reg .b32 d1, d2;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "add.u64 a1, %1, %6;\n\tadd.u64 a2, %1, %7;\n\t"
+      "add.u64 b1, %2, %4;\n\tadd.u64 b2, b1, %4;\n\t"
+      "add.u32 d1, %0, 64;\n\tadd.u32 d2, %0, 128;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [d1], a1, b1, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [d2], a2, b2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "l"(b_step), "r"(accumulate), "n"(ASTEP), "n"(2 * ASTEP)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"

@@ -448,9 +448,12 @@ def test_row_major_kernel_parity(fpc, cuda, row_major):
     assert dt < 1e-3 and da < 2.0
 
 
-def test_first_conv3d_tensor_core(cuda):
-    """3 -> 48 Conv3d on the tensor cores (K = 16 rows, SWIZZLE_32B, one A tile per filter column) against torch on the
-    same bf16-rounded operands, incl. the padded channels-last output and the GroupNorm statistics."""
+@pytest.mark.parametrize("persistent", ["0", "2"])
+def test_first_conv3d_tensor_core(cuda, persistent, monkeypatch):
+    """3 -> 48 Conv3d on the tensor cores (K = 16 rows, SWIZZLE_32B) against torch on the same bf16-rounded operands, incl.
+    the padded channels-last output and the GroupNorm statistics: the one-tile kernel (one A tile per filter column) and
+    the persistent weight-stationary one the large batches use (one A box per dx plane, several tiles per CTA)."""
+    monkeypatch.setenv("GLDM_CONV3D_PERSISTENT16", persistent)
     import torch.nn.functional as F
     from graspldm_b200 import _lib
     from graspldm_b200.engine import _aligned_bytes, _stream
