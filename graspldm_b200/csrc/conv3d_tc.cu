@@ -817,11 +817,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc16p_kernel(const __g
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * 128;
-      if (tile + (int)gridDim.x < n_tiles && elect_one_sync()) {       // the next tile's boxes on their way into L2
-        const long long rown = (long long)(tile + gridDim.x) * 128;
-        for (int dx = 0; dx < 3; ++dx) tma_prefetch_2d(&xmap, 0, (int)(rown + (dx - 1) * rp2 - rp - 1));
-      }
-      __syncwarp();
+      // (no L2 prefetch of the next tile here: with 32-byte rows the TMA unit's row rate, not the HBM leg, is the limit)
 #pragma unroll 1
       for (int dx = 0; dx < 3; ++dx, ++it) {
         const int s = it % stages, round = it / stages;
