@@ -267,7 +267,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulation); fp32: strict-fp32 SIMT parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=5,
                     help="batches in flight: consecutive steps are issued round-robin on this many CUDA streams, so the "
                          "encoder / decoder of one batch fill the SMs the persistent sampler of another leaves idle")
     args = ap.parse_args()
