@@ -766,6 +766,56 @@ __global__ void __launch_bounds__(c3::NTHREADS, 2) conv3d_tc16_kernel(const __gr
   if (wid == 1) tmem_dealloc<128>(tmem);
 }
 
+// Channels-last epilogue of ONE tile by a group of FOUR warps (one per TMEM lane quarter; a thread takes all channels of its
+// row): two such groups work on two tiles at once.  The epilogue of the narrow first layer is a latency chain (TMEM load ->
+// adds -> shuffle reduce-scatter -> barrier -> tile sums), not an instruction-count problem: with eight warps on one tile it
+// took ~4.0 k cycles per tile whatever else was changed, so the way to go faster is two chains in flight.
+template <int CO>
+__device__ __forceinline__ void conv3d_epilogue_g4(const Conv3dTcParams& p, float* wtot, uint32_t tmem, uint64_t* acc_full,
+                                                   long long row0, int lane, int q, int gw, int bar_id, const float* s_bias,
+                                                   uint32_t parity, long long tile) {
+  const int rp = p.r + 2, rp2 = rp * rp, P = rp2 * rp;
+  const long long m = row0 + q * 32 + lane;
+  const long long b0 = (p.rows < 0x7fffffffLL) ? (long long)((unsigned)row0 / (unsigned)P) : row0 / P;
+  int pp = (int)(row0 - b0 * P) + q * 32 + lane;
+  const long long b = b0 + (pp >= P ? 1 : 0);
+  pp -= pp >= P ? P : 0;
+  const int x = (int)__umulhi((unsigned)pp, p.magic_rp2), rem = pp - x * rp2;
+  const int yy = (int)__umulhi((unsigned)rem, p.magic_rp), z = rem - yy * rp;
+  const bool interior = m < p.rows && x >= 1 && x <= p.r && yy >= 1 && yy <= p.r && z >= 1 && z <= p.r;
+  mbar_wait(acc_full, parity);
+  tc_fence_after();
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  float st[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) st[i] = 0.f;
+  uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y_cl) + (size_t)m * p.out_stride * (p.out_mode == 1 ? 2 : 4);
+  conv3d_row_epilogue<CO, 0>(p, taddr, s_bias, interior, yrow, st);
+  conv3d_row_epilogue<CO, 1>(p, taddr, s_bias, interior, yrow, st);
+  // warp totals per cloud slot, then a fixed-order sum over the group's four warps (bit-reproducible, no atomics)
+  for (int slot = 0; slot < 2; ++slot) {
+    if (slot == 1 && !__any_sync(0xffffffffu, interior && b != b0)) {
+      if ((lane & 1) == 0) wtot[(gw * 2 + 1) * 16 + (lane >> 1)] = 0.f;
+      break;
+    }
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (interior && b == b0 + slot) ? st[i] : 0.f;
+    rs_step<16, 8>(a, lane); rs_step<8, 4>(a, lane); rs_step<4, 2>(a, lane); rs_step<2, 1>(a, lane);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    if ((lane & 1) == 0) wtot[(gw * 2 + slot) * 16 + (lane >> 1)] = a[0];
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  if (gw == 0) {
+    const int slot = lane >> 4, idx = lane & 15;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) t += (double)wtot[(w * 2 + slot) * 16 + idx];
+    p.stats[((size_t)tile * 2 + slot) * 16 + idx] = t;
+  }
+  tc_fence_before();
+}
+
 // Persistent form of the narrow first layer for large grids, built like conv3d_tc3p_kernel: the 27 K = 16 taps (27 x co x
 // 32 B) stay resident, one CTA per SM walks the tiles, one activation box per dx plane (130 + 2 (r + 2) rows of 32 bytes
 // serve the nine (dy, dz) taps), three accumulators per tile (one per dz) in two TMEM buffers so the epilogue of tile t runs
@@ -873,6 +923,118 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc16p_kernel(const __g
   tc_fence_before();
   __syncthreads();
   if (wid == 1) tmem_dealloc<512>(tmem);
+}
+
+// conv3d_tc16p_kernel with TWO tiles' epilogues in flight: four single-accumulator TMEM buffers (64 columns each, all 27 taps
+// of a tile accumulate into one), the eight epilogue warps as two groups of four (conv3d_epilogue_g4): group g takes the
+// CTA's tiles g, g + 2, ... while the issuer runs up to four tiles ahead.
+__global__ void __launch_bounds__(c3::NTHREADS, 1) conv3d_tc16g_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                       const __grid_constant__ Conv3dTcParams p, int n_tiles,
+                                                                       int stages, int a_rows, int a_slot, int w_slot) {
+  using namespace c3;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                                        // [27][w_slot]
+  uint8_t* s_a = s_w + 27 * w_slot;                           // [stages][a_slot]
+  uint8_t* s_scr = s_a + stages * a_slot;                     // [2 groups][4 warps][2 slots][16] floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scr + P_SCRATCH);
+  uint64_t* full = bars;             // [4]
+  uint64_t* empty = bars + 4;        // [4]
+  uint64_t* acc_full = bars + 8;     // [4]
+  uint64_t* acc_empty = bars + 12;   // [4]
+  uint64_t* w_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* s_bias = reinterpret_cast<float*>(bars) + 64;        // [128], 256 bytes into the barrier block
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias[i] = (p.bias && i < p.co) ? __ldg(p.bias + i) : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int rp = p.r + 2, rp2 = rp * rp;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  if (wid == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid == 0) {
+    // ---- producer: the filter bank once, then three plane boxes per tile
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)(27 * p.w_rows_bytes));
+      for (int k = 0; k < 27; ++k) bulk_g2s(s_w + (size_t)k * w_slot, p.w_img + (size_t)k * W16_BYTES, p.w_rows_bytes, w_full);
+    }
+    __syncwarp();
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * 128;
+#pragma unroll 1
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % stages, round = it / stages;
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], (uint32_t)a_rows * 32u);
+          tma_load_2d(s_a + s * a_slot, &xmap, 0, (int)(row0 + (dx - 1) * rp2 - rp - 1), &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid == 1) {
+    // ---- UMMA issuer: 27 K = 16 taps of a tile into one accumulator, three (the dz taps) per elect
+    const uint32_t idesc = idesc_bf16(128, (p.co + 15) & ~15);
+    const uint32_t hi = (256u >> 4) | (1u << 14) | ((uint32_t)SW_32 << 29);      // 8-row groups of 32-byte rows
+    const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+    const uint64_t b_tap = (uint64_t)(w_slot >> 4), rp2u = (uint64_t)(rp * 2);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int it = 0, tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl & 3;
+      if (tl >= 4) { mbar_wait(&acc_empty[buf], ((tl >> 2) - 1) & 1); tc_fence_after(); }
+      const uint32_t d = tmem + buf * 64;
+#pragma unroll 1
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full[s], (it / stages) & 1);
+        tc_fence_after();
+        const uint64_t a0 = ((uint64_t)hi << 32) | (0x10000u | ((a_base + s * a_slot) >> 4));
+        const uint64_t b0 = ((uint64_t)hi << 32) | (0x10000u | ((w_base + (uint32_t)(dx * 9 * w_slot)) >> 4));
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+          umma_bf16_x3_same_elect_a<2>(d, a0 + dy * rp2u, b0 + 3 * dy * b_tap, b_tap, idesc, (dx != 0 || dy != 0) ? 1u : 0u);
+        umma_commit_elect(&empty[s]);
+      }
+      umma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ---- epilogue: group g (warps 2 + 4 g .. 5 + 4 g, one per TMEM lane quarter) takes the CTA's tiles g, g + 2, ...
+    const int ew = wid - 2, g = ew >> 2, q = wid & 3, gw = ew & 3;
+    float* wtot = reinterpret_cast<float*>(s_scr) + g * 256;
+    int tl = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      if ((tl & 1) != g) continue;
+      const int buf = tl & 3;
+      const uint32_t par = (uint32_t)((tl >> 2) & 1);
+      if (p.co == 48)
+        conv3d_epilogue_g4<48>(p, wtot, tmem + buf * 64, &acc_full[buf], (long long)tile * 128, lane, q, gw, 1 + g, s_bias, par, tile);
+      else
+        conv3d_epilogue_g4<32>(p, wtot, tmem + buf * 64, &acc_full[buf], (long long)tile * 128, lane, q, gw, 1 + g, s_bias, par, tile);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");       // the group's scratch sums have been consumed
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 1) tmem_dealloc<256>(tmem);
 }
 
 // fp32 [b, c <= 16, r^3] -> bf16 zero-padded grid with 16 channels per row; one thread per padded voxel
@@ -1477,8 +1639,18 @@ extern "C" int gldm_conv3d_tc16_cl(const float* x, const void* w_img, const floa
       static SmemOptIn attr_p;
       if (int rc2 = opt_in_smem(attr_p, conv3d_tc16p_kernel, 27 * 4096 + 4 * 8192 + c3::P_SCRATCH + 768 + 1024, "conv3d_tc16p_kernel"))
         return rc2;
-      p.n_acc = 3;
-      conv3d_tc16p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot, w_slot);
+      // two tiles' epilogues in flight (widths with a compile-time epilogue); GLDM_CONV3D_TC16_GROUPS=1: one tile at a time
+      const char* evg = getenv("GLDM_CONV3D_TC16_GROUPS");
+      if ((co == 48 || co == 32) && !(evg && atoi(evg) == 1)) {
+        static SmemOptIn attr_g;
+        if (int rc2 = opt_in_smem(attr_g, conv3d_tc16g_kernel, 27 * 4096 + 4 * 8192 + c3::P_SCRATCH + 768 + 1024, "conv3d_tc16g_kernel"))
+          return rc2;
+        p.n_acc = 1;
+        conv3d_tc16g_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot, w_slot);
+      } else {
+        p.n_acc = 3;
+        conv3d_tc16p_kernel<<<min(n_tiles, kNumSMs), c3::NTHREADS, smem_p, s>>>(mapp, p, n_tiles, stages_p, a_rows, a_slot, w_slot);
+      }
       rc = check_launch("conv3d_tc16p_kernel");
       if (rc) return rc;
       conv_stats_finalize_kernel<<<b, 512, 0, s>>>(reinterpret_cast<const double*>(ws), (int)P, rows, stats);

@@ -195,6 +195,23 @@ __device__ __forceinline__ void umma_bf16_x3_elect_a(uint32_t tmem_d, uint64_t a
       "l"(adesc), "l"(bdesc), "r"(idesc), "l"(b_step), "r"(accumulate), "n"(ASTEP), "n"(2 * ASTEP)
       : "memory");
 }
+// three taps into ONE accumulator (the first with the caller's accumulate flag, the others accumulating)
+template <int ASTEP>
+__device__ __forceinline__ void umma_bf16_x3_same_elect_a(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint64_t b_step,
+                                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, b1, b2;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.u64 a1, %1, %6;\n\tadd.u64 a2, %1, %7;\n\t"
+      "add.u64 b1, %2, %4;\n\tadd.u64 b2, b1, %4;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "l"(b_step), "r"(accumulate), "n"(ASTEP), "n"(2 * ASTEP)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
