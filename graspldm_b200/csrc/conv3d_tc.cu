@@ -1138,7 +1138,7 @@ __global__ void block_partials_finalize_kernel(const double* __restrict__ part, 
 // epilogue accumulated (R/../pvcnn/modules/pvconv.py:52-57); optionally the per-channel sums of the result for the
 // SE squeeze (se.py:18-19).  Thread <-> (row lane, 8 channels); a block covers `rpb` padded voxels of one cloud.
 template <bool F32>
-__global__ void __launch_bounds__(256) gn_swish_cl_kernel(void* __restrict__ y, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256, F32 ? 3 : 4) gn_swish_cl_kernel(void* __restrict__ y, const double* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int c, int stride, int r, float eps, double* __restrict__ se_sum,
                                                           int rpb) {
