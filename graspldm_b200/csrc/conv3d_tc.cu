@@ -1,16 +1,26 @@
 // Tensor-core (tcgen05 / TMEM) Conv3d k3 p1 of the PVConv voxel branch (R/../pvcnn/modules/pvconv.py:48-67),
 // bf16 operands / fp32 accumulation, as an implicit GEMM over a zero-padded channels-last voxel grid.
 //
-// The input grid is first rewritten (cl_pad_kernel) as X[b * P + p][Cpad] bf16 with P = (r+2)^3 padded voxels per
-// cloud (halo = 0) and Cpad = channels rounded up to 64.  For a filter tap (dx,dy,dz) the A operand of a tile of
-// 128 consecutive padded voxels is then simply the SAME matrix shifted by dx*(r+2)^2 + dy*(r+2) + dz rows, which one
-// 2-D TMA tensor load fetches (SWIZZLE_128B, out-of-range rows read as zero) - no im2col buffer.  The weights are
-// pre-packed UMMA images [tap][K block][128 rows x 128 B] streamed with 1-D bulk copies.  One CTA = 128 padded voxels
-// x all output channels (UMMA M = 128, N = C_out <= 128): warp 0 producer, warp 1 UMMA issuer, warps 2-5 epilogue
-// (bias, drop halo voxels).  Two output forms: fp32 in the reference's [b, c, r^3] layout, or - for the fused voxel
-// branch - the same zero-padded channels-last grid the next Conv3d reads (bf16, or fp32 for the devoxelize input)
-// together with the GroupNorm statistics of the result (fp64 atomics per (cloud, group)), so that GroupNorm + Swish
-// becomes one in-place pass (gn_swish_cl_kernel) and devoxelize gathers channels-last rows (devox_cl_kernel).
+// The input grid is X[b * P + p][Cpad] bf16 with P = (r+2)^3 padded voxels per cloud (halo = 0) and Cpad = channels
+// rounded up to 64 (16 for the 3-channel first layer); the voxelisation or the previous layer's epilogue writes it in
+// that form.  For a filter tap (dx,dy,dz) the A operand of a tile of 128 consecutive padded voxels is then simply the
+// SAME matrix shifted by dx*(r+2)^2 + dy*(r+2) + dz rows, which one 2-D TMA tensor load fetches (SWIZZLE_128B / 32B,
+// out-of-range rows read as zero) - no im2col buffer.  The weights are pre-packed UMMA images [tap][K block][128 rows x
+// 128 B].  One tile = 128 padded voxels x all output channels (UMMA M = 128, N = C_out <= 128): warp 0 producer, warp 1
+// UMMA issuer, warps 2-9 epilogue (bias, drop halo voxels).  Two output forms: fp32 in the reference's [b, c, r^3] layout,
+// or - for the fused voxel branch - the same zero-padded channels-last grid the next Conv3d reads (bf16, or fp32 for the
+// devoxelize input) together with per-tile GroupNorm partial sums (no atomics; conv_stats_finalize_kernel adds the tiles
+// of a cloud in a fixed order), so that GroupNorm + Swish becomes one in-place pass (gn_swish_cl_kernel) and devoxelize
+// gathers channels-last rows (devox_cl_kernel).
+//
+// Kernels, by layer (the launchers pick; INTEGRATION.md section 5 lists the switches):
+//   conv3d_tc_kernel      one tile per CTA, one activation tile per tap (first version; fp32 [b, c, r^3] output path)
+//   conv3d_tc3_kernel     one tile per CTA, one activation tile per filter column (three dz taps per load)
+//   conv3d_tc3p_kernel    persistent, the whole filter bank resident (48 -> 48 at 24^3), one box per dx plane
+//   conv3d_tc3m_kernel    persistent, streamed weights, two tiles per weight stage (48 -> 96, 96 -> 96 at 12^3)
+//   conv3d_tc16_kernel    the 3 -> 48 first layer (16-channel rows, K = 16 per tap), one tile per CTA
+//   conv3d_tc16p_kernel   the same, persistent and weight-stationary
+//   conv3d_tc16g_kernel   the same with two tiles' epilogues in flight (default for large grids)
 #include <cuda.h>
 #include <stdlib.h>
 
