@@ -99,27 +99,31 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
 // ball query                                     R/ball_query/ball_query.cu:19-50
 // ------------------------------------------------------------------------------------------------
 // Thread = centre: a CTA stages the cloud once in shared memory (12 n bytes) and every thread scans it in ascending
-// index for its own centre, two points per step as packed f32x2 operations (FADD2 / FMUL2 / FFMA2 round per element
-// like the scalar chain, so the indices stay bit-exact).  A point is one broadcast LDS for the whole warp, a hit is an
-// append to the thread's own list - no ballot / compaction - and the tail of every list (slots the reference pre-fills
-// with the first hit) is written by the whole CTA, coalesced.  ~6 thread instructions per (centre, point) pair.
+// index for its own centre.  The scan is branch-free: 32 points per round, four points per broadcast LDS.128 and
+// coordinate, the distance chain as packed f32x2 operations (FADD2 / FMUL2 / FFMA2 round per element like the scalar
+// chain, so the indices stay bit-exact), and the test "d < r2" as the SIGN of the packed difference d - r2 shifted
+// into a per-thread hit mask (one funnel shift per point; d, r2 >= 0 and x - x = +0, so the sign is set exactly when
+// d < r2).  Only the hits are then walked (count-leading-zeros over the mask, ascending index): the divergent append
+// runs once per hit of the busiest lane of a 32-point round instead of once per point pair with a hit in any lane
+// (which was 40 % of the pairs at r = 0.2).  The tail of every list (slots the reference pre-fills with the first
+// hit) is written by the whole CTA, coalesced.  ~6 thread instructions per (centre, point) pair (was 16).
 constexpr int kBqThreads = 128;
 constexpr int kBqMaxSmemPoints = 16384;
 template <bool SMEM>
 __global__ void __launch_bounds__(kBqThreads) ball_query_kernel(const float* __restrict__ centers,
                                                                 const float* __restrict__ points, int n, int m,
                                                                 float r2, int u, int* __restrict__ out) {
-  extern __shared__ float s_pts[];           // SMEM: [3][np], np = n rounded up to 2, the padding at +inf (never a hit)
+  extern __shared__ __align__(16) float s_pts[];   // SMEM: [3][np], np = n rounded up to 32 (padding masked out below)
   __shared__ int s_cnt[kBqThreads], s_first[kBqThreads];
   const int b = blockIdx.y, tid = threadIdx.x;
-  const int np = (n + 1) & ~1;
+  const int np = (n + 31) & ~31;
   const float* gx = points + (size_t)b * 3 * n;
   if (SMEM) {
     for (int k = tid; k < np; k += kBqThreads) {
       const bool v = k < n;
-      s_pts[k] = v ? gx[k] : INFINITY;
-      s_pts[np + k] = v ? gx[n + k] : INFINITY;
-      s_pts[2 * np + k] = v ? gx[2 * n + k] : INFINITY;
+      s_pts[k] = v ? gx[k] : 0.f;
+      s_pts[np + k] = v ? gx[n + k] : 0.f;
+      s_pts[2 * np + k] = v ? gx[2 * n + k] : 0.f;
     }
     __syncthreads();
   }
@@ -128,33 +132,53 @@ __global__ void __launch_bounds__(kBqThreads) ball_query_kernel(const float* __r
   const float* cc = centers + (size_t)b * 3 * m;
   const float c0 = valid ? __ldg(cc + j) : 0.f, c1 = valid ? __ldg(cc + m + j) : 0.f, c2 = valid ? __ldg(cc + 2 * m + j) : 0.f;
   const float2 cx = make_float2(c0, c0), cy = make_float2(c1, c1), cz = make_float2(c2, c2);
+  const float2 nr2 = make_float2(-r2, -r2);
   int* o = out + ((size_t)b * m + (valid ? j : 0)) * u;
   int cnt = valid ? 0 : u, first = 0;
-  for (int k = 0; k < np; k += 2) {
-    float2 x, y, z;
-    if (SMEM) {
-      x = *reinterpret_cast<const float2*>(s_pts + k);
-      y = *reinterpret_cast<const float2*>(s_pts + np + k);
-      z = *reinterpret_cast<const float2*>(s_pts + 2 * np + k);
-    } else {
-      const bool v1 = k + 1 < n;
-      x = make_float2(__ldg(gx + k), v1 ? __ldg(gx + k + 1) : INFINITY);
-      y = make_float2(__ldg(gx + n + k), v1 ? __ldg(gx + n + k + 1) : INFINITY);
-      z = make_float2(__ldg(gx + 2 * n + k), v1 ? __ldg(gx + 2 * n + k + 1) : INFINITY);
+  for (int base = 0; base < np; base += 32) {
+    unsigned mask = 0;                                  // point base + i -> bit 31 - i
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = base + 4 * q;
+      float4 x, y, z;
+      if (SMEM) {
+        x = *reinterpret_cast<const float4*>(s_pts + k);
+        y = *reinterpret_cast<const float4*>(s_pts + np + k);
+        z = *reinterpret_cast<const float4*>(s_pts + 2 * np + k);
+      } else {
+        float t[12];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) t[4 * a + e] = k + e < n ? __ldg(gx + (size_t)a * n + k + e) : 0.f;
+        x = make_float4(t[0], t[1], t[2], t[3]);
+        y = make_float4(t[4], t[5], t[6], t[7]);
+        z = make_float4(t[8], t[9], t[10], t[11]);
+      }
+      // d = fma(dz, dz, fma(dx, dx, dy * dy)) with d* = centre - point (ball_query.cu:36-40, FMA chain of the reference build)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 px = h ? make_float2(x.z, x.w) : make_float2(x.x, x.y);
+        const float2 py = h ? make_float2(y.z, y.w) : make_float2(y.x, y.y);
+        const float2 pz = h ? make_float2(z.z, z.w) : make_float2(z.x, z.y);
+        const float2 dx = __fadd2_rn(cx, make_float2(-px.x, -px.y)), dy = __fadd2_rn(cy, make_float2(-py.x, -py.y)),
+                     dz = __fadd2_rn(cz, make_float2(-pz.x, -pz.y));
+        const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+        const float2 e = __fadd2_rn(d, nr2);            // sign(e) = (d < r2)
+        mask = __funnelshift_l(__float_as_uint(e.x), mask, 1);
+        mask = __funnelshift_l(__float_as_uint(e.y), mask, 1);
+      }
     }
-    // d = fma(dz, dz, fma(dx, dx, dy * dy)) with d* = centre - point (ball_query.cu:36-40, FMA chain of the reference build)
-    const float2 dx = __fadd2_rn(cx, make_float2(-x.x, -x.y)), dy = __fadd2_rn(cy, make_float2(-y.x, -y.y)),
-                 dz = __fadd2_rn(cz, make_float2(-z.x, -z.y));
-    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
-    if (d.x < r2 && cnt < u) {
-      if (cnt == 0) first = k;
-      o[cnt++] = k;
+    if (base + 32 > n) mask &= ~0u << (base + 32 - n);  // padding points are never hits
+    if (cnt >= u) mask = 0;
+    while (mask) {
+      const int i = __clz(mask);
+      mask &= ~(0x80000000u >> i);
+      if (cnt == 0) first = base + i;
+      o[cnt] = base + i;
+      if (++cnt >= u) mask = 0;
     }
-    if (d.y < r2 && cnt < u) {
-      if (cnt == 0) first = k + 1;
-      o[cnt++] = k + 1;
-    }
-    if ((k & 62) == 62 && __all_sync(0xffffffffu, cnt >= u)) break;
+    if (__all_sync(0xffffffffu, cnt >= u)) break;
   }
   // the first hit pre-fills every slot; no hit leaves zeros (ball_query.cu:39-44): tails written by the whole CTA
   s_cnt[tid] = cnt;
@@ -177,7 +201,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(256) ball_query_warp_kernel(const float* __restrict__ centers,
                                                               const float* __restrict__ points, int n, int m,
                                                               float r2, int u, int* __restrict__ out) {
-  extern __shared__ float s_pts[];           // SMEM: [3][np], np = n rounded up to 32, the padding at +inf (never a hit)
+  extern __shared__ __align__(16) float s_pts[];   // SMEM: [3][np], np = n rounded up to 32, the padding at +inf (never a hit)
   const int b = blockIdx.y;
   const int np = (n + 31) & ~31;
   const float* gx = points + (size_t)b * 3 * n;
@@ -743,7 +767,7 @@ extern "C" int gldm_ball_query(const float* centers, const float* points, int b,
   if ((long long)b * m >= 131072) {
     // throughput: thread = centre (fewest instructions per distance test)
     dim3 grid(ceil_div(m, kBqThreads), b);
-    const int smem = 3 * ((n + 1) & ~1) * (int)sizeof(float);
+    const int smem = 3 * ((n + 31) & ~31) * (int)sizeof(float);
     if (smem_ok && smem > 48 * 1024)
       if (int rc = opt_in_smem(attr_t, ball_query_kernel<true>, 3 * kBqMaxSmemPoints * (int)sizeof(float), "ball_query_kernel")) return rc;
     if (smem_ok) ball_query_kernel<true><<<grid, kBqThreads, smem, s>>>(centers, points, n, m, r2, u, neighbors);
