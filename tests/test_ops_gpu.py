@@ -88,6 +88,26 @@ def test_three_nn(be, cuda, ref_backend, gold, name, coords):
         np.testing.assert_allclose(out.cpu().numpy(), gold[f"{name}/nn_out"], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 131, 4100])
+def test_three_nn_centre_counts(be, cuda, ref_backend, m):
+    """Centre counts that are not a multiple of four (scalar tail of the packed scan), fewer than three centres (unused slots
+    keep index 0 and the clamped 1e10 distance, neighbor_interpolate.cu:38-39,60-62), and more than 4096 centres (the kernel
+    without the shared-memory copy); one lattice cloud for exact ties."""
+    pts = torch.cat([_data.synthetic_clouds(1, 300, 21, "G"), _data.quantised_clouds(1, 300, 22, 0.5)]).transpose(1, 2).contiguous()
+    g = torch.Generator().manual_seed(m)
+    ctr = torch.cat([torch.randn(1, 3, m, generator=g) * 0.7, torch.round(torch.randn(1, 3, m, generator=g) * 0.7 / 0.5) * 0.5])
+    cf = _data.features_for(ctr, 5, 3)
+    out, idx, w = be.three_nearest_neighbors_interpolate_forward(pts.to(cuda), ctr.to(cuda), cf.to(cuda))
+    o2, i2, w2 = ops_np.three_nearest_neighbors_interpolate_forward(pts.numpy(), ctr.numpy(), cf.numpy())
+    assert np.array_equal(idx.cpu().numpy(), i2)
+    np.testing.assert_allclose(w.cpu().numpy(), w2, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(out.cpu().numpy(), o2, rtol=1e-6, atol=1e-7)
+    if ref_backend is not None:
+        o3, i3, w3 = ref_backend.three_nearest_neighbors_interpolate_forward(pts.to(cuda), ctr.to(cuda), cf.to(cuda))
+        assert torch.equal(idx, i3)
+        np.testing.assert_allclose(w.cpu().numpy(), w3.cpu().numpy(), rtol=2e-6, atol=0)
+
+
 @pytest.mark.parametrize("name,coords", CASES, ids=[c[0] for c in CASES])
 def test_voxelize_devoxelize(be, cuda, ref_backend, gold, name, coords):
     for r, ch in ((24, 3), (12, 6)):

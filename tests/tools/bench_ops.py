@@ -49,6 +49,8 @@ def main():
             centers = be.gather_features_forward(coords, idx)
             r["ball_query_r0.2_u32_ms"] = timeit(lambda: be.ball_query(centers, coords, 0.2, 32))
             nb = be.ball_query(centers, coords, 0.2, 32)
+            cfeat = torch.randn(B, 32, 256, device=dev)
+            r["three_nn_interpolate_c32_ms"] = timeit(lambda: be.three_nearest_neighbors_interpolate_forward(coords, centers, cfeat))
             feats = torch.randn(B, 32, 1024, device=dev)
             r["grouping_c32_ms"] = timeit(lambda: be.grouping_forward(feats, nb))
             vc, nc = _data.vox_coords(coords.cpu(), 24)
