@@ -43,6 +43,19 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
   const int nwarps = blockDim.x >> 5;
   __shared__ unsigned s_bits[2][32];
   __shared__ unsigned s_key[2][32];
+  // slots of warps that do not exist hold the neutral element, so the second level reads all 32 without a branch; the
+  // slot addresses are formed once (inside the round loop the compiler rebuilt them, ~20 instructions per round)
+  if (tid < 64) {
+    (&s_bits[0][0])[tid] = 0u;
+    (&s_key[0][0])[tid] = 0xffffffffu;
+  }
+  // (32-bit shared-space addresses used through ld / st.shared below: with C++ pointers the cluster-window base was
+  // rebuilt from %cluster_ctarank inside every round)
+  unsigned wr_bits = (unsigned)__cvta_generic_to_shared(&s_bits[0][wid]);
+  unsigned wr_key = (unsigned)__cvta_generic_to_shared(&s_key[0][wid]);
+  unsigned rd_bits = (unsigned)__cvta_generic_to_shared(&s_bits[0][lane]);
+  unsigned rd_key = (unsigned)__cvta_generic_to_shared(&s_key[0][lane]);
+  asm volatile("" : "+r"(wr_bits), "+r"(wr_key), "+r"(rd_bits), "+r"(rd_key));   // opaque: keep them in registers
 
   float px[PPT], py[PPT], pz[PPT], dist[PPT];
   unsigned kk[PPT];                            // tie-break keys of this thread's points (0xffffffff: no point)
@@ -57,7 +70,7 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
     kk[j] = v ? fps_key(k) : 0xffffffffu;
     if (SMEM && v) { s_pts[k] = px[j]; s_pts[n + k] = py[j]; s_pts[2 * n + k] = pz[j]; }
   }
-  if (SMEM) __syncthreads();
+  __syncthreads();                             // the staged cloud and the neutral slots above
   int old = 0;
   if (tid == 0) out[0] = 0;
   for (int r = 1; r < m; ++r) {
@@ -79,14 +92,15 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ coo
     unsigned gb = __reduce_max_sync(0xffffffffu, bits);
     unsigned gk = __reduce_min_sync(0xffffffffu, bits == gb ? key : 0xffffffffu);
     if (nwarps > 1) {
-      const int buf = r & 1;
+      const unsigned buf = (r & 1) * 128u;
       if (lane == 0) {
-        s_bits[buf][wid] = gb;
-        s_key[buf][wid] = gk;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wr_bits + buf), "r"(gb) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wr_key + buf), "r"(gk) : "memory");
       }
       __syncthreads();
-      unsigned b2 = lane < nwarps ? s_bits[buf][lane] : 0u;
-      unsigned k2 = lane < nwarps ? s_key[buf][lane] : 0xffffffffu;
+      unsigned b2, k2;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b2) : "r"(rd_bits + buf) : "memory");
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(k2) : "r"(rd_key + buf) : "memory");
       gb = __reduce_max_sync(0xffffffffu, b2);
       gk = __reduce_min_sync(0xffffffffu, (b2 == gb) ? k2 : 0xffffffffu);
     }
@@ -402,6 +416,7 @@ __global__ void __launch_bounds__(128) three_nn_kernel(const float* __restrict__
   ib[j] = i0; ib[j + n] = i1; ib[j + 2 * n] = i2;
   const float* fb = feats + (size_t)b * c * m;
   float* ob = out + (size_t)b * c * n;
+#pragma unroll 4
   for (int ch = 0; ch < c; ++ch) {
     const float* f = fb + (size_t)ch * m;
     // reference SASS order: FMUL(2nd term), FFMA(1st), FFMA(3rd)
