@@ -20,7 +20,9 @@ implemented by diffusers >= 0.15 (Ho et al. 2020 eq. 7 / Song et al. 2021 eq. 12
 PARITY UNPINNED for this file: the reference has no test, golden vector or pinned
 version at this boundary.  All coefficients are 0-dim float32
 torch tensors combined in the same operator order as diffusers so that the tables
-are reproducible bit for bit.
+are reproducible bit for bit.  What is pinned offline: tests/test_scheduler_equations_cpu.py
+checks these coefficients (and the product's tables) against the papers' closed forms
+evaluated independently in float64.
 """
 import torch
 
