@@ -35,12 +35,17 @@ def _rtol(small):
     return max(5e-5, 1e-6 / small)
 
 
+# constructor defaults (gaussian_diffusion.py:30-31) and the betas of the reference's fpc / ppc configs
+BETAS = [(1e-4, 2e-2), (5e-5, 1e-3)]
+
+
+@pytest.mark.parametrize("betas", BETAS)
 @pytest.mark.parametrize("n_steps", [1000, 100, 10])
 @pytest.mark.parametrize("variance_type", ["fixed_small", "fixed_large"])
-def test_ddpm_coefficients_are_the_posterior_of_ho_et_al(n_steps, variance_type):
+def test_ddpm_coefficients_are_the_posterior_of_ho_et_al(n_steps, variance_type, betas):
     T = 1000
-    abar = _abar64(T)
-    sch = S.SchedulerOracle("ddpm", num_train_timesteps=T, variance_type=variance_type)
+    abar = _abar64(T, *betas)
+    sch = S.SchedulerOracle("ddpm", num_train_timesteps=T, variance_type=variance_type, beta_start=betas[0], beta_end=betas[1])
     sch.set_timesteps(n_steps)
     ts = S.timestep_list(T, n_steps)
     assert ts[0] == T - T // n_steps and ts[-1] == 0 and len(ts) == n_steps
@@ -122,13 +127,14 @@ def test_clip_sample_clamps_the_predicted_x0_only():
     assert float(free[0, 0]) > float(got[0, 0])
 
 
+@pytest.mark.parametrize("betas", BETAS)
 @pytest.mark.parametrize("kind,n_steps", [("ddpm", 1000), ("ddpm", 100), ("ddim", 10), ("ddim", 50)])
-def test_product_tables_satisfy_the_same_closed_forms(kind, n_steps):
+def test_product_tables_satisfy_the_same_closed_forms(kind, n_steps, betas):
     """The kernel's coefficient table (graspldm_b200/schedulers.py, what gldm_sampler_* consumes) against float64 closed
     forms directly - independent of the oracle."""
     T = 1000
-    abar = _abar64(T)
-    sch = NoiseSchedule(kind, num_train_timesteps=T, variance_type="fixed_large")
+    abar = _abar64(T, *betas)
+    sch = NoiseSchedule(kind, num_train_timesteps=T, variance_type="fixed_large", beta_start=betas[0], beta_end=betas[1])
     sch.set_timesteps(n_steps)
     ts, tab = sch.table()
     tab = tab.double().numpy()
