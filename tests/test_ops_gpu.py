@@ -88,6 +88,22 @@ def test_three_nn(be, cuda, ref_backend, gold, name, coords):
         np.testing.assert_allclose(out.cpu().numpy(), gold[f"{name}/nn_out"], rtol=1e-5, atol=1e-6)
 
 
+def test_ball_query_clouds_too_large_for_shared_memory(be, cuda):
+    """More than 16384 points per cloud: both ball-query kernels read the cloud through the read-only cache instead of a
+    shared-memory copy.  Few centres -> the warp-cooperative kernel; the same eight centres tiled to 131072 -> the
+    thread = centre kernel (point count not a multiple of 32: the masked last round)."""
+    g = torch.Generator().manual_seed(17)
+    n = 16400 + 13
+    pts = torch.randn(1, 3, n, generator=g) * 0.7
+    ctr = pts[:, :, torch.randint(0, n, (8,), generator=g)].contiguous() + 0.01
+    for r, u in ((0.15, 32), (0.4, 5)):
+        want = ops_np.ball_query(ctr.numpy(), pts.numpy(), r, u)
+        got = be.ball_query(ctr.to(cuda), pts.to(cuda), r, u)
+        assert np.array_equal(got.cpu().numpy(), want), (r, u)
+        big = be.ball_query(ctr.repeat(1, 1, 16384).to(cuda), pts.to(cuda), r, u)
+        assert torch.equal(big, got.repeat(1, 16384, 1)), (r, u)
+
+
 @pytest.mark.parametrize("m", [1, 2, 3, 5, 131, 4100])
 def test_three_nn_centre_counts(be, cuda, ref_backend, m):
     """Centre counts that are not a multiple of four (scalar tail of the packed scan), fewer than three centres (unused slots
