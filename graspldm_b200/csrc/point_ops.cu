@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) group_scatter_add_kernel(const float* __r
 // (four per broadcast LDS.128 and coordinate), the distance chain is packed f32x2 (same rounding per element), and the
 // insertion is branch-free (three compares, five selects, five min / max): with a divergent insert some lane of a warp
 // took the branch on more than half of the centres.  Strict "<" as in the reference: an equal distance stays behind the
-// earlier centre.  18 instead of 44 thread instructions per (point, centre) pair.
+// earlier centre.  20 instead of 44 thread instructions per (point, centre) pair.
 constexpr int kNnMaxSmemCenters = 4096;          // 3 x 16 KB: within the default dynamic shared-memory limit
 template <bool SMEM>
 __global__ void __launch_bounds__(128) three_nn_kernel(const float* __restrict__ points,
