@@ -7,7 +7,10 @@
 //   * FPS keeps every point and its running min-distance in registers, picks the round winner with
 //     two REDUX (warp max of the distance bits, warp min of the tie-break key) per level and one
 //     block barrier per round;
-//   * ball query is a warp-per-centre ballot/popc compaction with early exit;
+//   * ball query has two kernels: small batches take four centres per warp (ballot / popc compaction, early exit),
+//     large ones a thread per centre that scans 32 points per round branch-free into a hit mask and walks only the hits;
+//   * 3-NN keeps the three best distances in fp32 registers with a branch-free insertion (same decisions as the
+//     reference's double-typed bests, which only ever hold floats);
 //   * grouping / gather are 128-bit vectorised, write-coalesced gathers;
 //   * voxelisation buckets the points by voxel with a shared-memory counting sort, orders every bucket by point index
 //     and accumulates in that order, so results are deterministic.
